@@ -1,0 +1,233 @@
+// Shared device/host helpers for the sm_100a kernels: error plumbing, bf16 packing,
+// mbarrier / TMA / tcgen05 inline-PTX wrappers.  Everything here is hand-written PTX for
+// Blackwell (tcgen05 + TMEM + TMA); there is no fallback path for other architectures.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+namespace sonic {
+
+// ------------------------------------------------------------------ host-side error state
+void set_error(const char* fmt, ...);
+const char* last_error();
+int check_cuda(cudaError_t e, const char* what, const char* file, int line);
+
+#define SONIC_CUDA(expr)                                                         \
+  do {                                                                           \
+    if (int _rc = ::sonic::check_cuda((expr), #expr, __FILE__, __LINE__)) return _rc; \
+  } while (0)
+#define SONIC_REQUIRE(cond, ...)                                                 \
+  do {                                                                           \
+    if (!(cond)) { ::sonic::set_error(__VA_ARGS__); return -2; }                 \
+  } while (0)
+
+// cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda link dependency).
+// dims/strides are innermost-first; strides[i] is the byte stride of dim i+1.
+int encode_tensor_map(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                      const uint64_t* strides_bytes, const uint32_t* box, bool swizzle128);
+
+#ifdef __CUDACC__
+// ------------------------------------------------------------------ small device utilities
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ float bf16_lo(uint32_t v) { return __uint_as_float(v << 16); }
+__device__ __forceinline__ float bf16_hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
+__device__ __forceinline__ float round_bf16(float x) {
+  return __bfloat162float(__float2bfloat16_rn(x));
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
+// ------------------------------------------------------------------ mbarrier
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_smem() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug becomes a trap (-> cudaErrorLaunchFailure) instead of a hang
+// that would wedge a shared GPU box.  ~4 s at 2 GHz; never reached in a correct run.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 8000000000LL) {
+      printf("sonic: mbarrier timeout block %d thread %d\n", blockIdx.x, threadIdx.x);
+      __trap();
+    }
+  }
+}
+
+// ------------------------------------------------------------------ TMA (cp.async.bulk.tensor)
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0,
+                                            int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0,
+                                            int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* m, uint64_t* bar, int c0,
+                                            int c1, int c2, int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes"
+      " [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+
+// ------------------------------------------------------------------ tcgen05 / TMEM
+template <int kCols>
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst) {  // whole warp, .sync.aligned
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                   smem_u32(smem_dst)),
+               "n"(kCols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <int kCols>
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {  // whole warp
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(kCols)
+               : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]; issued by ONE thread for the CTA.
+__device__ __forceinline__ void umma_bf16_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b,
+                                             uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// Arrive on an mbarrier once every tcgen05.mma issued so far by this thread has completed
+// (implies tcgen05.fence::before_thread_sync).
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
+                   smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() {
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+// 32 lanes x 16 consecutive fp32 columns: thread i of the warp reads TMEM lane (base_lane + i).
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+        "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
+        "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+        "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
+        "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]),
+        "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]),
+        "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+
+// Shared-memory matrix descriptor (sm_100 "version 1") for a 128B-swizzled tile whose rows
+// are 128 bytes (64 bf16) at a 128 B pitch, i.e. exactly what a TMA box with inner extent 64
+// and CU_TENSOR_MAP_SWIZZLE_128B writes.  Bit layout (PTX ISA "tcgen05 matrix descriptor"):
+//   [0,14)  start address >> 4         [16,30) leading byte offset >> 4
+//   [32,46) stride byte offset >> 4    [46,48) version = 1     [61,64) swizzle: 2 = 128B
+// K-major use (rows = M or N, 64 K-elements per row): SBO = 1024 B between 8-row groups, LBO
+// unused.  MN-major use (rows = K, 64 MN-elements per row): SBO = 1024 B between 8-K groups,
+// LBO = byte distance between consecutive 64-element MN atoms.
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr, uint32_t lbo_bytes,
+                                                    uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3ffff) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3fff) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3fff) << 32;
+  d |= 1ull << 46;
+  d |= 2ull << 61;
+  return d;
+}
+#endif  // __CUDACC__
+
+// Instruction descriptor for tcgen05.mma kind::f16 with bf16 A/B and fp32 accumulate.
+//   [4,6) D fmt: 1=f32   [7,10) A fmt: 1=bf16   [10,13) B fmt: 1=bf16
+//   [15] A major (0=K)   [16] B major (0=K, 1=MN)   [17,23) N>>3   [24,29) M>>4
+inline uint32_t make_idesc_bf16(int m, int n, bool b_mn_major) {
+  uint32_t d = 0;
+  d |= 1u << 4;
+  d |= 1u << 7;
+  d |= 1u << 10;
+  d |= (b_mn_major ? 1u : 0u) << 16;
+  d |= static_cast<uint32_t>(n >> 3) << 17;
+  d |= static_cast<uint32_t>(m >> 4) << 24;
+  return d;
+}
+
+}  // namespace sonic

@@ -1,0 +1,358 @@
+// tcgen05 implicit-GEMM kernel: conv3x3 / conv1x1 / Linear for the SD UNet (see gemm.cuh).
+//
+// Warp roles (192 threads, one persistent CTA per SM):
+//   warp 0      TMA producer   : A box (128 pixels x 64 ch, shifted per filter tap) + B box
+//   warp 1      MMA issuer     : tcgen05.mma kind::f16, M=128, N=block_n, K=16 x4 per stage;
+//                                owns the 512-column TMEM allocation (2 accumulator buffers)
+//   warps 2..5  epilogue       : tcgen05.ld -> bias / per-image bias / residual / GEGLU -> bf16
+// Pipelines: smem full/empty ring (TMA <-> MMA) and TMEM full/empty pair (MMA <-> epilogue),
+// so the epilogue of tile i overlaps the main loop of tile i+1.
+#include "gemm.cuh"
+
+#include <algorithm>
+
+namespace sonic {
+
+namespace {
+
+constexpr int kGemmThreads = 192;
+constexpr int kTileM = 128;
+constexpr int kTileK = 64;                 // bf16 elements = one 128B swizzle row
+constexpr int kABytes = kTileM * kTileK * 2;
+constexpr int kAccStride = 256;            // TMEM columns per accumulator buffer
+
+__device__ __forceinline__ float gelu_erf(float x) {
+  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
+}
+
+__global__ void __launch_bounds__(kGemmThreads, 1)
+conv_gemm_kernel(const __grid_constant__ GemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  const int stage_bytes = kABytes + p.block_n * kTileK * 2;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.stages * stage_bytes);
+  uint64_t* empty_bar = full_bar + p.stages;
+  uint64_t* tmem_full = empty_bar + p.stages;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int total_tiles = p.m_tiles * p.n_tiles;
+  const int k_chunks = p.k_chunks0 + p.k_chunks1;
+  const int k_iters = p.taps * k_chunks;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full[a], 1);
+      mbar_init(&tmem_empty[a], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      tma_prefetch_desc(&p.tm_a0);
+      tma_prefetch_desc(&p.tm_b);
+      if (p.k_chunks1) tma_prefetch_desc(&p.tm_a1);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int n_tile = tile % p.n_tiles;
+        const int m_tile = tile / p.n_tiles;
+        const int w0 = (m_tile % p.tiles_w) * p.tile_w;
+        const int h0 = ((m_tile / p.tiles_w) % p.tiles_h) * p.tile_h;
+        const int i0 = (m_tile / (p.tiles_w * p.tiles_h)) * p.tile_n;
+        const int ncol0 = n_tile * p.block_n;
+        for (int tap = 0; tap < p.taps; ++tap) {
+          const int dy = p.taps == 9 ? tap / 3 - 1 : 0;
+          const int dx = p.taps == 9 ? tap % 3 - 1 : 0;
+          for (int ch = 0; ch < k_chunks; ++ch) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            mbar_expect_tx(&full_bar[stage], stage_bytes);
+            uint8_t* sa = smem + stage * stage_bytes;
+            if (ch < p.k_chunks0)
+              tma_load_4d(sa, &p.tm_a0, &full_bar[stage], ch * kTileK, w0 + dx, h0 + dy, i0);
+            else
+              tma_load_4d(sa, &p.tm_a1, &full_bar[stage], (ch - p.k_chunks0) * kTileK, w0 + dx,
+                          h0 + dy, i0);
+            tma_load_3d(sa + kABytes, &p.tm_b, &full_bar[stage], ch * kTileK, ncol0, tap);
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      int stage = 0, acc = 0;
+      uint32_t phase = 0, acc_phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * kAccStride;
+        for (int kit = 0; kit < k_iters; ++kit) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * stage_bytes);
+          const uint64_t da = make_sw128_desc(sa, 16, 1024);
+          const uint64_t db = make_sw128_desc(sa + kABytes, 16, 1024);
+#pragma unroll
+          for (int k = 0; k < kTileK / 16; ++k)  // +32 B per K=16 step inside the 128B atom
+            umma_bf16_ss(d_tmem, da + 2 * k, db + 2 * k, p.idesc, (kit | k) != 0);
+          umma_commit(&empty_bar[stage]);
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tmem_full[acc]);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------------ epilogue (4 warps)
+    const int quarter = warp & 3;                // TMEM lane quarter this warp may read
+    const int r = quarter * 32 + lane;           // row inside the 128-row tile
+    const bool geglu = p.epilogue == kEpiGeglu;
+    const int out_cols = geglu ? p.block_n / 2 : p.block_n;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      const int n_tile = tile % p.n_tiles;
+      const int m_tile = tile / p.n_tiles;
+      const int w = (m_tile % p.tiles_w) * p.tile_w + r % p.tile_w;
+      const int h = ((m_tile / p.tiles_w) % p.tiles_h) * p.tile_h + (r / p.tile_w) % p.tile_h;
+      const int img = (m_tile / (p.tiles_w * p.tiles_h)) * p.tile_n + r / (p.tile_w * p.tile_h);
+      const bool row_ok = w < p.W && h < p.H && img < p.n_img;
+      const size_t grow = (static_cast<size_t>(img) * p.H + h) * p.W + w;
+      const int ncol0 = n_tile * p.block_n;                 // B-row / bias index base
+      const int ocol0 = n_tile * out_cols;                  // output column base
+      const int n_out_total = geglu ? p.N / 2 : p.N;
+
+      mbar_wait(&tmem_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * kAccStride;
+      for (int c = 0; c < out_cols; c += 16) {
+        uint32_t v[16];
+        tmem_ld16(t_row + c, v);
+        float f[16];
+        if (geglu) {
+          uint32_t g[16];
+          tmem_ld16(t_row + out_cols + c, g);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            float val = __uint_as_float(v[j]);
+            float gate = __uint_as_float(g[j]);
+            if (p.bias) {
+              val += __ldg(p.bias + ncol0 + c + j);
+              gate += __ldg(p.bias + ncol0 + out_cols + c + j);
+            }
+            f[j] = val * gelu_erf(gate);
+          }
+        } else {
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+        }
+        const int oc = ocol0 + c;
+        if (row_ok && oc < n_out_total) {
+          if (p.bias && !geglu) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) f[j] += __ldg(p.bias + ncol0 + c + j);
+          }
+          if (p.row_bias) {
+            const float* rb = p.row_bias + static_cast<size_t>(img) * p.N + oc;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) f[j] += __ldg(rb + j);
+          }
+          if (p.residual) {
+            const uint4* rp = reinterpret_cast<const uint4*>(p.residual + grow * p.ld_res + oc);
+            uint4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
+            const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              f[2 * j] += bf16_lo(rr[j]);
+              f[2 * j + 1] += bf16_hi(rr[j]);
+            }
+          }
+          uint4 o0, o1;
+          o0.x = pack_bf16(f[0], f[1]);   o0.y = pack_bf16(f[2], f[3]);
+          o0.z = pack_bf16(f[4], f[5]);   o0.w = pack_bf16(f[6], f[7]);
+          o1.x = pack_bf16(f[8], f[9]);   o1.y = pack_bf16(f[10], f[11]);
+          o1.z = pack_bf16(f[12], f[13]); o1.w = pack_bf16(f[14], f[15]);
+          uint4* op = reinterpret_cast<uint4*>(p.out + grow * p.ld_out + oc);
+          op[0] = o0;
+          op[1] = o1;
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+int g_num_sms = 0;
+bool g_attr_set = false;
+
+int pick_block_n(int N, int m_tiles, bool geglu, int num_sms) {
+  // Prefer wide tiles (A re-use, fewer smem bytes per MMA cycle) but avoid tail waves.
+  static const int cands[] = {256, 240, 224, 208, 192, 176, 160, 144, 128, 112, 96, 80, 64, 48, 32, 16};
+  int best = 0;
+  double best_cost = 1e30;
+  for (int bn : cands) {
+    if (bn > N && bn != 16) continue;
+    if (geglu && (bn % 32 != 0 || N % bn != 0)) continue;
+    const int n_tiles = (N + bn - 1) / bn;
+    const long tiles = static_cast<long>(m_tiles) * n_tiles;
+    const long waves = (tiles + num_sms - 1) / num_sms;
+    // per-tile time ~ max(MMA cycles ~ bn, smem-feed cycles ~ (128+bn)/2) + fixed overhead
+    const double per_tile = std::max<double>(bn, (128.0 + bn) * 0.5 * 1.1) + 12.0;
+    const double cost = waves * per_tile;
+    if (cost < best_cost - 1e-9) { best_cost = cost; best = bn; }
+  }
+  return best ? best : 16;
+}
+
+}  // namespace
+
+int gemm_choose_block_n(int N, int n_img, int H, int W, int epilogue) {
+  if (!g_num_sms) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+      g_num_sms = 148;
+  }
+  int m_tiles;
+  if (W >= kTileM) {
+    m_tiles = ((W + kTileM - 1) / kTileM) * H * n_img;
+  } else {
+    const int th = std::min(H, kTileM / W);
+    const int tn = kTileM / (W * th);
+    m_tiles = (H / th) * ((n_img + tn - 1) / tn);
+  }
+  return pick_block_n(N, m_tiles, epilogue == kEpiGeglu, g_num_sms);
+}
+
+int gemm_plan(const GemmOp& op, GemmPlan* plan) {
+  SONIC_REQUIRE(op.a0 && op.w && op.out, "gemm: null operand");
+  SONIC_REQUIRE(op.taps == 1 || op.taps == 9, "gemm: taps must be 1 or 9 (got %d)", op.taps);
+  SONIC_REQUIRE(op.N % 16 == 0, "gemm: N=%d must be a multiple of 16", op.N);
+  SONIC_REQUIRE(op.c0 % 8 == 0 && op.c1 % 8 == 0 && op.ld0 % 8 == 0 && op.ld1 % 8 == 0,
+                "gemm: channel counts / strides must be multiples of 8");
+  SONIC_REQUIRE(op.c0 % 64 == 0 || op.a1 == nullptr, "gemm: concat needs c0 %% 64 == 0");
+  SONIC_REQUIRE(op.ld_out % 8 == 0 && (op.residual == nullptr || op.ld_res % 8 == 0),
+                "gemm: output / residual stride must be a multiple of 8");
+  if (!g_num_sms) {
+    int dev = 0;
+    SONIC_CUDA(cudaGetDevice(&dev));
+    SONIC_CUDA(cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  GemmParams& p = plan->p;
+  p = GemmParams{};
+  const int K = op.c0 + (op.a1 ? op.c1 : 0);
+  p.M = op.n_img * op.H * op.W;
+  p.N = op.N;
+  p.k_chunks0 = (op.c0 + kTileK - 1) / kTileK;
+  p.k_chunks1 = op.a1 ? (op.c1 + kTileK - 1) / kTileK : 0;
+  p.taps = op.taps;
+  p.H = op.H; p.W = op.W; p.n_img = op.n_img;
+  if (op.W >= kTileM) {
+    p.tile_w = kTileM; p.tile_h = 1; p.tile_n = 1;
+  } else {
+    SONIC_REQUIRE(kTileM % op.W == 0, "gemm: W=%d must divide 128", op.W);
+    p.tile_w = op.W;
+    p.tile_h = std::min(op.H, kTileM / p.tile_w);
+    SONIC_REQUIRE((kTileM / p.tile_w) % p.tile_h == 0 && op.H % p.tile_h == 0,
+                  "gemm: H=%d does not tile", op.H);
+    p.tile_n = kTileM / (p.tile_w * p.tile_h);
+  }
+  p.tiles_w = (op.W + p.tile_w - 1) / p.tile_w;
+  p.tiles_h = (op.H + p.tile_h - 1) / p.tile_h;
+  p.tiles_img = (op.n_img + p.tile_n - 1) / p.tile_n;
+  p.m_tiles = p.tiles_w * p.tiles_h * p.tiles_img;
+  const bool geglu = op.epilogue == kEpiGeglu;
+  p.block_n = op.block_n ? op.block_n : pick_block_n(op.N, p.m_tiles, geglu, g_num_sms);
+  SONIC_REQUIRE(p.block_n % 16 == 0 && p.block_n >= 16 && p.block_n <= 256, "gemm: bad block_n %d",
+                p.block_n);
+  SONIC_REQUIRE(!geglu || (p.block_n % 32 == 0 && op.N % p.block_n == 0),
+                "gemm: GEGLU needs block_n %% 32 == 0 and N %% block_n == 0");
+  p.n_tiles = (op.N + p.block_n - 1) / p.block_n;
+  const int stage_bytes = kABytes + p.block_n * kTileK * 2;
+  p.stages = std::max(2, std::min(8, (200 * 1024) / stage_bytes));
+  p.idesc = make_idesc_bf16(kTileM, p.block_n, false);
+  p.bias = op.bias;
+  p.row_bias = op.row_bias;
+  p.residual = static_cast<const __nv_bfloat16*>(op.residual);
+  p.out = static_cast<__nv_bfloat16*>(op.out);
+  p.ld_res = op.ld_res;
+  p.ld_out = op.ld_out;
+  p.epilogue = op.epilogue;
+
+  {
+    uint64_t dims[4] = {static_cast<uint64_t>(op.c0), static_cast<uint64_t>(op.W),
+                        static_cast<uint64_t>(op.H), static_cast<uint64_t>(op.n_img)};
+    uint64_t str[3] = {static_cast<uint64_t>(op.ld0) * 2, static_cast<uint64_t>(op.W) * op.ld0 * 2,
+                       static_cast<uint64_t>(op.H) * op.W * op.ld0 * 2};
+    uint32_t box[4] = {kTileK, static_cast<uint32_t>(p.tile_w), static_cast<uint32_t>(p.tile_h),
+                       static_cast<uint32_t>(p.tile_n)};
+    if (int rc = encode_tensor_map(&p.tm_a0, op.a0, 4, dims, str, box, true)) return rc;
+    if (op.a1) {
+      dims[0] = op.c1;
+      str[0] = static_cast<uint64_t>(op.ld1) * 2;
+      str[1] = static_cast<uint64_t>(op.W) * op.ld1 * 2;
+      str[2] = static_cast<uint64_t>(op.H) * op.W * op.ld1 * 2;
+      if (int rc = encode_tensor_map(&p.tm_a1, op.a1, 4, dims, str, box, true)) return rc;
+    } else {
+      p.tm_a1 = p.tm_a0;
+    }
+  }
+  {
+    const uint64_t Kp = static_cast<uint64_t>(p.k_chunks0 + p.k_chunks1) * kTileK;
+    SONIC_REQUIRE(Kp == static_cast<uint64_t>(K) || op.a1 == nullptr,
+                  "gemm: concat operands must be multiples of 64 channels");
+    uint64_t dims[3] = {static_cast<uint64_t>(K), static_cast<uint64_t>(op.N),
+                        static_cast<uint64_t>(op.taps)};
+    uint64_t str[2] = {static_cast<uint64_t>(K) * 2, static_cast<uint64_t>(op.N) * K * 2};
+    uint32_t box[3] = {kTileK, static_cast<uint32_t>(p.block_n), 1};
+    if (int rc = encode_tensor_map(&p.tm_b, op.w, 3, dims, str, box, true)) return rc;
+  }
+  plan->grid = std::min(p.m_tiles * p.n_tiles, g_num_sms);
+  plan->smem = static_cast<size_t>(p.stages) * stage_bytes + 1024 /*align*/ + 256 /*barriers*/;
+  plan->flops = 2.0 * p.M * static_cast<double>(op.N) * K * op.taps;
+  return 0;
+}
+
+int gemm_launch(const GemmPlan& plan, cudaStream_t stream) {
+  if (!g_attr_set) {
+    SONIC_CUDA(cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    227 * 1024));
+    g_attr_set = true;
+  }
+  conv_gemm_kernel<<<plan.grid, kGemmThreads, plan.smem, stream>>>(plan.p);
+  SONIC_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace sonic

@@ -1,0 +1,56 @@
+// Implicit-GEMM operator (3x3 / 1x1 convolution and Linear) on tcgen05 tensor cores.
+// One persistent, warp-specialised kernel serves every GEMM-shaped layer of the UNet:
+//   out[M, N] = epilogue( sum_{tap, k} A[pixel(m) + offset(tap), k] * Wt[tap][n][k] )
+// A is an NHWC bf16 activation (optionally the channel-concat of two tensors), fetched by
+// TMA as shifted (tile_n x tile_h x tile_w) x 64-channel boxes -- out-of-image taps are
+// zero-filled by the TMA unit, so no im2col buffer ever exists.
+#pragma once
+#include "common.cuh"
+
+namespace sonic {
+
+enum GemmEpilogue { kEpiNone = 0, kEpiGeglu = 1 };
+
+struct GemmParams {
+  CUtensorMap tm_a0, tm_a1, tm_b;
+  int M, N;                      // GEMM rows (= n_img*H*W) and B rows (= out channels before GEGLU)
+  int k_chunks0, k_chunks1;      // 64-wide K chunks taken from source 0 / source 1
+  int taps;                      // 1 or 9
+  int H, W, n_img;
+  int tile_w, tile_h, tile_n;    // tile_w*tile_h*tile_n == 128 rows of one M tile
+  int tiles_w, tiles_h, tiles_img;
+  int m_tiles, n_tiles, block_n, stages;
+  uint32_t idesc;
+  const float* bias;             // [N] or null
+  const float* row_bias;         // [n_img][N] or null
+  const __nv_bfloat16* residual; // [M][ld_res] or null
+  __nv_bfloat16* out;            // [M][ld_out]
+  int ld_res, ld_out;
+  int epilogue;
+};
+
+struct GemmOp {                  // host-side description; pointers are borrowed
+  const void* a0 = nullptr; int c0 = 0, ld0 = 0;
+  const void* a1 = nullptr; int c1 = 0, ld1 = 0;
+  int n_img = 1, H = 1, W = 1;
+  const void* w = nullptr; int N = 0, taps = 1;
+  const float* bias = nullptr;
+  const float* row_bias = nullptr;
+  const void* residual = nullptr; int ld_res = 0;
+  void* out = nullptr; int ld_out = 0;
+  int epilogue = kEpiNone;
+  int block_n = 0;               // 0 = choose
+};
+
+struct GemmPlan {
+  GemmParams p;
+  int grid = 0;
+  size_t smem = 0;
+  double flops = 0;              // algorithmic 2*M*N*K
+};
+
+int gemm_choose_block_n(int N, int n_img, int H, int W, int epilogue);
+int gemm_plan(const GemmOp& op, GemmPlan* plan);
+int gemm_launch(const GemmPlan& plan, cudaStream_t stream);
+
+}  // namespace sonic

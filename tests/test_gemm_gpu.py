@@ -1,0 +1,87 @@
+"""Parity of the tcgen05 implicit-GEMM operator (sonic_conv_gemm) against fp32 PyTorch.
+
+The fp32 torch reference here is the per-operator form of the oracle UNet's layers
+(oracle/unet.py: nn.Conv2d / nn.Linear / GEGLU); inputs are rounded to bf16 first so the only
+differences are accumulation order and the single bf16 rounding of the output.
+"""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel_err(got, ref):
+    return ((got.float() - ref).abs().max() / ref.abs().max().clamp_min(1e-6)).item()
+
+
+def _bf(x):
+    return x.to(torch.bfloat16)
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 64, 64), (256, 320, 320), (77 * 2, 640, 768), (1000, 1280, 1280),
+                                    (4096, 960, 320)])
+def test_linear(cuda, M, N, K):
+    from sonicdiffusionbayeslab_b200 import kernels as k
+
+    g = torch.Generator(device="cuda").manual_seed(M + N + K)
+    a = _bf(torch.randn(M, K, device=cuda, generator=g))
+    w = _bf(torch.randn(N, K, device=cuda, generator=g) / K ** 0.5)
+    b = torch.randn(N, device=cuda, generator=g)
+    res = _bf(torch.randn(M, N, device=cuda, generator=g))
+    out = k.conv_gemm(a, w, N, bias=b, residual=res)
+    ref = a.float() @ w.float().t() + b + res.float()
+    torch.cuda.synchronize()
+    assert _rel_err(out, ref) < 1e-2
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout", [(2, 64, 64, 320, 320), (3, 32, 32, 640, 640), (2, 16, 16, 1280, 1280),
+                                             (3, 8, 8, 1280, 1280), (1, 8, 8, 64, 64)])
+def test_conv3x3(cuda, B, H, W, Cin, Cout):
+    from sonicdiffusionbayeslab_b200 import kernels as k
+
+    g = torch.Generator(device="cuda").manual_seed(B * H + Cin)
+    x = _bf(torch.randn(B, H, W, Cin, device=cuda, generator=g))
+    w = _bf(torch.randn(Cout, Cin, 3, 3, device=cuda, generator=g) / (9 * Cin) ** 0.5)
+    b = torch.randn(Cout, device=cuda, generator=g)
+    rb = torch.randn(B, Cout, device=cuda, generator=g)
+    out = k.conv_gemm(x, k.pack_conv3x3_weight(w), Cout, taps=9, n_img=B, H=H, W=W, bias=b, row_bias=rb)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), b, padding=1) + rb[:, :, None, None]
+    ref = ref.permute(0, 2, 3, 1).reshape(B * H * W, Cout)
+    torch.cuda.synchronize()
+    assert _rel_err(out, ref) < 1e-2
+
+
+def test_conv3x3_concat_and_1x1(cuda):
+    from sonicdiffusionbayeslab_b200 import kernels as k
+
+    g = torch.Generator(device="cuda").manual_seed(7)
+    B, H, W, C0, C1, Cout = 2, 32, 32, 640, 320, 640
+    x0 = _bf(torch.randn(B, H, W, C0, device=cuda, generator=g))
+    x1 = _bf(torch.randn(B, H, W, C1, device=cuda, generator=g))
+    w = _bf(torch.randn(Cout, C0 + C1, 3, 3, device=cuda, generator=g) / (9 * (C0 + C1)) ** 0.5)
+    out = k.conv_gemm(x0, k.pack_conv3x3_weight(w), Cout, taps=9, n_img=B, H=H, W=W, a1=x1)
+    xc = torch.cat([x0, x1], dim=-1).float().permute(0, 3, 1, 2)
+    ref = F.conv2d(xc, w.float(), padding=1).permute(0, 2, 3, 1).reshape(-1, Cout)
+    assert _rel_err(out, ref) < 1e-2
+    w1 = _bf(torch.randn(Cout, C0 + C1, device=cuda, generator=g) / (C0 + C1) ** 0.5)
+    out1 = k.conv_gemm(x0, w1, Cout, taps=1, n_img=B, H=H, W=W, a1=x1)
+    ref1 = torch.cat([x0, x1], dim=-1).float().reshape(-1, C0 + C1) @ w1.float().t()
+    assert _rel_err(out1, ref1) < 1e-2
+
+
+@pytest.mark.parametrize("M,C", [(4096, 320), (256, 1280)])
+def test_geglu(cuda, M, C):
+    from sonicdiffusionbayeslab_b200 import kernels as k
+
+    g = torch.Generator(device="cuda").manual_seed(C)
+    x = _bf(torch.randn(M, C, device=cuda, generator=g))
+    w = _bf(torch.randn(8 * C, C, device=cuda, generator=g) / C ** 0.5)
+    b = torch.randn(8 * C, device=cuda, generator=g)
+    bn = k.gemm_block_n(8 * C, 1, 1, M, k.EPI_GEGLU)
+    wp, bp = k.pack_geglu(w, b, bn)
+    out = k.conv_gemm(x, wp, 8 * C, bias=bp, epilogue=k.EPI_GEGLU, block_n=bn)
+    h = x.float() @ w.float().t() + b
+    ref = h[:, :4 * C] * F.gelu(h[:, 4 * C:])
+    assert out.shape == (M, 4 * C)
+    assert _rel_err(out, ref) < 1e-2
