@@ -61,6 +61,102 @@ int sonic_conv_gemm(const sonic_gemm_args* args, sonic_stream_t stream);
 /* Tile width the library would choose for (N, M) -- needed to pack GEGLU weights. */
 int sonic_gemm_block_n(int32_t N, int32_t n_img, int32_t H, int32_t W, int32_t epilogue);
 
+/* ---------------------------------------------------------------------------------------
+ * Flash attention on tcgen05 (self- and cross-attention of BasicTransformerBlock; replaces
+ * F.scaled_dot_product_attention reached from src/models.py:227-235).
+ * Element (b, s, h, d) of q/k/v/o lives at ((b*seq + s)*ld + h*head_dim + d); bf16.
+ */
+typedef struct sonic_attention_args {
+  const void* q; const void* k; const void* v; void* o;
+  int32_t ld_q, ld_k, ld_v, ld_o;
+  int32_t batch, heads, seq_q, seq_k, head_dim;
+  float scale;
+} sonic_attention_args;
+int sonic_attention(const sonic_attention_args* args, sonic_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * HBM-bound fused kernels.
+ * GroupNorm(groups) [+SiLU] over NHWC bf16, optionally over the channel concat (x0 | x1).
+ * stats: fp32 scratch of n_img*groups*2 floats.  LayerNorm over rows of C bf16.
+ */
+int sonic_groupnorm_silu(const void* x0, int32_t c0, const void* x1, int32_t c1, int32_t n_img,
+                         int32_t hw, int32_t groups, float eps, const float* gamma,
+                         const float* beta, int32_t silu, float* stats, void* y,
+                         sonic_stream_t stream);
+int sonic_layernorm(const void* x, void* y, int32_t rows, int32_t C, float eps, const float* gamma,
+                    const float* beta, sonic_stream_t stream);
+
+/* Fused classifier-free-guidance combine + scheduler update + x0 prediction + history write:
+ * one kernel for the whole of src/models.py:238-242 and :253-255 (scheduler.step of
+ * src/schedulers.py:98-187 and of the diffusers DDIM / LCM / PNDM schedulers).  Every
+ * scheduler on the path is a linear multistep rule, so the host reduces it to coefficients:
+ *   e   = eps_text ? eps_uncond + guidance*(eps_text - eps_uncond) : eps_uncond  (rounded to dtype)
+ *   m0  = m_x*x + m_e*e            (converted model output; written to out_m0, rounded to dtype)
+ *   x0  = x0_x*x + x0_e*e          (pred_original_sample / denoised; written to out_x0)
+ *   x'  = c_x*x + c_e*e + c_m0*m0 + c_h1*h1 + c_h2*h2 + c_h3*h3 + c_z*z   (written to out_sample)
+ * Pointers whose coefficient is zero may be NULL; out_* may be NULL; out_sample may alias
+ * sample or a history tensor.  dtype: 0 = fp32, 1 = bf16 (all tensors).  n = element count.
+ */
+typedef struct sonic_update_coeffs {
+  float guidance;
+  float m_x, m_e;
+  float x0_x, x0_e;
+  float c_x, c_e, c_m0, c_h1, c_h2, c_h3, c_z;
+} sonic_update_coeffs;
+int sonic_latent_update(const sonic_update_coeffs* k, const void* eps_uncond, const void* eps_text,
+                        const void* sample, const void* h1, const void* h2, const void* h3,
+                        const void* noise, void* out_sample, void* out_m0, void* out_x0, int64_t n,
+                        int32_t dtype, sonic_stream_t stream);
+
+/* Layout helpers used around the UNet (exposed for tests). */
+int sonic_nchw_to_nhwc8(const void* x, int32_t dtype, int32_t n_img, int32_t C, int32_t hw,
+                        int32_t dup, void* y, sonic_stream_t stream);
+int sonic_nhwc_to_nchw(const void* x, int32_t ld, int32_t n_img, int32_t C, int32_t hw, void* y,
+                       int32_t dtype, sonic_stream_t stream);
+int sonic_upsample2x(const void* x, void* y, int32_t n_img, int32_t H, int32_t W, int32_t C,
+                     sonic_stream_t stream);
+int sonic_im2col_s2(const void* x, void* y, int32_t n_img, int32_t H, int32_t W, int32_t C,
+                    sonic_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------
+ * Launch plans: the native runtime under the engine.  The host records every operator of a
+ * network once (TMA descriptors and tile shapes are resolved at record time); running the plan
+ * is a native launch loop on `stream`, or -- after sonic_plan_capture -- one CUDA-graph replay.
+ * A plan is what replaces one `self.unet(...)` call (src/models.py:227-235); the DeepCache
+ * cached step (src/experiments/deep_cache.py:24-29) is a second, shorter plan over the same
+ * buffers.  The `add` functions take the same arguments as the eager entry points above.
+ */
+typedef void* sonic_plan_t;
+int sonic_plan_create(sonic_plan_t* out);
+int sonic_plan_destroy(sonic_plan_t plan);
+int sonic_plan_add_conv_gemm(sonic_plan_t plan, const sonic_gemm_args* args);
+int sonic_plan_add_attention(sonic_plan_t plan, const sonic_attention_args* args);
+int sonic_plan_add_groupnorm(sonic_plan_t plan, const void* x0, int32_t c0, const void* x1, int32_t c1,
+                             int32_t n_img, int32_t hw, int32_t groups, float eps, const float* gamma,
+                             const float* beta, int32_t silu, float* stats, void* y);
+int sonic_plan_add_layernorm(sonic_plan_t plan, const void* x, void* y, int32_t rows, int32_t C,
+                             float eps, const float* gamma, const float* beta);
+int sonic_plan_add_nchw_to_nhwc8(sonic_plan_t plan, const void* x, int32_t dtype, int32_t n_img,
+                                 int32_t C, int32_t hw, int32_t dup, void* y);
+int sonic_plan_add_nhwc_to_nchw(sonic_plan_t plan, const void* x, int32_t ld, int32_t n_img, int32_t C,
+                                int32_t hw, void* y, int32_t dtype);
+int sonic_plan_add_upsample2x(sonic_plan_t plan, const void* x, void* y, int32_t n_img, int32_t H,
+                              int32_t W, int32_t C);
+int sonic_plan_add_im2col_s2(sonic_plan_t plan, const void* x, void* y, int32_t n_img, int32_t H,
+                             int32_t W, int32_t C);
+/* out[dim] = [cos(t f_j) | sin(t f_j)], t read from DEVICE memory at run time (graph-safe). */
+int sonic_plan_add_timestep_embedding(sonic_plan_t plan, const float* t_dev, int32_t dim, float* out);
+/* Batched M=1 GEMV: y_j = bias_j + add_j + W_j[N_j x K] * act(x), act = SiLU if silu_in.
+ * The pointer tables are HOST arrays of n_jobs device pointers (bias/add tables may be NULL). */
+int sonic_plan_add_gemv(sonic_plan_t plan, int32_t n_jobs, const void* const* w,
+                        const float* const* bias, const float* const* add, float* const* y,
+                        const int32_t* N, const float* x, int32_t K, int32_t silu_in);
+int sonic_plan_run(sonic_plan_t plan, sonic_stream_t stream);
+/* Capture the plan into a CUDA graph on `stream` (non-default); later runs replay it. */
+int sonic_plan_capture(sonic_plan_t plan, sonic_stream_t stream);
+/* Kernel launches per run and algorithmic FLOPs (2*M*N*K of every GEMM/conv/attention). */
+int sonic_plan_stats(sonic_plan_t plan, int32_t* n_launches, double* flops);
+
 #ifdef __cplusplus
 }
 #endif

@@ -3,6 +3,7 @@
 
 #include "common.cuh"
 #include "gemm.cuh"
+#include "ops.cuh"
 
 using namespace sonic;
 
@@ -29,6 +30,63 @@ int sonic_conv_gemm(const sonic_gemm_args* a, sonic_stream_t stream) {
 
 int sonic_gemm_block_n(int32_t N, int32_t n_img, int32_t H, int32_t W, int32_t epilogue) {
   return gemm_choose_block_n(N, n_img, H, W, epilogue);
+}
+
+int sonic_attention(const sonic_attention_args* a, sonic_stream_t stream) {
+  SONIC_REQUIRE(a != nullptr, "sonic_attention: null args");
+  AttentionOp op;
+  op.q = a->q; op.k = a->k; op.v = a->v; op.o = a->o;
+  op.ld_q = a->ld_q; op.ld_k = a->ld_k; op.ld_v = a->ld_v; op.ld_o = a->ld_o;
+  op.batch = a->batch; op.heads = a->heads; op.seq_q = a->seq_q; op.seq_k = a->seq_k;
+  op.head_dim = a->head_dim; op.scale = a->scale;
+  AttentionPlan* plan = nullptr;
+  if (int rc = attention_plan(op, &plan)) return rc;
+  int rc = attention_launch(plan, static_cast<cudaStream_t>(stream));
+  attention_plan_free(plan);
+  return rc;
+}
+
+int sonic_groupnorm_silu(const void* x0, int32_t c0, const void* x1, int32_t c1, int32_t n_img, int32_t hw,
+                         int32_t groups, float eps, const float* gamma, const float* beta, int32_t silu,
+                         float* stats, void* y, sonic_stream_t stream) {
+  GroupNormOp op;
+  op.x0 = x0; op.c0 = c0; op.x1 = x1; op.c1 = c1;
+  op.n_img = n_img; op.hw = hw; op.groups = groups; op.eps = eps;
+  op.gamma = gamma; op.beta = beta; op.silu = silu; op.stats = stats; op.y = y;
+  return groupnorm_launch(op, static_cast<cudaStream_t>(stream));
+}
+
+int sonic_layernorm(const void* x, void* y, int32_t rows, int32_t C, float eps, const float* gamma,
+                    const float* beta, sonic_stream_t stream) {
+  return layernorm_launch(x, y, rows, C, eps, gamma, beta, static_cast<cudaStream_t>(stream));
+}
+
+int sonic_latent_update(const sonic_update_coeffs* k, const void* eps_uncond, const void* eps_text,
+                        const void* sample, const void* h1, const void* h2, const void* h3, const void* noise,
+                        void* out_sample, void* out_m0, void* out_x0, int64_t n, int32_t dtype,
+                        sonic_stream_t stream) {
+  SONIC_REQUIRE(k != nullptr, "sonic_latent_update: null coefficients");
+  UpdateCoeffs c{k->guidance, k->m_x, k->m_e, k->x0_x, k->x0_e, k->c_x, k->c_e, k->c_m0, k->c_h1, k->c_h2,
+                 k->c_h3, k->c_z};
+  return latent_update_launch(c, eps_uncond, eps_text, sample, h1, h2, h3, noise, out_sample, out_m0, out_x0,
+                              static_cast<long>(n), dtype, static_cast<cudaStream_t>(stream));
+}
+
+int sonic_nchw_to_nhwc8(const void* x, int32_t dtype, int32_t n_img, int32_t C, int32_t hw, int32_t dup, void* y,
+                        sonic_stream_t stream) {
+  return nchw_to_nhwc8_launch(x, dtype, n_img, C, hw, dup, y, static_cast<cudaStream_t>(stream));
+}
+int sonic_nhwc_to_nchw(const void* x, int32_t ld, int32_t n_img, int32_t C, int32_t hw, void* y, int32_t dtype,
+                       sonic_stream_t stream) {
+  return nhwc_to_nchw_launch(x, ld, n_img, C, hw, y, dtype, static_cast<cudaStream_t>(stream));
+}
+int sonic_upsample2x(const void* x, void* y, int32_t n_img, int32_t H, int32_t W, int32_t C,
+                     sonic_stream_t stream) {
+  return upsample2x_launch(x, y, n_img, H, W, C, static_cast<cudaStream_t>(stream));
+}
+int sonic_im2col_s2(const void* x, void* y, int32_t n_img, int32_t H, int32_t W, int32_t C,
+                    sonic_stream_t stream) {
+  return im2col_s2_launch(x, y, n_img, H, W, C, static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

@@ -1,0 +1,77 @@
+// Host-side launch interfaces of the HBM-bound operators (norm.cu, elementwise.cu) and of the
+// attention kernel (attention.cu).  All pointers are device pointers borrowed from the caller.
+#pragma once
+#include "common.cuh"
+
+#include <algorithm>
+
+namespace sonic {
+
+enum DType { kF32 = 0, kBF16 = 1 };
+
+struct GroupNormOp {
+  const void* x0 = nullptr; int c0 = 0, ld0 = 0;   // NHWC bf16, channels [0,c0)
+  const void* x1 = nullptr; int c1 = 0, ld1 = 0;   // optional channel-concat source
+  int n_img = 1, hw = 1, groups = 32;
+  float eps = 1e-5f;
+  const float* gamma = nullptr; const float* beta = nullptr;   // [c0+c1]
+  int silu = 1;
+  float* stats = nullptr;                           // scratch [n_img][groups][2] fp32
+  void* y = nullptr;                                // [n_img*hw][c0+c1] bf16
+};
+int groupnorm_launch(const GroupNormOp& op, cudaStream_t stream);
+
+int layernorm_launch(const void* x, void* y, int rows, int C, float eps, const float* gamma,
+                     const float* beta, cudaStream_t stream);
+
+// Coefficients of the fused CFG-combine + scheduler update (see include/sonic.h).
+struct UpdateCoeffs {
+  float guidance;
+  float m_x, m_e;
+  float x0_x, x0_e;
+  float c_x, c_e, c_m0, c_h1, c_h2, c_h3, c_z;
+};
+int latent_update_launch(const UpdateCoeffs& k, const void* eps_uncond, const void* eps_text,
+                         const void* sample, const void* h1, const void* h2, const void* h3,
+                         const void* noise, void* out_sample, void* out_m0, void* out_x0, long n,
+                         int dtype, cudaStream_t stream);
+
+// NCHW (fp32 or bf16) latents -> NHWC bf16 padded to 8 channels; `dup` writes each image twice
+// (image i and image i + n_img) for the classifier-free-guidance batch.
+int nchw_to_nhwc8_launch(const void* x, int dtype, int n_img, int C, int hw, int dup, void* y,
+                         cudaStream_t stream);
+// [M][ld] bf16 rows (first C channels) -> NCHW tensor of `dtype`.
+int nhwc_to_nchw_launch(const void* x, int ld, int n_img, int C, int hw, void* y, int dtype,
+                        cudaStream_t stream);
+int upsample2x_launch(const void* x, void* y, int n_img, int H, int W, int C, cudaStream_t stream);
+// stride-2, pad-1 3x3 patches: y[n][ho][wo][tap*C + c]  (Ho = H/2, Wo = W/2)
+int im2col_s2_launch(const void* x, void* y, int n_img, int H, int W, int C, cudaStream_t stream);
+
+// Batched GEMV for the timestep path: for every job j, y_j[n] = b_j[n] + add_j[n] + sum_k W_j[n][k]*act(x[k]).
+struct GemvJob {
+  const __nv_bfloat16* w;     // [N][K]
+  const float* bias;          // [N] or null
+  const float* add;           // [N] or null (e.g. conv1.bias folded into the time-embedding bias)
+  float* y;                   // [N]
+  int N;
+  int row_start;              // prefix sum of N over jobs (filled by the launcher's caller)
+};
+int gemv_batched_launch(const GemvJob* jobs_dev, int n_jobs, int total_rows, const float* x, int K,
+                        int silu_in, cudaStream_t stream);
+// t -> [cos(t f_j) | sin(t f_j)] (flip_sin_to_cos, freq_shift 0), fp32 out[dim]
+int timestep_embedding_launch(const float* t_dev, int dim, float* out, cudaStream_t stream);
+
+struct AttentionOp {
+  const void* q; const void* k; const void* v;   // bf16; element (b, s, h, d) at ((b*S + s)*ld + h*D + d)
+  int ld_q = 0, ld_k = 0, ld_v = 0;
+  void* o; int ld_o = 0;
+  int batch = 1, heads = 8, seq_q = 0, seq_k = 0, head_dim = 0;
+  float scale = 1.f;
+};
+struct AttentionPlan;
+int attention_plan(const AttentionOp& op, AttentionPlan** out);
+int attention_launch(const AttentionPlan* plan, cudaStream_t stream);
+void attention_plan_free(AttentionPlan* plan);
+double attention_flops(const AttentionOp& op);
+
+}  // namespace sonic

@@ -77,3 +77,118 @@ def conv_gemm(a0, w, N, *, taps=1, n_img=1, H=1, W=None, c0=None, a1=None, c1=0,
     args.epilogue, args.block_n = epilogue, block_n
     check(lib().sonic_conv_gemm(C.byref(args), stream_ptr()), "sonic_conv_gemm")
     return out
+
+
+class AttentionArgs(C.Structure):
+    _fields_ = [("q", C.c_void_p), ("k", C.c_void_p), ("v", C.c_void_p), ("o", C.c_void_p),
+                ("ld_q", C.c_int32), ("ld_k", C.c_int32), ("ld_v", C.c_int32), ("ld_o", C.c_int32),
+                ("batch", C.c_int32), ("heads", C.c_int32), ("seq_q", C.c_int32), ("seq_k", C.c_int32),
+                ("head_dim", C.c_int32), ("scale", C.c_float)]
+
+
+class UpdateCoeffs(C.Structure):
+    _fields_ = [(n, C.c_float) for n in ("guidance", "m_x", "m_e", "x0_x", "x0_e", "c_x", "c_e", "c_m0",
+                                         "c_h1", "c_h2", "c_h3", "c_z")]
+
+
+def _dtype_code(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return 0
+    if t.dtype == torch.bfloat16:
+        return 1
+    raise TypeError(f"unsupported dtype {t.dtype}: the engine handles float32 and bfloat16 latents")
+
+
+def attention_args(q, k, v, out, *, batch, heads, seq_q, seq_k, head_dim, scale=None) -> AttentionArgs:
+    for t in (q, k, v, out):
+        assert t.is_cuda and t.dtype == torch.bfloat16 and t.stride(-1) == 1
+    a = AttentionArgs()
+    a.q, a.k, a.v, a.o = q.data_ptr(), k.data_ptr(), v.data_ptr(), out.data_ptr()
+    a.ld_q, a.ld_k, a.ld_v, a.ld_o = q.stride(0), k.stride(0), v.stride(0), out.stride(0)
+    a.batch, a.heads, a.seq_q, a.seq_k, a.head_dim = batch, heads, seq_q, seq_k, head_dim
+    a.scale = float(head_dim ** -0.5 if scale is None else scale)
+    return a
+
+
+def attention(q, k, v, *, batch, heads, seq_q, seq_k, head_dim, scale=None, out=None):
+    """q/k/v: bf16 2-D views [batch*seq, ld] (may be column slices of a fused QKV buffer)."""
+    if out is None:
+        out = torch.empty((batch * seq_q, heads * head_dim), device=q.device, dtype=torch.bfloat16)
+    a = attention_args(q, k, v, out, batch=batch, heads=heads, seq_q=seq_q, seq_k=seq_k, head_dim=head_dim,
+                       scale=scale)
+    check(lib().sonic_attention(C.byref(a), stream_ptr()), "sonic_attention")
+    return out
+
+
+def groupnorm(x0, gamma, beta, *, n_img, hw, groups=32, eps=1e-5, silu=True, x1=None, out=None):
+    """x0 (and optional x1): NHWC bf16 [n_img*hw, C]; returns bf16 [n_img*hw, C0+C1]."""
+    _bf16c(x0)
+    c0 = x0.shape[-1]
+    c1 = 0 if x1 is None else _bf16c(x1).shape[-1]
+    if out is None:
+        out = torch.empty((n_img * hw, c0 + c1), device=x0.device, dtype=torch.bfloat16)
+    stats = torch.empty((n_img, groups, 2), device=x0.device, dtype=torch.float32)
+    check(lib().sonic_groupnorm_silu(ptr(x0), c0, ptr(x1), c1, n_img, hw, groups, C.c_float(eps), ptr(gamma),
+                                     ptr(beta), int(silu), ptr(stats), ptr(out), stream_ptr()),
+          "sonic_groupnorm_silu")
+    return out
+
+
+def layernorm(x, gamma, beta, eps=1e-5, out=None):
+    _bf16c(x)
+    rows, Cc = x.numel() // x.shape[-1], x.shape[-1]
+    if out is None:
+        out = torch.empty_like(x)
+    check(lib().sonic_layernorm(ptr(x), ptr(out), rows, Cc, C.c_float(eps), ptr(gamma), ptr(beta), stream_ptr()),
+          "sonic_layernorm")
+    return out
+
+
+def make_coeffs(coeffs: dict) -> UpdateCoeffs:
+    k = UpdateCoeffs()
+    for name, _ in UpdateCoeffs._fields_:
+        setattr(k, name, float(coeffs.get(name, 0.0)))
+    return k
+
+
+def latent_update(coeffs: dict, eps, sample, *, eps_text=None, h1=None, h2=None, h3=None, noise=None,
+                  out_sample=None, out_m0=None, out_x0=None):
+    """Fused CFG + scheduler update; see ``sonic_latent_update`` in include/sonic.h."""
+    k = make_coeffs(coeffs)
+    code = _dtype_code(sample)
+    for t in (eps, eps_text, h1, h2, h3, noise, out_sample, out_m0, out_x0):
+        assert t is None or (t.dtype == sample.dtype and t.is_cuda and t.is_contiguous())
+    n = sample.numel()
+    check(lib().sonic_latent_update(C.byref(k), ptr(eps), ptr(eps_text), ptr(sample), ptr(h1), ptr(h2), ptr(h3),
+                                    ptr(noise), ptr(out_sample), ptr(out_m0), ptr(out_x0), C.c_int64(n), code,
+                                    stream_ptr()), "sonic_latent_update")
+    return out_sample, out_m0, out_x0
+
+
+def nchw_to_nhwc8(x, dup=False):
+    n, c, h, w = x.shape
+    y = torch.empty((n * (2 if dup else 1), h, w, 8), device=x.device, dtype=torch.bfloat16)
+    check(lib().sonic_nchw_to_nhwc8(ptr(x.contiguous()), _dtype_code(x), n, c, h * w, int(dup), ptr(y),
+                                    stream_ptr()), "sonic_nchw_to_nhwc8")
+    return y
+
+
+def nhwc_to_nchw(x, n_img, C_, H, W, dtype):
+    y = torch.empty((n_img, C_, H, W), device=x.device, dtype=dtype)
+    check(lib().sonic_nhwc_to_nchw(ptr(x), x.shape[-1], n_img, C_, H * W, ptr(y), _dtype_code(y), stream_ptr()),
+          "sonic_nhwc_to_nchw")
+    return y
+
+
+def upsample2x(x):
+    n, h, w, c = x.shape
+    y = torch.empty((n, 2 * h, 2 * w, c), device=x.device, dtype=torch.bfloat16)
+    check(lib().sonic_upsample2x(ptr(_bf16c(x)), ptr(y), n, h, w, c, stream_ptr()), "sonic_upsample2x")
+    return y
+
+
+def im2col_s2(x):
+    n, h, w, c = x.shape
+    y = torch.empty((n, h // 2, w // 2, 9 * c), device=x.device, dtype=torch.bfloat16)
+    check(lib().sonic_im2col_s2(ptr(_bf16c(x)), ptr(y), n, h, w, c, stream_ptr()), "sonic_im2col_s2")
+    return y

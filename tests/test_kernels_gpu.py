@@ -1,0 +1,118 @@
+"""GPU parity of the attention / normalisation / elementwise kernels against fp32 PyTorch
+(the per-operator form of oracle/unet.py and oracle/schedulers.py)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _bf(x):
+    return x.to(torch.bfloat16)
+
+
+def _rel(got, ref):
+    return ((got.float() - ref).abs().max() / ref.abs().max().clamp_min(1e-6)).item()
+
+
+@pytest.mark.parametrize("B,H,Sq,Sk,d", [(2, 8, 4096, 4096, 40), (2, 8, 1024, 1024, 80), (2, 8, 256, 256, 160),
+                                          (3, 8, 64, 64, 160), (2, 8, 4096, 77, 40), (2, 8, 1024, 77, 80),
+                                          (2, 8, 256, 77, 160), (1, 8, 64, 77, 160), (1, 2, 200, 333, 64)])
+def test_attention(cuda, B, H, Sq, Sk, d):
+    from sonicdiffusionbayeslab_b200 import kernels as k
+
+    g = torch.Generator(device="cuda").manual_seed(Sq + Sk + d)
+    C = H * d
+    if Sq == Sk:   # read q/k/v as column slices of one fused projection buffer
+        qkv = _bf(torch.randn(B * Sq, 3 * C, device=cuda, generator=g))
+        q, kk, v = qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:]
+    else:
+        q = _bf(torch.randn(B * Sq, C, device=cuda, generator=g))
+        kv = _bf(torch.randn(B * Sk, 2 * C, device=cuda, generator=g))
+        kk, v = kv[:, :C], kv[:, C:]
+    out = k.attention(q, kk, v, batch=B, heads=H, seq_q=Sq, seq_k=Sk, head_dim=d)
+    qf = q.float().reshape(B, Sq, H, d).transpose(1, 2)
+    kf = kk.float().reshape(B, Sk, H, d).transpose(1, 2)
+    vf = v.float().reshape(B, Sk, H, d).transpose(1, 2)
+    ref = F.scaled_dot_product_attention(qf, kf, vf).transpose(1, 2).reshape(B * Sq, C)
+    torch.cuda.synchronize()
+    assert _rel(out, ref) < 2e-2
+
+
+@pytest.mark.parametrize("B,hw,C0,C1,silu,eps", [(2, 4096, 320, 0, True, 1e-5), (2, 1024, 640, 320, True, 1e-5),
+                                                  (3, 64, 1280, 1280, True, 1e-5), (2, 256, 1280, 0, False, 1e-6),
+                                                  (2, 4096, 320, 320, True, 1e-5)])
+def test_groupnorm(cuda, B, hw, C0, C1, silu, eps):
+    from sonicdiffusionbayeslab_b200 import kernels as k
+
+    g = torch.Generator(device="cuda").manual_seed(hw + C0)
+    x0 = _bf(torch.randn(B * hw, C0, device=cuda, generator=g) * 2 + 0.5)
+    x1 = _bf(torch.randn(B * hw, C1, device=cuda, generator=g)) if C1 else None
+    C = C0 + C1
+    gamma = torch.randn(C, device=cuda, generator=g)
+    beta = torch.randn(C, device=cuda, generator=g)
+    out = k.groupnorm(x0, gamma, beta, n_img=B, hw=hw, eps=eps, silu=silu, x1=x1)
+    xc = x0 if x1 is None else torch.cat([x0, x1], dim=-1)
+    xf = xc.float().reshape(B, hw, C).permute(0, 2, 1)
+    ref = F.group_norm(xf, 32, gamma, beta, eps)
+    if silu:
+        ref = F.silu(ref)
+    ref = ref.permute(0, 2, 1).reshape(B * hw, C)
+    assert _rel(out, ref) < 1e-2
+
+
+@pytest.mark.parametrize("rows,C", [(8192, 320), (2048, 640), (512, 1280), (77, 768)])
+def test_layernorm(cuda, rows, C):
+    from sonicdiffusionbayeslab_b200 import kernels as k
+
+    g = torch.Generator(device="cuda").manual_seed(rows + C)
+    x = _bf(torch.randn(rows, C, device=cuda, generator=g) * 3 + 1)
+    gamma = torch.randn(C, device=cuda, generator=g)
+    beta = torch.randn(C, device=cuda, generator=g)
+    out = k.layernorm(x, gamma, beta)
+    ref = F.layer_norm(x.float(), (C,), gamma, beta, 1e-5)
+    assert _rel(out, ref) < 1e-2
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-5), (torch.bfloat16, 2e-2)])
+def test_latent_update_generic(cuda, dtype, tol):
+    from sonicdiffusionbayeslab_b200 import kernels as k
+
+    g = torch.Generator(device="cuda").manual_seed(5)
+    B = 3
+    mk = lambda: torch.randn(B, 4, 64, 64, device=cuda, generator=g).to(dtype)
+    eps2 = torch.randn(2 * B, 4, 64, 64, device=cuda, generator=g).to(dtype)
+    x, h1, h2, h3, z = mk(), mk(), mk(), mk(), mk()
+    c = dict(guidance=7.5, m_x=0.9, m_e=-0.3, x0_x=1.1, x0_e=-0.7, c_x=0.5, c_e=0.2, c_m0=-0.4, c_h1=0.3, c_h2=-0.2,
+             c_h3=0.1, c_z=0.05)
+    ox, om, o0 = torch.empty_like(x), torch.empty_like(x), torch.empty_like(x)
+    k.latent_update(c, eps2[:B], x, eps_text=eps2[B:], h1=h1, h2=h2, h3=h3, noise=z, out_sample=ox, out_m0=om,
+                    out_x0=o0)
+    f = lambda t: t.float()
+    e = (f(eps2[:B]) + 7.5 * (f(eps2[B:]) - f(eps2[:B]))).to(dtype).float()
+    m0 = (0.9 * f(x) - 0.3 * e).to(dtype).float()
+    x0 = 1.1 * f(x) - 0.7 * e
+    xn = 0.5 * f(x) + 0.2 * e - 0.4 * m0 + 0.3 * f(h1) - 0.2 * f(h2) + 0.1 * f(h3) + 0.05 * f(z)
+    for got, ref in ((ox, xn), (om, m0), (o0, x0)):
+        assert (got.float() - ref).abs().max().item() <= tol * max(1.0, ref.abs().max().item())
+
+
+def test_layout_helpers(cuda):
+    from sonicdiffusionbayeslab_b200 import kernels as k
+
+    g = torch.Generator(device="cuda").manual_seed(9)
+    x = torch.randn(3, 4, 64, 64, device=cuda, generator=g)
+    y = k.nchw_to_nhwc8(x, dup=True)
+    ref = torch.zeros(6, 64, 64, 8, device=cuda)
+    ref[:3, ..., :4] = x.permute(0, 2, 3, 1)
+    ref[3:, ..., :4] = x.permute(0, 2, 3, 1)
+    assert torch.equal(y, ref.to(torch.bfloat16))
+    a = _bf(torch.randn(2, 16, 16, 64, device=cuda, generator=g))
+    up = k.upsample2x(a)
+    assert torch.equal(up, a.repeat_interleave(2, dim=1).repeat_interleave(2, dim=2))
+    col = k.im2col_s2(a)
+    unf = F.unfold(a.float().permute(0, 3, 1, 2), 3, padding=1, stride=2)          # [n, C*9, L]
+    unf = unf.reshape(2, 64, 9, 8, 8).permute(0, 3, 4, 2, 1).reshape(2, 8, 8, 9 * 64)
+    assert torch.equal(col.float(), unf)
+    back = k.nhwc_to_nchw(a.reshape(-1, 64), 2, 4, 16, 16, torch.float32)
+    assert torch.equal(back, a[..., :4].float().permute(0, 3, 1, 2))

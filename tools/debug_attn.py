@@ -1,0 +1,54 @@
+"""GPU debugging aid for the attention kernel: small cases first, with error localisation."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+import torch.nn.functional as F
+
+from sonicdiffusionbayeslab_b200 import kernels as k
+
+dev = torch.device("cuda:0")
+g = torch.Generator(device="cuda").manual_seed(0)
+
+
+def run(B, H, Sq, Sk, d):
+    C = H * d
+    q = torch.randn(B * Sq, C, device=dev, generator=g).bfloat16()
+    kk = torch.randn(B * Sk, C, device=dev, generator=g).bfloat16()
+    v = torch.randn(B * Sk, C, device=dev, generator=g).bfloat16()
+    out = k.attention(q, kk, v, batch=B, heads=H, seq_q=Sq, seq_k=Sk, head_dim=d)
+    torch.cuda.synchronize()
+    qf = q.float().reshape(B, Sq, H, d).transpose(1, 2)
+    kf = kk.float().reshape(B, Sk, H, d).transpose(1, 2)
+    vf = v.float().reshape(B, Sk, H, d).transpose(1, 2)
+    ref = F.scaled_dot_product_attention(qf, kf, vf).transpose(1, 2).reshape(B * Sq, C)
+    err = (out.float() - ref).abs()
+    print(f"attn B{B} H{H} Sq{Sq} Sk{Sk} d{d}: max_abs={err.max().item():.3e} ref_max={ref.abs().max().item():.3f}",
+          flush=True)
+    if err.max().item() > 0.05:
+        bad = (err > 0.05).nonzero()
+        print("  bad", len(bad), "of", err.numel(), "rows", torch.unique(bad[:, 0])[:12].tolist(), "cols",
+              torch.unique(bad[:, 1])[:24].tolist())
+        print("  out", out[0, :8].float().tolist())
+        print("  ref", ref[0, :8].tolist())
+
+
+for cfg in [(1, 1, 128, 128, 64), (1, 1, 128, 128, 40), (1, 1, 128, 256, 64), (1, 2, 256, 384, 40),
+            (1, 1, 128, 77, 64), (1, 1, 64, 64, 160), (1, 1, 128, 128, 80), (1, 1, 128, 256, 160),
+            (2, 8, 1024, 1024, 80)]:
+    run(*cfg)
+
+B, H, S, d = 32, 8, 4096, 40
+qkv = torch.randn(B * S, 3 * H * d, device=dev, generator=g).bfloat16()
+C = H * d
+for _ in range(2):
+    k.attention(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], batch=B, heads=H, seq_q=S, seq_k=S, head_dim=d)
+s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+s.record()
+for _ in range(5):
+    k.attention(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], batch=B, heads=H, seq_q=S, seq_k=S, head_dim=d)
+e.record()
+torch.cuda.synchronize()
+ms = s.elapsed_time(e) / 5
+print(f"self-attn 64x64 b32 d40: {ms:.3f} ms  {4 * B * H * S * S * d / ms / 1e9:.1f} TFLOP/s")
