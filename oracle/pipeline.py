@@ -1,0 +1,115 @@
+"""Oracle restatement of the reference's denoising loops (test infrastructure only).
+
+``denoise``      <- /root/reference/src/models.py:154-155,167-182,210-282 (single scheduler)
+``denoise_two``  <- /root/reference/src/models.py:487-502,545-621,704-730 (two-scheduler switch)
+Same op order and dtypes as the reference: latents duplicated with ``torch.cat``, UNet call,
+``uncond + g * (text - uncond)`` in the model dtype, ``scheduler.step``.  Optional DeepCache via
+``oracle.deepcache.DeepCacheOracle`` and teacher forcing (``forced_latents``) for parity tests.
+PARITY UNPINNED (see oracle/__init__.py).
+"""
+from __future__ import annotations
+
+import inspect
+
+import numpy as np
+import torch
+
+from .schedulers import randn_tensor
+
+
+def prepare_latents(shape, generator, device, dtype, init_noise_sigma=1.0, latents=None):
+    if latents is None:
+        latents = randn_tensor(shape, generator=generator, device=device, dtype=dtype)
+    else:
+        latents = latents.to(device)
+    return latents * init_noise_sigma
+
+
+def _extra(scheduler, generator, eta):
+    params = set(inspect.signature(scheduler.step).parameters)
+    kw = {}
+    if "eta" in params:
+        kw["eta"] = eta
+    if "generator" in params:
+        kw["generator"] = generator
+    return kw
+
+
+@torch.no_grad()
+def denoise(unet, scheduler, prompt_embeds, negative_prompt_embeds, latents, num_inference_steps,
+            guidance_scale=7.5, generator=None, eta=0.0, deepcache=None, forced_latents=None):
+    """Returns dict(latents=final, per_step=[latents after each step], x0=[x0 preds], timesteps=[...]).
+
+    ``forced_latents[i]`` (if given) replaces the loop's latents before step i (teacher forcing)."""
+    do_cfg = guidance_scale > 1
+    ctx = torch.cat([negative_prompt_embeds, prompt_embeds]) if do_cfg else prompt_embeds
+    device = latents.device
+    scheduler.set_timesteps(num_inference_steps, device=device)
+    timesteps = scheduler.timesteps
+    t_list = [int(t) for t in timesteps.tolist()]
+    latents = latents * scheduler.init_noise_sigma
+    extra = _extra(scheduler, generator, eta)
+    per_step, x0s = [], []
+    if deepcache is not None:
+        deepcache.reset()
+    for i, t in enumerate(timesteps):
+        if forced_latents is not None:
+            latents = forced_latents[i]
+        x_in = torch.cat([latents] * 2) if do_cfg else latents
+        x_in = scheduler.scale_model_input(x_in, t)
+        if deepcache is not None:
+            noise_pred = deepcache.forward(x_in, t, ctx, t_list.index(int(t)))
+        else:
+            noise_pred = unet(x_in, t, encoder_hidden_states=ctx)[0]
+        if do_cfg:
+            u, c = noise_pred.chunk(2)
+            noise_pred = u + guidance_scale * (c - u)
+        step = scheduler.step(noise_pred, t, latents, **extra, return_dict=False)
+        latents = step[0]
+        if len(step) == 2:
+            x0s.append(step[1][0].unsqueeze(0))
+        per_step.append(latents)
+    return dict(latents=latents, per_step=per_step, x0=x0s, timesteps=t_list)
+
+
+def switch_timestamp(timesteps_first, timesteps_second, num_step_switch, type_switch="closest"):
+    """/root/reference/src/models.py:704-730."""
+    first = list(timesteps_first[:num_step_switch].cpu().numpy())
+    if type_switch == "closest":
+        dist = [abs(t - first[-1]) for t in timesteps_second.cpu()]
+        second = list(timesteps_second[np.argmin(dist):].cpu().numpy())
+    elif type_switch == "left_closest":
+        idx = [i for i, t in enumerate(timesteps_second.cpu()) if t - first[-1] >= 0]
+        second = list(timesteps_second[idx[-1]:].cpu().numpy())
+    else:
+        idx = [i for i, t in enumerate(timesteps_second.cpu()) if t - first[-1] <= 0]
+        second = list(timesteps_second[idx[0]:].cpu().numpy())
+    return first, second
+
+
+@torch.no_grad()
+def denoise_two(unet, scheduler_first, scheduler_second, prompt_embeds, negative_prompt_embeds, latents,
+                num_inference_steps_first, num_step_switch, type_switch="closest", guidance_scale=7.5,
+                generator=None, eta=0.0):
+    do_cfg = guidance_scale > 1
+    ctx = torch.cat([negative_prompt_embeds, prompt_embeds]) if do_cfg else prompt_embeds
+    device = latents.device
+    scheduler_first.set_timesteps(num_inference_steps_first, device=device)
+    ts1 = scheduler_first.timesteps
+    scheduler_second.set_timesteps(device=device, timesteps=ts1.cpu().numpy())
+    ts2 = scheduler_second.timesteps
+    first, second = switch_timestamp(ts1, ts2, num_step_switch, type_switch)
+    latents = latents * scheduler_first.init_noise_sigma
+    e1, e2 = _extra(scheduler_first, generator, eta), _extra(scheduler_second, generator, eta)
+    per_step = []
+    for i, t in enumerate(first + second):
+        sched, extra = (scheduler_first, e1) if i < len(first) else (scheduler_second, e2)
+        x_in = torch.cat([latents] * 2) if do_cfg else latents
+        noise_pred = unet(x_in, torch.as_tensor(t, device=device), encoder_hidden_states=ctx)[0]
+        if do_cfg:
+            u, c = noise_pred.chunk(2)
+            noise_pred = u + guidance_scale * (c - u)
+        # the history seeding of models.py:603-611 cannot run (SURVEY C-4) and is a no-op for order <= 2
+        latents = sched.step(noise_pred, t, latents, **extra, return_dict=False)[0]
+        per_step.append(latents)
+    return dict(latents=latents, per_step=per_step, timesteps=([int(t) for t in first], [int(t) for t in second]))

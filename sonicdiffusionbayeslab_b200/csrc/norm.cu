@@ -24,15 +24,13 @@ __device__ __forceinline__ uint4 gn_load(const GnSrc& s, size_t pix, int ch) {
 // chunk, folds channels into groups and adds 2 floats per group to stats[n_img][groups][2].
 __global__ void __launch_bounds__(kGnThreads)
 gn_stats_kernel(GnSrc s, int hw, int groups, float* __restrict__ stats) {
-  extern __shared__ float sm[];                  // [2][C]
+  extern __shared__ float sm[];                  // [ppp][2][C] per-pixel-lane partials
   const int C = s.c0 + s.c1;
   const int vpp = C / 8;                         // vectors per pixel
-  float* s_sum = sm;
-  float* s_sq = sm + C;
-  for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sm[i] = 0.f;
+  const int ppp = kGnThreads / vpp > 0 ? kGnThreads / vpp : 1;   // pixels per pass
+  for (int i = threadIdx.x; i < ppp * 2 * C; i += blockDim.x) sm[i] = 0.f;
   __syncthreads();
   const int img = blockIdx.y;
-  const int ppp = kGnThreads / vpp > 0 ? kGnThreads / vpp : 1;   // pixels per pass
   const int chunk = (hw + gridDim.x - 1) / gridDim.x;
   const int p_begin = blockIdx.x * chunk;
   const int p_end = min(hw, p_begin + chunk);
@@ -51,13 +49,16 @@ gn_stats_kernel(GnSrc s, int hw, int groups, float* __restrict__ stats) {
           a[2 * j + 1] += hi; q[2 * j + 1] += hi * hi;
         }
       }
+      // every (pixel-lane, vector) slot has exactly one writer: no atomics, fixed reduction order
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
-        atomicAdd(&s_sum[v * 8 + j], a[j]);
-        atomicAdd(&s_sq[v * 8 + j], q[j]);
+        sm[(pl * 2) * C + v * 8 + j] = a[j];
+        sm[(pl * 2 + 1) * C + v * 8 + j] = q[j];
       }
     }
-  } else {  // very wide rows (C > 2048): loop over vectors
+  } else {  // very wide rows (C > 2048): loop over vectors (ppp == 1, one owner per vector)
+    float* s_sum = sm;
+    float* s_sq = sm + C;
     for (int p = p_begin; p < p_end; ++p)
       for (int v = threadIdx.x; v < vpp; v += blockDim.x) {
         uint4 u = gn_load(s, static_cast<size_t>(img) * hw + p, v * 8);
@@ -74,9 +75,15 @@ gn_stats_kernel(GnSrc s, int hw, int groups, float* __restrict__ stats) {
   const int cpg = C / groups;
   for (int g = threadIdx.x; g < groups; g += blockDim.x) {
     float a = 0.f, q = 0.f;
-    for (int c = g * cpg; c < (g + 1) * cpg; ++c) { a += s_sum[c]; q += s_sq[c]; }
-    atomicAdd(&stats[(static_cast<size_t>(img) * groups + g) * 2], a);
-    atomicAdd(&stats[(static_cast<size_t>(img) * groups + g) * 2 + 1], q);
+    for (int pl = 0; pl < ppp; ++pl)
+      for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+        a += sm[(pl * 2) * C + c];
+        q += sm[(pl * 2 + 1) * C + c];
+      }
+    // per-CTA partials, reduced in a fixed order by the apply kernel: bit-reproducible, no memset
+    float* dst = stats + ((static_cast<size_t>(img) * gridDim.x + blockIdx.x) * groups + g) * 2;
+    dst[0] = a;
+    dst[1] = q;
   }
 }
 
@@ -90,14 +97,26 @@ gn_apply_kernel(GnSrc s, int hw, int groups, float eps, const float* __restrict_
   const int cpg = C / groups;
   const int img = blockIdx.y;
   const float inv_n = 1.0f / (static_cast<float>(hw) * cpg);
+  float* s_mean = sm + 2 * C;                    // [groups]
+  float* s_rstd = s_mean + groups;               // [groups]
+  for (int g = threadIdx.x; g < groups; g += blockDim.x) {
+    const float* src = stats + (static_cast<size_t>(img) * gridDim.x * groups + g) * 2;
+    float a = 0.f, q = 0.f;
+    for (int ch = 0; ch < static_cast<int>(gridDim.x); ++ch) {
+      a += src[static_cast<size_t>(ch) * groups * 2];
+      q += src[static_cast<size_t>(ch) * groups * 2 + 1];
+    }
+    const float mean = a * inv_n;
+    const float var = fmaxf(q * inv_n - mean * mean, 0.f);
+    s_mean[g] = mean;
+    s_rstd[g] = rsqrtf(var + eps);
+  }
+  __syncthreads();
   for (int c = threadIdx.x; c < C; c += blockDim.x) {
     const int g = c / cpg;
-    const float mean = stats[(static_cast<size_t>(img) * groups + g) * 2] * inv_n;
-    const float var = fmaxf(stats[(static_cast<size_t>(img) * groups + g) * 2 + 1] * inv_n - mean * mean, 0.f);
-    const float rstd = rsqrtf(var + eps);
-    const float sc = rstd * gamma[c];
+    const float sc = s_rstd[g] * gamma[c];
     sm[c] = sc;
-    sm[C + c] = beta[c] - mean * sc;
+    sm[C + c] = beta[c] - s_mean[g] * sc;
   }
   __syncthreads();
   const int vpp = C / 8;
@@ -196,12 +215,14 @@ int groupnorm_launch(const GroupNormOp& op, cudaStream_t stream) {
           op.x1 ? op.c1 : 0, op.ld0 ? op.ld0 : op.c0, op.ld1 ? op.ld1 : op.c1};
   // enough CTAs to fill the machine, but at least ~32 pixels per CTA
   int chunks = std::max(1, std::min(op.hw / 32, (4 * 148 + op.n_img - 1) / op.n_img));
+  chunks = std::min(chunks, kGroupNormMaxChunks);
   dim3 grid(chunks, op.n_img);
   const size_t smem = 2 * C * sizeof(float);
-  SONIC_CUDA(cudaMemsetAsync(op.stats, 0, sizeof(float) * 2 * op.groups * op.n_img, stream));
-  gn_stats_kernel<<<grid, kGnThreads, smem, stream>>>(s, op.hw, op.groups, op.stats);
-  gn_apply_kernel<<<grid, kGnThreads, smem, stream>>>(s, op.hw, op.groups, op.eps, op.stats, op.gamma, op.beta,
-                                                       op.silu, static_cast<__nv_bfloat16*>(op.y));
+  const int ppp = std::max(1, kGnThreads / (C / 8));
+  SONIC_REQUIRE(ppp * smem <= 48 * 1024, "groupnorm: C=%d needs too much shared memory", C);
+  gn_stats_kernel<<<grid, kGnThreads, ppp * smem, stream>>>(s, op.hw, op.groups, op.stats);
+  gn_apply_kernel<<<grid, kGnThreads, smem + 2 * op.groups * sizeof(float), stream>>>(
+      s, op.hw, op.groups, op.eps, op.stats, op.gamma, op.beta, op.silu, static_cast<__nv_bfloat16*>(op.y));
   SONIC_CUDA(cudaGetLastError());
   return 0;
 }

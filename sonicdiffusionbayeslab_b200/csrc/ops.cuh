@@ -9,6 +9,9 @@ namespace sonic {
 
 enum DType { kF32 = 0, kBF16 = 1 };
 
+// GroupNorm scratch: per-CTA partial (sum, sumsq) per group, at most this many CTAs per image.
+constexpr int kGroupNormMaxChunks = 160;
+
 struct GroupNormOp {
   const void* x0 = nullptr; int c0 = 0, ld0 = 0;   // NHWC bf16, channels [0,c0)
   const void* x1 = nullptr; int c1 = 0, ld1 = 0;   // optional channel-concat source
@@ -16,7 +19,7 @@ struct GroupNormOp {
   float eps = 1e-5f;
   const float* gamma = nullptr; const float* beta = nullptr;   // [c0+c1]
   int silu = 1;
-  float* stats = nullptr;                           // scratch [n_img][groups][2] fp32
+  float* stats = nullptr;                           // scratch [n_img][kGroupNormMaxChunks][groups][2] fp32
   void* y = nullptr;                                // [n_img*hw][c0+c1] bf16
 };
 int groupnorm_launch(const GroupNormOp& op, cudaStream_t stream);

@@ -14,6 +14,7 @@ from . import _lib
 from ._lib import GemmArgs, check, lib, ptr, stream_ptr
 
 EPI_NONE, EPI_GEGLU = 0, 1
+GN_MAX_CHUNKS = 160          # SONIC_GROUPNORM_MAX_CHUNKS in include/sonic.h
 
 
 def _bf16c(t: torch.Tensor) -> torch.Tensor:
@@ -127,7 +128,7 @@ def groupnorm(x0, gamma, beta, *, n_img, hw, groups=32, eps=1e-5, silu=True, x1=
     c1 = 0 if x1 is None else _bf16c(x1).shape[-1]
     if out is None:
         out = torch.empty((n_img * hw, c0 + c1), device=x0.device, dtype=torch.bfloat16)
-    stats = torch.empty((n_img, groups, 2), device=x0.device, dtype=torch.float32)
+    stats = torch.empty((n_img, GN_MAX_CHUNKS, groups, 2), device=x0.device, dtype=torch.float32)
     check(lib().sonic_groupnorm_silu(ptr(x0), c0, ptr(x1), c1, n_img, hw, groups, C.c_float(eps), ptr(gamma),
                                      ptr(beta), int(silu), ptr(stats), ptr(out), stream_ptr()),
           "sonic_groupnorm_silu")

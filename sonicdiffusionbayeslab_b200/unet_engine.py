@@ -206,8 +206,10 @@ class UNetEngine:
     def _gn(self, plan, x0, x1, prefix, hw, eps, silu):
         c = x0.shape[-1] + (0 if x1 is None else x1.shape[-1])
         y = self.arena.alloc((x0.shape[0], c))
-        stats = self.arena.alloc((self.n, self.arch.norm_num_groups, 2), torch.float32)
-        self._keep.append(stats)                              # tiny; never recycled
+        if not hasattr(self, "_gn_stats"):                    # one scratch: plans run in stream order
+            self._gn_stats = torch.empty((self.n, K.GN_MAX_CHUNKS, self.arch.norm_num_groups, 2),
+                                         device=self.dev, dtype=torch.float32)
+        stats = self._gn_stats
         check(lib().sonic_plan_add_groupnorm(
             plan.h, K.ptr(x0), x0.shape[-1], K.ptr(x1), 0 if x1 is None else x1.shape[-1], self.n, hw,
             self.arch.norm_num_groups, C.c_float(eps), K.ptr(self._f32(prefix + ".weight")),

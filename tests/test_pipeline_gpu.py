@@ -1,0 +1,265 @@
+"""GPU parity of the sampling loop: fused scheduler steps and whole pipelines vs the oracle.
+
+Tolerances (stated, per BASELINE.json north_star):
+  * timestep / index schedules, DeepCache full/cached pattern, switch point: bit-exact;
+  * scheduler update given the SAME epsilon (isolates the fused latent-update kernel):
+        fp32 I/O  max-abs <= 1e-4      bf16 I/O  max-abs <= 2e-2 (x' is bf16-rounded, |x| <~ 5);
+  * whole step through the bf16 engine UNet, teacher-forced from the oracle's latents, vs the fp32
+    oracle UNet: max-abs <= TF_TOL.  The UNet itself is bf16-vs-fp32 (max-abs ~1.5e-2 on eps) and
+    classifier-free guidance 7.5 amplifies the eps error ~7.5*sqrt(2)x, so the same comparison is
+    also made for stock PyTorch bf16 (the reference's own library path) and printed beside it.
+"""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+TF_TOL = 2e-2          # teacher-forced, per step, bf16 engine vs fp32 oracle, CFG 7.5: max-abs relative
+                       # to max(1, |latents|max) -- a random-init UNet drives |latents| to 10-80, where
+                       # an absolute 2e-2 is below one bf16 ulp (0.25 at 32-64)
+FREE_TOL_REL = 0.10    # free-running final latents: max-abs relative to the latent range
+
+
+def _rel(got, ref):
+    ref = ref.float()
+    return (got.float() - ref).abs().max().item() / max(1.0, ref.abs().max().item())
+
+
+@pytest.fixture(scope="module")
+def world(cuda):
+    from oracle.unet import make_unet
+    from sonicdiffusionbayeslab_b200 import models as M
+    from sonicdiffusionbayeslab_b200 import schedulers as S
+    from sonicdiffusionbayeslab_b200.text import HashTokenizer
+
+    net = make_unet(29).to(cuda)
+    sd = dict(net.state_dict())
+
+    def make(cls=M.StableDiffusionModel, dtype=torch.bfloat16):
+        sched = S.PNDMScheduler.from_config(M.SD15_SCHEDULER_CONFIG)
+        m = cls(sd, vae=None, text_encoder=None, tokenizer=HashTokenizer(), scheduler=sched, torch_dtype=dtype)
+        m.device = cuda
+        return m
+
+    g = torch.Generator(device="cuda").manual_seed(29)
+    B = 2
+    pe = torch.randn(B, 77, 768, device=cuda, generator=g).bfloat16().float()
+    ne = torch.randn(B, 77, 768, device=cuda, generator=g).bfloat16().float()
+    lat = torch.randn(B, 4, 64, 64, device=cuda, generator=g)
+    import copy
+
+    net16 = copy.deepcopy(net).to(torch.bfloat16)      # stock PyTorch bf16 path (noise floor / LCM reference)
+    return dict(net=net, net16=net16, make=make, pe=pe, ne=ne, lat=lat, B=B, dev=cuda)
+
+
+def _sched_pairs():
+    from oracle import schedulers as O
+    from sonicdiffusionbayeslab_b200 import schedulers as S
+
+    return {
+        "ddim": (S.DDIMSchedulerMy, O.DDIMScheduler, {}, 20),
+        "dpm++2": (S.DPMSolverScheduler, O.DPMSolverScheduler,
+                   dict(solver_order=2, algorithm_type="dpmsolver++", final_sigmas_type="zero"), 25),
+        "dpm2": (S.DPMSolverScheduler, O.DPMSolverScheduler,
+                 dict(solver_order=2, algorithm_type="dpmsolver", final_sigmas_type="sigma_min"), 10),
+        "dpm++3": (S.DPMSolverScheduler, O.DPMSolverScheduler,
+                   dict(solver_order=3, algorithm_type="dpmsolver++", final_sigmas_type="zero"), 20),
+        "dpm++2heun": (S.DPMSolverScheduler, O.DPMSolverScheduler,
+                       dict(solver_order=2, algorithm_type="dpmsolver++", solver_type="heun"), 8),
+        "sde-dpm++2": (S.DPMSolverScheduler, O.DPMSolverScheduler,
+                       dict(solver_order=2, algorithm_type="sde-dpmsolver++"), 10),
+        "lcm": (S.LCMScheduler, O.LCMScheduler, {}, 4),
+        "pndm": (S.PNDMScheduler, O.PNDMScheduler, {}, 12),
+    }
+
+
+@pytest.mark.parametrize("name", list(_sched_pairs()))
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-4), (torch.bfloat16, 2e-2)])
+def test_fused_scheduler_step_matches_oracle(cuda, name, dtype, tol):
+    """Same epsilon sequence into both: isolates schedule + fused update kernel (no UNet)."""
+    from oracle.schedulers import SD15_SCHEDULER_CONFIG
+
+    P, Oc, kw, n = _sched_pairs()[name]
+    ps, os_ = P.from_config(SD15_SCHEDULER_CONFIG, **kw), Oc.from_config(SD15_SCHEDULER_CONFIG, **kw)
+    ps.set_timesteps(n, device=cuda)
+    os_.set_timesteps(n, device=cuda)
+    assert ps.timesteps.tolist() == os_.timesteps.tolist()
+    g = torch.Generator(device="cuda").manual_seed(3)
+    x = torch.randn(2, 4, 64, 64, device=cuda, generator=g).to(dtype)
+    xp, xo = x.clone(), x.clone()
+    gp, go = (torch.Generator(device="cuda").manual_seed(11) for _ in range(2))
+    worst = 0.0
+    for t in os_.timesteps:
+        eps = (0.7 * torch.randn(2, 4, 64, 64, device=cuda, generator=g) + 0.2 * xo.float()).to(dtype)
+        kwp = {"generator": gp} if name in ("lcm", "sde-dpm++2") else {}
+        kwo = {"generator": go} if name in ("lcm", "sde-dpm++2") else {}
+        rp = ps.step(eps, t, xp, **kwp)
+        ro = os_.step(eps, t, xo, **kwo)
+        assert len(rp) == len(ro)
+        for a, b in zip(rp, ro):
+            # scaled by the tensor's range: early-step x0 predictions reach |x0| ~ 50, where one
+            # bf16 ulp is 0.25 (the oracle itself rounds every op to bf16 there)
+            scale = max(1.0, b.float().abs().max().item()) if dtype == torch.bfloat16 else 1.0
+            worst = max(worst, (a.float() - b.float()).abs().max().item() / scale)
+        # teacher-force the product from the oracle's state so errors do not compound
+        xp, xo = ro[0].clone(), ro[0]
+    assert worst <= tol, f"{name} {dtype}: max-abs {worst:.3e} > {tol}"
+
+
+def _torch_bf16_floor(world, Oc, kw, n, forced):
+    """Stock PyTorch bf16 UNet (the reference's own kind of path), teacher-forced the same way."""
+    from oracle.pipeline import denoise
+    from oracle.schedulers import SD15_SCHEDULER_CONFIG
+
+    r = denoise(world["net16"], Oc.from_config(SD15_SCHEDULER_CONFIG, **kw), world["pe"].bfloat16(),
+                world["ne"].bfloat16(), world["lat"].bfloat16(), n, forced_latents=[f.bfloat16() for f in forced])
+    return r["per_step"]
+
+
+@pytest.mark.parametrize("name", ["ddim", "dpm++2", "pndm"])
+def test_pipeline_teacher_forced(world, name):
+    from oracle.pipeline import denoise
+    from oracle.schedulers import SD15_SCHEDULER_CONFIG
+
+    P, Oc, kw, n = _sched_pairs()[name]
+    n = min(n, 8)
+    ref = denoise(world["net"], Oc.from_config(SD15_SCHEDULER_CONFIG, **kw), world["pe"], world["ne"], world["lat"], n)
+    forced = [world["lat"]] + ref["per_step"][:-1]          # oracle's latents entering step i
+    model = world["make"]()
+    model.scheduler = P.from_config(SD15_SCHEDULER_CONFIG, **kw)
+    errs = []
+
+    def cb(pipe, i, t, kwargs):
+        errs.append(_rel(kwargs["latents"], ref["per_step"][i]))
+        return {"latents": ref["per_step"][i].to(kwargs["latents"].dtype)}
+
+    out, secs, _ = model(prompt_embeds=world["pe"], negative_prompt_embeds=world["ne"], latents=world["lat"],
+                         num_inference_steps=n, guidance_scale=7.5, output_type="latent", callback_on_step_end=cb)
+    assert model.scheduler.timesteps.tolist() == ref["timesteps"]
+    floor = _torch_bf16_floor(world, Oc, kw, n, forced)
+    floor_err = [_rel(f, r) for f, r in zip(floor, ref["per_step"])]
+    print(f"\n[{name}] teacher-forced per-step relative max-abs: engine {max(errs):.3e}  torch-bf16 {max(floor_err):.3e}")
+    assert max(errs) <= TF_TOL, errs
+    assert max(errs) <= 1.5 * max(floor_err) + 2e-3, (errs, floor_err)
+
+
+def test_pipeline_free_running_dpm(world):
+    """configs[1] shape (DPM-Solver++ 2M, CFG 7.5) end to end at a reduced step count."""
+    from oracle.pipeline import denoise
+    from oracle.schedulers import SD15_SCHEDULER_CONFIG
+
+    P, Oc, kw, _ = _sched_pairs()["dpm++2"]
+    n = 10
+    ref = denoise(world["net"], Oc.from_config(SD15_SCHEDULER_CONFIG, **kw), world["pe"], world["ne"], world["lat"], n)
+    model = world["make"]()
+    model.scheduler = P.from_config(SD15_SCHEDULER_CONFIG, **kw)
+    out, secs, x0s = model(prompt_embeds=world["pe"], negative_prompt_embeds=world["ne"], latents=world["lat"],
+                           num_inference_steps=n, guidance_scale=7.5, output_type="latent")
+    got = out.images.float()
+    rng = ref["latents"].abs().max().item()
+    err = (got - ref["latents"]).abs().max().item()
+    print(f"\n[dpm++2 free-running {n} steps] max-abs {err:.3e} of range {rng:.2f}; loop {secs * 1e3:.1f} ms")
+    assert len(x0s) == 0 or len(x0s) == n
+    assert model.num_timesteps == n
+    assert err <= FREE_TOL_REL * rng
+
+
+def test_pipeline_lcm_no_cfg(world):
+    from oracle.pipeline import denoise
+    from oracle.schedulers import SD15_SCHEDULER_CONFIG, LCMScheduler
+    from sonicdiffusionbayeslab_b200 import schedulers as S
+
+    n = 4
+    go = torch.Generator(device="cuda").manual_seed(5)
+    gp = torch.Generator(device="cuda").manual_seed(5)
+    # noise must be drawn with the same torch call on both sides: bf16 latents
+    lat16 = world["lat"].bfloat16()
+    ref = denoise(world["net16"], LCMScheduler.from_config(SD15_SCHEDULER_CONFIG), world["pe"].bfloat16(),
+                  world["ne"].bfloat16(), lat16, n, guidance_scale=0, generator=go)
+    model = world["make"]()
+    model.scheduler = S.LCMScheduler.from_config(SD15_SCHEDULER_CONFIG)
+    out, _, x0s = model(prompt_embeds=world["pe"], latents=lat16, num_inference_steps=n, guidance_scale=0,
+                        generator=gp, output_type="latent")
+    assert model.scheduler.timesteps.tolist() == [999, 759, 499, 259]
+    rng = ref["latents"].float().abs().max().item()
+    err = (out.images.float() - ref["latents"].float()).abs().max().item()
+    print(f"\n[lcm 4 steps, no CFG] engine vs torch-bf16 oracle: max-abs {err:.3e} of range {rng:.2f}")
+    assert err <= FREE_TOL_REL * rng
+    assert len(x0s) == 0      # output_type latent: x0 decodes are skipped
+
+
+def test_deepcache_pattern_and_parity(world):
+    from oracle.deepcache import DeepCacheOracle
+    from oracle.pipeline import denoise
+    from oracle.schedulers import SD15_SCHEDULER_CONFIG, PNDMScheduler
+    from sonicdiffusionbayeslab_b200.deepcache import DeepCacheSDHelper
+
+    n, interval = 7, 3
+    dc = DeepCacheOracle(world["net"])
+    dc.set_params(cache_interval=interval, cache_branch_id=0)
+    ref = denoise(world["net"], PNDMScheduler.from_config(SD15_SCHEDULER_CONFIG), world["pe"], world["ne"],
+                  world["lat"], n, deepcache=dc)
+    model = world["make"]()
+    helper = DeepCacheSDHelper(pipe=model)
+    helper.set_params(cache_interval=interval, cache_branch_id=0)
+    helper.enable()
+    errs = []
+
+    def cb(pipe, i, t, kwargs):
+        errs.append(_rel(kwargs["latents"], ref["per_step"][i]))
+        return {"latents": ref["per_step"][i].to(kwargs["latents"].dtype)}
+
+    out, _, _ = model(prompt_embeds=world["pe"], negative_prompt_embeds=world["ne"], latents=world["lat"],
+                      num_inference_steps=n, guidance_scale=7.5, output_type="latent", callback_on_step_end=cb)
+    helper.disable()
+    # PNDM-7: timesteps 858,715,715,572,429,286,143,1 -> cur = 0,1,1,3,4,5,6,7 ; full iff cur % 3 == 0
+    assert model.scheduler.timesteps.tolist() == ref["timesteps"]
+    assert model.last_step_kinds == ["full", "cached", "cached", "full", "cached", "cached", "full", "cached"]
+    print(f"\n[deepcache interval {interval}] teacher-forced per-step max-abs {max(errs):.3e}")
+    assert max(errs) <= TF_TOL, errs
+
+
+def test_two_schedulers_switch(world):
+    from oracle import schedulers as O
+    from oracle.pipeline import denoise_two
+    from sonicdiffusionbayeslab_b200 import models as M
+    from sonicdiffusionbayeslab_b200 import schedulers as S
+
+    cfg = O.SD15_SCHEDULER_CONFIG
+    ref = denoise_two(world["net"], O.DDIMScheduler.from_config(cfg), O.DPMSolverScheduler.from_config(cfg),
+                      world["pe"], world["ne"], world["lat"], 10, 3)
+    model = world["make"](M.StableDiffusionModelTwoSchedulers)
+    model.scheduler_first = S.DDIMSchedulerMy.from_config(cfg)
+    model.scheduler_second = S.DPMSolverScheduler.from_config(cfg)
+    errs = []
+
+    def cb(pipe, i, t, kwargs):
+        errs.append(_rel(kwargs["latents"], ref["per_step"][i]))
+        return {"latents": ref["per_step"][i].to(kwargs["latents"].dtype)}
+
+    out, _, _ = model(prompt_embeds=world["pe"], negative_prompt_embeds=world["ne"], latents=world["lat"],
+                      num_inference_steps_first=10, num_inference_steps_second=10, num_step_switch=3,
+                      type_switch="closest", guidance_scale=7.5, output_type="latent", callback_on_step_end=cb)
+    first, second = model.last_timesteps
+    assert ([int(t) for t in first], [int(t) for t in second]) == ref["timesteps"]
+    assert ref["timesteps"] == ([901, 801, 701], [701, 601, 501, 401, 301, 201, 101, 1])
+    assert model.num_timesteps == 11
+    print(f"\n[two schedulers 10/k=3] teacher-forced per-step max-abs {max(errs):.3e}")
+    assert max(errs) <= TF_TOL, errs
+
+
+def test_cuda_graph_replay_equals_eager(world):
+    from sonicdiffusionbayeslab_b200.unet_engine import UNetEngine
+
+    sd = dict(world["net"].state_dict())
+    eng = UNetEngine(sd, n_latents=1, cfg_dup=True, io_dtype=torch.bfloat16, device=world["dev"])
+    eng.x_in.copy_(world["lat"][:1].bfloat16())
+    eng.set_context(torch.cat([world["ne"][:1], world["pe"][:1]]).bfloat16())
+    eager = eng.forward(777.0).clone()
+    eager_c = eng.forward(700.0, cached=True).clone()
+    eng.capture_graphs()
+    graph = eng.forward(777.0).clone()
+    graph_c = eng.forward(700.0, cached=True).clone()
+    torch.cuda.synchronize()
+    assert torch.equal(eager, graph)
+    assert torch.equal(eager_c, graph_c)
