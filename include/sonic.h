@@ -158,6 +158,11 @@ int sonic_plan_run(sonic_plan_t plan, sonic_stream_t stream);
 int sonic_plan_capture(sonic_plan_t plan, sonic_stream_t stream);
 /* Kernel launches per run and algorithmic FLOPs (2*M*N*K of every GEMM/conv/attention). */
 int sonic_plan_stats(sonic_plan_t plan, int32_t* n_launches, double* flops);
+/* One eager run with a CUDA event between operators: ms[i] = device time of operator i,
+ * kinds[i]: 0 gemm/conv, 1 attention, 2 groupnorm, 3 layernorm, 4 layout, 5 timestep path;
+ * flops[i] = algorithmic FLOPs (0 for HBM-bound operators).  Used by bench.py for the roofline. */
+int sonic_plan_profile(sonic_plan_t plan, sonic_stream_t stream, int32_t max_ops, float* ms,
+                       int32_t* kinds, double* flops, int32_t* n_ops);
 
 #ifdef __cplusplus
 }

@@ -305,6 +305,8 @@ int attention_plan(const AttentionOp& op, AttentionPlan** out) {
 
 void attention_plan_free(AttentionPlan* plan) { delete plan; }
 
+double attention_plan_flops(const AttentionPlan* plan) { return plan ? attention_flops(plan->op) : 0.0; }
+
 int attention_launch(const AttentionPlan* pl, cudaStream_t stream) {
   if (!g_att_attr_set) {
     SONIC_CUDA(cudaFuncSetAttribute(attention_kernel<48>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));

@@ -76,5 +76,6 @@ int attention_plan(const AttentionOp& op, AttentionPlan** out);
 int attention_launch(const AttentionPlan* plan, cudaStream_t stream);
 void attention_plan_free(AttentionPlan* plan);
 double attention_flops(const AttentionOp& op);
+double attention_plan_flops(const AttentionPlan* plan);
 
 }  // namespace sonic

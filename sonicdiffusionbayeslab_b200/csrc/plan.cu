@@ -261,6 +261,46 @@ int sonic_plan_capture(sonic_plan_t h, sonic_stream_t stream) {
   return 0;
 }
 
+// Per-operator device times of one eager (non-graph) run, measured with CUDA events on `stream`.
+// kinds[i]: 0 gemm/conv, 1 attention, 2 groupnorm, 3 layernorm, 4 layout/elementwise, 5 gemv/time.
+int sonic_plan_profile(sonic_plan_t h, sonic_stream_t stream, int32_t max_ops, float* ms, int32_t* kinds,
+                       double* flops, int32_t* n_ops) {
+  SONIC_REQUIRE(h && ms && kinds && flops && n_ops, "sonic_plan_profile: null argument");
+  Plan* plan = static_cast<Plan*>(h);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int n = static_cast<int>(plan->ops.size());
+  SONIC_REQUIRE(n <= max_ops, "sonic_plan_profile: plan has %d ops, buffer holds %d", n, max_ops);
+  std::vector<cudaEvent_t> ev(n + 1);
+  for (auto& e : ev) SONIC_CUDA(cudaEventCreate(&e));
+  Plan one;
+  one.ops.resize(1);
+  int rc = 0;
+  SONIC_CUDA(cudaEventRecord(ev[0], s));
+  for (int i = 0; i < n && !rc; ++i) {
+    one.ops[0] = plan->ops[i];
+    rc = run_ops(one, s);
+    cudaEventRecord(ev[i + 1], s);
+  }
+  for (auto& op : one.ops) { op.att = nullptr; op.jobs_dev = nullptr; }   // borrowed, not owned
+  if (!rc) rc = check_cuda(cudaStreamSynchronize(s), "sync", __FILE__, __LINE__);
+  for (int i = 0; i < n && !rc; ++i) {
+    cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]);
+    const PlanOp& op = plan->ops[i];
+    flops[i] = 0;
+    switch (op.kind) {
+      case PlanOp::kGemm: kinds[i] = 0; flops[i] = op.gemm.flops; break;
+      case PlanOp::kAttention: kinds[i] = 1; flops[i] = attention_plan_flops(op.att); break;
+      case PlanOp::kGroupNorm: kinds[i] = 2; break;
+      case PlanOp::kLayerNorm: kinds[i] = 3; break;
+      case PlanOp::kGemv: case PlanOp::kTimeEmb: kinds[i] = 5; break;
+      default: kinds[i] = 4; break;
+    }
+  }
+  for (auto& e : ev) cudaEventDestroy(e);
+  *n_ops = n;
+  return rc;
+}
+
 int sonic_plan_stats(sonic_plan_t h, int32_t* n_launches, double* flops) {
   SONIC_REQUIRE(h != nullptr, "sonic_plan_stats: null plan");
   Plan* plan = static_cast<Plan*>(h);

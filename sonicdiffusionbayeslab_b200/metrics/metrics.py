@@ -1,0 +1,196 @@
+"""Metric plugins (/root/reference/src/metrics/metrics.py): ``clip_score``, ``time_metric``, and
+``image_reward`` / ``fid`` placeholders.
+
+torchmetrics is not installable here, so a minimal ``Metric`` base provides the surface the drivers
+use (``update`` / ``compute`` / ``reset`` / ``to``; sum-reduced states).  ``ClipScoreMetric`` restates
+torchmetrics 1.6.1 ``CLIPScore`` on ``transformers.CLIPModel``:
+``max(0, mean_i 100 * cos(f_img(i), f_txt(i)))`` -- with the image preprocessing (resize shortest side
+to 224 bicubic + antialias, centre crop, 1/255, CLIP mean/std) done on the GPU instead of PIL on
+the host, which is where the reference spends its metric time.
+ImageReward and FID need downloaded networks and the real COCO images (no network): they stay
+registered so ``BaseMethod.setup_metrics`` works, and report NaN.
+"""
+from __future__ import annotations
+
+import os
+
+import torch
+import torch.nn.functional as F
+
+from ..registry import metrics_registry
+from ..text import HashTokenizer, load_tokenizer
+
+CLIP_MEAN = (0.48145466, 0.4578275, 0.40821073)
+CLIP_STD = (0.26862954, 0.26130258, 0.27577711)
+
+
+class Metric:
+    """Sum-reduced metric states, torchmetrics-style."""
+
+    def __init__(self):
+        self._defaults = {}
+        self.device = torch.device("cpu")
+
+    def add_state(self, name, default, dist_reduce_fx="sum"):
+        self._defaults[name] = default.clone()
+        setattr(self, name, default.clone())
+
+    def reset(self):
+        for k, v in self._defaults.items():
+            setattr(self, k, v.clone().to(self.device))
+
+    def to(self, device):
+        self.device = torch.device(device)
+        for k in self._defaults:
+            setattr(self, k, getattr(self, k).to(self.device))
+        return self
+
+    def state_tensor(self):
+        return torch.stack([getattr(self, k).double().to(self.device) for k in self._defaults])
+
+    def load_state_tensor(self, t):
+        for k, v in zip(self._defaults, t):
+            setattr(self, k, v.to(getattr(self, k).dtype))
+
+
+def clip_preprocess(images: torch.Tensor, size: int = 224) -> torch.Tensor:
+    """uint8 (n,3,H,W) -> normalised float (n,3,size,size); HF CLIPImageProcessor semantics on device."""
+    if images.dtype != torch.uint8:
+        raise TypeError("CLIP score expects uint8 images (the in-pipeline path, base_experiment.py:198-201); "
+                        "float [0,1] inputs are the calc_clip_score.py defect (SURVEY C-8)")
+    x = images.float()
+    h, w = x.shape[-2:]
+    s = size / min(h, w)
+    nh, nw = max(size, round(h * s)), max(size, round(w * s))
+    if (nh, nw) != (h, w):
+        x = F.interpolate(x, size=(nh, nw), mode="bicubic", antialias=True, align_corners=False)
+        x = x.round().clamp(0, 255)                        # PIL resize returns uint8
+    top, left = (nh - size) // 2, (nw - size) // 2
+    x = x[..., top:top + size, left:left + size] / 255.0
+    mean = torch.tensor(CLIP_MEAN, device=x.device).view(1, 3, 1, 1)
+    std = torch.tensor(CLIP_STD, device=x.device).view(1, 3, 1, 1)
+    return (x - mean) / std
+
+
+def make_clip_model(model_name_or_path=None, seed=29):
+    """CLIP ViT-B/16 from a local directory, else seeded random-init of that architecture."""
+    from transformers import CLIPConfig, CLIPModel
+
+    if model_name_or_path and os.path.isdir(model_name_or_path):
+        return CLIPModel.from_pretrained(model_name_or_path).eval(), load_tokenizer(model_name_or_path)
+    cfg = CLIPConfig(text_config=dict(vocab_size=49408, hidden_size=512, intermediate_size=2048,
+                                      num_hidden_layers=12, num_attention_heads=8, max_position_embeddings=77,
+                                      bos_token_id=49406, eos_token_id=49407, pad_token_id=1),
+                     vision_config=dict(hidden_size=768, intermediate_size=3072, num_hidden_layers=12,
+                                        num_attention_heads=12, image_size=224, patch_size=16),
+                     projection_dim=512)
+    state = torch.random.get_rng_state()
+    torch.manual_seed(seed + 3)
+    try:
+        model = CLIPModel(cfg)
+    finally:
+        torch.random.set_rng_state(state)
+    return model.eval(), HashTokenizer()
+
+
+@metrics_registry.add_to_registry("clip_score")
+class ClipScoreMetric(Metric):
+    def __init__(self, model_name_or_path: str = "openai/clip-vit-base-patch16", **kwargs):
+        super().__init__()
+        self.model, self.tokenizer = make_clip_model(model_name_or_path)
+        self.add_state("score", torch.tensor(0.0))
+        self.add_state("n_samples", torch.tensor(0, dtype=torch.long))
+        self.keep_features = False
+        self._feats = []
+
+    def to(self, device):
+        super().to(device)
+        self.model.to(self.device)
+        return self
+
+    @torch.no_grad()
+    def features(self, images, text):
+        if isinstance(images, (list, tuple)):
+            images = torch.stack(list(images))
+        if images.dim() == 3:
+            images = images[None]
+        text = [text] if isinstance(text, str) else list(text)
+        if len(text) != images.shape[0]:
+            raise ValueError("Expected the number of images and text examples to be the same")
+        pixel = clip_preprocess(images.to(self.device))
+        ids, mask = self.tokenizer(text)
+        ids, mask = ids.to(self.device), mask.to(self.device)
+        fi = self.model.get_image_features(pixel_values=pixel.to(self.model.dtype))
+        ft = self.model.get_text_features(input_ids=ids, attention_mask=mask)
+        fi = getattr(fi, "pooler_output", fi)
+        ft = getattr(ft, "pooler_output", ft)
+        fi = fi / fi.norm(p=2, dim=-1, keepdim=True)
+        ft = ft / ft.norm(p=2, dim=-1, keepdim=True)
+        return fi.float(), ft.float()
+
+    def update(self, images, text):
+        fi, ft = self.features(images, text)
+        score = 100 * (fi * ft).sum(dim=-1)
+        self.score = self.score.to(self.device) + score.sum()
+        self.n_samples = self.n_samples.to(self.device) + len(score)
+        if self.keep_features:
+            self._feats.append((fi, ft))
+
+    def compute(self):
+        return torch.max(self.score / self.n_samples, torch.zeros_like(self.score))
+
+    def reset(self):
+        super().reset()
+        self._feats = []
+
+    def calc_metric(self, data, prompts, batch_size: int = 4) -> float:
+        """metrics.py:27-41: score a list of PIL images against prompts."""
+        from torchvision.transforms.functional import pil_to_tensor
+
+        tensors = [pil_to_tensor(img) for img in data]
+        for i in range(0, len(tensors), batch_size):
+            self.update(torch.stack(tensors[i:i + batch_size]), list(prompts[i:i + batch_size]))
+        return self.compute().item()
+
+
+@metrics_registry.add_to_registry("time_metric")
+class TimeMetric(Metric):
+    """metrics.py:115-131: seconds of denoising-loop time per image."""
+
+    def __init__(self):
+        super().__init__()
+        self.add_state("time", torch.tensor(0.0))
+        self.add_state("total", torch.tensor(0))
+
+    def update(self, time: float, batch_size: int) -> None:
+        self.time = self.time + torch.tensor(float(time))
+        self.total = self.total + torch.tensor(int(batch_size))
+
+    def compute(self):
+        return self.time / self.total
+
+
+class _Unavailable(Metric):
+    reason = ""
+
+    def update(self, *a, **k):
+        pass
+
+    def compute(self):
+        return torch.tensor(float("nan"))
+
+
+@metrics_registry.add_to_registry("image_reward")
+class RewardModel(_Unavailable):
+    reason = "ImageReward-v1.0 weights are an external download"
+
+    def __init__(self, model_name: str = "ImageReward-v1.0", device: str = "cpu", **kwargs):
+        super().__init__()
+
+
+@metrics_registry.add_to_registry("fid")
+class FID(_Unavailable):
+    reason = "Inception weights and the real COCO images are external downloads"
+
+    def __init__(self, feature: int = 64, input_img_size: int = 512, normalize: bool = False, **kwargs):
+        super().__init__()

@@ -87,6 +87,16 @@ class _Plan:
         check(lib().sonic_plan_stats(self.h, C.byref(n), C.byref(f)), "sonic_plan_stats")
         return n.value, f.value
 
+    def profile(self, stream_ptr, max_ops=4096):
+        """Per-operator device time of one eager run: list of (kind, ms, flops)."""
+        ms = (C.c_float * max_ops)()
+        kinds = (C.c_int32 * max_ops)()
+        flops = (C.c_double * max_ops)()
+        n = C.c_int32()
+        check(lib().sonic_plan_profile(self.h, stream_ptr, max_ops, ms, kinds, flops, C.byref(n)),
+              "sonic_plan_profile")
+        return [(kinds[i], ms[i], flops[i]) for i in range(n.value)]
+
     def __del__(self):
         try:
             if self.h:

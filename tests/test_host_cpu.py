@@ -1,0 +1,224 @@
+"""CPU tests of the product's host logic: C-ABI surface, registries, scheduler schedules and the
+coefficient reduction of every scheduler (checked by emulating the fused kernel in float64)."""
+import ctypes
+import dataclasses
+import json
+import os
+import re
+import subprocess
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+KAT = json.load(open(os.path.join(ROOT, "tests", "golden", "schedule_kat.json")))
+
+
+def _declared_symbols():
+    hdr = open(os.path.join(ROOT, "include", "sonic.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    return sorted(set(re.findall(r"\b(sonic_[a-z0-9_]+)\s*\(", hdr)))
+
+
+def test_library_exports_every_declared_symbol():
+    from sonicdiffusionbayeslab_b200 import _lib
+
+    assert os.path.exists(_lib.LIB_PATH), "libsonic.so missing: run __graft_entry__.build()"
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    names = _declared_symbols()
+    assert len(names) >= 25
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/sonic.h but not exported"
+    lib.sonic_version.restype = ctypes.c_char_p
+    assert b"sm_100a" in lib.sonic_version()
+
+
+def test_library_is_blackwell_native():
+    """SASS must contain tcgen05 MMA, TMEM loads and TMA loads (B200_PROFILING.md evidence table)."""
+    from sonicdiffusionbayeslab_b200 import _lib
+
+    try:
+        sass = subprocess.run(["cuobjdump", "-sass", _lib.LIB_PATH], capture_output=True, text=True, timeout=120).stdout
+    except (OSError, subprocess.TimeoutExpired):
+        pytest.skip("cuobjdump unavailable")
+    for mnemonic in ("UTCHMMA", "LDTM", "UTMALDG"):
+        assert mnemonic in sass, mnemonic
+    assert "HMMA.16816" not in sass            # no legacy mma.sync tensor path
+
+
+def test_missing_library_fails_loudly(monkeypatch):
+    from sonicdiffusionbayeslab_b200 import _lib
+
+    monkeypatch.setattr(_lib, "_lib", None)
+    monkeypatch.setattr(_lib, "LIB_PATH", "/nonexistent/libsonic.so")
+    with pytest.raises(_lib.SonicError):
+        _lib.lib()
+
+
+def test_registries_hold_reference_names():
+    import sonicdiffusionbayeslab_b200 as pkg  # noqa: F401  (registration is an import side effect)
+    from sonicdiffusionbayeslab_b200.registry import (methods_registry, metrics_registry, models_registry,
+                                                      schedulers_registry)
+
+    for n in ("stable_diffusion_model", "stable_diffusion_model_two_schedulers",
+              "stable_diffusion_model_interliving_schedulers", "stable_diffusion_model_skip_timesteps"):
+        assert n in models_registry
+    for n in ("dpm_solver_scheduler", "ddim_scheduler", "lcm_scheduler"):
+        assert n in schedulers_registry
+    for n in ("ddim", "dpm_solver", "deep_cache", "consistency_model", "two_schedulers", "default"):
+        assert n in methods_registry
+    for n in ("clip_score", "time_metric", "image_reward", "fid"):
+        assert n in metrics_registry
+    fields = [f.name for f in dataclasses.fields(schedulers_registry.args["dpm_solver_scheduler"])]
+    assert "solver_order" in fields and "algorithm_type" in fields
+
+
+def test_class_registry_contract():
+    from sonicdiffusionbayeslab_b200.utils.class_registry import MISSING, ClassRegistry
+
+    reg = ClassRegistry()
+
+    @reg.add_to_registry("thing")
+    class Thing:
+        def __init__(self, a, b=None, c=3, *args, **kwargs):
+            pass
+
+    assert reg["thing"] is Thing
+    fs = {f.name: f for f in dataclasses.fields(reg.args["thing"])}
+    assert set(fs) == {"a", "b", "c"}
+    assert fs["a"].default == MISSING and fs["b"].default is None and fs["c"].default == 3
+
+
+def _pairs():
+    from oracle import schedulers as O
+    from sonicdiffusionbayeslab_b200 import schedulers as S
+
+    return [
+        (S.DDIMSchedulerMy, O.DDIMScheduler, {}, 20, {}),
+        (S.DDIMSchedulerMy, O.DDIMScheduler, {}, 7, {"eta": 0.5}),
+        (S.DPMSolverScheduler, O.DPMSolverScheduler, dict(solver_order=2, algorithm_type="dpmsolver++"), 25, {}),
+        (S.DPMSolverScheduler, O.DPMSolverScheduler, dict(solver_order=2, algorithm_type="dpmsolver++"), 6, {}),
+        (S.DPMSolverScheduler, O.DPMSolverScheduler,
+         dict(solver_order=2, algorithm_type="dpmsolver", final_sigmas_type="sigma_min"), 10, {}),
+        (S.DPMSolverScheduler, O.DPMSolverScheduler,
+         dict(solver_order=2, algorithm_type="dpmsolver", final_sigmas_type="sigma_min", solver_type="heun"), 10, {}),
+        (S.DPMSolverScheduler, O.DPMSolverScheduler, dict(solver_order=3, algorithm_type="dpmsolver++"), 20, {}),
+        (S.DPMSolverScheduler, O.DPMSolverScheduler,
+         dict(solver_order=3, algorithm_type="dpmsolver", final_sigmas_type="sigma_min"), 16, {}),
+        (S.DPMSolverScheduler, O.DPMSolverScheduler, dict(solver_order=1, algorithm_type="dpmsolver++"), 5, {}),
+        (S.DPMSolverScheduler, O.DPMSolverScheduler, dict(solver_order=2, algorithm_type="sde-dpmsolver++"), 8, {}),
+        (S.DPMSolverScheduler, O.DPMSolverScheduler,
+         dict(solver_order=2, algorithm_type="sde-dpmsolver", final_sigmas_type="sigma_min"), 8, {}),
+        (S.LCMScheduler, O.LCMScheduler, {}, 4, {}),
+        (S.PNDMScheduler, O.PNDMScheduler, {}, 12, {}),
+    ]
+
+
+def _emulated_launch(self, coeffs, eps, eps_text, sample, hist=(), noise=None, want_m0=False, want_x0=True, out=None):
+    """float64 model of sonic_latent_update (include/sonic.h) for fp32 tensors on the CPU."""
+    c = {k: float(coeffs.get(k, 0.0)) for k in ("guidance", "m_x", "m_e", "x0_x", "x0_e", "c_x", "c_e", "c_m0",
+                                                "c_h1", "c_h2", "c_h3", "c_z")}
+    d = torch.float64
+    e = eps.to(d) if eps_text is None else eps.to(d) + c["guidance"] * (eps_text.to(d) - eps.to(d))
+    x = sample.to(d)
+    m0 = c["m_x"] * x + c["m_e"] * e
+    x0 = c["x0_x"] * x + c["x0_e"] * e
+    h = [t.to(d) for t in hist] + [torch.zeros_like(x)] * (3 - len(hist))
+    z = torch.zeros_like(x) if noise is None else noise.to(d)
+    xn = c["c_x"] * x + c["c_e"] * e + c["c_m0"] * m0 + c["c_h1"] * h[0] + c["c_h2"] * h[1] + c["c_h3"] * h[2] + c["c_z"] * z
+    f = sample.dtype
+    return xn.to(f), (m0.to(f) if want_m0 else None), (x0.to(f) if want_x0 else None)
+
+
+@pytest.mark.parametrize("idx", range(13))
+def test_scheduler_coefficients_reproduce_oracle_updates(idx, monkeypatch):
+    """Every scheduler's reduction to linear-combination coefficients, step by step, against the
+    oracle's literal formulas (fp32, CPU, no GPU needed)."""
+    from oracle.schedulers import SD15_SCHEDULER_CONFIG
+    from sonicdiffusionbayeslab_b200 import schedulers as S
+
+    monkeypatch.setattr(S.FusedScheduler, "_launch", _emulated_launch)
+    P, Oc, kw, n, step_kw = _pairs()[idx]
+    ps, os_ = P.from_config(SD15_SCHEDULER_CONFIG, **kw), Oc.from_config(SD15_SCHEDULER_CONFIG, **kw)
+    ps.set_timesteps(n)
+    os_.set_timesteps(n)
+    assert ps.timesteps.tolist() == os_.timesteps.tolist()
+    assert torch.equal(ps.alphas_cumprod, os_.alphas_cumprod)
+    if hasattr(os_, "sigmas"):
+        assert torch.equal(ps.sigmas, os_.sigmas)
+    g = torch.Generator().manual_seed(idx)
+    xp = xo = torch.randn(2, 4, 8, 8, generator=g)
+    needs_gen = "generator" in step_kw or P is S.LCMScheduler or "sde" in kw.get("algorithm_type", "") or step_kw.get("eta")
+    gp, go = torch.Generator().manual_seed(99), torch.Generator().manual_seed(99)
+    for t in os_.timesteps:
+        eps = torch.randn(2, 4, 8, 8, generator=g)
+        kp, ko = dict(step_kw), dict(step_kw)
+        if needs_gen:
+            kp["generator"], ko["generator"] = gp, go
+        rp, ro = ps.step(eps, t, xp, **kp), os_.step(eps, t, xo, **ko)
+        assert len(rp) == len(ro)
+        for a, b in zip(rp, ro):
+            scale = max(1.0, b.abs().max().item())
+            assert (a - b).abs().max().item() / scale < 2e-5, (type(ps).__name__, kw, int(t))
+        xp, xo = rp[0], ro[0]
+    assert ps.step_index == os_.step_index or P is S.DDIMSchedulerMy or P is S.PNDMScheduler
+
+
+def test_product_schedules_match_golden():
+    from sonicdiffusionbayeslab_b200 import models as M
+    from sonicdiffusionbayeslab_b200 import schedulers as S
+
+    cfg = M.SD15_SCHEDULER_CONFIG
+    d = S.DDIMSchedulerMy.from_config(cfg)
+    d.set_timesteps(20)
+    assert d.timesteps.tolist() == KAT["ddim_20"]
+    p = S.DPMSolverScheduler.from_config(cfg, solver_order=2, algorithm_type="dpmsolver++", final_sigmas_type="zero")
+    p.set_timesteps(25)
+    assert p.timesteps.tolist() == KAT["dpm_25"]
+    l = S.LCMScheduler.from_config(cfg)
+    l.set_timesteps(4)
+    assert l.timesteps.tolist() == KAT["lcm_4"]
+    q = S.PNDMScheduler.from_config(cfg)
+    q.set_timesteps(50)
+    assert q.timesteps.tolist() == KAT["pndm_50"]
+    # typo'd / unknown keys are dropped silently, as diffusers' from_config does (two_schedulers.py:51)
+    S.DPMSolverScheduler.from_config(cfg, sovler_order=3)
+    with pytest.raises(ValueError):
+        S.DPMSolverScheduler.from_config(cfg, algorithm_type="dpmsolver", final_sigmas_type="zero")
+
+
+def test_two_scheduler_switch_host_logic():
+    from sonicdiffusionbayeslab_b200 import models as M
+    from sonicdiffusionbayeslab_b200 import schedulers as S
+
+    cfg = M.SD15_SCHEDULER_CONFIG
+    a, b = S.DDIMSchedulerMy.from_config(cfg), S.DPMSolverScheduler.from_config(cfg)
+    a.set_timesteps(10)
+    b.set_timesteps(timesteps=a.timesteps.numpy())
+    sw = M.StableDiffusionModelTwoSchedulers.switch_timestamp
+    for mode in ("closest", "left_closest", "right_closest"):
+        first, second = sw(None, a.timesteps, b.timesteps, 3, mode)
+        assert ([int(t) for t in first], [int(t) for t in second]) == tuple(KAT["two_10_3"])
+
+
+def test_unet_spec_matches_oracle_keys():
+    from oracle.unet import UNet2DConditionModel
+    from sonicdiffusionbayeslab_b200.unet_spec import unet_param_shapes
+
+    with torch.device("meta"):
+        net = UNet2DConditionModel()
+    want = {k: tuple(v.shape) for k, v in net.state_dict().items()}
+    got = dict(unet_param_shapes())
+    assert got == want
+    assert sum(torch.Size(s).numel() for s in got.values()) == KAT["unet_params"]
+
+
+def test_step_requires_cuda():
+    from sonicdiffusionbayeslab_b200 import models as M
+    from sonicdiffusionbayeslab_b200 import schedulers as S
+
+    s = S.DDIMSchedulerMy.from_config(M.SD15_SCHEDULER_CONFIG)
+    s.set_timesteps(4)
+    x = torch.zeros(1, 4, 8, 8)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        s.step(x, s.timesteps[0], x)
