@@ -77,10 +77,14 @@ int sonic_attention(const sonic_attention_args* args, sonic_stream_t stream);
 /* ---------------------------------------------------------------------------------------
  * HBM-bound fused kernels.
  * GroupNorm(groups) [+SiLU] over NHWC bf16, optionally over the channel concat (x0 | x1).
- * stats: fp32 scratch of n_img*SONIC_GROUPNORM_MAX_CHUNKS*groups*2 floats (per-CTA partial sums,
- * reduced in a fixed order: results are bit-reproducible).  LayerNorm over rows of C bf16.
+ * stats: ZERO-INITIALISED fp32 scratch of SONIC_GROUPNORM_SCRATCH_FLOATS(n_img, groups) floats
+ * (per-CTA partial sums folded in a fixed order by the last CTA of each image: results are
+ * bit-reproducible; the kernel leaves the scratch ready for the next launch on the same stream).
+ * LayerNorm over rows of C bf16.
  */
 #define SONIC_GROUPNORM_MAX_CHUNKS 160
+#define SONIC_GROUPNORM_SCRATCH_FLOATS(n_img, groups) \
+  ((n_img) * ((SONIC_GROUPNORM_MAX_CHUNKS + 1) * (groups) * 2 + 1))
 int sonic_groupnorm_silu(const void* x0, int32_t c0, const void* x1, int32_t c1, int32_t n_img,
                          int32_t hw, int32_t groups, float eps, const float* gamma,
                          const float* beta, int32_t silu, float* stats, void* y,

@@ -1,10 +1,11 @@
 // tcgen05 implicit-GEMM kernel: conv3x3 / conv1x1 / Linear for the SD UNet (see gemm.cuh).
 //
-// Warp roles (192 threads, one persistent CTA per SM):
+// Warp roles (320 threads, one persistent CTA per SM):
 //   warp 0      TMA producer   : A box (128 pixels x 64 ch, shifted per filter tap) + B box
 //   warp 1      MMA issuer     : tcgen05.mma kind::f16, M=128, N=block_n, K=16 x4 per stage;
 //                                owns the 512-column TMEM allocation (2 accumulator buffers)
-//   warps 2..5  epilogue       : tcgen05.ld -> bias / per-image bias / residual / GEGLU -> bf16
+//   warps 2..9  epilogue       : tcgen05.ld -> bias / per-image bias / residual / GEGLU -> bf16
+//                                (two warps per TMEM lane quarter, each half of the columns)
 // Pipelines: smem full/empty ring (TMA <-> MMA) and TMEM full/empty pair (MMA <-> epilogue),
 // so the epilogue of tile i overlaps the main loop of tile i+1.
 #include "gemm.cuh"
@@ -15,14 +16,23 @@ namespace sonic {
 
 namespace {
 
-constexpr int kGemmThreads = 192;
+constexpr int kGemmThreads = 320;         // TMA warp + MMA warp + 8 epilogue warps
 constexpr int kTileM = 128;
 constexpr int kTileK = 64;                 // bf16 elements = one 128B swizzle row
 constexpr int kABytes = kTileM * kTileK * 2;
 constexpr int kAccStride = 256;            // TMEM columns per accumulator buffer
 
+// Exact (erf) GELU with erf from Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7, far below bf16):
+// one MUFU.RCP + one MUFU.EX2 + a handful of FMAs instead of the ~25-instruction libm erff.
 __device__ __forceinline__ float gelu_erf(float x) {
-  return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f));
+  const float z = fabsf(x) * 0.70710678118654752f;
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float erf_abs = 1.0f - poly * t * __expf(-z * z);
+  return 0.5f * x * (1.0f + copysignf(erf_abs, x));
 }
 
 __global__ void __launch_bounds__(kGemmThreads, 1)
@@ -50,7 +60,7 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
-      mbar_init(&tmem_empty[a], 4);
+      mbar_init(&tmem_empty[a], 8);
     }
     fence_barrier_init();
   }
@@ -123,6 +133,7 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
   } else {
     // ------------------------------------------------------------------ epilogue (4 warps)
     const int quarter = warp & 3;                // TMEM lane quarter this warp may read
+    const int col_half = (warp - 2) >> 2;        // warps 2-5 take the low columns, 6-9 the high ones
     const int r = quarter * 32 + lane;           // row inside the 128-row tile
     const bool geglu = p.epilogue == kEpiGeglu;
     const int out_cols = geglu ? p.block_n / 2 : p.block_n;
@@ -143,7 +154,11 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * kAccStride;
-      for (int c = 0; c < out_cols; c += 16) {
+      // the two warps sharing a lane quarter split the tile's columns (16-column granules)
+      const int granules = out_cols / 16;
+      const int c_begin = col_half == 0 ? 0 : (granules + 1) / 2 * 16;
+      const int c_end = col_half == 0 ? (granules + 1) / 2 * 16 : out_cols;
+      for (int c = c_begin; c < c_end; c += 16) {
         uint32_t v[16];
         tmem_ld16(t_row + c, v);
         float f[16];

@@ -1,13 +1,15 @@
 // HBM-bound normalisation kernels over channels-last bf16 activations:
 //   GroupNorm(32 groups) [+ SiLU] over the channel-concat of up to two tensors, and LayerNorm.
-// Both read each element once per pass with 128-bit accesses and reduce with warp shuffles.
+// Both read each element once per pass with 128-bit accesses; GroupNorm statistics are reduced in
+// a fixed order (per-CTA partials, finalised by the last CTA of each image), so results are
+// bit-reproducible without atomics on the data path.
 #include "ops.cuh"
 
 namespace sonic {
 
 namespace {
 
-constexpr int kGnThreads = 256;
+constexpr int kGnThreads = 512;
 
 struct GnSrc {
   const __nv_bfloat16* x0; const __nv_bfloat16* x1;
@@ -20,129 +22,140 @@ __device__ __forceinline__ uint4 gn_load(const GnSrc& s, size_t pix, int ch) {
   return __ldg(reinterpret_cast<const uint4*>(p));
 }
 
-// grid (chunks, n_img); each CTA accumulates per-channel sum / sum-of-squares over its pixel
-// chunk, folds channels into groups and adds 2 floats per group to stats[n_img][groups][2].
+// Scratch layout (floats): partial[n_img][kGroupNormMaxChunks][groups][2] | final[n_img][groups][2]
+//                          | ticket[n_img] (int, zero between launches)
+__device__ __forceinline__ float* gn_final(float* stats, int n_img, int groups) {
+  return stats + static_cast<size_t>(n_img) * kGroupNormMaxChunks * groups * 2;
+}
+
+// grid (chunks, n_img).  Thread (pl, v): 8-channel vector v of every ppp-th pixel of the chunk.
 __global__ void __launch_bounds__(kGnThreads)
-gn_stats_kernel(GnSrc s, int hw, int groups, float* __restrict__ stats) {
+gn_stats_kernel(GnSrc s, int hw, int groups, float eps, float* __restrict__ stats) {
   extern __shared__ float sm[];                  // [ppp][2][C] per-pixel-lane partials
+  __shared__ int s_last;
   const int C = s.c0 + s.c1;
   const int vpp = C / 8;                         // vectors per pixel
-  const int ppp = kGnThreads / vpp > 0 ? kGnThreads / vpp : 1;   // pixels per pass
-  for (int i = threadIdx.x; i < ppp * 2 * C; i += blockDim.x) sm[i] = 0.f;
-  __syncthreads();
-  const int img = blockIdx.y;
+  const int ppp = kGnThreads / vpp;              // pixel lanes
+  const int img = blockIdx.y, n_img = gridDim.y;
   const int chunk = (hw + gridDim.x - 1) / gridDim.x;
   const int p_begin = blockIdx.x * chunk;
   const int p_end = min(hw, p_begin + chunk);
-  if (vpp <= kGnThreads) {
-    const int v = threadIdx.x % vpp;
-    const int pl = threadIdx.x / vpp;
-    if (pl < ppp) {
-      float a[8] = {0, 0, 0, 0, 0, 0, 0, 0}, q[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-      for (int p = p_begin + pl; p < p_end; p += ppp) {
-        uint4 u = gn_load(s, static_cast<size_t>(img) * hw + p, v * 8);
-        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+  const int v = threadIdx.x % vpp;
+  const int pl = threadIdx.x / vpp;
+  if (pl < ppp) {
+    float a[8] = {0, 0, 0, 0, 0, 0, 0, 0}, q[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const size_t base = static_cast<size_t>(img) * hw;
+    auto acc = [&](const uint4& u) {
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          float lo = bf16_lo(w[j]), hi = bf16_hi(w[j]);
-          a[2 * j] += lo; q[2 * j] += lo * lo;
-          a[2 * j + 1] += hi; q[2 * j + 1] += hi * hi;
-        }
+      for (int j = 0; j < 4; ++j) {
+        const float lo = bf16_lo(w[j]), hi = bf16_hi(w[j]);
+        a[2 * j] += lo; q[2 * j] = fmaf(lo, lo, q[2 * j]);
+        a[2 * j + 1] += hi; q[2 * j + 1] = fmaf(hi, hi, q[2 * j + 1]);
       }
-      // every (pixel-lane, vector) slot has exactly one writer: no atomics, fixed reduction order
+    };
+    int p = p_begin + pl;
+    for (; p + 3 * ppp < p_end; p += 4 * ppp) {          // four 16-byte loads in flight per thread
+      uint4 u[4];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        sm[(pl * 2) * C + v * 8 + j] = a[j];
-        sm[(pl * 2 + 1) * C + v * 8 + j] = q[j];
-      }
+      for (int k = 0; k < 4; ++k) u[k] = gn_load(s, base + p + k * ppp, v * 8);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) acc(u[k]);
     }
-  } else {  // very wide rows (C > 2048): loop over vectors (ppp == 1, one owner per vector)
-    float* s_sum = sm;
-    float* s_sq = sm + C;
-    for (int p = p_begin; p < p_end; ++p)
-      for (int v = threadIdx.x; v < vpp; v += blockDim.x) {
-        uint4 u = gn_load(s, static_cast<size_t>(img) * hw + p, v * 8);
-        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+    for (; p < p_end; p += ppp) acc(gn_load(s, base + p, v * 8));
+    // every (pixel-lane, vector) slot has exactly one writer: no atomics, fixed reduction order
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          float lo = bf16_lo(w[j]), hi = bf16_hi(w[j]);
-          s_sum[v * 8 + 2 * j] += lo; s_sq[v * 8 + 2 * j] += lo * lo;
-          s_sum[v * 8 + 2 * j + 1] += hi; s_sq[v * 8 + 2 * j + 1] += hi * hi;
-        }
-      }
+    for (int j = 0; j < 8; ++j) {
+      sm[(pl * 2) * C + v * 8 + j] = a[j];
+      sm[(pl * 2 + 1) * C + v * 8 + j] = q[j];
+    }
   }
   __syncthreads();
   const int cpg = C / groups;
+  float* part = stats + (static_cast<size_t>(img) * kGroupNormMaxChunks + blockIdx.x) * groups * 2;
   for (int g = threadIdx.x; g < groups; g += blockDim.x) {
     float a = 0.f, q = 0.f;
-    for (int pl = 0; pl < ppp; ++pl)
+    for (int l = 0; l < ppp; ++l)
       for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
-        a += sm[(pl * 2) * C + c];
-        q += sm[(pl * 2 + 1) * C + c];
+        a += sm[(l * 2) * C + c];
+        q += sm[(l * 2 + 1) * C + c];
       }
-    // per-CTA partials, reduced in a fixed order by the apply kernel: bit-reproducible, no memset
-    float* dst = stats + ((static_cast<size_t>(img) * gridDim.x + blockIdx.x) * groups + g) * 2;
-    dst[0] = a;
-    dst[1] = q;
+    part[g * 2] = a;
+    part[g * 2 + 1] = q;
   }
-}
-
-// grid (chunks, n_img): y = act((x - mean) * rstd * gamma + beta), one 8-channel vector per thread.
-__global__ void __launch_bounds__(kGnThreads)
-gn_apply_kernel(GnSrc s, int hw, int groups, float eps, const float* __restrict__ stats,
-                const float* __restrict__ gamma, const float* __restrict__ beta, int silu,
-                __nv_bfloat16* __restrict__ y) {
-  extern __shared__ float sm[];                  // scale[C], shift[C]
-  const int C = s.c0 + s.c1;
-  const int cpg = C / groups;
-  const int img = blockIdx.y;
+  // the last CTA of this image to finish folds the partials (in chunk order) into mean / rstd
+  __threadfence();
+  __syncthreads();
+  int* ticket = reinterpret_cast<int*>(gn_final(stats, n_img, groups) + static_cast<size_t>(n_img) * groups * 2);
+  if (threadIdx.x == 0) s_last = atomicAdd(&ticket[img], 1) == static_cast<int>(gridDim.x) - 1;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
   const float inv_n = 1.0f / (static_cast<float>(hw) * cpg);
-  float* s_mean = sm + 2 * C;                    // [groups]
-  float* s_rstd = s_mean + groups;               // [groups]
+  float* fin = gn_final(stats, n_img, groups) + static_cast<size_t>(img) * groups * 2;
+  const float* src = stats + static_cast<size_t>(img) * kGroupNormMaxChunks * groups * 2;
   for (int g = threadIdx.x; g < groups; g += blockDim.x) {
-    const float* src = stats + (static_cast<size_t>(img) * gridDim.x * groups + g) * 2;
     float a = 0.f, q = 0.f;
     for (int ch = 0; ch < static_cast<int>(gridDim.x); ++ch) {
-      a += src[static_cast<size_t>(ch) * groups * 2];
-      q += src[static_cast<size_t>(ch) * groups * 2 + 1];
+      a += __ldcg(src + (static_cast<size_t>(ch) * groups + g) * 2);
+      q += __ldcg(src + (static_cast<size_t>(ch) * groups + g) * 2 + 1);
     }
     const float mean = a * inv_n;
     const float var = fmaxf(q * inv_n - mean * mean, 0.f);
-    s_mean[g] = mean;
-    s_rstd[g] = rsqrtf(var + eps);
+    fin[g * 2] = mean;
+    fin[g * 2 + 1] = rsqrtf(var + eps);
   }
-  __syncthreads();
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    const int g = c / cpg;
-    const float sc = s_rstd[g] * gamma[c];
-    sm[c] = sc;
-    sm[C + c] = beta[c] - s_mean[g] * sc;
-  }
-  __syncthreads();
+  if (threadIdx.x == 0) ticket[img] = 0;         // ready for the next launch / graph replay
+}
+
+// grid (chunks, n_img): y = act((x - mean) * rstd * gamma + beta); scale / shift in registers.
+__global__ void __launch_bounds__(kGnThreads)
+gn_apply_kernel(GnSrc s, int hw, int groups, float* __restrict__ stats, const float* __restrict__ gamma,
+                const float* __restrict__ beta, int silu, __nv_bfloat16* __restrict__ y) {
+  const int C = s.c0 + s.c1;
+  const int cpg = C / groups;
   const int vpp = C / 8;
+  const int ppp = kGnThreads / vpp;
+  const int img = blockIdx.y;
+  const int v = threadIdx.x % vpp;
+  const int pl = threadIdx.x / vpp;
+  if (pl >= ppp) return;
+  const float* fin = gn_final(stats, gridDim.y, groups) + static_cast<size_t>(img) * groups * 2;
+  float sc[8], sh[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int c = v * 8 + j;
+    const int g = c / cpg;
+    sc[j] = fin[g * 2 + 1] * __ldg(gamma + c);
+    sh[j] = __ldg(beta + c) - fin[g * 2] * sc[j];
+  }
   const int chunk = (hw + gridDim.x - 1) / gridDim.x;
   const int p_begin = blockIdx.x * chunk;
   const int p_end = min(hw, p_begin + chunk);
-  const long total = static_cast<long>(p_end - p_begin) * vpp;
-  for (long i = threadIdx.x; i < total; i += blockDim.x) {
-    const int p = p_begin + static_cast<int>(i / vpp);
-    const int v = static_cast<int>(i % vpp);
-    const size_t pix = static_cast<size_t>(img) * hw + p;
-    uint4 u = gn_load(s, pix, v * 8);
+  const size_t base = static_cast<size_t>(img) * hw;
+  auto norm_store = [&](const uint4& u, size_t pix) {
     uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const int c = v * 8 + 2 * j;
-      float lo = bf16_lo(w[j]) * sm[c] + sm[C + c];
-      float hi = bf16_hi(w[j]) * sm[c + 1] + sm[C + c + 1];
+      float lo = fmaf(bf16_lo(w[j]), sc[2 * j], sh[2 * j]);
+      float hi = fmaf(bf16_hi(w[j]), sc[2 * j + 1], sh[2 * j + 1]);
       if (silu) {
-        lo = lo / (1.0f + __expf(-lo));
-        hi = hi / (1.0f + __expf(-hi));
+        lo = __fdividef(lo, 1.0f + __expf(-lo));
+        hi = __fdividef(hi, 1.0f + __expf(-hi));
       }
       w[j] = pack_bf16(lo, hi);
     }
     *reinterpret_cast<uint4*>(y + pix * C + v * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+  };
+  int p = p_begin + pl;
+  for (; p + 3 * ppp < p_end; p += 4 * ppp) {
+    uint4 u[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) u[k] = gn_load(s, base + p + k * ppp, v * 8);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) norm_store(u[k], base + p + k * ppp);
   }
+  for (; p < p_end; p += ppp) norm_store(gn_load(s, base + p, v * 8), base + p);
 }
 
 // One warp per row; the row lives in registers between the statistics and the normalise pass.
@@ -210,19 +223,19 @@ int groupnorm_launch(const GroupNormOp& op, cudaStream_t stream) {
   SONIC_REQUIRE(op.x0 && op.y && op.stats && op.gamma && op.beta, "groupnorm: null operand");
   SONIC_REQUIRE(C % op.groups == 0 && op.c0 % 8 == 0 && C % 8 == 0, "groupnorm: C=%d groups=%d unsupported",
                 C, op.groups);
-  SONIC_REQUIRE(2 * C * sizeof(float) <= 48 * 1024, "groupnorm: C=%d too wide", C);
+  SONIC_REQUIRE(C / 8 <= kGnThreads, "groupnorm: C=%d too wide (max %d)", C, 8 * kGnThreads);
   GnSrc s{static_cast<const __nv_bfloat16*>(op.x0), static_cast<const __nv_bfloat16*>(op.x1), op.c0,
           op.x1 ? op.c1 : 0, op.ld0 ? op.ld0 : op.c0, op.ld1 ? op.ld1 : op.c1};
-  // enough CTAs to fill the machine, but at least ~32 pixels per CTA
-  int chunks = std::max(1, std::min(op.hw / 32, (4 * 148 + op.n_img - 1) / op.n_img));
+  const int ppp = kGnThreads / (C / 8);
+  // >= 4 pixels per pixel-lane per CTA, and enough CTAs for ~2 waves of 4 resident CTAs per SM
+  int chunks = std::max(1, std::min(op.hw / (4 * ppp), (8 * 148 + op.n_img - 1) / op.n_img));
   chunks = std::min(chunks, kGroupNormMaxChunks);
   dim3 grid(chunks, op.n_img);
-  const size_t smem = 2 * C * sizeof(float);
-  const int ppp = std::max(1, kGnThreads / (C / 8));
-  SONIC_REQUIRE(ppp * smem <= 48 * 1024, "groupnorm: C=%d needs too much shared memory", C);
-  gn_stats_kernel<<<grid, kGnThreads, ppp * smem, stream>>>(s, op.hw, op.groups, op.stats);
-  gn_apply_kernel<<<grid, kGnThreads, smem + 2 * op.groups * sizeof(float), stream>>>(
-      s, op.hw, op.groups, op.eps, op.stats, op.gamma, op.beta, op.silu, static_cast<__nv_bfloat16*>(op.y));
+  const size_t smem = static_cast<size_t>(ppp) * 2 * C * sizeof(float);
+  SONIC_REQUIRE(smem <= 48 * 1024, "groupnorm: C=%d needs too much shared memory", C);
+  gn_stats_kernel<<<grid, kGnThreads, smem, stream>>>(s, op.hw, op.groups, op.eps, op.stats);
+  gn_apply_kernel<<<grid, kGnThreads, 0, stream>>>(s, op.hw, op.groups, op.stats, op.gamma, op.beta, op.silu,
+                                                   static_cast<__nv_bfloat16*>(op.y));
   SONIC_CUDA(cudaGetLastError());
   return 0;
 }

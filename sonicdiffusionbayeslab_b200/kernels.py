@@ -121,6 +121,12 @@ def attention(q, k, v, *, batch, heads, seq_q, seq_k, head_dim, scale=None, out=
     return out
 
 
+def groupnorm_scratch(n_img, groups, device):
+    """Zero-initialised GroupNorm scratch: per-CTA partials, final (mean, rstd), per-image tickets
+    (SONIC_GROUPNORM_SCRATCH_FLOATS in include/sonic.h); reusable across launches on one stream."""
+    return torch.zeros(n_img * ((GN_MAX_CHUNKS + 1) * groups * 2 + 1), device=device, dtype=torch.float32)
+
+
 def groupnorm(x0, gamma, beta, *, n_img, hw, groups=32, eps=1e-5, silu=True, x1=None, out=None):
     """x0 (and optional x1): NHWC bf16 [n_img*hw, C]; returns bf16 [n_img*hw, C0+C1]."""
     _bf16c(x0)
@@ -128,7 +134,7 @@ def groupnorm(x0, gamma, beta, *, n_img, hw, groups=32, eps=1e-5, silu=True, x1=
     c1 = 0 if x1 is None else _bf16c(x1).shape[-1]
     if out is None:
         out = torch.empty((n_img * hw, c0 + c1), device=x0.device, dtype=torch.bfloat16)
-    stats = torch.empty((n_img, GN_MAX_CHUNKS, groups, 2), device=x0.device, dtype=torch.float32)
+    stats = groupnorm_scratch(n_img, groups, x0.device)
     check(lib().sonic_groupnorm_silu(ptr(x0), c0, ptr(x1), c1, n_img, hw, groups, C.c_float(eps), ptr(gamma),
                                      ptr(beta), int(silu), ptr(stats), ptr(out), stream_ptr()),
           "sonic_groupnorm_silu")

@@ -74,6 +74,7 @@ class Arena:
 class _Plan:
     def __init__(self):
         self.h = C.c_void_p()
+        self.log = []                      # one human-readable line per recorded operator, in order
         check(lib().sonic_plan_create(C.byref(self.h)), "sonic_plan_create")
 
     def run(self, stream_ptr):
@@ -211,19 +212,22 @@ class UNetEngine:
         g.out, g.ld_out = out.data_ptr(), out.shape[-1]
         g.epilogue, g.block_n = epilogue, block_n
         check(lib().sonic_plan_add_conv_gemm(plan.h, C.byref(g)), "sonic_plan_add_conv_gemm")
+        kk = g.c0 + (g.c1 if a1 is not None else 0)
+        plan.log.append(f"gemm M={M} N={N} K={kk}x{taps} img={n_img}x{H}x{W} epi={epilogue}"
+                        f"{' +res' if residual is not None else ''}")
         return out
 
     def _gn(self, plan, x0, x1, prefix, hw, eps, silu):
         c = x0.shape[-1] + (0 if x1 is None else x1.shape[-1])
         y = self.arena.alloc((x0.shape[0], c))
         if not hasattr(self, "_gn_stats"):                    # one scratch: plans run in stream order
-            self._gn_stats = torch.empty((self.n, K.GN_MAX_CHUNKS, self.arch.norm_num_groups, 2),
-                                         device=self.dev, dtype=torch.float32)
+            self._gn_stats = K.groupnorm_scratch(self.n, self.arch.norm_num_groups, self.dev)
         stats = self._gn_stats
         check(lib().sonic_plan_add_groupnorm(
             plan.h, K.ptr(x0), x0.shape[-1], K.ptr(x1), 0 if x1 is None else x1.shape[-1], self.n, hw,
             self.arch.norm_num_groups, C.c_float(eps), K.ptr(self._f32(prefix + ".weight")),
             K.ptr(self._f32(prefix + ".bias")), int(silu), K.ptr(stats), K.ptr(y)), "sonic_plan_add_groupnorm")
+        plan.log.append(f"groupnorm rows={x0.shape[0]} C={c} silu={int(silu)}")
         return y
 
     def _ln(self, plan, x, prefix):
@@ -231,6 +235,7 @@ class UNetEngine:
         check(lib().sonic_plan_add_layernorm(plan.h, K.ptr(x), K.ptr(y), x.shape[0], x.shape[1], C.c_float(1e-5),
                                              K.ptr(self._f32(prefix + ".weight")),
                                              K.ptr(self._f32(prefix + ".bias"))), "sonic_plan_add_layernorm")
+        plan.log.append(f"layernorm rows={x.shape[0]} C={x.shape[1]}")
         return y
 
     def _attn(self, plan, q, k, v, seq_q, seq_k, d):
@@ -238,6 +243,7 @@ class UNetEngine:
         a = K.attention_args(q, k, v, out, batch=self.n, heads=self.arch.num_heads, seq_q=seq_q, seq_k=seq_k,
                              head_dim=d)
         check(lib().sonic_plan_add_attention(plan.h, C.byref(a)), "sonic_plan_add_attention")
+        plan.log.append(f"attention B={self.n} H={self.arch.num_heads} Sq={seq_q} Sk={seq_k} d={d}")
         return out
 
     # ------------------------------------------------------------------ blocks
@@ -370,6 +376,7 @@ class UNetEngine:
                 self._temb_bias[pfx] = torch.zeros(n, device=self.dev, dtype=torch.float32)
         check(lib().sonic_plan_add_timestep_embedding(plan.h, K.ptr(self.t_dev), c0, K.ptr(self._t_sin)),
               "sonic_plan_add_timestep_embedding")
+        plan.log.append("timestep_embedding")
 
         def gemv(jobs, x, Kdim, silu_in):
             n = len(jobs)
@@ -380,6 +387,7 @@ class UNetEngine:
             arr_n = (C.c_int32 * n)(*[j[3].numel() for j in jobs])
             check(lib().sonic_plan_add_gemv(plan.h, n, arr_w, arr_b, arr_a, arr_y, arr_n, K.ptr(x), Kdim,
                                             int(silu_in)), "sonic_plan_add_gemv")
+            plan.log.append(f"gemv jobs={n} rows={sum(j[3].numel() for j in jobs)} K={Kdim}")
 
         gemv([(self._lin("time_embedding.linear_1.weight"), self._f32("time_embedding.linear_1.bias"), None,
                self._t_e1)], self._t_sin, c0, False)
@@ -405,6 +413,7 @@ class UNetEngine:
         check(lib().sonic_plan_add_nchw_to_nhwc8(plan.h, K.ptr(self.x_in), K._dtype_code(self.x_in), self.n_lat,
                                                  a.in_channels, H * W, int(self.cfg_dup), K.ptr(x8)),
               "sonic_plan_add_nchw_to_nhwc8")
+        plan.log.append("nchw_to_nhwc8")
         key = ("conv_in",)
         if key not in self._w:
             w = self._p("conv_in.weight")
@@ -438,6 +447,7 @@ class UNetEngine:
                     col = self.arena.alloc((n * (H // 2) * (W // 2), 9 * cout))
                     check(lib().sonic_plan_add_im2col_s2(plan.h, K.ptr(h), K.ptr(col), n, H, W, cout),
                           "sonic_plan_add_im2col_s2")
+                    plan.log.append(f"im2col_s2 {n}x{H}x{W}x{cout}")
                     key = ("down", b)
                     if key not in self._w:
                         w = self._p(f"down_blocks.{b}.downsamplers.0.conv.weight")
@@ -474,6 +484,7 @@ class UNetEngine:
                     up = self.arena.alloc((n * 4 * H * W, cout))
                     check(lib().sonic_plan_add_upsample2x(plan.h, K.ptr(h), K.ptr(up), n, H, W, cout),
                           "sonic_plan_add_upsample2x")
+                    plan.log.append(f"upsample2x {n}x{H}x{W}x{cout}")
                     self.arena.release(h)
                     H, W = 2 * H, 2 * W
                     h = self._gemm(plan, up, self._conv3(f"up_blocks.{b}.upsamplers.0.conv.weight"), cout, n_img=n,
@@ -497,6 +508,7 @@ class UNetEngine:
         check(lib().sonic_plan_add_nhwc_to_nchw(plan.h, K.ptr(o16), 16, n, a.out_channels, self.H * self.W,
                                                 K.ptr(self.eps), K._dtype_code(self.eps)),
               "sonic_plan_add_nhwc_to_nchw")
+        plan.log.append("nhwc_to_nchw")
         self.arena.release(o16)
         return plan
 
