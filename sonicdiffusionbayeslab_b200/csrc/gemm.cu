@@ -21,6 +21,7 @@ constexpr int kTileM = 128;
 constexpr int kTileK = 64;                 // bf16 elements = one 128B swizzle row
 constexpr int kABytes = kTileM * kTileK * 2;
 constexpr int kAccStride = 256;            // TMEM columns per accumulator buffer
+constexpr int kMaxGranules = 8;            // 16-column granules per epilogue warp (block_n 256 / 2 / 16)
 
 // Exact (erf) GELU with erf from Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7, far below bf16):
 // one MUFU.RCP + one MUFU.EX2 + a handful of FMAs instead of the ~25-instruction libm erff.
@@ -151,31 +152,51 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
       const int ocol0 = n_tile * out_cols;                  // output column base
       const int n_out_total = geglu ? p.N / 2 : p.N;
 
+      // the two warps sharing a lane quarter split the tile's columns (16-column granules)
+      const int granules = out_cols / 16;
+      const int g_begin = col_half == 0 ? 0 : (granules + 1) / 2;
+      const int g_count = col_half == 0 ? (granules + 1) / 2 : granules - (granules + 1) / 2;
+      // Issue the residual loads of the whole row slice BEFORE waiting on the accumulator: their
+      // HBM latency overlaps the main loop instead of serialising inside the granule loop.
+      uint4 res[kMaxGranules][2];
+      const bool has_res = p.residual != nullptr && row_ok;
+      if (has_res) {
+        const uint4* rp = reinterpret_cast<const uint4*>(p.residual + grow * p.ld_res + ocol0 + g_begin * 16);
+#pragma unroll
+        for (int g = 0; g < kMaxGranules; ++g) {
+          if (g < g_count && ocol0 + (g_begin + g) * 16 < n_out_total) {
+            res[g][0] = __ldg(rp + 2 * g);
+            res[g][1] = __ldg(rp + 2 * g + 1);
+          }
+        }
+      }
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * kAccStride;
-      // the two warps sharing a lane quarter split the tile's columns (16-column granules)
-      const int granules = out_cols / 16;
-      const int c_begin = col_half == 0 ? 0 : (granules + 1) / 2 * 16;
-      const int c_end = col_half == 0 ? (granules + 1) / 2 * 16 : out_cols;
-      for (int c = c_begin; c < c_end; c += 16) {
+#pragma unroll
+      for (int g = 0; g < kMaxGranules; ++g) {
+        if (g >= g_count) break;
+        const int c = (g_begin + g) * 16;
         uint32_t v[16];
         tmem_ld16(t_row + c, v);
         float f[16];
         if (geglu) {
-          uint32_t g[16];
-          tmem_ld16(t_row + out_cols + c, g);
+          uint32_t gt[16];
+          tmem_ld16(t_row + out_cols + c, gt);
+          float bv[16], bg[16];
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) {
+            const float4 a = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + ncol0 + c + j))
+                                    : make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 b = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + ncol0 + out_cols + c + j))
+                                    : make_float4(0.f, 0.f, 0.f, 0.f);
+            bv[j] = a.x; bv[j + 1] = a.y; bv[j + 2] = a.z; bv[j + 3] = a.w;
+            bg[j] = b.x; bg[j + 1] = b.y; bg[j + 2] = b.z; bg[j + 3] = b.w;
+          }
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            float val = __uint_as_float(v[j]);
-            float gate = __uint_as_float(g[j]);
-            if (p.bias) {
-              val += __ldg(p.bias + ncol0 + c + j);
-              gate += __ldg(p.bias + ncol0 + out_cols + c + j);
-            }
-            f[j] = val * gelu_erf(gate);
-          }
+          for (int j = 0; j < 16; ++j)
+            f[j] = (__uint_as_float(v[j]) + bv[j]) * gelu_erf(__uint_as_float(gt[j]) + bg[j]);
         } else {
           tmem_ld_wait();
 #pragma unroll
@@ -185,17 +206,19 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
         if (row_ok && oc < n_out_total) {
           if (p.bias && !geglu) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) f[j] += __ldg(p.bias + ncol0 + c + j);
+            for (int j = 0; j < 16; j += 4) {
+              const float4 a = __ldg(reinterpret_cast<const float4*>(p.bias + ncol0 + c + j));
+              f[j] += a.x; f[j + 1] += a.y; f[j + 2] += a.z; f[j + 3] += a.w;
+            }
           }
           if (p.row_bias) {
             const float* rb = p.row_bias + static_cast<size_t>(img) * p.N + oc;
 #pragma unroll
             for (int j = 0; j < 16; ++j) f[j] += __ldg(rb + j);
           }
-          if (p.residual) {
-            const uint4* rp = reinterpret_cast<const uint4*>(p.residual + grow * p.ld_res + oc);
-            uint4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
-            const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+          if (has_res) {
+            const uint32_t rr[8] = {res[g][0].x, res[g][0].y, res[g][0].z, res[g][0].w,
+                                    res[g][1].x, res[g][1].y, res[g][1].z, res[g][1].w};
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               f[2 * j] += bf16_lo(rr[j]);
