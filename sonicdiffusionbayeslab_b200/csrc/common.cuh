@@ -79,10 +79,13 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// try_wait with a suspend-time hint: the thread is parked in hardware until the phase completes (or the
-// hint, in ns, expires) instead of polling -- a polling producer / MMA-issuer lane otherwise burns the
-// issue slots of the sub-partition it shares with the math warps (ncu: 39% of all issued instructions of
-// the attention kernel were spin-loop overhead before this).
+// try_wait with a suspend-time hint: the thread is parked in hardware (SASS: NANOSLEEP.SYNCS) for at most
+// `hint_ns` instead of polling -- a polling producer / MMA-issuer lane otherwise burns the issue slots of
+// the sub-partition it shares with the math warps (ncu: 39% of all issued instructions of the attention
+// kernel were spin-loop overhead).  The hint is kept SHORT: measured with clock64 traces, a parked warp is
+// not reliably woken by completions that come from the async proxy (tcgen05.commit, TMA complete_tx) and
+// with a long hint overslept by microseconds; with a bounded hint the worst oversleep is the hint itself.
+template <uint32_t kHintNs>
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
@@ -90,17 +93,18 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}\n"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity), "r"(0x989680u)
+      : "r"(smem_u32(bar)), "r"(parity), "n"(kHintNs)
       : "memory");
   return ok != 0;
 }
 // Bounded wait: a protocol bug becomes a trap (-> cudaErrorLaunchFailure) instead of a hang that would
-// wedge a shared GPU box.  Each attempt may park for up to the 10 ms hint, so the bound is ~seconds and
-// is never reached in a correct run.
+// wedge a shared GPU box (2^26 attempts of >= kHintNs each: seconds; never reached in a correct run).
+// kHintNs: ~100 for waits on the critical path of a pipeline, ~500 for producers that run ahead.
+template <uint32_t kHintNs = 128>
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if (++spins == (1u << 20)) {
+  while (!mbar_try_wait<kHintNs>(bar, parity)) {
+    if (++spins == (1u << 26)) {
       printf("sonic: mbarrier timeout block %d thread %d\n", blockIdx.x, threadIdx.x);
       __trap();
     }

@@ -90,7 +90,7 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
           const int dy = p.taps == 9 ? tap / 3 - 1 : 0;
           const int dx = p.taps == 9 ? tap % 3 - 1 : 0;
           for (int ch = 0; ch < k_chunks; ++ch) {
-            mbar_wait(&empty_bar[stage], phase ^ 1);
+            mbar_wait<512>(&empty_bar[stage], phase ^ 1);
             mbar_expect_tx(&full_bar[stage], stage_bytes);
             uint8_t* sa = smem + stage * stage_bytes;
             if (ch < p.k_chunks0)

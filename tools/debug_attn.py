@@ -39,16 +39,23 @@ for cfg in [(1, 1, 128, 128, 64), (1, 1, 128, 128, 40), (1, 1, 128, 256, 64), (1
             (2, 8, 1024, 1024, 80)]:
     run(*cfg)
 
-B, H, S, d = 32, 8, 4096, 40
-qkv = torch.randn(B * S, 3 * H * d, device=dev, generator=g).bfloat16()
-C = H * d
-for _ in range(2):
-    k.attention(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], batch=B, heads=H, seq_q=S, seq_k=S, head_dim=d)
-s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-s.record()
-for _ in range(5):
-    k.attention(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], batch=B, heads=H, seq_q=S, seq_k=S, head_dim=d)
-e.record()
-torch.cuda.synchronize()
-ms = s.elapsed_time(e) / 5
-print(f"self-attn 64x64 b32 d40: {ms:.3f} ms  {4 * B * H * S * S * d / ms / 1e9:.1f} TFLOP/s")
+def bench(B, H, Sq, Sk, d, reps=5):
+    C = H * d
+    q = torch.randn(B * Sq, C, device=dev, generator=g).bfloat16()
+    kv = torch.randn(B * Sk, 2 * C, device=dev, generator=g).bfloat16()
+    f = lambda: k.attention(q, kv[:, :C], kv[:, C:], batch=B, heads=H, seq_q=Sq, seq_k=Sk, head_dim=d)
+    for _ in range(2):
+        f()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(reps):
+        f()
+    e.record()
+    torch.cuda.synchronize()
+    ms = s.elapsed_time(e) / reps
+    print(f"attention B{B} H{H} Sq{Sq} Sk{Sk} d{d}: {ms:.3f} ms  {4 * B * H * Sq * Sk * d / ms / 1e9:.1f} TFLOP/s", flush=True)
+
+
+for cfg in [(32, 8, 4096, 4096, 40), (32, 8, 1024, 1024, 80), (32, 8, 256, 256, 160), (32, 8, 4096, 77, 40),
+            (32, 8, 1024, 77, 80), (32, 8, 256, 77, 160)]:
+    bench(*cfg)
