@@ -328,7 +328,7 @@ int make_qkv_map(CUtensorMap* m, const void* base, int ld, int seq, int batch, i
   uint64_t str[3] = {static_cast<uint64_t>(d) * 2, static_cast<uint64_t>(ld) * 2,
                      static_cast<uint64_t>(seq) * ld * 2};
   uint32_t box[4] = {64, 1, static_cast<uint32_t>(rows), 1};
-  return encode_tensor_map(m, base, 4, dims, str, box, true);
+  return encode_tensor_map(m, base, 4, dims, str, box, 128);
 }
 
 int round_dpv(int d16) { return d16 <= 48 ? 48 : d16 <= 64 ? 64 : d16 <= 80 ? 80 : d16 <= 128 ? 128 : 160; }

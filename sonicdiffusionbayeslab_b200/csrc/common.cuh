@@ -26,8 +26,9 @@ int check_cuda(cudaError_t e, const char* what, const char* file, int line);
 
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda link dependency).
 // dims/strides are innermost-first; strides[i] is the byte stride of dim i+1.
+// swizzle_bytes: 0 (none), 64 or 128.
 int encode_tensor_map(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
-                      const uint64_t* strides_bytes, const uint32_t* box, bool swizzle128);
+                      const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes);
 
 #ifdef __CUDACC__
 // ------------------------------------------------------------------ small device utilities
@@ -138,6 +139,30 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* m, uin
       " [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(smem_u32(dst)),
       "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
+}
+
+// smem -> global tile store (bulk async group); coordinates innermost-first.  Out-of-bounds parts of the
+// box are clipped by the TMA unit.
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                   reinterpret_cast<uint64_t>(m)),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* m, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(reinterpret_cast<uint64_t>(m)),
+               "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+// Wait until at most kPending of this thread's most recent bulk groups are still READING shared memory.
+template <int kPending>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(kPending) : "memory");
+}
+template <int kPending>
+__device__ __forceinline__ void bulk_wait_all() {
+  asm volatile("cp.async.bulk.wait_group %0;" ::"n"(kPending) : "memory");
 }
 
 // ------------------------------------------------------------------ tcgen05 / TMEM

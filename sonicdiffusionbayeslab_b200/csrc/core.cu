@@ -32,7 +32,7 @@ int check_cuda(cudaError_t e, const char* what, const char* file, int line) {
 }
 
 int encode_tensor_map(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
-                      const uint64_t* strides_bytes, const uint32_t* box, bool swizzle128) {
+                      const uint64_t* strides_bytes, const uint32_t* box, int swizzle_bytes) {
   if (!g_encode) {
     void* fn = nullptr;
     cudaDriverEntryPointQueryResult q;
@@ -59,7 +59,7 @@ int encode_tensor_map(CUtensorMap* out, const void* base, int rank, const uint64
   }
   CUresult r = g_encode(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank),
                         const_cast<void*>(base), d, s, b, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                        swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
+                        swizzle_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : swizzle_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_NONE,
                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   SONIC_REQUIRE(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d (rank %d)",
                 static_cast<int>(r), rank);

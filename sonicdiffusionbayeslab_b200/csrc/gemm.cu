@@ -3,9 +3,16 @@
 // Warp roles (320 threads, one persistent CTA per SM):
 //   warp 0      TMA producer   : A box (128 pixels x 64 ch, shifted per filter tap) + B box
 //   warp 1      MMA issuer     : tcgen05.mma kind::f16, M=128, N=block_n, K=16 x4 per stage;
-//                                owns the 512-column TMEM allocation (2 accumulator buffers)
-//   warps 2..9  epilogue       : tcgen05.ld -> bias / per-image bias / residual / GEGLU -> bf16
-//                                (two warps per TMEM lane quarter, each half of the columns)
+//                                owns the 512-column TMEM allocation (2 accumulator buffers).  The whole
+//                                warp runs the loop (uniform registers), one elected lane issues.
+//   warps 2..9  epilogue       : two warps per TMEM lane quarter; each handles 32 rows x 32-column chunks:
+//                                tcgen05.ld -> bias / per-image bias / residual / GEGLU -> bf16 -> a private
+//                                64B-swizzled staging buffer in shared memory -> TMA tile store.  The
+//                                residual tile arrives the same way (TMA load into the staging buffer, L2
+//                                prefetch one tile ahead), so global traffic is whole 64-byte row segments
+//                                instead of one 16-byte piece per lane (a clock64 trace showed the old
+//                                scattered-store epilogue taking 5800 cycles per 128x160 tile against a
+//                                2600-cycle main loop at K=320).
 // Pipelines: smem full/empty ring (TMA <-> MMA) and TMEM full/empty pair (MMA <-> epilogue),
 // so the epilogue of tile i overlaps the main loop of tile i+1.
 #include "gemm.cuh"
@@ -22,6 +29,11 @@ constexpr int kTileK = 64;                 // bf16 elements = one 128B swizzle r
 constexpr int kABytes = kTileM * kTileK * 2;
 constexpr int kAccStride = 256;            // TMEM columns per accumulator buffer
 constexpr int kMaxGranules = 8;            // 16-column granules per epilogue warp (block_n 256 / 2 / 16)
+constexpr int kEpiWarps = 8;
+constexpr int kChunkCols = 32;             // output columns per staged chunk (64 B of bf16: one swizzle-64B row)
+constexpr int kStgBufBytes = 32 * kChunkCols * 2;       // 32 rows x 64 B
+constexpr int kStgBufs = 2;                // staging buffers per epilogue warp
+constexpr int kStgBytes = kEpiWarps * kStgBufs * kStgBufBytes;   // 32 KB
 
 // Exact (erf) GELU with erf from Abramowitz-Stegun 7.1.26 (|err| <= 1.5e-7, far below bf16):
 // one MUFU.RCP + one MUFU.EX2 + a handful of FMAs instead of the ~25-instruction libm erff.
@@ -36,17 +48,27 @@ __device__ __forceinline__ float gelu_erf(float x) {
   return 0.5f * x * (1.0f + copysignf(erf_abs, x));
 }
 
+#ifdef SONIC_GEMM_TRACE
+// Debug timeline (compile with -DSONIC_GEMM_TRACE): clock64 stamps of CTA 0's pipeline events per tile.
+__device__ long long g_gemm_trace[3][64][4];
+#define GEMM_TRACE(role, i, k) do { if (blockIdx.x == 0 && (i) < 64) g_gemm_trace[role][i][k] = clock64(); } while (0)
+#else
+#define GEMM_TRACE(role, i, k) do { } while (0)
+#endif
+
 __global__ void __launch_bounds__(kGemmThreads, 1)
 conv_gemm_kernel(const __grid_constant__ GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
-  const int stage_bytes = kABytes + p.block_n * kTileK * 2;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.stages * stage_bytes);
+  const int stage_bytes = kABytes + p.block_n * kTileK * 2;          // multiple of 1024
+  uint8_t* stg_base = smem + p.stages * stage_bytes;                 // epilogue staging, 32 KB
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(stg_base + kStgBytes);
   uint64_t* empty_bar = full_bar + p.stages;
   uint64_t* tmem_full = empty_bar + p.stages;
   uint64_t* tmem_empty = tmem_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* res_full = tmem_empty + 2;                               // [kEpiWarps][kStgBufs]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_full + kEpiWarps * kStgBufs);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -61,8 +83,9 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
-      mbar_init(&tmem_empty[a], 8);
+      mbar_init(&tmem_empty[a], kEpiWarps);
     }
+    for (int i = 0; i < kEpiWarps * kStgBufs; ++i) mbar_init(&res_full[i], 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<512>(tmem_slot);
@@ -79,7 +102,9 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
       if (p.k_chunks1) tma_prefetch_desc(&p.tm_a1);
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+      int ti = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
+        GEMM_TRACE(0, ti, 0);
         const int n_tile = tile % p.n_tiles;
         const int m_tile = tile / p.n_tiles;
         const int w0 = (m_tile % p.tiles_w) * p.tile_w;
@@ -102,37 +127,185 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
           }
         }
+        GEMM_TRACE(0, ti, 1);
       }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
-      int stage = 0, acc = 0;
-      uint32_t phase = 0, acc_phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+    // Warp-uniform loop (descriptors stay in uniform registers), one elected lane issues.
+    const bool leader = elect_one();
+    const uint64_t desc0 = make_sw128_desc(smem_u32(smem), 16, 1024);
+    int stage = 0, acc = 0;
+    uint32_t phase = 0, acc_phase = 0;
+    int ti = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
+      if (lane == 0) GEMM_TRACE(1, ti, 0);
+      mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+      if (lane == 0) GEMM_TRACE(1, ti, 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * kAccStride;
+      for (int kit = 0; kit < k_iters; ++kit) {
+        mbar_wait<64>(&full_bar[stage], phase);
+        if (kit == 0 && lane == 0) GEMM_TRACE(1, ti, 2);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * kAccStride;
-        for (int kit = 0; kit < k_iters; ++kit) {
-          mbar_wait(&full_bar[stage], phase);
-          tc_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * stage_bytes);
-          const uint64_t da = make_sw128_desc(sa, 16, 1024);
-          const uint64_t db = make_sw128_desc(sa + kABytes, 16, 1024);
+        const uint64_t da = desc0 + static_cast<uint64_t>((stage * stage_bytes) >> 4);
+        const uint64_t db = da + (kABytes >> 4);
+        if (leader) {
 #pragma unroll
           for (int k = 0; k < kTileK / 16; ++k)  // +32 B per K=16 step inside the 128B atom
             umma_bf16_ss(d_tmem, da + 2 * k, db + 2 * k, p.idesc, (kit | k) != 0);
           umma_commit(&empty_bar[stage]);
-          if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tmem_full[acc]);
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1;
+        __syncwarp();
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
+      if (leader) umma_commit(&tmem_full[acc]);
+      __syncwarp();
+      if (lane == 0) GEMM_TRACE(1, ti, 3);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
     }
-    __syncwarp();
+  } else if (p.tma_epilogue) {
+    // ------------------------------------------------------------------ epilogue, staged through smem
+    const int ew = warp - 2;
+    const int quarter = warp & 3;                // TMEM lane quarter this warp may read
+    const int col_half = ew >> 2;                // even / odd 32-column chunks
+    const bool geglu = p.epilogue == kEpiGeglu;
+    const bool has_res = p.residual != nullptr;
+    const int out_cols = geglu ? p.block_n / 2 : p.block_n;
+    const int n_chunks = out_cols / kChunkCols;
+    uint8_t* stg = stg_base + ew * (kStgBufs * kStgBufBytes);
+    uint64_t* r_full = res_full + ew * kStgBufs;
+    const uint32_t sw = (lane >> 1) & 3;         // swizzle-64B: 16-byte piece j of row r sits at j ^ ((r >> 1) & 3)
+    uint32_t slot = 0;                           // chunks staged so far: buffer = slot & 1, phase = (slot >> 1) & 1
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    int ti = 0;
+    if (lane == 0) {
+      tma_prefetch_desc(&p.tm_out);
+      if (has_res) tma_prefetch_desc(&p.tm_res);
+    }
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
+      if (threadIdx.x == 64) GEMM_TRACE(2, ti, 0);
+      const int n_tile = tile % p.n_tiles;
+      const int m_tile = tile / p.n_tiles;
+      const int row0 = m_tile * kTileM + quarter * 32;       // tiles are 128 consecutive rows of [M][N]
+      const int ncol0 = n_tile * p.block_n;                  // B-row / bias index base
+      const int ocol0 = n_tile * out_cols;                   // output column base
+      int my_n = 0;                                          // chunks col_half, col_half + 2, ... inside the matrix
+      for (int c = col_half; c < n_chunks && ocol0 + c * kChunkCols < p.n_out_total; c += 2) ++my_n;
+      if (has_res && lane == 0) {
+        // residual of the NEXT tile into L2 now; this tile's first chunk into the staging buffer
+        const int tile2 = tile + gridDim.x;
+        if (tile2 < total_tiles) {
+          const int o2 = (tile2 % p.n_tiles) * out_cols, r2 = (tile2 / p.n_tiles) * kTileM + quarter * 32;
+          for (int c = col_half; c < n_chunks && o2 + c * kChunkCols < p.n_out_total; c += 2)
+            tma_prefetch_l2_2d(&p.tm_res, o2 + c * kChunkCols, r2);
+        }
+        if (my_n > 0) {
+          const uint32_t b = slot & 1;
+          bulk_wait_read<1>();                               // the store that last used this buffer has read it
+          mbar_expect_tx(&r_full[b], kStgBufBytes);
+          tma_load_2d(stg + b * kStgBufBytes, &p.tm_res, &r_full[b], ocol0 + col_half * kChunkCols, row0);
+        }
+      }
+      if (threadIdx.x == 64) GEMM_TRACE(2, ti, 1);
+      mbar_wait<64>(&tmem_full[acc], acc_phase);
+      if (threadIdx.x == 64) GEMM_TRACE(2, ti, 2);
+      tc_fence_after();
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * kAccStride;
+      if (my_n == 0) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      }
+      for (int i = 0; i < my_n; ++i) {
+        const int c = col_half + 2 * i;
+        const uint32_t b = slot & 1;
+        uint8_t* buf = stg + b * kStgBufBytes;
+        uint32_t v[32];
+        float f[32];
+        tmem_ld32(t_row + c * kChunkCols, v);
+        if (geglu) {
+          uint32_t gt[32];
+          tmem_ld32(t_row + out_cols + c * kChunkCols, gt);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float4 bv = make_float4(0.f, 0.f, 0.f, 0.f), bg = bv;
+            if (p.bias) {
+              bv = __ldg(reinterpret_cast<const float4*>(p.bias + ncol0 + c * kChunkCols + j));
+              bg = __ldg(reinterpret_cast<const float4*>(p.bias + ncol0 + out_cols + c * kChunkCols + j));
+            }
+            f[j] = (__uint_as_float(v[j]) + bv.x) * gelu_erf(__uint_as_float(gt[j]) + bg.x);
+            f[j + 1] = (__uint_as_float(v[j + 1]) + bv.y) * gelu_erf(__uint_as_float(gt[j + 1]) + bg.y);
+            f[j + 2] = (__uint_as_float(v[j + 2]) + bv.z) * gelu_erf(__uint_as_float(gt[j + 2]) + bg.z);
+            f[j + 3] = (__uint_as_float(v[j + 3]) + bv.w) * gelu_erf(__uint_as_float(gt[j + 3]) + bg.w);
+          }
+        } else {
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.bias) bv = __ldg(reinterpret_cast<const float4*>(p.bias + ncol0 + c * kChunkCols + j));
+            f[j] = __uint_as_float(v[j]) + bv.x;
+            f[j + 1] = __uint_as_float(v[j + 1]) + bv.y;
+            f[j + 2] = __uint_as_float(v[j + 2]) + bv.z;
+            f[j + 3] = __uint_as_float(v[j + 3]) + bv.w;
+          }
+        }
+        if (i == my_n - 1) {                                 // every TMEM read of this tile is done
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        }
+        if (p.row_bias) {
+          const int img = min((row0 + lane) / (p.H * p.W), p.n_img - 1);
+          const float* rb = p.row_bias + static_cast<size_t>(img) * p.N + ocol0 + c * kChunkCols;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) f[j] += __ldg(rb + j);
+        }
+        uint8_t* my_row = buf + lane * 64;
+        if (has_res) {
+          mbar_wait<64>(&r_full[b], (slot >> 1) & 1);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const uint4 rr = *reinterpret_cast<const uint4*>(my_row + ((q ^ sw) << 4));
+            f[8 * q] += bf16_lo(rr.x);     f[8 * q + 1] += bf16_hi(rr.x);
+            f[8 * q + 2] += bf16_lo(rr.y); f[8 * q + 3] += bf16_hi(rr.y);
+            f[8 * q + 4] += bf16_lo(rr.z); f[8 * q + 5] += bf16_hi(rr.z);
+            f[8 * q + 6] += bf16_lo(rr.w); f[8 * q + 7] += bf16_hi(rr.w);
+          }
+        } else {
+          if (lane == 0) bulk_wait_read<1>();                // the store that last used this buffer has read it
+          __syncwarp();
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          *reinterpret_cast<uint4*>(my_row + ((q ^ sw) << 4)) =
+              make_uint4(pack_bf16(f[8 * q], f[8 * q + 1]), pack_bf16(f[8 * q + 2], f[8 * q + 3]),
+                         pack_bf16(f[8 * q + 4], f[8 * q + 5]), pack_bf16(f[8 * q + 6], f[8 * q + 7]));
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_store_2d(&p.tm_out, buf, ocol0 + c * kChunkCols, row0);
+          bulk_commit();
+          if (has_res && i + 1 < my_n) {                     // next chunk's residual into the other buffer
+            const uint32_t nb = b ^ 1;
+            bulk_wait_read<1>();
+            mbar_expect_tx(&r_full[nb], kStgBufBytes);
+            tma_load_2d(stg + nb * kStgBufBytes, &p.tm_res, &r_full[nb], ocol0 + (c + 2) * kChunkCols, row0);
+          }
+        }
+        ++slot;
+      }
+      if (threadIdx.x == 64) GEMM_TRACE(2, ti, 3);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+    if (lane == 0) bulk_wait_all<0>();
   } else {
-    // ------------------------------------------------------------------ epilogue (4 warps)
+    // ------------------------------------------------------------------ epilogue, direct stores
+    // (block_n not a multiple of 32, e.g. the 4 -> 16 padded conv_out, or non-contiguous tiles)
     const int quarter = warp & 3;                // TMEM lane quarter this warp may read
     const int col_half = (warp - 2) >> 2;        // warps 2-5 take the low columns, 6-9 the high ones
     const int r = quarter * 32 + lane;           // row inside the 128-row tile
@@ -150,32 +323,13 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
       const size_t grow = (static_cast<size_t>(img) * p.H + h) * p.W + w;
       const int ncol0 = n_tile * p.block_n;                 // B-row / bias index base
       const int ocol0 = n_tile * out_cols;                  // output column base
-      const int n_out_total = geglu ? p.N / 2 : p.N;
-
-      // the two warps sharing a lane quarter split the tile's columns (16-column granules)
       const int granules = out_cols / 16;
       const int g_begin = col_half == 0 ? 0 : (granules + 1) / 2;
       const int g_count = col_half == 0 ? (granules + 1) / 2 : granules - (granules + 1) / 2;
-      // Issue the residual loads of the whole row slice BEFORE waiting on the accumulator: their
-      // HBM latency overlaps the main loop instead of serialising inside the granule loop.
-      uint4 res[kMaxGranules][2];
-      const bool has_res = p.residual != nullptr && row_ok;
-      if (has_res) {
-        const uint4* rp = reinterpret_cast<const uint4*>(p.residual + grow * p.ld_res + ocol0 + g_begin * 16);
-#pragma unroll
-        for (int g = 0; g < kMaxGranules; ++g) {
-          if (g < g_count && ocol0 + (g_begin + g) * 16 < n_out_total) {
-            res[g][0] = __ldg(rp + 2 * g);
-            res[g][1] = __ldg(rp + 2 * g + 1);
-          }
-        }
-      }
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * kAccStride;
-#pragma unroll
-      for (int g = 0; g < kMaxGranules; ++g) {
-        if (g >= g_count) break;
+      for (int g = 0; g < g_count; ++g) {
         const int c = (g_begin + g) * 16;
         uint32_t v[16];
         tmem_ld16(t_row + c, v);
@@ -183,42 +337,29 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
         if (geglu) {
           uint32_t gt[16];
           tmem_ld16(t_row + out_cols + c, gt);
-          float bv[16], bg[16];
-#pragma unroll
-          for (int j = 0; j < 16; j += 4) {
-            const float4 a = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + ncol0 + c + j))
-                                    : make_float4(0.f, 0.f, 0.f, 0.f);
-            const float4 b = p.bias ? __ldg(reinterpret_cast<const float4*>(p.bias + ncol0 + out_cols + c + j))
-                                    : make_float4(0.f, 0.f, 0.f, 0.f);
-            bv[j] = a.x; bv[j + 1] = a.y; bv[j + 2] = a.z; bv[j + 3] = a.w;
-            bg[j] = b.x; bg[j + 1] = b.y; bg[j + 2] = b.z; bg[j + 3] = b.w;
-          }
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 16; ++j)
-            f[j] = (__uint_as_float(v[j]) + bv[j]) * gelu_erf(__uint_as_float(gt[j]) + bg[j]);
+          for (int j = 0; j < 16; ++j) {
+            const float bv = p.bias ? __ldg(p.bias + ncol0 + c + j) : 0.f;
+            const float bg = p.bias ? __ldg(p.bias + ncol0 + out_cols + c + j) : 0.f;
+            f[j] = (__uint_as_float(v[j]) + bv) * gelu_erf(__uint_as_float(gt[j]) + bg);
+          }
         } else {
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+          for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]) + (p.bias ? __ldg(p.bias + ncol0 + c + j) : 0.f);
         }
         const int oc = ocol0 + c;
-        if (row_ok && oc < n_out_total) {
-          if (p.bias && !geglu) {
-#pragma unroll
-            for (int j = 0; j < 16; j += 4) {
-              const float4 a = __ldg(reinterpret_cast<const float4*>(p.bias + ncol0 + c + j));
-              f[j] += a.x; f[j + 1] += a.y; f[j + 2] += a.z; f[j + 3] += a.w;
-            }
-          }
+        if (row_ok && oc < p.n_out_total) {
           if (p.row_bias) {
             const float* rb = p.row_bias + static_cast<size_t>(img) * p.N + oc;
 #pragma unroll
             for (int j = 0; j < 16; ++j) f[j] += __ldg(rb + j);
           }
-          if (has_res) {
-            const uint32_t rr[8] = {res[g][0].x, res[g][0].y, res[g][0].z, res[g][0].w,
-                                    res[g][1].x, res[g][1].y, res[g][1].z, res[g][1].w};
+          if (p.residual) {
+            const uint4* rp = reinterpret_cast<const uint4*>(p.residual + grow * p.ld_res + oc);
+            const uint4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
+            const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
               f[2 * j] += bf16_lo(rr[j]);
@@ -251,17 +392,26 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
   }
 }
 
+}  // namespace
+#ifdef SONIC_GEMM_TRACE
+}  // namespace sonic
+extern "C" int sonic_debug_gemm_trace(long long* host_out) {
+  return cudaMemcpyFromSymbol(host_out, sonic::g_gemm_trace, sizeof(long long) * 3 * 64 * 4) == cudaSuccess ? 0 : -1;
+}
+namespace sonic {
+#endif
+namespace {
 int g_num_sms = 0;
 bool g_attr_set = false;
 
 int pick_block_n(int N, int m_tiles, bool geglu, int num_sms) {
   // Prefer wide tiles (A re-use, fewer smem bytes per MMA cycle) but avoid tail waves.
-  static const int cands[] = {256, 240, 224, 208, 192, 176, 160, 144, 128, 112, 96, 80, 64, 48, 32, 16};
+  static const int cands[] = {256, 224, 192, 160, 128, 96, 64, 32, 16};   // multiples of 32: staged epilogue chunks
   int best = 0;
   double best_cost = 1e30;
   for (int bn : cands) {
     if (bn > N && bn != 16) continue;
-    if (geglu && (bn % 32 != 0 || N % bn != 0)) continue;
+    if (geglu && (bn % 64 != 0 || N % bn != 0)) continue;
     const int n_tiles = (N + bn - 1) / bn;
     const long tiles = static_cast<long>(m_tiles) * n_tiles;
     const long waves = (tiles + num_sms - 1) / num_sms;
@@ -336,9 +486,14 @@ int gemm_plan(const GemmOp& op, GemmPlan* plan) {
                 p.block_n);
   SONIC_REQUIRE(!geglu || (p.block_n % 32 == 0 && op.N % p.block_n == 0),
                 "gemm: GEGLU needs block_n %% 32 == 0 and N %% block_n == 0");
+  p.n_out_total = geglu ? op.N / 2 : op.N;
+  // staged (TMA-store) epilogue: 32-column chunks of tiles that are 128 consecutive rows of [M][N]
+  const int out_cols = geglu ? p.block_n / 2 : p.block_n;
+  const bool flat = op.W < kTileM || op.W % kTileM == 0 || (op.H == 1 && op.n_img == 1);
+  p.tma_epilogue = (out_cols % kChunkCols == 0 && flat) ? 1 : 0;
   p.n_tiles = (op.N + p.block_n - 1) / p.block_n;
   const int stage_bytes = kABytes + p.block_n * kTileK * 2;
-  p.stages = std::max(2, std::min(8, (200 * 1024) / stage_bytes));
+  p.stages = std::max(2, std::min(8, (225 * 1024 - kStgBytes) / stage_bytes));
   p.idesc = make_idesc_bf16(kTileM, p.block_n, false);
   p.bias = op.bias;
   p.row_bias = op.row_bias;
@@ -355,13 +510,13 @@ int gemm_plan(const GemmOp& op, GemmPlan* plan) {
                        static_cast<uint64_t>(op.H) * op.W * op.ld0 * 2};
     uint32_t box[4] = {kTileK, static_cast<uint32_t>(p.tile_w), static_cast<uint32_t>(p.tile_h),
                        static_cast<uint32_t>(p.tile_n)};
-    if (int rc = encode_tensor_map(&p.tm_a0, op.a0, 4, dims, str, box, true)) return rc;
+    if (int rc = encode_tensor_map(&p.tm_a0, op.a0, 4, dims, str, box, 128)) return rc;
     if (op.a1) {
       dims[0] = op.c1;
       str[0] = static_cast<uint64_t>(op.ld1) * 2;
       str[1] = static_cast<uint64_t>(op.W) * op.ld1 * 2;
       str[2] = static_cast<uint64_t>(op.H) * op.W * op.ld1 * 2;
-      if (int rc = encode_tensor_map(&p.tm_a1, op.a1, 4, dims, str, box, true)) return rc;
+      if (int rc = encode_tensor_map(&p.tm_a1, op.a1, 4, dims, str, box, 128)) return rc;
     } else {
       p.tm_a1 = p.tm_a0;
     }
@@ -374,10 +529,22 @@ int gemm_plan(const GemmOp& op, GemmPlan* plan) {
                         static_cast<uint64_t>(op.taps)};
     uint64_t str[2] = {static_cast<uint64_t>(K) * 2, static_cast<uint64_t>(op.N) * K * 2};
     uint32_t box[3] = {kTileK, static_cast<uint32_t>(p.block_n), 1};
-    if (int rc = encode_tensor_map(&p.tm_b, op.w, 3, dims, str, box, true)) return rc;
+    if (int rc = encode_tensor_map(&p.tm_b, op.w, 3, dims, str, box, 128)) return rc;
+  }
+  p.tm_out = p.tm_b;
+  p.tm_res = p.tm_b;
+  if (p.tma_epilogue) {
+    uint64_t dims[2] = {static_cast<uint64_t>(p.n_out_total), static_cast<uint64_t>(p.M)};
+    uint64_t str[1] = {static_cast<uint64_t>(op.ld_out) * 2};
+    uint32_t box[2] = {kChunkCols, 32};
+    if (int rc = encode_tensor_map(&p.tm_out, op.out, 2, dims, str, box, 64)) return rc;
+    if (op.residual) {
+      str[0] = static_cast<uint64_t>(op.ld_res) * 2;
+      if (int rc = encode_tensor_map(&p.tm_res, op.residual, 2, dims, str, box, 64)) return rc;
+    }
   }
   plan->grid = std::min(p.m_tiles * p.n_tiles, g_num_sms);
-  plan->smem = static_cast<size_t>(p.stages) * stage_bytes + 1024 /*align*/ + 256 /*barriers*/;
+  plan->smem = static_cast<size_t>(p.stages) * stage_bytes + kStgBytes + 1024 /*align*/ + 512 /*barriers*/;
   plan->flops = 2.0 * p.M * static_cast<double>(op.N) * K * op.taps;
   return 0;
 }

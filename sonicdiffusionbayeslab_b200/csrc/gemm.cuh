@@ -13,6 +13,7 @@ enum GemmEpilogue { kEpiNone = 0, kEpiGeglu = 1 };
 
 struct GemmParams {
   CUtensorMap tm_a0, tm_a1, tm_b;
+  CUtensorMap tm_out, tm_res;    // [M][n_out] output / residual, 32x32 boxes (staged epilogue)
   int M, N;                      // GEMM rows (= n_img*H*W) and B rows (= out channels before GEGLU)
   int k_chunks0, k_chunks1;      // 64-wide K chunks taken from source 0 / source 1
   int taps;                      // 1 or 9
@@ -27,6 +28,8 @@ struct GemmParams {
   __nv_bfloat16* out;            // [M][ld_out]
   int ld_res, ld_out;
   int epilogue;
+  int n_out_total;               // output columns (N, or N/2 for GEGLU)
+  int tma_epilogue;              // 1: smem-staged TMA-store epilogue, 0: direct stores
 };
 
 struct GemmOp {                  // host-side description; pointers are borrowed
