@@ -16,6 +16,13 @@ struct GnSrc {
   int c0, c1, ld0, ld1;
 };
 
+__device__ __forceinline__ float silu_tanh(float x) {
+  const float h = 0.5f * x;
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+  return fmaf(h, t, h);
+}
+
 __device__ __forceinline__ uint4 gn_load(const GnSrc& s, size_t pix, int ch) {
   // ch is a multiple of 8; c0 is a multiple of 8, so a vector never straddles the two sources
   const __nv_bfloat16* p = ch < s.c0 ? s.x0 + pix * s.ld0 + ch : s.x1 + pix * s.ld1 + (ch - s.c0);
@@ -55,12 +62,12 @@ gn_stats_kernel(GnSrc s, int hw, int groups, float eps, float* __restrict__ stat
       }
     };
     int p = p_begin + pl;
-    for (; p + 3 * ppp < p_end; p += 4 * ppp) {          // four 16-byte loads in flight per thread
-      uint4 u[4];
+    for (; p + 7 * ppp < p_end; p += 8 * ppp) {          // eight 16-byte loads in flight per thread
+      uint4 u[8];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) u[k] = gn_load(s, base + p + k * ppp, v * 8);
+      for (int k = 0; k < 8; ++k) u[k] = gn_load(s, base + p + k * ppp, v * 8);
 #pragma unroll
-      for (int k = 0; k < 4; ++k) acc(u[k]);
+      for (int k = 0; k < 8; ++k) acc(u[k]);
     }
     for (; p < p_end; p += ppp) acc(gn_load(s, base + p, v * 8));
     // every (pixel-lane, vector) slot has exactly one writer: no atomics, fixed reduction order
@@ -139,79 +146,89 @@ gn_apply_kernel(GnSrc s, int hw, int groups, float* __restrict__ stats, const fl
     for (int j = 0; j < 4; ++j) {
       float lo = fmaf(bf16_lo(w[j]), sc[2 * j], sh[2 * j]);
       float hi = fmaf(bf16_hi(w[j]), sc[2 * j + 1], sh[2 * j + 1]);
-      if (silu) {
-        lo = __fdividef(lo, 1.0f + __expf(-lo));
-        hi = __fdividef(hi, 1.0f + __expf(-hi));
+      if (silu) {            // x * sigmoid(x) = h + h * tanh(h), h = x / 2: ONE MUFU op per element
+        lo = silu_tanh(lo);  // (the exp + divide form needs two and made this kernel XU-bound: 48% XU busy)
+        hi = silu_tanh(hi);
       }
       w[j] = pack_bf16(lo, hi);
     }
     *reinterpret_cast<uint4*>(y + pix * C + v * 8) = make_uint4(w[0], w[1], w[2], w[3]);
   };
   int p = p_begin + pl;
-  for (; p + 3 * ppp < p_end; p += 4 * ppp) {
-    uint4 u[4];
+  for (; p + 7 * ppp < p_end; p += 8 * ppp) {
+    uint4 u[8];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) u[k] = gn_load(s, base + p + k * ppp, v * 8);
+    for (int k = 0; k < 8; ++k) u[k] = gn_load(s, base + p + k * ppp, v * 8);
 #pragma unroll
-    for (int k = 0; k < 4; ++k) norm_store(u[k], base + p + k * ppp);
+    for (int k = 0; k < 8; ++k) norm_store(u[k], base + p + k * ppp);
   }
   for (; p < p_end; p += ppp) norm_store(gn_load(s, base + p, v * 8), base + p);
 }
 
-// One warp per row; the row lives in registers between the statistics and the normalise pass.
-template <int kVecPerLane>
+// One warp per kRows rows (all loads of the warp's rows are issued before the first reduction, so enough
+// bytes are in flight per SM to cover HBM latency); rows live in registers between the two passes.
+template <int kVecPerLane, int kRows>
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const __nv_bfloat16* __restrict__ x, int rows, int C, float eps,
                  const float* __restrict__ gamma, const float* __restrict__ beta,
                  __nv_bfloat16* __restrict__ y) {
-  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int row0 = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * kRows;
   const int lane = threadIdx.x & 31;
-  if (row >= rows) return;
+  if (row0 >= rows) return;
   const int nvec = C / 8;
-  const uint4* xr = reinterpret_cast<const uint4*>(x + static_cast<size_t>(row) * C);
-  float f[kVecPerLane][8];
-  float sum = 0.f;
+  uint4 u[kRows][kVecPerLane];
 #pragma unroll
-  for (int i = 0; i < kVecPerLane; ++i) {
-    const int v = lane + i * 32;
-    if (v < nvec) {
-      uint4 u = __ldg(xr + v);
-      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+  for (int r = 0; r < kRows; ++r) {
+    const uint4* xr = reinterpret_cast<const uint4*>(x + static_cast<size_t>(min(row0 + r, rows - 1)) * C);
+#pragma unroll
+    for (int i = 0; i < kVecPerLane; ++i) {
+      const int v = lane + i * 32;
+      u[r][i] = v < nvec ? __ldg(xr + v) : make_uint4(0, 0, 0, 0);
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < kRows; ++r) {
+    if (row0 + r >= rows) break;
+    float f[kVecPerLane][8];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < kVecPerLane; ++i) {
+      const uint32_t w[4] = {u[r][i].x, u[r][i].y, u[r][i].z, u[r][i].w};
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         f[i][2 * j] = bf16_lo(w[j]);
         f[i][2 * j + 1] = bf16_hi(w[j]);
-        sum += f[i][2 * j] + f[i][2 * j + 1];
+        sum += f[i][2 * j] + f[i][2 * j + 1];       // padding vectors are zero
       }
     }
-  }
-  const float mean = warp_sum(sum) / C;
-  float sq = 0.f;
+    const float mean = warp_sum(sum) / C;
+    float sq = 0.f;
 #pragma unroll
-  for (int i = 0; i < kVecPerLane; ++i) {
-    if (lane + i * 32 < nvec) {
+    for (int i = 0; i < kVecPerLane; ++i) {
+      if (lane + i * 32 < nvec) {
 #pragma unroll
-      for (int j = 0; j < 8; ++j) { const float d = f[i][j] - mean; sq += d * d; }
+        for (int j = 0; j < 8; ++j) { const float d = f[i][j] - mean; sq += d * d; }
+      }
     }
-  }
-  const float rstd = rsqrtf(warp_sum(sq) / C + eps);
-  uint4* yr = reinterpret_cast<uint4*>(y + static_cast<size_t>(row) * C);
+    const float rstd = rsqrtf(warp_sum(sq) / C + eps);
+    uint4* yr = reinterpret_cast<uint4*>(y + static_cast<size_t>(row0 + r) * C);
 #pragma unroll
-  for (int i = 0; i < kVecPerLane; ++i) {
-    const int v = lane + i * 32;
-    if (v < nvec) {
-      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + v * 8));
-      const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + v * 8 + 4));
-      const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + v * 8));
-      const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + v * 8 + 4));
-      const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
-      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-      uint32_t w[4];
+    for (int i = 0; i < kVecPerLane; ++i) {
+      const int v = lane + i * 32;
+      if (v < nvec) {
+        const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + v * 8));
+        const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + v * 8 + 4));
+        const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + v * 8));
+        const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + v * 8 + 4));
+        const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+        const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        uint32_t w[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
-        w[j] = pack_bf16((f[i][2 * j] - mean) * rstd * gg[2 * j] + bb[2 * j],
-                         (f[i][2 * j + 1] - mean) * rstd * gg[2 * j + 1] + bb[2 * j + 1]);
-      yr[v] = make_uint4(w[0], w[1], w[2], w[3]);
+        for (int j = 0; j < 4; ++j)
+          w[j] = pack_bf16((f[i][2 * j] - mean) * rstd * gg[2 * j] + bb[2 * j],
+                           (f[i][2 * j + 1] - mean) * rstd * gg[2 * j + 1] + bb[2 * j + 1]);
+        yr[v] = make_uint4(w[0], w[1], w[2], w[3]);
+      }
     }
   }
 }
@@ -227,8 +244,9 @@ int groupnorm_launch(const GroupNormOp& op, cudaStream_t stream) {
   GnSrc s{static_cast<const __nv_bfloat16*>(op.x0), static_cast<const __nv_bfloat16*>(op.x1), op.c0,
           op.x1 ? op.c1 : 0, op.ld0 ? op.ld0 : op.c0, op.ld1 ? op.ld1 : op.c1};
   const int ppp = kGnThreads / (C / 8);
-  // >= 4 pixels per pixel-lane per CTA, and enough CTAs for ~2 waves of 4 resident CTAs per SM
-  int chunks = std::max(1, std::min(op.hw / (4 * ppp), (8 * 148 + op.n_img - 1) / op.n_img));
+  // >= 4 pixels per pixel-lane per CTA; ONE wave of 3 resident CTAs per SM: fat CTAs amortise the
+  // per-CTA reduction / ticket tail (37 thin chunks per image ran the statistics pass at 27% of HBM peak)
+  int chunks = std::max(1, std::min(op.hw / (4 * ppp), (3 * 148) / std::max(1, op.n_img)));
   chunks = std::min(chunks, kGroupNormMaxChunks);
   dim3 grid(chunks, op.n_img);
   const size_t smem = static_cast<size_t>(ppp) * 2 * C * sizeof(float);
@@ -246,17 +264,20 @@ int layernorm_launch(const void* x, void* y, int rows, int C, float eps, const f
   const int nvec = C / 8;
   const int vpl = (nvec + 31) / 32;
   const int warps = 8;
-  dim3 grid((rows + warps - 1) / warps);
   auto xb = static_cast<const __nv_bfloat16*>(x);
   auto yb = static_cast<__nv_bfloat16*>(y);
+#define SONIC_LN(V, R)                                                                                     \
+  layernorm_kernel<V, R><<<dim3((rows + warps * R - 1) / (warps * R)), warps * 32, 0, stream>>>(xb, rows, C, eps, \
+                                                                                                gamma, beta, yb)
   switch (vpl) {
-    case 1: layernorm_kernel<1><<<grid, warps * 32, 0, stream>>>(xb, rows, C, eps, gamma, beta, yb); break;
-    case 2: layernorm_kernel<2><<<grid, warps * 32, 0, stream>>>(xb, rows, C, eps, gamma, beta, yb); break;
-    case 3: layernorm_kernel<3><<<grid, warps * 32, 0, stream>>>(xb, rows, C, eps, gamma, beta, yb); break;
-    case 4: layernorm_kernel<4><<<grid, warps * 32, 0, stream>>>(xb, rows, C, eps, gamma, beta, yb); break;
-    case 5: layernorm_kernel<5><<<grid, warps * 32, 0, stream>>>(xb, rows, C, eps, gamma, beta, yb); break;
-    default: layernorm_kernel<8><<<grid, warps * 32, 0, stream>>>(xb, rows, C, eps, gamma, beta, yb); break;
+    case 1: SONIC_LN(1, 4); break;
+    case 2: SONIC_LN(2, 4); break;
+    case 3: SONIC_LN(3, 2); break;
+    case 4: SONIC_LN(4, 2); break;
+    case 5: SONIC_LN(5, 2); break;
+    default: SONIC_LN(8, 1); break;
   }
+#undef SONIC_LN
   SONIC_CUDA(cudaGetLastError());
   return 0;
 }
