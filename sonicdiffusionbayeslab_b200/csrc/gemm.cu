@@ -52,7 +52,7 @@ __device__ __forceinline__ float gelu_erf(float x) {
 
 #ifdef SONIC_GEMM_TRACE
 // Debug timeline (compile with -DSONIC_GEMM_TRACE): clock64 stamps of CTA 0's pipeline events per tile.
-__device__ long long g_gemm_trace[3][64][4];
+__device__ long long g_gemm_trace[4][64][4];
 #define GEMM_TRACE(role, i, k) do { if (blockIdx.x == 0 && (i) < 64) g_gemm_trace[role][i][k] = clock64(); } while (0)
 #else
 #define GEMM_TRACE(role, i, k) do { } while (0)
@@ -227,6 +227,7 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
         uint32_t v[32];
         float f[32];
         tmem_ld32(t_row + c * kChunkCols, v);
+        if (i == 0 && threadIdx.x == 64) GEMM_TRACE(3, ti, 0);
         if (geglu) {
           uint32_t gt[32];
           tmem_ld32(t_row + out_cols + c * kChunkCols, gt);
@@ -255,6 +256,7 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
             f[j + 3] = __uint_as_float(v[j + 3]) + bv.w;
           }
         }
+        if (i == 0 && threadIdx.x == 64) GEMM_TRACE(3, ti, 1);
         if (i == my_n - 1) {                                 // every TMEM read of this tile is done
           tc_fence_before();
           __syncwarp();
@@ -286,6 +288,7 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
           *reinterpret_cast<uint4*>(my_row + ((q ^ sw) << 4)) =
               make_uint4(pack_bf16(f[8 * q], f[8 * q + 1]), pack_bf16(f[8 * q + 2], f[8 * q + 3]),
                          pack_bf16(f[8 * q + 4], f[8 * q + 5]), pack_bf16(f[8 * q + 6], f[8 * q + 7]));
+        if (i == 0 && threadIdx.x == 64) GEMM_TRACE(3, ti, 2);
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
@@ -298,6 +301,7 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
             tma_load_2d(stg + nb * kStgBufBytes, &p.tm_res, &r_full[nb], ocol0 + (c + 2) * kChunkCols, row0);
           }
         }
+        if (i == 0 && threadIdx.x == 64) GEMM_TRACE(3, ti, 3);
         ++slot;
       }
       if (threadIdx.x == 64) GEMM_TRACE(2, ti, 3);
@@ -398,7 +402,7 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
 #ifdef SONIC_GEMM_TRACE
 }  // namespace sonic
 extern "C" int sonic_debug_gemm_trace(long long* host_out) {
-  return cudaMemcpyFromSymbol(host_out, sonic::g_gemm_trace, sizeof(long long) * 3 * 64 * 4) == cudaSuccess ? 0 : -1;
+  return cudaMemcpyFromSymbol(host_out, sonic::g_gemm_trace, sizeof(long long) * 4 * 64 * 4) == cudaSuccess ? 0 : -1;
 }
 namespace sonic {
 #endif

@@ -22,6 +22,13 @@ def _bf16c(t: torch.Tensor) -> torch.Tensor:
     return t
 
 
+def _rows2d(t: torch.Tensor) -> torch.Tensor:
+    """[M, N] bf16 rows with unit column stride (a column slice of a wider buffer is fine)."""
+    assert t.is_cuda and t.dtype == torch.bfloat16 and t.dim() == 2 and t.stride(1) == 1 and t.stride(0) % 8 == 0, \
+        "expected a 2-D bf16 CUDA tensor with unit column stride and a row pitch that is a multiple of 8"
+    return t
+
+
 def pack_conv3x3_weight(w_oihw: torch.Tensor) -> torch.Tensor:
     """OIHW -> [tap=kh*3+kw][O][I] bf16 (K-major per tap), the layout the TMA B-box reads."""
     O, I, kh, kw = w_oihw.shape
@@ -72,9 +79,10 @@ def conv_gemm(a0, w, N, *, taps=1, n_img=1, H=1, W=None, c0=None, a1=None, c1=0,
             assert t.dtype == torch.float32 and t.is_cuda and t.is_contiguous()
             setattr(args, name, t.data_ptr())
     if residual is not None:
-        _bf16c(residual)
-        args.residual, args.ld_res = residual.data_ptr(), residual.shape[-1]
-    args.out, args.ld_out = out.data_ptr(), out.shape[-1]
+        _rows2d(residual)
+        args.residual, args.ld_res = residual.data_ptr(), residual.stride(0)
+    _rows2d(out)
+    args.out, args.ld_out = out.data_ptr(), out.stride(0)
     args.epilogue, args.block_n = epilogue, block_n
     check(lib().sonic_conv_gemm(C.byref(args), stream_ptr()), "sonic_conv_gemm")
     return out

@@ -85,3 +85,41 @@ def test_geglu(cuda, M, C):
     ref = h[:, :4 * C] * F.gelu(h[:, 4 * C:])
     assert out.shape == (M, 4 * C)
     assert _rel_err(out, ref) < 1e-2
+
+
+def test_residual_in_place_and_ragged_rows(cuda):
+    """out aliases residual (the transformer blocks update h in place) and M is not a multiple of the 128-row tile /
+    32-row staging chunk: the TMA-store epilogue must clip, never write past row M."""
+    from sonicdiffusionbayeslab_b200 import kernels as k
+
+    g = torch.Generator(device="cuda").manual_seed(11)
+    M, N, K = 1000 + 13, 320, 640
+    a = _bf(torch.randn(M, K, device=cuda, generator=g))
+    w = _bf(torch.randn(N, K, device=cuda, generator=g) / K ** 0.5)
+    b = torch.randn(N, device=cuda, generator=g)
+    buf = _bf(torch.randn(M + 64, N, device=cuda, generator=g))       # guard rows behind the matrix
+    h = buf[:M]
+    guard = buf[M:].clone()
+    ref = a.float() @ w.float().t() + b + h.float()
+    k.conv_gemm(a, w, N, bias=b, residual=h, out=h)
+    torch.cuda.synchronize()
+    assert _rel_err(h, ref) < 1e-2
+    assert torch.equal(buf[M:], guard), "epilogue wrote past the last row"
+
+
+def test_narrow_and_strided_outputs(cuda):
+    """N=16 (the padded conv_out) takes the direct-store epilogue; a column slice of a wider buffer (ld_out > N) and a
+    non-multiple-of-32 N tail take the staged one."""
+    from sonicdiffusionbayeslab_b200 import kernels as k
+
+    g = torch.Generator(device="cuda").manual_seed(12)
+    for M, N, K in [(4096, 16, 320), (512, 80, 128), (640, 352, 256)]:
+        a = _bf(torch.randn(M, K, device=cuda, generator=g))
+        w = _bf(torch.randn(N, K, device=cuda, generator=g) / K ** 0.5)
+        wide = torch.zeros(M, N + 64, device=cuda, dtype=torch.bfloat16)
+        out = wide[:, 32:32 + N]
+        k.conv_gemm(a, w, N, out=out)
+        torch.cuda.synchronize()
+        ref = a.float() @ w.float().t()
+        assert _rel_err(out, ref) < 1e-2, (M, N, K)
+        assert wide[:, :32].abs().max().item() == 0 and wide[:, 32 + N:].abs().max().item() == 0, (M, N, K)
