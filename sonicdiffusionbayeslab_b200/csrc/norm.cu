@@ -61,15 +61,16 @@ gn_stats_kernel(GnSrc s, int hw, int groups, float eps, float* __restrict__ stat
         a[2 * j + 1] += hi; q[2 * j + 1] = fmaf(hi, hi, q[2 * j + 1]);
       }
     };
-    int p = p_begin + pl;
-    for (; p + 7 * ppp < p_end; p += 8 * ppp) {          // eight 16-byte loads in flight per thread
+    // eight 16-byte loads in flight per thread; the tail is predicated inside the same batch (a separate
+    // one-pixel-at-a-time tail loop serialised on memory latency and dominated the small feature maps)
+    for (int p = p_begin + pl; p < p_end; p += 8 * ppp) {
       uint4 u[8];
 #pragma unroll
-      for (int k = 0; k < 8; ++k) u[k] = gn_load(s, base + p + k * ppp, v * 8);
+      for (int k = 0; k < 8; ++k)
+        u[k] = p + k * ppp < p_end ? gn_load(s, base + p + k * ppp, v * 8) : make_uint4(0, 0, 0, 0);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) acc(u[k]);
+      for (int k = 0; k < 8; ++k) acc(u[k]);               // zeros add nothing to sum / sum of squares
     }
-    for (; p < p_end; p += ppp) acc(gn_load(s, base + p, v * 8));
     // every (pixel-lane, vector) slot has exactly one writer: no atomics, fixed reduction order
 #pragma unroll
     for (int j = 0; j < 8; ++j) {
@@ -78,17 +79,26 @@ gn_stats_kernel(GnSrc s, int hw, int groups, float eps, float* __restrict__ stat
     }
   }
   __syncthreads();
+  // Fold the per-pixel-lane partials: 2 * groups outputs, 8 threads each (a fixed assignment and a fixed
+  // shuffle tree, so the result is still bit-reproducible).  The old one-thread-per-group loop summed 240
+  // shared-memory values back to back: a ~4 us serial tail on every CTA.
   const int cpg = C / groups;
   float* part = stats + (static_cast<size_t>(img) * kGroupNormMaxChunks + blockIdx.x) * groups * 2;
-  for (int g = threadIdx.x; g < groups; g += blockDim.x) {
-    float a = 0.f, q = 0.f;
-    for (int l = 0; l < ppp; ++l)
-      for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
-        a += sm[(l * 2) * C + c];
-        q += sm[(l * 2 + 1) * C + c];
+  {
+    const int o = threadIdx.x >> 3, sub = threadIdx.x & 7;       // o = g * 2 + (0: sum, 1: sum of squares)
+    float acc = 0.f;
+    if (o < 2 * groups) {
+      const int g = o >> 1, which = o & 1;
+      const int n = ppp * cpg;
+      for (int k = sub; k < n; k += 8) {
+        const int l = k / cpg, c = g * cpg + k % cpg;
+        acc += sm[(l * 2 + which) * C + c];
       }
-    part[g * 2] = a;
-    part[g * 2 + 1] = q;
+    }
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+    if (o < 2 * groups && sub == 0) part[o] = acc;
   }
   // the last CTA of this image to finish folds the partials (in chunk order) into mean / rstd
   __threadfence();
@@ -101,16 +111,21 @@ gn_stats_kernel(GnSrc s, int hw, int groups, float eps, float* __restrict__ stat
   const float inv_n = 1.0f / (static_cast<float>(hw) * cpg);
   float* fin = gn_final(stats, n_img, groups) + static_cast<size_t>(img) * groups * 2;
   const float* src = stats + static_cast<size_t>(img) * kGroupNormMaxChunks * groups * 2;
-  for (int g = threadIdx.x; g < groups; g += blockDim.x) {
-    float a = 0.f, q = 0.f;
-    for (int ch = 0; ch < static_cast<int>(gridDim.x); ++ch) {
-      a += __ldcg(src + (static_cast<size_t>(ch) * groups + g) * 2);
-      q += __ldcg(src + (static_cast<size_t>(ch) * groups + g) * 2 + 1);
+  {
+    const int o = threadIdx.x >> 3, sub = threadIdx.x & 7;
+    float acc = 0.f;
+    if (o < 2 * groups)
+      for (int ch = sub; ch < static_cast<int>(gridDim.x); ch += 8) acc += __ldcg(src + static_cast<size_t>(ch) * groups * 2 + o);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+    const float other = __shfl_xor_sync(0xffffffffu, acc, 8);    // lanes of o ^ 1: (sum, sumsq) pair up
+    if (o < 2 * groups && sub == 0 && (o & 1) == 0) {
+      const float mean = acc * inv_n;
+      const float var = fmaxf(other * inv_n - mean * mean, 0.f);
+      fin[o] = mean;
+      fin[o + 1] = rsqrtf(var + eps);
     }
-    const float mean = a * inv_n;
-    const float var = fmaxf(q * inv_n - mean * mean, 0.f);
-    fin[g * 2] = mean;
-    fin[g * 2 + 1] = rsqrtf(var + eps);
   }
   if (threadIdx.x == 0) ticket[img] = 0;         // ready for the next launch / graph replay
 }
@@ -154,15 +169,15 @@ gn_apply_kernel(GnSrc s, int hw, int groups, float* __restrict__ stats, const fl
     }
     *reinterpret_cast<uint4*>(y + pix * C + v * 8) = make_uint4(w[0], w[1], w[2], w[3]);
   };
-  int p = p_begin + pl;
-  for (; p + 7 * ppp < p_end; p += 8 * ppp) {
+  for (int p = p_begin + pl; p < p_end; p += 8 * ppp) {
     uint4 u[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) u[k] = gn_load(s, base + p + k * ppp, v * 8);
+    for (int k = 0; k < 8; ++k)
+      u[k] = p + k * ppp < p_end ? gn_load(s, base + p + k * ppp, v * 8) : make_uint4(0, 0, 0, 0);
 #pragma unroll
-    for (int k = 0; k < 8; ++k) norm_store(u[k], base + p + k * ppp);
+    for (int k = 0; k < 8; ++k)
+      if (p + k * ppp < p_end) norm_store(u[k], base + p + k * ppp);
   }
-  for (; p < p_end; p += ppp) norm_store(gn_load(s, base + p, v * 8), base + p);
 }
 
 // One warp per kRows rows (all loads of the warp's rows are issued before the first reduction, so enough
@@ -233,6 +248,84 @@ layernorm_kernel(const __nv_bfloat16* __restrict__ x, int rows, int C, float eps
   }
 }
 
+// LayerNorm for C = 40 * kLanes (320 / 640 / 1280: every LayerNorm of the SD UNet): kLanes lanes share a row,
+// five 16-byte vectors each, so all 32 lanes carry data (the one-row-per-warp kernel idles 24 lanes on its
+// second vector at C=320) and a row reduction is log2(kLanes) shuffles.  Each warp walks kGroups row groups
+// with the NEXT group's loads in flight; gamma / beta live in registers for the whole walk.
+template <int kLanes>
+__global__ void __launch_bounds__(128, 3)
+layernorm40_kernel(const __nv_bfloat16* __restrict__ x, int rows, float eps, const float* __restrict__ gamma,
+                   const float* __restrict__ beta, __nv_bfloat16* __restrict__ y, int groups_per_warp) {
+  constexpr int kRowsPerGroup = 32 / kLanes;
+  constexpr int C = 40 * kLanes;
+  const int lane = threadIdx.x & 31;
+  const int sub = lane / kLanes;                 // row inside the group
+  const int l = lane % kLanes;                   // position inside the row
+  const int warp_global = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int group0 = warp_global * groups_per_warp;
+  float g[5][8], b[5][8];
+#pragma unroll
+  for (int i = 0; i < 5; ++i) {
+    const int v = l + i * kLanes;
+    const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + v * 8));
+    const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma + v * 8 + 4));
+    const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + v * 8));
+    const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta + v * 8 + 4));
+    g[i][0] = g0.x; g[i][1] = g0.y; g[i][2] = g0.z; g[i][3] = g0.w; g[i][4] = g1.x; g[i][5] = g1.y; g[i][6] = g1.z; g[i][7] = g1.w;
+    b[i][0] = b0.x; b[i][1] = b0.y; b[i][2] = b0.z; b[i][3] = b0.w; b[i][4] = b1.x; b[i][5] = b1.y; b[i][6] = b1.z; b[i][7] = b1.w;
+  }
+  auto load = [&](int grp, uint4 (&u)[5]) {
+    const int row = min((group0 + grp) * kRowsPerGroup + sub, rows - 1);
+    const uint4* xr = reinterpret_cast<const uint4*>(x + static_cast<size_t>(row) * C);
+#pragma unroll
+    for (int i = 0; i < 5; ++i) u[i] = __ldg(xr + l + i * kLanes);
+  };
+  uint4 cur[5], nxt[5];
+  load(0, cur);
+  for (int grp = 0; grp < groups_per_warp; ++grp) {
+    const int row = (group0 + grp) * kRowsPerGroup + sub;
+    if ((group0 + grp) * kRowsPerGroup >= rows) break;
+    if (grp + 1 < groups_per_warp) load(grp + 1, nxt);
+    float f[5][8];
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+      const uint32_t w[4] = {cur[i].x, cur[i].y, cur[i].z, cur[i].w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        f[i][2 * j] = bf16_lo(w[j]);
+        f[i][2 * j + 1] = bf16_hi(w[j]);
+        sum += f[i][2 * j] + f[i][2 * j + 1];
+      }
+    }
+#pragma unroll
+    for (int o = kLanes / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum * (1.0f / C);
+    float sq = 0.f;
+#pragma unroll
+    for (int i = 0; i < 5; ++i)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { const float d = f[i][j] - mean; sq = fmaf(d, d, sq); }
+#pragma unroll
+    for (int o = kLanes / 2; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+    const float rstd = rsqrtf(sq * (1.0f / C) + eps);
+    if (row < rows) {
+      uint4* yr = reinterpret_cast<uint4*>(y + static_cast<size_t>(row) * C);
+#pragma unroll
+      for (int i = 0; i < 5; ++i) {
+        uint32_t w[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          w[j] = pack_bf16((f[i][2 * j] - mean) * rstd * g[i][2 * j] + b[i][2 * j],
+                           (f[i][2 * j + 1] - mean) * rstd * g[i][2 * j + 1] + b[i][2 * j + 1]);
+        yr[l + i * kLanes] = make_uint4(w[0], w[1], w[2], w[3]);
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 5; ++i) cur[i] = nxt[i];
+  }
+}
+
 }  // namespace
 
 int groupnorm_launch(const GroupNormOp& op, cudaStream_t stream) {
@@ -266,6 +359,20 @@ int layernorm_launch(const void* x, void* y, int rows, int C, float eps, const f
   const int warps = 8;
   auto xb = static_cast<const __nv_bfloat16*>(x);
   auto yb = static_cast<__nv_bfloat16*>(y);
+  if (C == 320 || C == 640 || C == 1280) {
+    const int lanes = C / 40, rows_per_group = 32 / lanes;
+    const int n_groups = (rows + rows_per_group - 1) / rows_per_group;
+    // ~4 resident waves of warps (3 CTAs x 4 warps per SM), at least 2 groups per warp
+    const int w40 = 4;
+    const int gpw = std::max(2, (n_groups + 4 * 148 * 3 * w40 - 1) / (4 * 148 * 3 * w40));
+    const int n_warps = (n_groups + gpw - 1) / gpw;
+    dim3 grid((n_warps + w40 - 1) / w40);
+    if (lanes == 8) layernorm40_kernel<8><<<grid, w40 * 32, 0, stream>>>(xb, rows, eps, gamma, beta, yb, gpw);
+    else if (lanes == 16) layernorm40_kernel<16><<<grid, w40 * 32, 0, stream>>>(xb, rows, eps, gamma, beta, yb, gpw);
+    else layernorm40_kernel<32><<<grid, w40 * 32, 0, stream>>>(xb, rows, eps, gamma, beta, yb, gpw);
+    SONIC_CUDA(cudaGetLastError());
+    return 0;
+  }
 #define SONIC_LN(V, R)                                                                                     \
   layernorm_kernel<V, R><<<dim3((rows + warps * R - 1) / (warps * R)), warps * 32, 0, stream>>>(xb, rows, C, eps, \
                                                                                                 gamma, beta, yb)

@@ -34,7 +34,7 @@ __global__ void __launch_bounds__(128) k(int n, int N, int mode, long long* out)
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(s32(&slot)) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;" ::"r"(s32(&slot)) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -47,16 +47,16 @@ __global__ void __launch_bounds__(128) k(int n, int N, int mode, long long* out)
     uint32_t leader;
     asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(leader));
     const uint64_t da = desc128(s32(sm), 16, 1024), db = desc128(s32(sm) + 16384, 16, 1024);
-    for (int rep = 0; rep < 3; ++rep) {
+    for (int rep = 0; rep < 4; ++rep) {
       long long t0 = clock64();
       for (int i = 0; i < n; i += 4) {
         if (leader) {
 #pragma unroll
           for (int u = 0; u < 4; ++u) {
             if (i + u < n) {
-              const uint32_t d = tm + ((mode & 1) ? (u & 1) * 256 : 0);
+              const uint32_t d = tm + 64;
               const uint32_t acc = (i + u) > 1 || (!(mode & 1) && (i + u) > 0);
-              if (mode & 2) mma_ts(d, tm + 256 + 128 + u * 8, db + u * 2, idesc, acc);
+              if (mode & 2) mma_ts(d, tm + u * 8, db + u * 2, idesc, acc);
               else mma_ss(d, da + u * 2, db + u * 2, idesc, acc);
             }
           }
@@ -72,22 +72,23 @@ __global__ void __launch_bounds__(128) k(int n, int N, int mode, long long* out)
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}\n"
                      : "=r"(ok) : "r"(s32(&bar)), "r"(rep & 1) : "memory");
       long long t3 = clock64();
-      if (blockIdx.x == 0 && threadIdx.x == 0) { out[rep * 3 + 0] = t1 - t0; out[rep * 3 + 1] = t2 - t0; out[rep * 3 + 2] = t3 - t0; }
+      if (blockIdx.x == 0 && threadIdx.x == 0 && rep < 3) { out[rep * 3 + 0] = t1 - t0; out[rep * 3 + 1] = t2 - t0; out[rep * 3 + 2] = t3 - t0; }
     }
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(slot) : "memory");
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" ::"r"(slot) : "memory");
 }
 int main() {
   long long* out; CK(cudaMalloc(&out, 9 * 8));
-  CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
+  CK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 48 * 1024));
   printf("mode: 0 SS dependent, 1 SS two accumulators, 2 TS dependent; cycles (3rd repetition): issue-done / after-commit / complete\n");
-  for (int mode : {0, 1, 2})
-    for (int N : {48, 64, 128, 256})
-      for (int n : {1, 2, 4, 8, 16, 32}) {
-        if ((mode & 1) && N > 192) continue;
-        k<<<148, 128, 64 * 1024>>>(n, N, mode, out);
+  for (int cps : {1, 2, 4})
+  for (int mode : {0, 2})
+    for (int N : {48, 64})
+      for (int n : {32}) {
+        printf("CTAs/SM=%d ", cps);
+        k<<<148 * cps, 128, 48 * 1024>>>(n, N, mode, out);
         CK(cudaDeviceSynchronize());
         long long h[9]; CK(cudaMemcpy(h, out, sizeof(h), cudaMemcpyDeviceToHost));
         printf("mode %d N=%3d n=%2d : %5lld / %5lld / %5lld   (%.1f cycles per MMA, floor %d)\n", mode, N, n, h[6], h[7], h[8],
