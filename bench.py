@@ -43,6 +43,17 @@ GUIDANCE = 7.5
 FLOP_PER_SAMPLE_FWD = 803.27e9
 
 
+def _traffic():
+    """DRAM bytes per conv_gemm_kernel launch (mean over the 194 launches of one UNet step) from the committed ncu
+    launch list (profiles/traffic.json, written by the round's profiling pass); None if absent."""
+    path = os.path.join(ROOT, "profiles", "traffic.json")
+    try:
+        t = json.load(open(path))["conv_gemm_kernel"]
+        return round((t["dram_read_bytes"] + t["dram_write_bytes"]) / t["launches"])
+    except (OSError, KeyError, ValueError):
+        return None
+
+
 def _peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -115,6 +126,9 @@ def run_own(args):
     dist = None
     if world > 1:
         import torch.distributed as dist_mod
+
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"          # NCCL prints its version banner on stdout otherwise
 
         dist = dist_mod
         dist.init_process_group("nccl", device_id=dev)
@@ -225,7 +239,11 @@ def run_own(args):
             "roofline": {"kernel": "conv_gemm_kernel (all conv3x3/conv1x1/linear launches of one UNet forward)",
                          "bound": "tensor", "achieved": round(achieved, 1), "peak": sustained, "unit": "TFLOP/s",
                          "frac": round(achieved / sustained, 4), "peak_kind": f"bf16_tflops_sustained ({how})",
-                         "frac_of_burst": round(achieved / burst, 4), "traffic": None},
+                         "frac_of_burst": round(achieved / burst, 4), "traffic": _traffic(),
+                         "algorithmic_per_launch": round(gemm[2] / gemm[0]), "launches_per_step": gemm[0],
+                         "note": "achieved = sum of 2*M*N*K over the step's conv/linear launches / sum of their CUDA-event "
+                                 "durations (same stream); traffic = mean DRAM bytes per launch from the committed ncu "
+                                 "launch list (cold cache per launch)"},
             "kernels": kernels,
             "clocks": clocks,
         }

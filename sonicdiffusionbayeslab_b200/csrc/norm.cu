@@ -36,7 +36,7 @@ __device__ __forceinline__ float* gn_final(float* stats, int n_img, int groups) 
 }
 
 // grid (chunks, n_img).  Thread (pl, v): 8-channel vector v of every ppp-th pixel of the chunk.
-__global__ void __launch_bounds__(kGnThreads)
+__global__ void __launch_bounds__(kGnThreads, 2)
 gn_stats_kernel(GnSrc s, int hw, int groups, float eps, float* __restrict__ stats) {
   extern __shared__ float sm[];                  // [ppp][2][C] per-pixel-lane partials
   __shared__ int s_last;
@@ -131,7 +131,7 @@ gn_stats_kernel(GnSrc s, int hw, int groups, float eps, float* __restrict__ stat
 }
 
 // grid (chunks, n_img): y = act((x - mean) * rstd * gamma + beta); scale / shift in registers.
-__global__ void __launch_bounds__(kGnThreads)
+__global__ void __launch_bounds__(kGnThreads, 2)
 gn_apply_kernel(GnSrc s, int hw, int groups, float* __restrict__ stats, const float* __restrict__ gamma,
                 const float* __restrict__ beta, int silu, __nv_bfloat16* __restrict__ y) {
   const int C = s.c0 + s.c1;
