@@ -56,6 +56,10 @@ typedef struct sonic_gemm_args {
   void* out; int32_t ld_out;
   int32_t epilogue;
   int32_t block_n;       /* 0 = let the library choose */
+  /* Optional GroupNorm pre-reduction of the OUTPUT: [ceil(M/32)][n_out][2] fp32 (sum, sum of squares) of the
+   * bf16-rounded output over each block of 32 consecutive rows, per channel.  sonic_groupnorm_fused turns
+   * these into group statistics, so the separate statistics pass over the tensor disappears. */
+  float* gn_partial;
 } sonic_gemm_args;
 int sonic_conv_gemm(const sonic_gemm_args* args, sonic_stream_t stream);
 /* Tile width the library would choose for (N, M) -- needed to pack GEGLU weights. */
@@ -89,6 +93,13 @@ int sonic_groupnorm_silu(const void* x0, int32_t c0, const void* x1, int32_t c1,
                          int32_t hw, int32_t groups, float eps, const float* gamma,
                          const float* beta, int32_t silu, float* stats, void* y,
                          sonic_stream_t stream);
+/* GroupNorm whose statistics come from the producing GEMMs' `gn_partial` buffers (hw must be a multiple of 32):
+ * a small finalize kernel folds the per-32-row partials of each image in a fixed order (bit-reproducible), then
+ * the same apply kernel as above runs.  part0 / part1 have row pitch c0 / c1 channels. */
+int sonic_groupnorm_fused(const void* x0, int32_t c0, const float* part0, const void* x1, int32_t c1,
+                          const float* part1, int32_t n_img, int32_t hw, int32_t groups, float eps,
+                          const float* gamma, const float* beta, int32_t silu, float* stats, void* y,
+                          sonic_stream_t stream);
 int sonic_layernorm(const void* x, void* y, int32_t rows, int32_t C, float eps, const float* gamma,
                     const float* beta, sonic_stream_t stream);
 
@@ -140,6 +151,10 @@ int sonic_plan_add_attention(sonic_plan_t plan, const sonic_attention_args* args
 int sonic_plan_add_groupnorm(sonic_plan_t plan, const void* x0, int32_t c0, const void* x1, int32_t c1,
                              int32_t n_img, int32_t hw, int32_t groups, float eps, const float* gamma,
                              const float* beta, int32_t silu, float* stats, void* y);
+int sonic_plan_add_groupnorm_fused(sonic_plan_t plan, const void* x0, int32_t c0, const float* part0,
+                                   const void* x1, int32_t c1, const float* part1, int32_t n_img, int32_t hw,
+                                   int32_t groups, float eps, const float* gamma, const float* beta,
+                                   int32_t silu, float* stats, void* y);
 int sonic_plan_add_layernorm(sonic_plan_t plan, const void* x, void* y, int32_t rows, int32_t C,
                              float eps, const float* gamma, const float* beta);
 int sonic_plan_add_nchw_to_nhwc8(sonic_plan_t plan, const void* x, int32_t dtype, int32_t n_img,

@@ -26,6 +26,7 @@ class GemmArgs(C.Structure):
         ("residual", C.c_void_p), ("ld_res", C.c_int32),
         ("out", C.c_void_p), ("ld_out", C.c_int32),
         ("epilogue", C.c_int32), ("block_n", C.c_int32),
+        ("gn_partial", C.c_void_p),
     ]
 
 

@@ -22,7 +22,7 @@ int sonic_conv_gemm(const sonic_gemm_args* a, sonic_stream_t stream) {
   op.bias = a->bias; op.row_bias = a->row_bias;
   op.residual = a->residual; op.ld_res = a->ld_res;
   op.out = a->out; op.ld_out = a->ld_out;
-  op.epilogue = a->epilogue; op.block_n = a->block_n;
+  op.epilogue = a->epilogue; op.block_n = a->block_n; op.gn_partial = a->gn_partial;
   GemmPlan plan;
   if (int rc = gemm_plan(op, &plan)) return rc;
   return gemm_launch(plan, static_cast<cudaStream_t>(stream));
@@ -53,6 +53,18 @@ int sonic_groupnorm_silu(const void* x0, int32_t c0, const void* x1, int32_t c1,
   op.x0 = x0; op.c0 = c0; op.x1 = x1; op.c1 = c1;
   op.n_img = n_img; op.hw = hw; op.groups = groups; op.eps = eps;
   op.gamma = gamma; op.beta = beta; op.silu = silu; op.stats = stats; op.y = y;
+  return groupnorm_launch(op, static_cast<cudaStream_t>(stream));
+}
+
+int sonic_groupnorm_fused(const void* x0, int32_t c0, const float* part0, const void* x1, int32_t c1,
+                          const float* part1, int32_t n_img, int32_t hw, int32_t groups, float eps,
+                          const float* gamma, const float* beta, int32_t silu, float* stats, void* y,
+                          sonic_stream_t stream) {
+  GroupNormOp op;
+  op.x0 = x0; op.c0 = c0; op.x1 = x1; op.c1 = c1; op.part0 = part0; op.part1 = part1;
+  op.n_img = n_img; op.hw = hw; op.groups = groups; op.eps = eps;
+  op.gamma = gamma; op.beta = beta; op.silu = silu; op.stats = stats; op.y = y;
+  SONIC_REQUIRE(part0 != nullptr && (x1 == nullptr || part1 != nullptr), "sonic_groupnorm_fused: null partials");
   return groupnorm_launch(op, static_cast<cudaStream_t>(stream));
 }
 

@@ -291,6 +291,24 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
         if (i == 0 && threadIdx.x == 64) GEMM_TRACE(3, ti, 2);
         fence_proxy_async_smem();
         __syncwarp();
+        if (p.gn_partial) {
+          // GroupNorm pre-reduction: lane j sums column j of the staged (bf16-rounded) 32 x 32 chunk
+          const int rmax = min(32, p.M - row0);
+          const uint8_t* colp = buf + (lane & 7) * 2;
+          const uint32_t q = lane >> 3;
+          float sa[2] = {0.f, 0.f}, sq[2] = {0.f, 0.f};
+#pragma unroll 8
+          for (int r = 0; r < rmax; ++r) {
+            const uint16_t h = *reinterpret_cast<const uint16_t*>(colp + r * 64 + ((q ^ ((r >> 1) & 3)) << 4));
+            const float x = __uint_as_float(static_cast<uint32_t>(h) << 16);
+            sa[r & 1] += x;
+            sq[r & 1] = fmaf(x, x, sq[r & 1]);
+          }
+          const int col = ocol0 + c * kChunkCols + lane;
+          if (col < p.n_out_total && rmax > 0)
+            *reinterpret_cast<float2*>(p.gn_partial + (static_cast<size_t>(row0 >> 5) * p.n_out_total + col) * 2) =
+                make_float2(sa[0] + sa[1], sq[0] + sq[1]);
+        }
         if (lane == 0) {
           tma_store_2d(&p.tm_out, buf, ocol0 + c * kChunkCols, row0);
           bulk_commit();
@@ -417,6 +435,7 @@ int pick_block_n(int N, int m_tiles, bool geglu, int num_sms) {
   double best_cost = 1e30;
   for (int bn : cands) {
     if (bn > N && bn != 16) continue;
+    if (bn == 16 && N >= 32) continue;            // 16 only for the padded 4 -> 16 conv_out (direct-store epilogue)
     if (geglu && (bn % 64 != 0 || N % bn != 0)) continue;
     const int n_tiles = (N + bn - 1) / bn;
     const long tiles = static_cast<long>(m_tiles) * n_tiles;
@@ -497,6 +516,9 @@ int gemm_plan(const GemmOp& op, GemmPlan* plan) {
   const int out_cols = geglu ? p.block_n / 2 : p.block_n;
   const bool flat = op.W < kTileM || op.W % kTileM == 0 || (op.H == 1 && op.n_img == 1);
   p.tma_epilogue = (out_cols % kChunkCols == 0 && flat) ? 1 : 0;
+  p.gn_partial = op.gn_partial;
+  SONIC_REQUIRE(op.gn_partial == nullptr || p.tma_epilogue,
+                "gemm: gn_partial needs the staged epilogue (block_n %% 32 == 0, contiguous 128-row tiles)");
   p.n_tiles = (op.N + p.block_n - 1) / p.block_n;
   const int stage_bytes = kABytes + p.block_n * kTileK * 2;
   p.stages = std::max(2, std::min(8, (225 * 1024 - kStgBytes) / stage_bytes));

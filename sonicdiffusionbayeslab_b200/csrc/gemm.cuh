@@ -30,6 +30,7 @@ struct GemmParams {
   int epilogue;
   int n_out_total;               // output columns (N, or N/2 for GEGLU)
   int tma_epilogue;              // 1: smem-staged TMA-store epilogue, 0: direct stores
+  float* gn_partial;             // optional [ceil(M/32)][n_out_total][2] GroupNorm pre-reduction of the output
 };
 
 struct GemmOp {                  // host-side description; pointers are borrowed
@@ -43,6 +44,7 @@ struct GemmOp {                  // host-side description; pointers are borrowed
   void* out = nullptr; int ld_out = 0;
   int epilogue = kEpiNone;
   int block_n = 0;               // 0 = choose
+  float* gn_partial = nullptr;
 };
 
 struct GemmPlan {

@@ -130,6 +130,43 @@ gn_stats_kernel(GnSrc s, int hw, int groups, float eps, float* __restrict__ stat
   if (threadIdx.x == 0) ticket[img] = 0;         // ready for the next launch / graph replay
 }
 
+// Statistics from the producing GEMMs' epilogue partials ([row block of 32][channel][sum, sumsq]) instead of
+// a pass over the tensor.  grid (groups, n_img), 128 threads; fixed assignment + fixed reduction tree.
+__global__ void __launch_bounds__(128)
+gn_finalize_kernel(const float* __restrict__ part0, int c0, const float* __restrict__ part1, int c1, int hw,
+                   int groups, float eps, float* __restrict__ stats) {
+  __shared__ float s_a[4], s_q[4];
+  const int C = c0 + c1, cpg = C / groups;
+  const int g = blockIdx.x, img = blockIdx.y, n_img = gridDim.y;
+  const int nb = hw >> 5;                                  // 32-row blocks per image
+  const int items = nb * cpg;
+  float a = 0.f, q = 0.f;
+  for (int k = threadIdx.x; k < items; k += 128) {
+    const int b = k / cpg, c = g * cpg + k % cpg;
+    const size_t blk = static_cast<size_t>(img) * nb + b;
+    const float2 v = c < c0 ? __ldg(reinterpret_cast<const float2*>(part0 + (blk * c0 + c) * 2))
+                            : __ldg(reinterpret_cast<const float2*>(part1 + (blk * c1 + (c - c0)) * 2));
+    a += v.x;
+    q += v.y;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o);
+    q += __shfl_xor_sync(0xffffffffu, q, o);
+  }
+  if ((threadIdx.x & 31) == 0) { s_a[threadIdx.x >> 5] = a; s_q[threadIdx.x >> 5] = q; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const float ta = (s_a[0] + s_a[1]) + (s_a[2] + s_a[3]), tq = (s_q[0] + s_q[1]) + (s_q[2] + s_q[3]);
+    const float inv_n = 1.0f / (static_cast<float>(hw) * cpg);
+    const float mean = ta * inv_n;
+    const float var = fmaxf(tq * inv_n - mean * mean, 0.f);
+    float* fin = gn_final(stats, n_img, groups) + (static_cast<size_t>(img) * groups + g) * 2;
+    fin[0] = mean;
+    fin[1] = rsqrtf(var + eps);
+  }
+}
+
 // grid (chunks, n_img): y = act((x - mean) * rstd * gamma + beta); scale / shift in registers.
 __global__ void __launch_bounds__(kGnThreads, 2)
 gn_apply_kernel(GnSrc s, int hw, int groups, float* __restrict__ stats, const float* __restrict__ gamma,
@@ -344,7 +381,14 @@ int groupnorm_launch(const GroupNormOp& op, cudaStream_t stream) {
   dim3 grid(chunks, op.n_img);
   const size_t smem = static_cast<size_t>(ppp) * 2 * C * sizeof(float);
   SONIC_REQUIRE(smem <= 48 * 1024, "groupnorm: C=%d needs too much shared memory", C);
-  gn_stats_kernel<<<grid, kGnThreads, smem, stream>>>(s, op.hw, op.groups, op.eps, op.stats);
+  if (op.part0) {
+    SONIC_REQUIRE(op.hw % 32 == 0, "groupnorm: fused statistics need hw %% 32 == 0 (got %d)", op.hw);
+    SONIC_REQUIRE(s.ld0 == s.c0 && (!op.x1 || s.ld1 == s.c1), "groupnorm: fused statistics need dense rows");
+    gn_finalize_kernel<<<dim3(op.groups, op.n_img), 128, 0, stream>>>(op.part0, s.c0, op.part1, s.c1, op.hw, op.groups,
+                                                                      op.eps, op.stats);
+  } else {
+    gn_stats_kernel<<<grid, kGnThreads, smem, stream>>>(s, op.hw, op.groups, op.eps, op.stats);
+  }
   gn_apply_kernel<<<grid, kGnThreads, 0, stream>>>(s, op.hw, op.groups, op.stats, op.gamma, op.beta, op.silu,
                                                    static_cast<__nv_bfloat16*>(op.y));
   SONIC_CUDA(cudaGetLastError());

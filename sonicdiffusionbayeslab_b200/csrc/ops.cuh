@@ -15,6 +15,8 @@ constexpr int kGroupNormMaxChunks = 160;
 struct GroupNormOp {
   const void* x0 = nullptr; int c0 = 0, ld0 = 0;   // NHWC bf16, channels [0,c0)
   const void* x1 = nullptr; int c1 = 0, ld1 = 0;   // optional channel-concat source
+  const float* part0 = nullptr;                     // optional per-32-row (sum, sumsq) partials written by the
+  const float* part1 = nullptr;                     // producing GEMMs: replaces the statistics pass
   int n_img = 1, hw = 1, groups = 32;
   float eps = 1e-5f;
   const float* gamma = nullptr; const float* beta = nullptr;   // [c0+c1]

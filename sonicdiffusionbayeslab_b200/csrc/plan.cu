@@ -94,7 +94,7 @@ int sonic_plan_add_conv_gemm(sonic_plan_t h, const sonic_gemm_args* a) {
   op.bias = a->bias; op.row_bias = a->row_bias;
   op.residual = a->residual; op.ld_res = a->ld_res;
   op.out = a->out; op.ld_out = a->ld_out;
-  op.epilogue = a->epilogue; op.block_n = a->block_n;
+  op.epilogue = a->epilogue; op.block_n = a->block_n; op.gn_partial = a->gn_partial;
   PlanOp p;
   p.kind = PlanOp::kGemm;
   if (int rc = gemm_plan(op, &p.gemm)) return rc;
@@ -129,6 +129,23 @@ int sonic_plan_add_groupnorm(sonic_plan_t h, const void* x0, int32_t c0, const v
   PlanOp p;
   p.kind = PlanOp::kGroupNorm;
   p.gn.x0 = x0; p.gn.c0 = c0; p.gn.x1 = x1; p.gn.c1 = c1;
+  p.gn.n_img = n_img; p.gn.hw = hw; p.gn.groups = groups; p.gn.eps = eps;
+  p.gn.gamma = gamma; p.gn.beta = beta; p.gn.silu = silu; p.gn.stats = stats; p.gn.y = y;
+  plan->launches += 2;
+  plan->ops.push_back(p);
+  return 0;
+}
+
+int sonic_plan_add_groupnorm_fused(sonic_plan_t h, const void* x0, int32_t c0, const float* part0, const void* x1,
+                                   int32_t c1, const float* part1, int32_t n_img, int32_t hw, int32_t groups,
+                                   float eps, const float* gamma, const float* beta, int32_t silu, float* stats,
+                                   void* y) {
+  SONIC_REQUIRE(h && x0 && y && stats && part0 && (x1 == nullptr || part1 != nullptr),
+                "sonic_plan_add_groupnorm_fused: null argument");
+  Plan* plan = static_cast<Plan*>(h);
+  PlanOp p;
+  p.kind = PlanOp::kGroupNorm;
+  p.gn.x0 = x0; p.gn.c0 = c0; p.gn.x1 = x1; p.gn.c1 = c1; p.gn.part0 = part0; p.gn.part1 = part1;
   p.gn.n_img = n_img; p.gn.hw = hw; p.gn.groups = groups; p.gn.eps = eps;
   p.gn.gamma = gamma; p.gn.beta = beta; p.gn.silu = silu; p.gn.stats = stats; p.gn.y = y;
   plan->launches += 2;

@@ -52,7 +52,7 @@ def gemm_block_n(N: int, n_img: int, H: int, W: int, epilogue: int = EPI_NONE) -
 
 
 def conv_gemm(a0, w, N, *, taps=1, n_img=1, H=1, W=None, c0=None, a1=None, c1=0, bias=None,
-              row_bias=None, residual=None, out=None, epilogue=EPI_NONE, block_n=0):
+              row_bias=None, residual=None, out=None, epilogue=EPI_NONE, block_n=0, gn_partial=None):
     """out[M, N'] = epilogue(implicit_gemm(A, w)); see ``sonic_conv_gemm`` in include/sonic.h.
 
     ``a0`` / ``a1`` are NHWC bf16 tensors whose last dim is the pixel pitch; a Linear over
@@ -84,6 +84,10 @@ def conv_gemm(a0, w, N, *, taps=1, n_img=1, H=1, W=None, c0=None, a1=None, c1=0,
     _rows2d(out)
     args.out, args.ld_out = out.data_ptr(), out.stride(0)
     args.epilogue, args.block_n = epilogue, block_n
+    if gn_partial is not None:
+        assert gn_partial.dtype == torch.float32 and gn_partial.is_contiguous() and \
+            gn_partial.numel() >= (M + 31) // 32 * n_out * 2
+        args.gn_partial = gn_partial.data_ptr()
     check(lib().sonic_conv_gemm(C.byref(args), stream_ptr()), "sonic_conv_gemm")
     return out
 
@@ -135,14 +139,26 @@ def groupnorm_scratch(n_img, groups, device):
     return torch.zeros(n_img * ((GN_MAX_CHUNKS + 1) * groups * 2 + 1), device=device, dtype=torch.float32)
 
 
-def groupnorm(x0, gamma, beta, *, n_img, hw, groups=32, eps=1e-5, silu=True, x1=None, out=None):
-    """x0 (and optional x1): NHWC bf16 [n_img*hw, C]; returns bf16 [n_img*hw, C0+C1]."""
+def gn_partial_buffer(rows, channels, device):
+    """Buffer a GEMM fills with per-32-row (sum, sumsq) of its output (``gn_partial``)."""
+    return torch.zeros((rows + 31) // 32, channels, 2, device=device, dtype=torch.float32)
+
+
+def groupnorm(x0, gamma, beta, *, n_img, hw, groups=32, eps=1e-5, silu=True, x1=None, out=None, part0=None,
+              part1=None):
+    """x0 (and optional x1): NHWC bf16 [n_img*hw, C]; returns bf16 [n_img*hw, C0+C1].  With ``part0`` (and
+    ``part1``) the statistics come from the producing GEMMs' ``gn_partial`` buffers."""
     _bf16c(x0)
     c0 = x0.shape[-1]
     c1 = 0 if x1 is None else _bf16c(x1).shape[-1]
     if out is None:
         out = torch.empty((n_img * hw, c0 + c1), device=x0.device, dtype=torch.bfloat16)
     stats = groupnorm_scratch(n_img, groups, x0.device)
+    if part0 is not None:
+        check(lib().sonic_groupnorm_fused(ptr(x0), c0, ptr(part0), ptr(x1), c1, ptr(part1), n_img, hw, groups,
+                                          C.c_float(eps), ptr(gamma), ptr(beta), int(silu), ptr(stats), ptr(out),
+                                          stream_ptr()), "sonic_groupnorm_fused")
+        return out
     check(lib().sonic_groupnorm_silu(ptr(x0), c0, ptr(x1), c1, n_img, hw, groups, C.c_float(eps), ptr(gamma),
                                      ptr(beta), int(silu), ptr(stats), ptr(out), stream_ptr()),
           "sonic_groupnorm_silu")

@@ -67,6 +67,10 @@ class Arena:
         return t
 
     def release(self, t):
+        part = getattr(t, "_gn_part", None)
+        if part is not None:                      # GroupNorm pre-reduction buffer travels with its tensor
+            t._gn_part = None
+            self.release(part)
         raw = t._arena_raw
         self.free.setdefault(raw.numel(), []).append(raw)
 
@@ -143,6 +147,7 @@ class UNetEngine:
         self.H, self.W, self.ctx_len = height, width, ctx_len
         self.io_dtype = io_dtype
         self.arena = Arena(self.dev)
+        self.fuse_gn_stats = True                            # GroupNorm statistics from the producers' epilogues
         self._keep = []                                      # packed weights
         self.sd = state_dict
         a = arch
@@ -190,7 +195,7 @@ class UNetEngine:
 
     # ------------------------------------------------------------------ op recording helpers
     def _gemm(self, plan, a0, w, N, *, n_img=1, H=1, W=None, taps=1, c0=None, a1=None, bias=None,
-              residual=None, out=None, epilogue=K.EPI_NONE, block_n=0):
+              residual=None, out=None, epilogue=K.EPI_NONE, block_n=0, gn_stats=False):
         ld0 = a0.shape[-1]
         M = a0.numel() // ld0
         if W is None:
@@ -211,6 +216,14 @@ class UNetEngine:
             g.residual, g.ld_res = residual.data_ptr(), residual.shape[-1]
         g.out, g.ld_out = out.data_ptr(), out.shape[-1]
         g.epilogue, g.block_n = epilogue, block_n
+        if gn_stats and self.fuse_gn_stats:
+            # the epilogue also writes per-32-row (sum, sumsq) of the output: the consumer GroupNorm needs no
+            # statistics pass over the tensor
+            part = getattr(out, "_gn_part", None)
+            if part is None:
+                part = self.arena.alloc(((M + 31) // 32, n_out, 2), torch.float32)
+                out._gn_part = part
+            g.gn_partial = part.data_ptr()
         check(lib().sonic_plan_add_conv_gemm(plan.h, C.byref(g)), "sonic_plan_add_conv_gemm")
         kk = g.c0 + (g.c1 if a1 is not None else 0)
         plan.log.append(f"gemm M={M} N={N} K={kk}x{taps} img={n_img}x{H}x{W} epi={epilogue}"
@@ -223,6 +236,16 @@ class UNetEngine:
         if not hasattr(self, "_gn_stats"):                    # one scratch: plans run in stream order
             self._gn_stats = K.groupnorm_scratch(self.n, self.arch.norm_num_groups, self.dev)
         stats = self._gn_stats
+        p0 = getattr(x0, "_gn_part", None)
+        p1 = None if x1 is None else getattr(x1, "_gn_part", None)
+        if self.fuse_gn_stats and p0 is not None and (x1 is None or p1 is not None) and hw % 32 == 0:
+            check(lib().sonic_plan_add_groupnorm_fused(
+                plan.h, K.ptr(x0), x0.shape[-1], K.ptr(p0), K.ptr(x1), 0 if x1 is None else x1.shape[-1], K.ptr(p1),
+                self.n, hw, self.arch.norm_num_groups, C.c_float(eps), K.ptr(self._f32(prefix + ".weight")),
+                K.ptr(self._f32(prefix + ".bias")), int(silu), K.ptr(stats), K.ptr(y)),
+                "sonic_plan_add_groupnorm_fused")
+            plan.log.append(f"groupnorm rows={x0.shape[0]} C={c} silu={int(silu)} fused-stats")
+            return y
         check(lib().sonic_plan_add_groupnorm(
             plan.h, K.ptr(x0), x0.shape[-1], K.ptr(x1), 0 if x1 is None else x1.shape[-1], self.n, hw,
             self.arch.norm_num_groups, C.c_float(eps), K.ptr(self._f32(prefix + ".weight")),
@@ -254,7 +277,7 @@ class UNetEngine:
         h = self._gn(plan, x0, x1, prefix + ".norm1", hw, self.arch.norm_eps, True)
         tb = self._temb_bias[prefix]                          # conv1.bias + time_emb_proj(silu(temb))
         h1 = self._gemm(plan, h, self._conv3(prefix + ".conv1.weight"), cout, n_img=self.n, H=H, W=W, taps=9,
-                        bias=tb)
+                        bias=tb, gn_stats=True)
         self.arena.release(h)
         h2 = self._gn(plan, h1, None, prefix + ".norm2", hw, self.arch.norm_eps, True)
         self.arena.release(h1)
@@ -267,7 +290,7 @@ class UNetEngine:
             assert x1 is None
             res = x0
         out = self._gemm(plan, h2, self._conv3(prefix + ".conv2.weight"), cout, n_img=self.n, H=H, W=W, taps=9,
-                         bias=self._f32(prefix + ".conv2.bias"), residual=res)
+                         bias=self._f32(prefix + ".conv2.bias"), residual=res, gn_stats=True)
         self.arena.release(h2)
         if sc is not None:
             self.arena.release(sc)
@@ -321,7 +344,7 @@ class UNetEngine:
                    residual=h, out=h)
         self.arena.release(ff)
         self._gemm(plan, h, self._lin(prefix + ".proj_out.weight"), Cc, bias=self._f32(prefix + ".proj_out.bias"),
-                   residual=x, out=x)
+                   residual=x, out=x, gn_stats=True)
         self.arena.release(h)
         return x
 
@@ -420,7 +443,8 @@ class UNetEngine:
             wp = torch.zeros(w.shape[0], 8, 3, 3, device=self.dev, dtype=w.dtype)
             wp[:, : w.shape[1]] = w
             self._w[key] = K.pack_conv3x3_weight(wp)
-        h = self._gemm(plan, x8, self._w[key], boc[0], n_img=n, H=H, W=W, taps=9, bias=self._f32("conv_in.bias"))
+        h = self._gemm(plan, x8, self._w[key], boc[0], n_img=n, H=H, W=W, taps=9, bias=self._f32("conv_in.bias"),
+                       gn_stats=True)
         self.arena.release(x8)
 
         last_up = len(boc) - 1
@@ -454,7 +478,7 @@ class UNetEngine:
                         self._w[key] = w.permute(0, 2, 3, 1).reshape(w.shape[0], -1).to(torch.bfloat16).contiguous()
                     H, W = H // 2, W // 2
                     h = self._gemm(plan, col, self._w[key], cout,
-                                   bias=self._f32(f"down_blocks.{b}.downsamplers.0.conv.bias"))
+                                   bias=self._f32(f"down_blocks.{b}.downsamplers.0.conv.bias"), gn_stats=True)
                     self.arena.release(col)
                     skips.append((h, H, W))
             # ---- mid
@@ -488,7 +512,8 @@ class UNetEngine:
                     self.arena.release(h)
                     H, W = 2 * H, 2 * W
                     h = self._gemm(plan, up, self._conv3(f"up_blocks.{b}.upsamplers.0.conv.weight"), cout, n_img=n,
-                                   H=H, W=W, taps=9, bias=self._f32(f"up_blocks.{b}.upsamplers.0.conv.bias"))
+                                   H=H, W=W, taps=9, bias=self._f32(f"up_blocks.{b}.upsamplers.0.conv.bias"),
+                                   gn_stats=True)
                     self.arena.release(up)
             assert not skips
         # ---- out: GroupNorm+SiLU -> conv3x3 (4 output channels padded to one 16-wide MMA tile) -> NCHW

@@ -116,3 +116,35 @@ def test_layout_helpers(cuda):
     assert torch.equal(col.float(), unf)
     back = k.nhwc_to_nchw(a.reshape(-1, 64), 2, 4, 16, 16, torch.float32)
     assert torch.equal(back, a[..., :4].float().permute(0, 3, 1, 2))
+
+
+@pytest.mark.parametrize("B,hw,C0,C1,N0", [(2, 4096, 320, 0, 320), (3, 1024, 640, 320, 640), (2, 64, 1280, 1280, 1280)])
+def test_groupnorm_with_gemm_epilogue_statistics(cuda, B, hw, C0, C1, N0):
+    """The GEMM epilogue pre-reduces (sum, sumsq) of its OUTPUT per 32-row block; sonic_groupnorm_fused must give
+    the same result as the two-pass kernel and as torch.group_norm on the same tensors (single and concat)."""
+    from sonicdiffusionbayeslab_b200 import kernels as k
+
+    g = torch.Generator(device="cuda").manual_seed(hw + C0)
+    M = B * hw
+
+    def produce(C):
+        a = torch.randn(M, 128, device=cuda, generator=g).bfloat16()
+        w = (torch.randn(C, 128, device=cuda, generator=g) / 8).bfloat16()
+        res = torch.randn(M, C, device=cuda, generator=g).bfloat16()
+        part = k.gn_partial_buffer(M, C, cuda)
+        out = k.conv_gemm(a, w, C, bias=torch.randn(C, device=cuda, generator=g), residual=res, gn_partial=part)
+        return out, part
+
+    x0, p0 = produce(C0)
+    x1, p1 = produce(C1) if C1 else (None, None)
+    C = C0 + C1
+    gamma, beta = torch.randn(C, device=cuda, generator=g), torch.randn(C, device=cuda, generator=g)
+    y_fused = k.groupnorm(x0, gamma, beta, n_img=B, hw=hw, silu=True, x1=x1, part0=p0, part1=p1)
+    y_two = k.groupnorm(x0, gamma, beta, n_img=B, hw=hw, silu=True, x1=x1)
+    xc = x0 if x1 is None else torch.cat([x0, x1], dim=-1)
+    ref = torch.nn.functional.group_norm(xc.float().reshape(B, hw, C).transpose(1, 2), 32, gamma, beta, 1e-5)
+    ref = torch.nn.functional.silu(ref).transpose(1, 2).reshape(M, C)
+    torch.cuda.synchronize()
+    scale = max(1.0, ref.abs().max().item())                 # bf16 output: half an ulp is 2^-9 of the magnitude
+    assert (y_fused.float() - ref).abs().max().item() < 1e-2 * scale
+    assert (y_fused.float() - y_two.float()).abs().max().item() < 1e-2 * scale
