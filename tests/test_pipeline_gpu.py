@@ -263,3 +263,27 @@ def test_cuda_graph_replay_equals_eager(world):
     torch.cuda.synchronize()
     assert torch.equal(eager, graph)
     assert torch.equal(eager_c, graph_c)
+
+
+def test_main_py_runs_a_config_end_to_end(tmp_path):
+    """``python main.py --config <yaml>`` -- the reference's entry point (/root/reference/main.py:10-24) -- drives the
+    registry, the dpm_solver method, the engine, the VAE decode and the metric plugins and writes metrics.tsv."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cfg = open(os.path.join(root, "tests", "golden", "e2e_smoke_config.yaml")).read()
+    cfg = cfg.replace("./gpurun_out/e2e/", str(tmp_path) + "/")
+    path = tmp_path / "cfg.yaml"
+    path.write_text(cfg)
+    r = subprocess.run([sys.executable, os.path.join(root, "main.py"), "--config", str(path)], cwd=root,
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    tables = sorted(tmp_path.rglob("metrics.tsv"))
+    assert len(tables) == 2                                        # one per sweep point (3 and 5 steps)
+    rows = tables[-1].read_text().strip().splitlines()
+    assert rows[0].split("\t")[:2] == ["nfe", "clip_score_gen_image"]
+    assert [r.split("\t")[0] for r in rows[1:]] == ["3", "5"]      # nfe = number of UNet evaluations
+    assert all(float(r.split("\t")[-1]) > 0 for r in rows[1:])     # seconds per image, loop only
+    assert len(list(tmp_path.rglob("*.png"))) == 16                # 2 batches x 4 prompts x 2 sweep points
