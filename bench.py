@@ -41,6 +41,9 @@ STEPS_PER_IMAGE = 25
 BATCH = 16
 GUIDANCE = 7.5
 FLOP_PER_SAMPLE_FWD = 803.27e9
+CONFIG = {"workload": "configs/dpm_solver_config.yaml: SD-v1.5 UNet, DPM-Solver++(2M) 25 steps, 512x512, "
+                      "batch 16 per GPU, CFG 7.5 (UNet batch 32), bf16",
+          "per_gpu_batch": BATCH, "l2": "working set larger than L2 (weights 1.7 GB + streamed activations)"}
 
 
 def _traffic():
@@ -227,9 +230,7 @@ def run_own(args):
             "warmup": max(args.warmup, 3), "ms_per_step": round(ms_total / args.steps, 3),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic (random-init SD-v1.5 weights, N(0,1) prompt embeddings and latents, seed 29)",
-            "config": {"workload": "configs/dpm_solver_config.yaml: SD-v1.5 UNet, DPM-Solver++(2M) 25 steps, 512x512, "
-                                   "batch 16 per GPU, CFG 7.5 (UNet batch 32), bf16",
-                       "per_gpu_batch": BATCH, "l2": "working set larger than L2 (weights 1.7 GB + streamed activations)"},
+            "config": dict(CONFIG),
             "e2e": {"value": round(e2e_value, 3), "unit": "images/s",
                     "h2d_bytes_per_step": int(pe_host.numel() * 2 * 2 + lat_host.numel() * 2),
                     "d2h_bytes_per_step": int(out_host.numel() * 2)},
@@ -305,11 +306,11 @@ def run_reference(args):
         "value": round(value, 6), "unit": "images/s", "n_gpus": int(os.environ.get("WORLD_SIZE", 1)),
         "steps": len(times), "warmup": min(args.warmup, 1), "ms_per_step": round(s * 1e3 * STEPS_PER_IMAGE, 1),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "configs/dpm_solver_config.yaml path on CPU: oracle restatement of the reference "
-                               "(diffusers is not installable here), batch 1, CFG 7.5, one denoising step timed per "
-                               "bench step and extrapolated to 25"},
+        "config": dict(CONFIG),
         "cpu_baseline": {"value": round(value, 6), "unit": "images/s", "cores": threads, "kind": "port",
-                         "sample": f"{len(times)} x 1 CFG denoising step at batch 1, mean {s:.2f} s/step, x25"},
+                         "sample": f"oracle restatement of the reference path (diffusers is not installable here), fp32, "
+                                   f"all host threads: {len(times)} x 1 CFG denoising step at batch 1 (2 UNet "
+                                   f"sample-forwards), mean {s:.2f} s/step, extrapolated x25 steps per image"},
         "e2e": {"value": round(value, 6), "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
