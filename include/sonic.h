@@ -134,6 +134,10 @@ int sonic_upsample2x(const void* x, void* y, int32_t n_img, int32_t H, int32_t W
                      sonic_stream_t stream);
 int sonic_im2col_s2(const void* x, void* y, int32_t n_img, int32_t H, int32_t W, int32_t C,
                     sonic_stream_t stream);
+/* In-place row softmax of bf16 scores: x[r, :cols] = softmax(scale * x[r, :cols]); rows of pitch ld elements.
+ * With two sonic_conv_gemm calls this is the single-head d=512 attention of the VAE decoder
+ * (reference call site src/models.py:288-302 -> AutoencoderKL.decode). */
+int sonic_softmax_rows(void* x, int32_t rows, int32_t cols, int64_t ld, float scale, sonic_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------
  * Launch plans: the native runtime under the engine.  The host records every operator of a

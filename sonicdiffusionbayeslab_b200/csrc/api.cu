@@ -101,4 +101,9 @@ int sonic_im2col_s2(const void* x, void* y, int32_t n_img, int32_t H, int32_t W,
   return im2col_s2_launch(x, y, n_img, H, W, C, static_cast<cudaStream_t>(stream));
 }
 
+int sonic_softmax_rows(void* x, int32_t rows, int32_t cols, int64_t ld, float scale, sonic_stream_t stream) {
+  SONIC_REQUIRE(x != nullptr, "sonic_softmax_rows: null operand");
+  return softmax_rows_launch(x, rows, cols, static_cast<long>(ld), scale, static_cast<cudaStream_t>(stream));
+}
+
 }  // extern "C"

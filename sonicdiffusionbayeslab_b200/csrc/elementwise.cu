@@ -265,6 +265,68 @@ int nhwc_to_nchw_launch(const void* x, int ld, int n_img, int C, int hw, void* y
   return 0;
 }
 
+// In-place row softmax of a bf16 score matrix: x[r, :] = softmax(scale * x[r, :]).  One warp per row, the
+// row lives in registers (cols <= 8192).  Used by the VAE decoder's single-head d=512 attention, which
+// is expressed as two GEMMs around this kernel (the flash kernel covers head dims up to 160).
+template <int kVecPerLane>
+__global__ void __launch_bounds__(256)
+softmax_rows_kernel(__nv_bfloat16* __restrict__ x, int rows, int cols, long ld, float scale_log2) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  uint4* xr = reinterpret_cast<uint4*>(x + static_cast<size_t>(row) * ld);
+  const int nvec = cols / 8;
+  float f[kVecPerLane][8];
+  float m = -INFINITY;
+#pragma unroll
+  for (int i = 0; i < kVecPerLane; ++i) {
+    const int v = lane + i * 32;
+    if (v < nvec) {
+      const uint4 u = xr[v];
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        f[i][2 * j] = bf16_lo(w[j]);
+        f[i][2 * j + 1] = bf16_hi(w[j]);
+        m = fmaxf(m, fmaxf(f[i][2 * j], f[i][2 * j + 1]));
+      }
+    }
+  }
+  m = warp_max(m);
+  float sum = 0.f;
+#pragma unroll
+  for (int i = 0; i < kVecPerLane; ++i) {
+    if (lane + i * 32 < nvec) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        f[i][j] = exp2f((f[i][j] - m) * scale_log2);
+        sum += f[i][j];
+      }
+    }
+  }
+  const float inv = 1.0f / warp_sum(sum);
+#pragma unroll
+  for (int i = 0; i < kVecPerLane; ++i) {
+    const int v = lane + i * 32;
+    if (v < nvec)
+      xr[v] = make_uint4(pack_bf16(f[i][0] * inv, f[i][1] * inv), pack_bf16(f[i][2] * inv, f[i][3] * inv),
+                         pack_bf16(f[i][4] * inv, f[i][5] * inv), pack_bf16(f[i][6] * inv, f[i][7] * inv));
+  }
+}
+
+int softmax_rows_launch(void* x, int rows, int cols, long ld, float scale, cudaStream_t stream) {
+  SONIC_REQUIRE(cols % 8 == 0 && cols <= 8192 && ld % 8 == 0, "softmax_rows: cols=%d unsupported", cols);
+  const int vpl = (cols / 8 + 31) / 32;
+  const dim3 grid((rows + 7) / 8);
+  auto xb = static_cast<__nv_bfloat16*>(x);
+  const float s2 = scale * 1.4426950408889634f;
+  if (vpl <= 4) softmax_rows_kernel<4><<<grid, 256, 0, stream>>>(xb, rows, cols, ld, s2);
+  else if (vpl <= 16) softmax_rows_kernel<16><<<grid, 256, 0, stream>>>(xb, rows, cols, ld, s2);
+  else softmax_rows_kernel<32><<<grid, 256, 0, stream>>>(xb, rows, cols, ld, s2);
+  SONIC_CUDA(cudaGetLastError());
+  return 0;
+}
+
 int upsample2x_launch(const void* x, void* y, int n_img, int H, int W, int C, cudaStream_t stream) {
   SONIC_REQUIRE(C % 8 == 0, "upsample2x: C=%d", C);
   const long total = static_cast<long>(n_img) * 4 * H * W * (C / 8);

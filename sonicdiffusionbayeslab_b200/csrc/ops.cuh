@@ -49,6 +49,8 @@ int nchw_to_nhwc8_launch(const void* x, int dtype, int n_img, int C, int hw, int
 int nhwc_to_nchw_launch(const void* x, int ld, int n_img, int C, int hw, void* y, int dtype,
                         cudaStream_t stream);
 int upsample2x_launch(const void* x, void* y, int n_img, int H, int W, int C, cudaStream_t stream);
+// in place: x[r, :cols] = softmax(scale * x[r, :cols]) over bf16 rows of pitch ld
+int softmax_rows_launch(void* x, int rows, int cols, long ld, float scale, cudaStream_t stream);
 // stride-2, pad-1 3x3 patches: y[n][ho][wo][tap*C + c]  (Ho = H/2, Wo = W/2)
 int im2col_s2_launch(const void* x, void* y, int n_img, int H, int W, int C, cudaStream_t stream);
 

@@ -17,7 +17,7 @@
 namespace sonic {
 
 struct PlanOp {
-  enum Kind { kGemm, kAttention, kGroupNorm, kLayerNorm, kToNhwc8, kToNchw, kUpsample, kIm2col, kTimeEmb, kGemv };
+  enum Kind { kGemm, kAttention, kGroupNorm, kLayerNorm, kToNhwc8, kToNchw, kUpsample, kIm2col, kTimeEmb, kGemv, kSoftmaxRows };
   Kind kind;
   GemmPlan gemm;
   AttentionPlan* att = nullptr;
@@ -26,6 +26,7 @@ struct PlanOp {
   const void* src = nullptr; void* dst = nullptr;
   const float* f0 = nullptr; const float* f1 = nullptr;
   int i0 = 0, i1 = 0, i2 = 0, i3 = 0, i4 = 0;
+  long l0 = 0;
   float eps = 0.f;
   GemvJob* jobs_dev = nullptr;
 };
@@ -60,6 +61,7 @@ static int run_ops(const Plan& plan, cudaStream_t s) {
       case PlanOp::kIm2col: rc = im2col_s2_launch(op.src, op.dst, op.i0, op.i1, op.i2, op.i3, s); break;
       case PlanOp::kTimeEmb: rc = timestep_embedding_launch(op.f0, op.i0, static_cast<float*>(op.dst), s); break;
       case PlanOp::kGemv: rc = gemv_batched_launch(op.jobs_dev, op.i0, op.i1, op.f0, op.i2, op.i3, s); break;
+      case PlanOp::kSoftmaxRows: rc = softmax_rows_launch(op.dst, op.i0, op.i1, op.l0, op.eps, s); break;
     }
     if (rc) return rc;
   }
@@ -204,6 +206,16 @@ int sonic_plan_add_im2col_s2(sonic_plan_t h, const void* x, void* y, int32_t n_i
   PlanOp p;
   p.kind = PlanOp::kIm2col;
   p.src = x; p.dst = y; p.i0 = n_img; p.i1 = H; p.i2 = W; p.i3 = C;
+  static_cast<Plan*>(h)->launches += 1;
+  static_cast<Plan*>(h)->ops.push_back(p);
+  return 0;
+}
+
+int sonic_plan_add_softmax_rows(sonic_plan_t h, void* x, int32_t rows, int32_t cols, int64_t ld, float scale) {
+  SONIC_REQUIRE(h && x, "sonic_plan_add_softmax_rows: null argument");
+  PlanOp p;
+  p.kind = PlanOp::kSoftmaxRows;
+  p.dst = x; p.i0 = rows; p.i1 = cols; p.l0 = static_cast<long>(ld); p.eps = scale;
   static_cast<Plan*>(h)->launches += 1;
   static_cast<Plan*>(h)->ops.push_back(p);
   return 0;

@@ -83,6 +83,7 @@ class _PipelineBase:
         self._num_timesteps = 0
         self._deepcache = None                      # set by DeepCacheSDHelper.enable()
         self.use_cuda_graphs = True
+        self.use_native_vae = True
         self.decode_x0_preds = True
         self.unet = SimpleNamespace(config=SimpleNamespace(
             in_channels=arch.in_channels, sample_size=latent_size, time_cond_proj_dim=None))
@@ -239,6 +240,23 @@ class _PipelineBase:
         if new is not None and new.data_ptr() != eng.x_in.data_ptr():
             eng.x_in.copy_(new)
 
+    def vae_engine(self, n_img):
+        """Native decoder plan for ``n_img`` latents (vae_engine.VaeEngine), built on first use."""
+        from .vae_engine import VaeEngine
+
+        key = ("vae", n_img, self.dtype)
+        if key not in self._engines:
+            self._engines[key] = VaeEngine({k: v.detach() for k, v in self.vae.state_dict().items()}, n_img=n_img,
+                                           latent=self.latent_size, io_dtype=self.dtype, device=self.device)
+        return self._engines[key]
+
+    def _decode(self, z):
+        """``vae.decode`` (models.py:288-302) on the native engine; ``use_native_vae = False`` keeps the
+        PyTorch module (library kernels)."""
+        if self.use_native_vae and self.device.type == "cuda":
+            return self.vae_engine(z.shape[0]).decode(z.to(self.dtype)).clone()
+        return self.vae.decode(z)[0]
+
     def _finish(self, eng, x0_preds, output_type, exec_time):
         latents = eng.x_in.clone()
         images_x0 = []
@@ -246,11 +264,11 @@ class _PipelineBase:
             image = latents
         else:
             sf = self.vae.config.scaling_factor
-            image = self.vae.decode(latents / sf)[0]
+            image = self._decode(latents / sf)
             image = (image / 2 + 0.5).clamp(0, 1)
             if self.decode_x0_preds:
                 for x0 in x0_preds:
-                    images_x0.append((self.vae.decode(x0 / sf)[0] / 2 + 0.5).clamp(0, 1))
+                    images_x0.append((self._decode(x0 / sf) / 2 + 0.5).clamp(0, 1))
         return PipelineOutput(images=image, nsfw_content_detected=None), exec_time, images_x0
 
     def __call__(self, *args, return_execution_time=True, **kwargs):
