@@ -43,7 +43,7 @@ const char* sonic_version(void);
  * A = channel-concat of (a0[..., :c0], a1[..., :c1]) (a1 may be NULL), NHWC bf16.
  * A Linear over [M, K] is expressed as n_img=1, H=1, W=M, taps=1.
  * epilogue: 0 = none; 1 = GEGLU (w rows packed per block_n tile as [value half | gate half],
- *           out has N/2 columns: value * gelu(gate)).
+ *           out has N/2 columns: value * gelu(gate)); 2 = QuickGELU x * sigmoid(1.702 x) (CLIP MLPs).
  */
 typedef struct sonic_gemm_args {
   const void* a0; int32_t c0, ld0;
@@ -75,6 +75,7 @@ typedef struct sonic_attention_args {
   int32_t ld_q, ld_k, ld_v, ld_o;
   int32_t batch, heads, seq_q, seq_k, head_dim;
   float scale;
+  int32_t causal;        /* 1: key j of query i is masked when j > i (CLIP text towers); 0: full attention */
 } sonic_attention_args;
 int sonic_attention(const sonic_attention_args* args, sonic_stream_t stream);
 

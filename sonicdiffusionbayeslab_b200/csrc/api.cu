@@ -38,7 +38,7 @@ int sonic_attention(const sonic_attention_args* a, sonic_stream_t stream) {
   op.q = a->q; op.k = a->k; op.v = a->v; op.o = a->o;
   op.ld_q = a->ld_q; op.ld_k = a->ld_k; op.ld_v = a->ld_v; op.ld_o = a->ld_o;
   op.batch = a->batch; op.heads = a->heads; op.seq_q = a->seq_q; op.seq_k = a->seq_k;
-  op.head_dim = a->head_dim; op.scale = a->scale;
+  op.head_dim = a->head_dim; op.scale = a->scale; op.causal = a->causal;
   AttentionPlan* plan = nullptr;
   if (int rc = attention_plan(op, &plan)) return rc;
   int rc = attention_launch(plan, static_cast<cudaStream_t>(stream));

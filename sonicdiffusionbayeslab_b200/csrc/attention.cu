@@ -56,7 +56,7 @@ constexpr float kLazyLog2 = 8.0f;               // P <= 2^8 before the reference
 struct AttParams {
   CUtensorMap tm_q, tm_k, tm_v;
   __nv_bfloat16* o;
-  int ld_o, seq_q, seq_k, head_dim, atoms;
+  int ld_o, seq_q, seq_k, head_dim, atoms, causal;
   float scale_log2;
   uint32_t idesc_s, idesc_pv;
 };
@@ -262,12 +262,13 @@ attention_kernel(const __grid_constant__ AttParams p) {
     };
 
     for (int t = 0; t < n_sub; ++t) {
-      const int valid = p.seq_k - t * kSub;
+      int valid = p.seq_k - t * kSub;
+      if (p.causal) valid = min(valid, q0 + row - t * kSub + 1);   // per row: keys 0 .. query index
       ATT_TRACE(warp, t, 0);
       mbar_wait<64>(s_full, t & 1);
       ATT_TRACE(warp, t, 1);
       tc_fence_after();
-      if (valid >= kSub) softmax_sub(t, std::false_type{}, kSub);
+      if (__all_sync(0xffffffffu, valid >= kSub)) softmax_sub(t, std::false_type{}, kSub);
       else softmax_sub(t, std::true_type{}, valid);
       ATT_TRACE(warp, t, 2);
       tmem_st_wait();
@@ -379,6 +380,7 @@ int attention_launch(const AttentionPlan* pl, cudaStream_t stream) {
   prm.o = static_cast<__nv_bfloat16*>(op.o);
   prm.ld_o = op.ld_o; prm.seq_q = op.seq_q; prm.seq_k = op.seq_k; prm.head_dim = op.head_dim;
   prm.atoms = pl->atoms;
+  prm.causal = op.causal;
   prm.scale_log2 = op.scale * 1.4426950408889634f;
   prm.idesc_s = make_idesc_bf16(kBlockQ, kSub, false);
   prm.idesc_pv = make_idesc_bf16(kBlockQ, pl->dpv, true);

@@ -257,6 +257,14 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
           }
         }
         if (i == 0 && threadIdx.x == 64) GEMM_TRACE(3, ti, 1);
+        if (p.epilogue == kEpiQuickGelu) {                   // x * sigmoid(1.702 x), CLIP's MLP activation
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float e;
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(f[j] * -2.4554669595930156f));   // -1.702 * log2(e)
+            f[j] = __fdividef(f[j], 1.0f + e);
+          }
+        }
         if (i == my_n - 1) {                                 // every TMEM read of this tile is done
           tc_fence_before();
           __syncwarp();
@@ -517,6 +525,7 @@ int gemm_plan(const GemmOp& op, GemmPlan* plan) {
   const bool flat = op.W < kTileM || op.W % kTileM == 0 || (op.H == 1 && op.n_img == 1);
   p.tma_epilogue = (out_cols % kChunkCols == 0 && flat) ? 1 : 0;
   p.gn_partial = op.gn_partial;
+  SONIC_REQUIRE(op.epilogue != kEpiQuickGelu || p.tma_epilogue, "gemm: QuickGELU needs the staged epilogue");
   SONIC_REQUIRE(op.gn_partial == nullptr || p.tma_epilogue,
                 "gemm: gn_partial needs the staged epilogue (block_n %% 32 == 0, contiguous 128-row tiles)");
   p.n_tiles = (op.N + p.block_n - 1) / p.block_n;

@@ -9,7 +9,7 @@
 
 namespace sonic {
 
-enum GemmEpilogue { kEpiNone = 0, kEpiGeglu = 1 };
+enum GemmEpilogue { kEpiNone = 0, kEpiGeglu = 1, kEpiQuickGelu = 2 };
 
 struct GemmParams {
   CUtensorMap tm_a0, tm_a1, tm_b;

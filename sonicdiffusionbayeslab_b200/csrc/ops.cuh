@@ -74,6 +74,7 @@ struct AttentionOp {
   void* o; int ld_o = 0;
   int batch = 1, heads = 8, seq_q = 0, seq_k = 0, head_dim = 0;
   float scale = 1.f;
+  int causal = 0;
 };
 struct AttentionPlan;
 int attention_plan(const AttentionOp& op, AttentionPlan** out);

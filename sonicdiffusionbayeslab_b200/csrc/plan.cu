@@ -113,7 +113,7 @@ int sonic_plan_add_attention(sonic_plan_t h, const sonic_attention_args* a) {
   op.q = a->q; op.k = a->k; op.v = a->v; op.o = a->o;
   op.ld_q = a->ld_q; op.ld_k = a->ld_k; op.ld_v = a->ld_v; op.ld_o = a->ld_o;
   op.batch = a->batch; op.heads = a->heads; op.seq_q = a->seq_q; op.seq_k = a->seq_k;
-  op.head_dim = a->head_dim; op.scale = a->scale;
+  op.head_dim = a->head_dim; op.scale = a->scale; op.causal = a->causal;
   PlanOp p;
   p.kind = PlanOp::kAttention;
   if (int rc = attention_plan(op, &p.att)) return rc;

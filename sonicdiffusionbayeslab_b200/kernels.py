@@ -13,7 +13,7 @@ import torch
 from . import _lib
 from ._lib import GemmArgs, check, lib, ptr, stream_ptr
 
-EPI_NONE, EPI_GEGLU = 0, 1
+EPI_NONE, EPI_GEGLU, EPI_QUICK_GELU = 0, 1, 2
 GN_MAX_CHUNKS = 160          # SONIC_GROUPNORM_MAX_CHUNKS in include/sonic.h
 
 
@@ -96,7 +96,7 @@ class AttentionArgs(C.Structure):
     _fields_ = [("q", C.c_void_p), ("k", C.c_void_p), ("v", C.c_void_p), ("o", C.c_void_p),
                 ("ld_q", C.c_int32), ("ld_k", C.c_int32), ("ld_v", C.c_int32), ("ld_o", C.c_int32),
                 ("batch", C.c_int32), ("heads", C.c_int32), ("seq_q", C.c_int32), ("seq_k", C.c_int32),
-                ("head_dim", C.c_int32), ("scale", C.c_float)]
+                ("head_dim", C.c_int32), ("scale", C.c_float), ("causal", C.c_int32)]
 
 
 class UpdateCoeffs(C.Structure):
@@ -112,7 +112,7 @@ def _dtype_code(t: torch.Tensor) -> int:
     raise TypeError(f"unsupported dtype {t.dtype}: the engine handles float32 and bfloat16 latents")
 
 
-def attention_args(q, k, v, out, *, batch, heads, seq_q, seq_k, head_dim, scale=None) -> AttentionArgs:
+def attention_args(q, k, v, out, *, batch, heads, seq_q, seq_k, head_dim, scale=None, causal=False) -> AttentionArgs:
     for t in (q, k, v, out):
         assert t.is_cuda and t.dtype == torch.bfloat16 and t.stride(-1) == 1
     a = AttentionArgs()
@@ -120,15 +120,16 @@ def attention_args(q, k, v, out, *, batch, heads, seq_q, seq_k, head_dim, scale=
     a.ld_q, a.ld_k, a.ld_v, a.ld_o = q.stride(0), k.stride(0), v.stride(0), out.stride(0)
     a.batch, a.heads, a.seq_q, a.seq_k, a.head_dim = batch, heads, seq_q, seq_k, head_dim
     a.scale = float(head_dim ** -0.5 if scale is None else scale)
+    a.causal = int(causal)
     return a
 
 
-def attention(q, k, v, *, batch, heads, seq_q, seq_k, head_dim, scale=None, out=None):
+def attention(q, k, v, *, batch, heads, seq_q, seq_k, head_dim, scale=None, out=None, causal=False):
     """q/k/v: bf16 2-D views [batch*seq, ld] (may be column slices of a fused QKV buffer)."""
     if out is None:
         out = torch.empty((batch * seq_q, heads * head_dim), device=q.device, dtype=torch.bfloat16)
     a = attention_args(q, k, v, out, batch=batch, heads=heads, seq_q=seq_q, seq_k=seq_k, head_dim=head_dim,
-                       scale=scale)
+                       scale=scale, causal=causal)
     check(lib().sonic_attention(C.byref(a), stream_ptr()), "sonic_attention")
     return out
 

@@ -102,6 +102,8 @@ class ClipScoreMetric(Metric):
         self.add_state("n_samples", torch.tensor(0, dtype=torch.long))
         self.keep_features = False
         self._feats = []
+        self.use_native_towers = True           # clip_engine.py on a CUDA device; False = transformers modules
+        self._engines = {}
 
     def to(self, device):
         super().to(device)
@@ -120,13 +122,33 @@ class ClipScoreMetric(Metric):
         pixel = clip_preprocess(images.to(self.device))
         ids, mask = self.tokenizer(text)
         ids, mask = ids.to(self.device), mask.to(self.device)
-        fi = self.model.get_image_features(pixel_values=pixel.to(self.model.dtype))
-        ft = self.model.get_text_features(input_ids=ids, attention_mask=mask)
-        fi = getattr(fi, "pooler_output", fi)
-        ft = getattr(ft, "pooler_output", ft)
+        if self.use_native_towers and self.device.type == "cuda":
+            vis, txt = self._native(len(text))
+            fi, ft = vis.image_features(pixel).float(), txt.text_features(ids).float()
+        else:
+            fi = self.model.get_image_features(pixel_values=pixel.to(self.model.dtype))
+            ft = self.model.get_text_features(input_ids=ids, attention_mask=mask)
+            fi = getattr(fi, "pooler_output", fi)
+            ft = getattr(ft, "pooler_output", ft)
         fi = fi / fi.norm(p=2, dim=-1, keepdim=True)
         ft = ft / ft.norm(p=2, dim=-1, keepdim=True)
         return fi.float(), ft.float()
+
+    def _native(self, n):
+        """Native towers for a batch of n (built on first use from the transformers state dict)."""
+        if n not in self._engines:
+            from ..clip_engine import ClipTextEngine, ClipVisionEngine
+
+            sd = {k: v.detach() for k, v in self.model.state_dict().items()}
+            vc, tc = self.model.config.vision_config, self.model.config.text_config
+            self._engines[n] = (
+                ClipVisionEngine(sd, n=n, image_size=vc.image_size, patch=vc.patch_size, width=vc.hidden_size,
+                                 heads=vc.num_attention_heads, layers=vc.num_hidden_layers, mlp=vc.intermediate_size,
+                                 device=self.device),
+                ClipTextEngine(sd, n=n, seq=tc.max_position_embeddings, width=tc.hidden_size,
+                               heads=tc.num_attention_heads, layers=tc.num_hidden_layers, mlp=tc.intermediate_size,
+                               device=self.device))
+        return self._engines[n]
 
     def update(self, images, text):
         fi, ft = self.features(images, text)

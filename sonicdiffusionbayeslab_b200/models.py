@@ -84,6 +84,7 @@ class _PipelineBase:
         self._deepcache = None                      # set by DeepCacheSDHelper.enable()
         self.use_cuda_graphs = True
         self.use_native_vae = True
+        self.use_native_text = True
         self.decode_x0_preds = True
         self.unet = SimpleNamespace(config=SimpleNamespace(
             in_channels=arch.in_channels, sample_size=latent_size, time_cond_proj_dim=None))
@@ -180,16 +181,32 @@ class _PipelineBase:
             self._engines[key] = eng
         return self._engines[key]
 
+    def _encode(self, prompts):
+        """CLIP text tower (models.py:139-149) on the native engine (clip_engine.ClipTextEngine)."""
+        if not (self.use_native_text and self.device.type == "cuda"):
+            return encode_prompts(self.tokenizer, self.text_encoder, prompts, self.device)
+        from .clip_engine import ClipTextEngine
+
+        key = ("text", len(prompts))
+        if key not in self._engines:
+            c = self.text_encoder.config
+            sd = {k: v.detach() for k, v in self.text_encoder.state_dict().items()}
+            self._engines[key] = ClipTextEngine(sd, n=len(prompts), seq=c.max_position_embeddings, width=c.hidden_size,
+                                                heads=c.num_attention_heads, layers=c.num_hidden_layers,
+                                                mlp=c.intermediate_size, device=self.device)
+        ids, _ = self.tokenizer(list(prompts))
+        return self._engines[key].last_hidden_state(ids).clone()
+
     def encode_prompt(self, prompt, do_cfg, prompt_embeds=None, negative_prompt_embeds=None, negative_prompt=None):
         if prompt_embeds is None:
             prompts = [prompt] if isinstance(prompt, str) else list(prompt)
-            prompt_embeds = encode_prompts(self.tokenizer, self.text_encoder, prompts, self.device)
+            prompt_embeds = self._encode(prompts)
         prompt_embeds = prompt_embeds.to(device=self.device, dtype=torch.bfloat16)
         if do_cfg and negative_prompt_embeds is None:
             n = prompt_embeds.shape[0]
             neg = negative_prompt if negative_prompt is not None else ""
             neg = [neg] * n if isinstance(neg, str) else list(neg)
-            negative_prompt_embeds = encode_prompts(self.tokenizer, self.text_encoder, neg, self.device)
+            negative_prompt_embeds = self._encode(neg)
         if negative_prompt_embeds is not None:
             negative_prompt_embeds = negative_prompt_embeds.to(device=self.device, dtype=torch.bfloat16)
         return prompt_embeds, negative_prompt_embeds

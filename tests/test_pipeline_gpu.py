@@ -310,3 +310,52 @@ def test_native_vae_decoder_matches_torch_module(cuda, n_img, latent):
     err_bf = (bf - ref).abs().max().item() / scale
     assert out.shape == (n_img, 3, 8 * latent, 8 * latent)
     assert err < max(3e-2, 2.0 * err_bf), (err, err_bf)
+
+
+def test_native_clip_towers_match_transformers(cuda):
+    """ClipVisionEngine / ClipTextEngine (native LayerNorm, QKV / MLP GEMMs with QuickGELU epilogue, flash attention with
+    the causal mask for text) against transformers.CLIPModel (fp32) on the same seeded ViT-B/16 weights: per-pair
+    CLIP score 100*cos(f_img, f_txt) within the +-0.2 the north star allows."""
+    from sonicdiffusionbayeslab_b200.clip_engine import ClipTextEngine, ClipVisionEngine
+    from sonicdiffusionbayeslab_b200.metrics.metrics import make_clip_model
+
+    model, tok = make_clip_model(None)
+    model = model.to(cuda).float()
+    sd = {k: v.detach() for k, v in model.state_dict().items()}
+    n = 4
+    g = torch.Generator(device="cuda").manual_seed(3)
+    pixel = torch.randn(n, 3, 224, 224, device=cuda, generator=g)
+    ids, mask = tok(["a photo of a cat", "two dogs running on the beach at sunset", "x", "a " * 60])
+    ids, mask = ids.to(cuda), mask.to(cuda)
+    with torch.no_grad():
+        fi_ref = model.get_image_features(pixel_values=pixel)
+        ft_ref = model.get_text_features(input_ids=ids, attention_mask=mask)
+    fi_ref = getattr(fi_ref, "pooler_output", fi_ref)
+    ft_ref = getattr(ft_ref, "pooler_output", ft_ref)
+    vis = ClipVisionEngine(sd, n=n, device=cuda)
+    txt = ClipTextEngine(sd, n=n, device=cuda)
+    fi = vis.image_features(pixel).float()
+    ft = txt.text_features(ids).float()
+    torch.cuda.synchronize()
+
+    def score(a, b):
+        return 100 * torch.nn.functional.cosine_similarity(a, b, dim=-1)
+
+    assert (fi - fi_ref).abs().max().item() < 3e-2 * fi_ref.abs().max().item()
+    assert (ft - ft_ref).abs().max().item() < 3e-2 * ft_ref.abs().max().item()
+    assert (score(fi, ft) - score(fi_ref, ft_ref)).abs().max().item() < 0.2
+
+
+def test_native_prompt_encoder_matches_transformers(cuda):
+    """encode_prompt (models.py:139-149) through ClipTextEngine (CLIP-L text tower, causal attention, final LayerNorm)
+    against transformers.CLIPTextModel fp32 on the same seeded weights."""
+    from sonicdiffusionbayeslab_b200 import models as M
+    from sonicdiffusionbayeslab_b200.text import encode_prompts
+
+    model = M.StableDiffusionModel.from_pretrained("runwayml/stable-diffusion-v1-5", torch_dtype=torch.bfloat16).to(cuda)
+    prompts = ["a photo of an astronaut riding a horse", "", "sunset over mountains, oil painting"]
+    got = model._encode(prompts).float()
+    ref = encode_prompts(model.tokenizer, model.text_encoder.float(), prompts, cuda).float()
+    torch.cuda.synchronize()
+    assert got.shape == ref.shape == (3, 77, 768)
+    assert (got - ref).abs().max().item() < 3e-2 * ref.abs().max().item()
