@@ -26,6 +26,7 @@
 //                             them, and "S(t) complete" implies "PV(t-1) complete".
 #include "ops.cuh"
 
+#include <cstdlib>
 #include <type_traits>
 
 namespace sonic {
@@ -35,6 +36,7 @@ struct AttentionPlan {
   AttentionOp op;
   int dpv = 0;         // head dim rounded up to a supported MMA N of the PV product
   int atoms = 0;       // 64-column smem atoms per row (1, 2, 3)
+  int qt = 1;          // 128-query tiles per CTA: 2 = the ping-pong kernel (head dim <= 64)
   size_t smem = 0;
   dim3 grid;
 };
@@ -311,6 +313,256 @@ attention_kernel(const __grid_constant__ AttParams p) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Two-tile ("ping-pong") variant for head dims <= 64.  ncu on the one-tile kernel at d = 40: 40 % of all issued
+// instructions were mbarrier polling (a softmax warp waited for S(t+1) through 17 try_wait rounds per
+// sub-tile, at the MUFU pipe's expense: 0.79 IPC per sub-partition, XU 61 % busy).  Here one CTA owns TWO
+// 128-query tiles A and B and every softmax thread owns one row of each: while it exponentiates S_B(t) the
+// tensor pipe runs PV_A(t) and S_A(t+1), so the next scores are normally complete when the thread comes back and
+// the wait is a single successful try_wait.  Two CTAs per SM (2 x 224 TMEM columns, 2 x 97 KB of shared memory):
+// 168 registers per thread, so a whole 64-score row is loaded ONCE (tcgen05.ld .x64), reduced, exponentiated and
+// written back as 32 packed columns (tcgen05.st .x32); K / V tiles are fetched once per 256 queries through
+// 4-stage rings.
+//   TMEM columns of tile q:  q*128 + [0, 64) S / P,  q*128 + 64 + [0, kDPV) O.
+constexpr int kStages2 = 4;
+
+template <int kDPV>
+__global__ void __launch_bounds__(kAttThreads, 2)
+attention2_kernel(const __grid_constant__ AttParams p) {
+  static_assert(kSub + kDPV <= 128, "S/P + O of one query tile must fit 128 TMEM columns");
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint8_t* sm_q = smem;                                   // 2 tiles x 16 KB (head dim <= 64: one atom)
+  uint8_t* sm_k = sm_q + 2 * kQAtomBytes;                 // kStages2 x 8 KB
+  uint8_t* sm_v = sm_k + kStages2 * kKvAtomBytes;         // kStages2 x 8 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm_v + kStages2 * kKvAtomBytes);
+  uint64_t* q_full = bars;
+  uint64_t* k_full = bars + 1;                    // [kStages2]
+  uint64_t* k_empty = k_full + kStages2;          // [kStages2]
+  uint64_t* v_full = k_empty + kStages2;          // [kStages2]
+  uint64_t* v_empty = v_full + kStages2;          // [kStages2]
+  uint64_t* s_full = v_empty + kStages2;          // [2] S_q(t) complete (and every earlier MMA, incl. PV_q(t-1))
+  uint64_t* p_full = s_full + 2;                  // [2] P_q(t) written over S_q(t), O_q rescaled if it had to be
+  uint64_t* o_done = p_full + 2;                  // every PV complete
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * (2 * kBlockQ);
+  const int head = blockIdx.y;
+  const int batch = blockIdx.z;
+  const int n_sub = (p.seq_k + kSub - 1) / kSub;
+  const int k_steps_s = (p.head_dim + 15) / 16;
+  const int nq = q0 + kBlockQ < p.seq_q ? 2 : 1;  // the last CTA of an odd tile count owns one tile
+
+  if (threadIdx.x == 0) {
+    mbar_init(q_full, 1);
+    for (int i = 0; i < kStages2; ++i) {
+      mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1);
+      mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 4); }
+    mbar_init(o_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == kWarpMma) tmem_alloc<256>(tmem_slot);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == kWarpTma) {
+    if (lane == 0) {
+      tma_prefetch_desc(&p.tm_q); tma_prefetch_desc(&p.tm_k); tma_prefetch_desc(&p.tm_v);
+      mbar_expect_tx(q_full, nq * kQAtomBytes);
+      for (int q = 0; q < nq; ++q)
+        tma_load_4d(sm_q + q * kQAtomBytes, &p.tm_q, q_full, 0, head, q0 + q * kBlockQ, batch);
+      for (int t = 0; t < n_sub; ++t) {
+        const int st = t % kStages2;
+        const uint32_t ph = ((t / kStages2) & 1) ^ 1;
+        mbar_wait<512>(&k_empty[st], ph);
+        mbar_expect_tx(&k_full[st], kKvAtomBytes);
+        tma_load_4d(sm_k + st * kKvAtomBytes, &p.tm_k, &k_full[st], 0, head, t * kSub, batch);
+        mbar_wait<512>(&v_empty[st], ph);
+        mbar_expect_tx(&v_full[st], kKvAtomBytes);
+        tma_load_4d(sm_v + st * kKvAtomBytes, &p.tm_v, &v_full[st], 0, head, t * kSub, batch);
+      }
+    }
+  } else if (warp == kWarpMma) {
+    // Warp-uniform control flow, one elected lane issues (see attention_kernel).
+    const bool leader = elect_one();
+    const uint64_t q_desc0 = make_sw128_desc(smem_u32(sm_q), 16, 1024);
+    const uint64_t k_desc0 = make_sw128_desc(smem_u32(sm_k), 16, 1024);
+    const uint64_t v_desc0 = make_sw128_desc(smem_u32(sm_v), kKvAtomBytes, 1024);
+    constexpr int kMaxKS = (kDPV + 15) / 16;
+    auto issue_s = [&](int q, int st) {            // S_q = Q_q K^T of the K tile in stage st
+      const uint64_t qd = q_desc0 + static_cast<uint64_t>((q * kQAtomBytes) >> 4);
+      const uint64_t kd = k_desc0 + static_cast<uint64_t>((st * kKvAtomBytes) >> 4);
+      if (leader) {
+#pragma unroll
+        for (int ks = 0; ks < kMaxKS; ++ks)
+          if (ks < k_steps_s) umma_bf16_ss(tmem_base + q * 128, qd + ((ks * 32) >> 4), kd + ((ks * 32) >> 4), p.idesc_s, ks != 0);
+        umma_commit(&s_full[q]);
+      }
+      __syncwarp();
+    };
+    mbar_wait(q_full, 0);
+    mbar_wait(&k_full[0], 0);
+    tc_fence_after();
+    for (int q = 0; q < nq; ++q) issue_s(q, 0);
+    if (leader) umma_commit(&k_empty[0]);
+    __syncwarp();
+    for (int t = 0; t < n_sub; ++t) {
+      const int st = t % kStages2;
+      const int st1 = (t + 1) % kStages2;
+      const bool more = t + 1 < n_sub;
+      for (int q = 0; q < nq; ++q) {
+        mbar_wait<64>(&p_full[q], t & 1);
+        if (q == 0) mbar_wait(&v_full[st], (t / kStages2) & 1);
+        tc_fence_after();
+        const uint32_t ts = tmem_base + q * 128;
+        const uint64_t vd = v_desc0 + static_cast<uint64_t>((st * kKvAtomBytes) >> 4);
+        if (leader) {
+#pragma unroll
+          for (int ks = 0; ks < kSub / 16; ++ks)
+            umma_bf16_ts(ts + kSub, ts + ks * 8, vd + ks * (2048 >> 4), p.idesc_pv, (t | ks) != 0);
+          if (q == nq - 1) umma_commit(&v_empty[st]);
+          if (!more && q == nq - 1) umma_commit(o_done);
+        }
+        __syncwarp();
+        if (more) {
+          if (q == 0) { mbar_wait(&k_full[st1], ((t + 1) / kStages2) & 1); tc_fence_after(); }
+          issue_s(q, st1);
+          if (q == nq - 1) {
+            if (leader) umma_commit(&k_empty[st1]);
+            __syncwarp();
+          }
+        }
+      }
+    }
+  } else {
+    const int row = warp * 32 + lane;
+    const uint32_t lane_addr = static_cast<uint32_t>(warp * 32) << 16;
+    float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
+    const float lazy_raw = kLazyLog2 / p.scale_log2;
+
+    auto softmax_sub = [&](float& m_r, float& l_r, uint32_t t_s, int t, auto mask_tag, int valid) {
+      constexpr bool kMask = decltype(mask_tag)::value;
+      uint32_t v[kSub];
+      tmem_ld64(t_s, v);
+      tmem_ld_wait();
+      float tm[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+      for (int i = 0; i < kSub; ++i)
+        if (!kMask || i < valid) tm[i & 3] = fmaxf(tm[i & 3], __uint_as_float(v[i]));
+      const float tmax = fmaxf(fmaxf(tm[0], tm[1]), fmaxf(tm[2], tm[3]));
+      if (__any_sync(0xffffffffu, tmax > m_r + lazy_raw)) {
+        // Rare after the first sub-tile.  S_q(t) complete implies PV_q(t-1) complete and PV_q(t) is not issued
+        // before p_full[q](t): O_q is quiescent, rescale it in place.
+        const float m_new = fmaxf(m_r, tmax);
+        const float alpha = fast_exp2((m_r - m_new) * p.scale_log2);     // 0 on the first sub-tile
+        if (t > 0) {
+#pragma unroll
+          for (int c = 0; c < kDPV; c += 16) {
+            uint32_t o[16];
+            tmem_ld16(t_s + kSub + c, o);
+            tmem_ld_wait();
+#pragma unroll
+            for (int i = 0; i < 16; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
+            tmem_st16(t_s + kSub + c, o);
+          }
+        }
+        l_r *= alpha;
+        m_r = m_new;
+      }
+      const float m_scaled = m_r * p.scale_log2;
+      float ps[4] = {0.f, 0.f, 0.f, 0.f};
+      uint32_t pk[kSub / 2];
+#pragma unroll
+      for (int i = 0; i < kSub; i += 2) {
+        float e0 = fast_exp2(fmaf(__uint_as_float(v[i]), p.scale_log2, -m_scaled));
+        float e1 = fast_exp2(fmaf(__uint_as_float(v[i + 1]), p.scale_log2, -m_scaled));
+        if (kMask && i >= valid) e0 = 0.f;
+        if (kMask && i + 1 >= valid) e1 = 0.f;
+        ps[(i >> 1) & 3] += e0 + e1;
+        pk[i >> 1] = pack_bf16(e0, e1);
+      }
+      tmem_st32(t_s, pk);
+      l_r += (ps[0] + ps[1]) + (ps[2] + ps[3]);
+    };
+
+    for (int t = 0; t < n_sub; ++t) {
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        if (q < nq) {
+          int valid = p.seq_k - t * kSub;
+          if (p.causal) valid = min(valid, q0 + q * kBlockQ + row - t * kSub + 1);
+          const uint32_t t_s = tmem_base + q * 128 + lane_addr;
+          mbar_wait<64>(&s_full[q], t & 1);
+          tc_fence_after();
+          if (__all_sync(0xffffffffu, valid >= kSub)) softmax_sub(m_run[q], l_run[q], t_s, t, std::false_type{}, kSub);
+          else softmax_sub(m_run[q], l_run[q], t_s, t, std::true_type{}, valid);
+          tmem_st_wait();
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&p_full[q]);
+        }
+      }
+    }
+    mbar_wait<64>(o_done, 0);
+    tc_fence_after();
+
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      if (q < nq) {
+        const int s_idx = q0 + q * kBlockQ + row;
+        const float inv = 1.0f / l_run[q];
+        __nv_bfloat16* orow = p.o + (static_cast<size_t>(batch) * p.seq_q + s_idx) * p.ld_o + head * p.head_dim;
+        const uint32_t t_o = tmem_base + q * 128 + kSub + lane_addr;
+#pragma unroll
+        for (int c = 0; c < kDPV; c += 16) {
+          uint32_t v[16];
+          tmem_ld16(t_o + c, v);
+          tmem_ld_wait();
+          if (s_idx < p.seq_q) {
+#pragma unroll
+            for (int h = 0; h < 16; h += 8) {
+              if (c + h < p.head_dim) {
+                uint4 u = make_uint4(pack_bf16(__uint_as_float(v[h]) * inv, __uint_as_float(v[h + 1]) * inv),
+                                     pack_bf16(__uint_as_float(v[h + 2]) * inv, __uint_as_float(v[h + 3]) * inv),
+                                     pack_bf16(__uint_as_float(v[h + 4]) * inv, __uint_as_float(v[h + 5]) * inv),
+                                     pack_bf16(__uint_as_float(v[h + 6]) * inv, __uint_as_float(v[h + 7]) * inv));
+                *reinterpret_cast<uint4*>(orow + c + h) = u;
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == kWarpMma) {
+    tc_fence_after();
+    tmem_dealloc<256>(tmem_base);
+  }
+}
+
+template <int kDPV>
+int launch_att2(const AttentionPlan* pl, const AttParams& prm, cudaStream_t stream) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    SONIC_CUDA(cudaFuncSetAttribute(attention2_kernel<kDPV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  attention2_kernel<kDPV><<<pl->grid, kAttThreads, pl->smem, stream>>>(prm);
+  SONIC_CUDA(cudaGetLastError());
+  return 0;
+}
+
+
 template <int kDPV>
 int launch_att(const AttentionPlan* pl, const AttParams& prm, cudaStream_t stream) {
   static bool attr_set = false;
@@ -363,8 +615,14 @@ int attention_plan(const AttentionOp& op, AttentionPlan** out) {
   if (!rc) rc = make_qkv_map(&pl->tm_k, op.k, op.ld_k, op.seq_k, op.batch, op.heads, op.head_dim, kSub);
   if (!rc) rc = make_qkv_map(&pl->tm_v, op.v, op.ld_v, op.seq_k, op.batch, op.heads, op.head_dim, kSub);
   if (rc) { delete pl; return rc; }
-  pl->smem = static_cast<size_t>(pl->atoms) * (kQAtomBytes + 4 * kKvAtomBytes) + 1024 + 256;
-  pl->grid = dim3((op.seq_q + kBlockQ - 1) / kBlockQ, op.heads, op.batch);
+  // SONIC_ATT_QT=1 forces the one-tile kernel (A/B timing aid).
+  const char* force = getenv("SONIC_ATT_QT");
+  pl->qt = (pl->dpv <= 64 && op.seq_q > kBlockQ && !(force && force[0] == '1')) ? 2 : 1;
+  if (pl->qt == 2)
+    pl->smem = 2 * kQAtomBytes + 2 * kStages2 * kKvAtomBytes + 1024 + 256;
+  else
+    pl->smem = static_cast<size_t>(pl->atoms) * (kQAtomBytes + 4 * kKvAtomBytes) + 1024 + 256;
+  pl->grid = dim3((op.seq_q + kBlockQ * pl->qt - 1) / (kBlockQ * pl->qt), op.heads, op.batch);
   *out = pl;
   return 0;
 }
@@ -384,6 +642,7 @@ int attention_launch(const AttentionPlan* pl, cudaStream_t stream) {
   prm.scale_log2 = op.scale * 1.4426950408889634f;
   prm.idesc_s = make_idesc_bf16(kBlockQ, kSub, false);
   prm.idesc_pv = make_idesc_bf16(kBlockQ, pl->dpv, true);
+  if (pl->qt == 2) return pl->dpv == 48 ? launch_att2<48>(pl, prm, stream) : launch_att2<64>(pl, prm, stream);
   switch (pl->dpv) {
     case 48: return launch_att<48>(pl, prm, stream);
     case 64: return launch_att<64>(pl, prm, stream);

@@ -12,19 +12,19 @@ dev = torch.device("cuda:0")
 g = torch.Generator(device="cuda").manual_seed(0)
 
 
-def run(B, H, Sq, Sk, d):
+def run(B, H, Sq, Sk, d, causal=False):
     C = H * d
     q = torch.randn(B * Sq, C, device=dev, generator=g).bfloat16()
     kk = torch.randn(B * Sk, C, device=dev, generator=g).bfloat16()
     v = torch.randn(B * Sk, C, device=dev, generator=g).bfloat16()
-    out = k.attention(q, kk, v, batch=B, heads=H, seq_q=Sq, seq_k=Sk, head_dim=d)
+    out = k.attention(q, kk, v, batch=B, heads=H, seq_q=Sq, seq_k=Sk, head_dim=d, causal=causal)
     torch.cuda.synchronize()
     qf = q.float().reshape(B, Sq, H, d).transpose(1, 2)
     kf = kk.float().reshape(B, Sk, H, d).transpose(1, 2)
     vf = v.float().reshape(B, Sk, H, d).transpose(1, 2)
-    ref = F.scaled_dot_product_attention(qf, kf, vf).transpose(1, 2).reshape(B * Sq, C)
+    ref = F.scaled_dot_product_attention(qf, kf, vf, is_causal=causal).transpose(1, 2).reshape(B * Sq, C)
     err = (out.float() - ref).abs()
-    print(f"attn B{B} H{H} Sq{Sq} Sk{Sk} d{d}: max_abs={err.max().item():.3e} ref_max={ref.abs().max().item():.3f}",
+    print(f"attn B{B} H{H} Sq{Sq} Sk{Sk} d{d} causal={int(causal)}: max_abs={err.max().item():.3e} ref_max={ref.abs().max().item():.3f}",
           flush=True)
     if err.max().item() > 0.05:
         bad = (err > 0.05).nonzero()
@@ -36,8 +36,12 @@ def run(B, H, Sq, Sk, d):
 
 for cfg in [(1, 1, 128, 128, 64), (1, 1, 128, 128, 40), (1, 1, 128, 256, 64), (1, 2, 256, 384, 40),
             (1, 1, 128, 77, 64), (1, 1, 64, 64, 160), (1, 1, 128, 128, 80), (1, 1, 128, 256, 160),
-            (2, 8, 1024, 1024, 80)]:
+            (2, 8, 1024, 1024, 80), (1, 1, 256, 256, 40), (1, 2, 384, 320, 64), (2, 3, 197, 197, 64),
+            (1, 2, 300, 77, 40), (2, 8, 4096, 4096, 40), (2, 8, 4096, 77, 40), (1, 1, 256, 1024, 48)]:
     run(*cfg)
+run(2, 4, 200, 200, 64, causal=True)
+run(1, 2, 512, 512, 40, causal=True)
+run(2, 8, 77, 77, 64, causal=True)
 
 def bench(B, H, Sq, Sk, d, reps=5):
     C = H * d
@@ -56,6 +60,11 @@ def bench(B, H, Sq, Sk, d, reps=5):
     print(f"attention B{B} H{H} Sq{Sq} Sk{Sk} d{d}: {ms:.3f} ms  {4 * B * H * Sq * Sk * d / ms / 1e9:.1f} TFLOP/s", flush=True)
 
 
-for cfg in [(32, 8, 4096, 4096, 40), (32, 8, 1024, 1024, 80), (32, 8, 256, 256, 160), (32, 8, 4096, 77, 40),
-            (32, 8, 1024, 77, 80), (32, 8, 256, 77, 160)]:
+for qt in ("1", "2"):
+    os.environ["SONIC_ATT_QT"] = qt
+    print("SONIC_ATT_QT =", qt)
+    for cfg in [(32, 8, 4096, 4096, 40), (32, 8, 4096, 77, 40), (16, 12, 197, 197, 64)]:
+        bench(*cfg)
+os.environ.pop("SONIC_ATT_QT")
+for cfg in [(32, 8, 1024, 1024, 80), (32, 8, 256, 256, 160), (32, 8, 1024, 77, 80), (32, 8, 256, 77, 160)]:
     bench(*cfg)
