@@ -26,7 +26,6 @@
 //                             them, and "S(t) complete" implies "PV(t-1) complete".
 #include "ops.cuh"
 
-#include <cstdlib>
 #include <type_traits>
 
 namespace sonic {
@@ -615,9 +614,7 @@ int attention_plan(const AttentionOp& op, AttentionPlan** out) {
   if (!rc) rc = make_qkv_map(&pl->tm_k, op.k, op.ld_k, op.seq_k, op.batch, op.heads, op.head_dim, kSub);
   if (!rc) rc = make_qkv_map(&pl->tm_v, op.v, op.ld_v, op.seq_k, op.batch, op.heads, op.head_dim, kSub);
   if (rc) { delete pl; return rc; }
-  // SONIC_ATT_QT=1 forces the one-tile kernel (A/B timing aid).
-  const char* force = getenv("SONIC_ATT_QT");
-  pl->qt = (pl->dpv <= 64 && op.seq_q > kBlockQ && !(force && force[0] == '1')) ? 2 : 1;
+  pl->qt = (pl->dpv <= 64 && op.seq_q > kBlockQ) ? 2 : 1;
   if (pl->qt == 2)
     pl->smem = 2 * kQAtomBytes + 2 * kStages2 * kKvAtomBytes + 1024 + 256;
   else

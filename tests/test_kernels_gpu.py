@@ -17,7 +17,11 @@ def _rel(got, ref):
 
 @pytest.mark.parametrize("B,H,Sq,Sk,d", [(2, 8, 4096, 4096, 40), (2, 8, 1024, 1024, 80), (2, 8, 256, 256, 160),
                                           (3, 8, 64, 64, 160), (2, 8, 4096, 77, 40), (2, 8, 1024, 77, 80),
-                                          (2, 8, 256, 77, 160), (1, 8, 64, 77, 160), (1, 2, 200, 333, 64)])
+                                          (2, 8, 256, 77, 160), (1, 8, 64, 77, 160), (1, 2, 200, 333, 64),
+                                          # two-tile kernel (d <= 64, more than 128 queries): odd tile counts, ragged
+                                          # last tile / last key sub-tile, one key sub-tile, exactly two tiles
+                                          (1, 2, 384, 320, 64), (2, 3, 197, 197, 64), (1, 2, 300, 77, 40),
+                                          (1, 1, 256, 1024, 48), (1, 1, 640, 640, 40), (1, 3, 129, 64, 16)])
 def test_attention(cuda, B, H, Sq, Sk, d):
     from sonicdiffusionbayeslab_b200 import kernels as k
 
@@ -36,6 +40,49 @@ def test_attention(cuda, B, H, Sq, Sk, d):
     vf = v.float().reshape(B, Sk, H, d).transpose(1, 2)
     ref = F.scaled_dot_product_attention(qf, kf, vf).transpose(1, 2).reshape(B * Sq, C)
     torch.cuda.synchronize()
+    assert _rel(out, ref) < 2e-2
+
+
+@pytest.mark.parametrize("B,H,S,d", [(2, 4, 200, 64), (1, 2, 512, 40), (2, 8, 77, 64), (1, 2, 100, 80)])
+def test_attention_causal(cuda, B, H, S, d):
+    """Causal mask (the CLIP text towers): one- and two-tile kernels, ragged tiles."""
+    from sonicdiffusionbayeslab_b200 import kernels as k
+
+    g = torch.Generator(device="cuda").manual_seed(S + d)
+    C = H * d
+    qkv = _bf(torch.randn(B * S, 3 * C, device=cuda, generator=g))
+    q, kk, v = qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:]
+    out = k.attention(q, kk, v, batch=B, heads=H, seq_q=S, seq_k=S, head_dim=d, causal=True)
+    qf, kf, vf = (x.float().reshape(B, S, H, d).transpose(1, 2) for x in (q, kk, v))
+    ref = F.scaled_dot_product_attention(qf, kf, vf, is_causal=True).transpose(1, 2).reshape(B * S, C)
+    torch.cuda.synchronize()
+    assert _rel(out, ref) < 2e-2
+
+
+@pytest.mark.parametrize("d,Sq", [(40, 512), (40, 128), (80, 256)])
+def test_attention_rising_scores(cuda, d, Sq):
+    """Scores that keep growing along the key axis (up to e^60 between the first and the last sub-tile): the lazy
+    running reference must be raised, and the O accumulator rescaled in tensor memory, many times per row."""
+    from sonicdiffusionbayeslab_b200 import kernels as k
+
+    B, H, Sk = 1, 2, 1024
+    g = torch.Generator(device="cuda").manual_seed(d + Sq)
+    C = H * d
+    q = _bf(torch.randn(B * Sq, C, device=cuda, generator=g))
+    kk = torch.randn(B * Sk, C, device=cuda, generator=g) * 0.3
+    ramp = torch.linspace(0, 60, Sk, device=cuda).repeat(B)[:, None]          # added to every score of key j
+    qf = q.float().reshape(B, Sq, H, d).transpose(1, 2)
+    # k_j += ramp_j * q_dir / |q_dir|^2 would need per-query keys; instead give q a constant component.
+    q = q.clone()
+    q[:, ::d] = 4.0                                  # component 0 of every head
+    kk[:, ::d] = ramp[:, 0:1] * (d ** 0.5) / 4.0     # contributes ramp_j to the scaled score
+    kk = _bf(kk)
+    v = _bf(torch.randn(B * Sk, C, device=cuda, generator=g))
+    out = k.attention(q, kk, v, batch=B, heads=H, seq_q=Sq, seq_k=Sk, head_dim=d)
+    qf, kf, vf = (x.float().reshape(B, -1, H, d).transpose(1, 2) for x in (q, kk, v))
+    ref = F.scaled_dot_product_attention(qf, kf, vf).transpose(1, 2).reshape(B * Sq, C)
+    torch.cuda.synchronize()
+    assert torch.isfinite(out.float()).all()
     assert _rel(out, ref) < 2e-2
 
 

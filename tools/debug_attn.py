@@ -60,11 +60,6 @@ def bench(B, H, Sq, Sk, d, reps=5):
     print(f"attention B{B} H{H} Sq{Sq} Sk{Sk} d{d}: {ms:.3f} ms  {4 * B * H * Sq * Sk * d / ms / 1e9:.1f} TFLOP/s", flush=True)
 
 
-for qt in ("1", "2"):
-    os.environ["SONIC_ATT_QT"] = qt
-    print("SONIC_ATT_QT =", qt)
-    for cfg in [(32, 8, 4096, 4096, 40), (32, 8, 4096, 77, 40), (16, 12, 197, 197, 64)]:
-        bench(*cfg)
-os.environ.pop("SONIC_ATT_QT")
-for cfg in [(32, 8, 1024, 1024, 80), (32, 8, 256, 256, 160), (32, 8, 1024, 77, 80), (32, 8, 256, 77, 160)]:
+for cfg in [(32, 8, 4096, 4096, 40), (32, 8, 4096, 77, 40), (16, 12, 197, 197, 64), (32, 8, 1024, 1024, 80),
+            (32, 8, 256, 256, 160), (32, 8, 1024, 77, 80), (32, 8, 256, 77, 160)]:
     bench(*cfg)
