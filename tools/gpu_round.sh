@@ -13,7 +13,7 @@ if [ "${2:-}" != "skip-ncu" ]; then
   ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --profile-from-start off --csv \
       --log-file $O/launches_$TAG.csv python tools/ncu_target.py > $O/ncu_l_$TAG.log 2>&1
   echo "launch list rc=$?"
-  for k in conv_gemm_kernel:14 attention_kernel:2 gn_:2 layernorm:1; do
+  for k in conv_gemm_kernel:14 attention2_kernel:2 attention_kernel:2 gn_:2 layernorm:1; do
     name=${k%%:*}; cnt=${k##*:}
     ncu --set full --clock-control none --import-source on --profile-from-start off \
         -k regex:$name -c $cnt -f -o $O/prof_${TAG}_$name python tools/ncu_target.py > $O/ncu_f_${TAG}_$name.log 2>&1
