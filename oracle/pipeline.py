@@ -2,6 +2,7 @@
 
 ``denoise``      <- /root/reference/src/models.py:154-155,167-182,210-282 (single scheduler)
 ``denoise_two``  <- /root/reference/src/models.py:487-502,545-621,704-730 (two-scheduler switch)
+``denoise_interleaved`` <- /root/reference/src/models.py:880-897,939-961,963-1053 (interleaved schedulers)
 Same op order and dtypes as the reference: latents duplicated with ``torch.cat``, UNet call,
 ``uncond + g * (text - uncond)`` in the model dtype, ``scheduler.step``.  Optional DeepCache via
 ``oracle.deepcache.DeepCacheOracle`` and teacher forcing (``forced_latents``) for parity tests.
@@ -113,3 +114,61 @@ def denoise_two(unet, scheduler_first, scheduler_second, prompt_embeds, negative
         latents = sched.step(noise_pred, t, latents, **extra, return_dict=False)[0]
         per_step.append(latents)
     return dict(latents=latents, per_step=per_step, timesteps=([int(t) for t in first], [int(t) for t in second]))
+
+
+def interleave_partition(timesteps_main, solver_order, interliving_steps):
+    """/root/reference/src/models.py:944-961: main-grid steps are grouped ``solver_order`` at a time; in every
+    group listed in ``interliving_steps`` the first timestep is handed to the inter scheduler and the rest are
+    dropped.  Returns (kept timesteps, inter timesteps) as python ints."""
+    kept, inter = [], []
+    for i, t in enumerate(int(v) for v in timesteps_main):
+        if i // solver_order in interliving_steps:
+            if i % solver_order != 0:
+                continue
+            inter.append(t)
+        kept.append(t)
+    return kept, inter
+
+
+@torch.no_grad()
+def denoise_interleaved(unet, scheduler_main, scheduler_inter, prompt_embeds, negative_prompt_embeds, latents,
+                        num_inference_steps, interliving_steps, guidance_scale=7.5, generator=None, eta=0.0):
+    """The interleaved loop as written: the main (multistep DPM) scheduler walks its grid with its OWN step counter
+    (models.py:1035 passes ``t`` but the step index only ever increments, src/schedulers.py:176), the inter
+    scheduler (set up on N // order steps, models.py:888-894) replaces whole groups, and after every step the
+    OTHER scheduler's history is fed ``convert_model_output(noise_pred, sample=new latents)``
+    (models.py:1024-1031, 1045-1053).  ``convert_model_output`` returns one tensor for the ``++`` types and a pair
+    otherwise (SURVEY C-1), so the literal history entry is only well-formed for ``++``; here it is the converted
+    model output in both cases (the evident intent)."""
+    do_cfg = guidance_scale > 1
+    ctx = torch.cat([negative_prompt_embeds, prompt_embeds]) if do_cfg else prompt_embeds
+    device = latents.device
+    order = scheduler_main.config.solver_order
+    scheduler_main.set_timesteps(num_inference_steps, device=device)
+    scheduler_inter.set_timesteps(num_inference_steps // order, device=device)
+    kept, inter = interleave_partition(scheduler_main.timesteps.tolist(), order, interliving_steps)
+    latents = latents * scheduler_main.init_noise_sigma          # prepare_latents uses self.scheduler (sigma 1.0)
+    e_main, e_inter = _extra(scheduler_main, generator, eta), _extra(scheduler_inter, generator, eta)
+    per_step = []
+
+    def feed(s, noise_pred, new_latents):
+        m = s.convert_model_output(noise_pred, sample=new_latents)[0]
+        for j in range(s.config.solver_order - 1):
+            s.model_outputs[j] = s.model_outputs[j + 1]
+        s.model_outputs[-1] = m
+
+    for t in kept:
+        x_in = torch.cat([latents] * 2) if do_cfg else latents
+        noise_pred = unet(x_in, torch.as_tensor(t, device=device), encoder_hidden_states=ctx)[0]
+        if do_cfg:
+            u, c = noise_pred.chunk(2)
+            noise_pred = u + guidance_scale * (c - u)
+        if t in inter:
+            latents = scheduler_inter.step(noise_pred, t, latents, **e_inter, return_dict=False)[0]
+            feed(scheduler_main, noise_pred, latents)
+        else:
+            latents = scheduler_main.step(noise_pred, t, latents, **e_main, return_dict=False)[0]
+            if isinstance(scheduler_inter, type(scheduler_main)):
+                feed(scheduler_inter, noise_pred, latents)
+        per_step.append(latents)
+    return dict(latents=latents, per_step=per_step, timesteps=(kept, inter))

@@ -7,7 +7,7 @@
 ``two_schedulers``    /root/reference/src/experiments/two_schedulers.py:10
 ``default``           /root/reference/src/experiments/default_sd.py:10
 ``skip_steps``        /root/reference/src/experiments/skip_steps_exp.py:10
-``interliving_schedulers`` is registered but not implemented (no config ships for it).
+``interliving_schedulers`` /root/reference/src/experiments/interliving_exp.py:10
 
 They read the same ``experiment_params`` keys and build schedulers with the same
 ``schedulers_registry[name].from_config(model.scheduler.config, **kw)`` call.
@@ -159,6 +159,33 @@ class SkipStepsMethod(BaseMethod):
 
 @methods_registry.add_to_registry("interliving_schedulers")
 class InterlivingSchedulersMethod(BaseMethod):
+    """interliving_exp.py:10-188: ``scheduler.scheduler_main`` / ``scheduler.scheduler_inter`` with per-scheduler
+    ``{main,inter}_{order_solver,algorithm_type,final_sigmas_type}``; one sweep point per
+    (num_inference_steps_first[i], interliving_steps[i]).  "" = class default, as for two_schedulers (C-3)."""
+
+    def setup_exp_params(self):
+        p = self.config.experiment_params
+        self.num_inference_steps_first = p.num_inference_steps_first
+        self.interliving_steps = p.interliving_steps
+        self.main = {k: p.get(f"main_{k}", "") for k in ("order_solver", "algorithm_type", "final_sigmas_type")}
+        self.inter = {k: p.get(f"inter_{k}", "") for k in ("order_solver", "algorithm_type", "final_sigmas_type")}
+        self.batch_size = self.config.inference.get("batch_size", 1)
+
+    def _make(self, name, opts):
+        kw = {"solver_order": opts["order_solver"], "algorithm_type": opts["algorithm_type"],
+              "final_sigmas_type": opts["final_sigmas_type"]}                # interliving_exp.py:44-47 spells it right
+        kw = {k: v for k, v in kw.items() if v != ""}
+        return schedulers_registry[name].from_config(self.model.scheduler.config, **kw)
+
+    def setup_scheduler(self):
+        self.model.scheduler_main = self._make(self.config.scheduler.scheduler_main, self.main)
+        self.model.scheduler_inter = self._make(self.config.scheduler.scheduler_inter, self.inter)
+
     def run_experiment(self):
-        raise NotImplementedError("interleaving schedulers: no reference config ships for it; outside the "
-                                  "accelerated hot path (SURVEY.md section 8(f) row 4)")
+        for n, inter in zip(self.num_inference_steps_first, self.interliving_steps):
+            inter = [int(v) for v in inter]
+            self._sweep_point(self.batch_size, n,
+                              f"{self.config.experiment_name}, Step main: {n}, Inter steps:{' '.join(map(str, inter))}",
+                              additional_values={"num_inference_steps_main": n,
+                                                 "num_inter_steps": " ".join(map(str, inter))},
+                              interliving_steps=inter)

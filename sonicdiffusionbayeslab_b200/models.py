@@ -412,8 +412,71 @@ class StableDiffusionModelTwoSchedulers(_PipelineBase):
 
 @models_registry.add_to_registry("stable_diffusion_model_interliving_schedulers")
 class StableDiffusionModelInterlivingSchedulers(_PipelineBase):
-    """models.py:733-1135 alternates two schedulers per step; no reference config ships for it
-    (out of scope) -- registered so the name resolves, fails loudly."""
+    """src/models.py:733-1135: a multistep main scheduler whose grid is grouped ``solver_order`` steps at a time;
+    the groups listed in ``interliving_steps`` are replaced by ONE step of the inter scheduler (set up on
+    N // order steps, so e.g. a DDIM step spans the whole group), and after every step the other scheduler's
+    multistep history is fed the converted model output (``feed_history``)."""
 
-    def call(self, *args, **kwargs):
-        raise NotImplementedError("interleaving pipeline is outside the accelerated hot path (SURVEY section 8(f))")
+    scheduler_main = None
+    scheduler_inter = None
+
+    @staticmethod
+    def partition(timesteps_main, solver_order, interliving_steps):
+        """models.py:944-961 -> (timesteps that are evaluated, those of them the inter scheduler takes)."""
+        kept, inter = [], []
+        for i, t in enumerate(int(v) for v in timesteps_main):
+            if i // solver_order in interliving_steps:
+                if i % solver_order != 0:
+                    continue
+                inter.append(t)
+            kept.append(t)
+        return kept, inter
+
+    @torch.no_grad()
+    def call(self, prompt=None, height=None, width=None, num_inference_steps: int = 50, interliving_steps=None,
+             timesteps=None, sigmas=None, guidance_scale: float = 7.5, negative_prompt=None,
+             num_images_per_prompt=1, eta: float = 0.0, generator=None, latents=None, prompt_embeds=None,
+             negative_prompt_embeds=None, output_type="pil", return_dict=True, guidance_rescale: float = 0.0,
+             callback_on_step_end=None, **kwargs):
+        if output_type not in ("pt", "latent"):
+            raise NotImplementedError("output_type must be 'pt' or 'latent'")
+        main, inter_s = self.scheduler_main, self.scheduler_inter
+        if main is None or inter_s is None:
+            raise ValueError("scheduler_main / scheduler_inter must be set (interliving_exp.py:40-62)")
+        interliving_steps = list(interliving_steps or [])
+        self._guidance_scale = guidance_scale
+        batch = (1 if isinstance(prompt, str) else len(prompt)) if prompt is not None else prompt_embeds.shape[0]
+        do_cfg = self.do_classifier_free_guidance
+        pe, ne = self.encode_prompt(prompt, do_cfg, prompt_embeds, negative_prompt_embeds, negative_prompt)
+        ctx = torch.cat([ne, pe]) if do_cfg else pe
+        order = main.config.solver_order
+        ts_main, _ = retrieve_timesteps(main, num_inference_steps, self.device, timesteps)        # models.py:880-886
+        retrieve_timesteps(inter_s, num_inference_steps // order, self.device, timesteps)         # models.py:888-894
+        kept, t_inter = self.partition(ts_main.tolist(), order, interliving_steps)
+        self._num_timesteps = len(ts_main) - len(interliving_steps)                               # models.py:939
+        self.last_timesteps = (kept, t_inter)
+        latents = self.prepare_latents(batch, generator, latents, self.scheduler.init_noise_sigma)
+        extra_main = self._extra_step_kwargs(main, generator, eta)
+        extra_inter = self._extra_step_kwargs(inter_s, generator, eta)
+        feed_inter = isinstance(inter_s, S.DPMSolverScheduler)                                    # models.py:1045
+        eng = self.engine(batch, do_cfg)
+        eng.set_context(ctx)
+        eng.x_in.copy_(latents)
+        B = eng.n_lat
+        x0_preds = []
+        torch.cuda.synchronize(self.device)
+        start = time.perf_counter()
+        for i, t in enumerate(kept):
+            stepper, extra, other = (inter_s, extra_inter, main) if t in t_inter else (main, extra_main,
+                                                                                       inter_s if feed_inter else None)
+            eps = eng.forward(float(t))
+            eps_u, eps_c, g = (eps[:B], eps[B:], guidance_scale) if do_cfg else (eps, None, 0.0)
+            step = stepper._step(eps_u, eps_c, g, t, eng.x_in, out=eng.x_in, **extra)
+            if len(step) == 2:
+                x0_preds.append(step[1][0:1])
+            if other is not None:
+                other.feed_history(eps_u, eps_c, g, eng.x_in)       # post-step latents, pre-step noise: as written
+            self._run_callback(callback_on_step_end, eng, i, t)
+        torch.cuda.synchronize(self.device)
+        exec_time = time.perf_counter() - start
+        return self._finish(eng, x0_preds, output_type, exec_time)

@@ -313,6 +313,20 @@ class DPMSolverScheduler(FusedScheduler):
         _, m0, x0 = self._launch(c, model_output, None, sample, want_m0=True)
         return m0, x0
 
+    def feed_history(self, eps, eps_text, guidance, sample):
+        """``model_outputs <- shift + convert_model_output(uncond + g (text - uncond), sample=sample)`` at the CURRENT
+        step index, without stepping: how the interleaved pipeline keeps this scheduler's multistep history alive
+        while the other scheduler advances the latents (src/models.py:1024-1031, 1045-1053).  One fused launch."""
+        if self.step_index is None:
+            raise ValueError("feed_history needs an initialised step index (src/schedulers.py:40 indexes "
+                             "sigmas[None] in the reference: the main scheduler has to take a step first)")
+        c = dict(guidance=guidance, **self._convert_coeffs())
+        c["c_x"] = 1.0
+        _, m0, _ = self._launch(c, eps, eps_text, sample, want_m0=True, want_x0=False)
+        for i in range(self.config.solver_order - 1):
+            self.model_outputs[i] = self.model_outputs[i + 1]
+        self.model_outputs[-1] = m0
+
     def _update_coeffs(self, order):
         """Linear-combination form of dpm_solver_first_order_update /
         multistep_dpm_solver_{second,third}_order_update (diffusers 0.32.1)."""

@@ -201,6 +201,36 @@ def test_two_scheduler_switch_host_logic():
         assert ([int(t) for t in first], [int(t) for t in second]) == tuple(KAT["two_10_3"])
 
 
+def test_interleaved_host_logic_and_config():
+    """Interleaved-scheduler partition (src/models.py:944-961) equals the oracle's; the example YAML parses and its
+    model / method / scheduler names resolve through the registries."""
+    import os
+
+    from oracle.pipeline import interleave_partition
+    from sonicdiffusionbayeslab_b200 import models as M
+    from sonicdiffusionbayeslab_b200 import schedulers as S
+    from sonicdiffusionbayeslab_b200.config import load as load_config
+    from sonicdiffusionbayeslab_b200.registry import methods_registry, models_registry, schedulers_registry
+
+    main = S.DPMSolverScheduler.from_config(M.SD15_SCHEDULER_CONFIG)
+    main.set_timesteps(20)
+    ts = main.timesteps.tolist()
+    part = M.StableDiffusionModelInterlivingSchedulers.partition
+    for order, groups in ((2, [2, 5]), (2, [0, 9]), (3, [1, 4]), (1, [3]), (2, [])):
+        assert part(ts, order, groups) == interleave_partition(ts, order, groups)
+    kept, inter = part(ts, 2, [2, 5])
+    assert len(kept) == 18 and inter == [ts[4], ts[10]] and ts[5] not in kept and ts[11] not in kept
+
+    cfg = load_config(os.path.join(ROOT, "configs", "interliving_schedulers_config.yaml"))
+    assert models_registry[cfg.model.model_name] is M.StableDiffusionModelInterlivingSchedulers
+    assert methods_registry[cfg.experiment.method].__name__ == "InterlivingSchedulersMethod"
+    assert schedulers_registry[cfg.scheduler.scheduler_main] is S.DPMSolverScheduler
+    assert schedulers_registry[cfg.scheduler.scheduler_inter] is S.DDIMSchedulerMy
+    assert [list(v) for v in cfg.experiment_params.interliving_steps] == [[2, 5], [1, 3, 5, 7]]
+    with pytest.raises(ValueError):                    # the reference indexes sigmas[None] here (C-4 analogue)
+        main.feed_history(None, None, 0.0, None)
+
+
 def test_unet_spec_matches_oracle_keys():
     from oracle.unet import UNet2DConditionModel
     from sonicdiffusionbayeslab_b200.unet_spec import unet_param_shapes

@@ -153,3 +153,32 @@ def test_lcm_consumes_generator_in_order():
     c = denoise(net, _sd15(LCMScheduler), pe, pe, x, 4, guidance_scale=0, generator=torch.Generator().manual_seed(8))
     assert torch.equal(a["latents"], b["latents"]) and not torch.equal(a["latents"], c["latents"])
     assert len(a["x0"]) == 4
+
+
+def test_interleaved_partition_and_history_feed():
+    """Interleaved-scheduler host logic (models.py:944-961, 1010-1053) on a toy epsilon model: which timesteps are
+    evaluated, which go to the inter scheduler, and that the main scheduler's history is fed after an inter step."""
+    from oracle import schedulers as O
+    from oracle.pipeline import denoise_interleaved, interleave_partition
+
+    assert interleave_partition(range(12), 3, [0, 2]) == ([0, 3, 4, 5, 6, 9, 10, 11], [0, 6])
+    assert interleave_partition([951, 901, 851, 801], 2, []) == ([951, 901, 851, 801], [])
+
+    class Toy(torch.nn.Module):
+        def forward(self, x, t, encoder_hidden_states=None):
+            return (0.1 * x + 0.001 * float(t),)
+
+    cfg = O.SD15_SCHEDULER_CONFIG
+    lat = torch.randn(2, 4, 8, 8, generator=torch.Generator().manual_seed(0))
+    pe, ne = torch.zeros(2, 77, 8), torch.zeros(2, 77, 8)
+    main, inter = O.DPMSolverScheduler.from_config(cfg), O.DDIMScheduler.from_config(cfg)
+    out = denoise_interleaved(Toy(), main, inter, pe, ne, lat, 10, [1, 3], guidance_scale=7.5)
+    assert out["timesteps"] == ([901, 811, 721, 541, 451, 361, 181, 91], [721, 361])
+    assert len(out["per_step"]) == 8 and torch.isfinite(out["latents"]).all()
+    assert main.step_index == 6                       # six main steps: its counter ignores the two inter steps
+    # no interleaving == the plain DPM loop
+    from oracle.pipeline import denoise
+    a = denoise_interleaved(Toy(), O.DPMSolverScheduler.from_config(cfg), O.DDIMScheduler.from_config(cfg), pe, ne,
+                            lat, 10, [], guidance_scale=7.5)
+    b = denoise(Toy(), O.DPMSolverScheduler.from_config(cfg), pe, ne, lat, 10, guidance_scale=7.5)
+    assert torch.equal(a["latents"], b["latents"])

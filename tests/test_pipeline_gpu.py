@@ -248,6 +248,35 @@ def test_two_schedulers_switch(world):
     assert max(errs) <= TF_TOL, errs
 
 
+def test_interleaved_schedulers(world):
+    """models.py:733-1135: DPM-Solver++(2M) main grid of 10 steps, groups 1 and 3 replaced by one DDIM step each
+    (DDIM set up on 10 // 2 = 5 steps, so its stride spans the group); history feed after every inter step."""
+    from oracle import schedulers as O
+    from oracle.pipeline import denoise_interleaved
+    from sonicdiffusionbayeslab_b200 import models as M
+    from sonicdiffusionbayeslab_b200 import schedulers as S
+
+    cfg = O.SD15_SCHEDULER_CONFIG
+    ref = denoise_interleaved(world["net"], O.DPMSolverScheduler.from_config(cfg), O.DDIMScheduler.from_config(cfg),
+                              world["pe"], world["ne"], world["lat"], 10, [1, 3])
+    assert ref["timesteps"] == ([901, 811, 721, 541, 451, 361, 181, 91], [721, 361])
+    model = world["make"](M.StableDiffusionModelInterlivingSchedulers)
+    model.scheduler_main = S.DPMSolverScheduler.from_config(cfg)
+    model.scheduler_inter = S.DDIMSchedulerMy.from_config(cfg)
+    errs = []
+
+    def cb(pipe, i, t, kwargs):
+        errs.append(_rel(kwargs["latents"], ref["per_step"][i]))
+        return {"latents": ref["per_step"][i].to(kwargs["latents"].dtype)}
+
+    model(prompt_embeds=world["pe"], negative_prompt_embeds=world["ne"], latents=world["lat"], num_inference_steps=10,
+          interliving_steps=[1, 3], guidance_scale=7.5, output_type="latent", callback_on_step_end=cb)
+    assert model.last_timesteps == ref["timesteps"]
+    assert model.num_timesteps == 8
+    print(f"\n[interleaved 10 / groups 1,3] teacher-forced per-step max-abs {max(errs):.3e}")
+    assert len(errs) == 8 and max(errs) <= TF_TOL, errs
+
+
 def test_cuda_graph_replay_equals_eager(world):
     from sonicdiffusionbayeslab_b200.unet_engine import UNetEngine
 
