@@ -36,6 +36,7 @@ struct AttentionPlan {
   int dpv = 0;         // head dim rounded up to a supported MMA N of the PV product
   int atoms = 0;       // 64-column smem atoms per row (1, 2, 3)
   int qt = 1;          // 128-query tiles per CTA: 2 = the ping-pong kernel (head dim <= 64)
+  bool resident = false;   // two-tile kernel with K / V resident in shared memory, one CTA per (batch, head)
   size_t smem = 0;
   dim3 grid;
 };
@@ -325,38 +326,49 @@ attention_kernel(const __grid_constant__ AttParams p) {
 //   TMEM columns of tile q:  q*128 + [0, 64) S / P,  q*128 + 64 + [0, kDPV) O.
 constexpr int kStages2 = 4;
 
-template <int kDPV>
+// kResident (cross-attention: at most two key sub-tiles, i.e. <= 128 keys): ONE CTA per (batch, head) keeps K and V
+// in shared memory and walks over ALL query-tile pairs of that head, Q double-buffered.  The streaming form launched
+// 4096 CTAs of two sub-tiles each for the 64x64 cross-attention layers and spent its time in per-CTA latency
+// (TMEM allocation, barrier set-up, the first Q / K / V loads from HBM, the output stores): 126 us for 0.1 ms of
+// arithmetic-free work.  Here those costs are paid once per head and the next pair's Q is in flight while the
+// current one is processed.
+template <int kDPV, bool kResident>
 __global__ void __launch_bounds__(kAttThreads, 2)
 attention2_kernel(const __grid_constant__ AttParams p) {
   static_assert(kSub + kDPV <= 128, "S/P + O of one query tile must fit 128 TMEM columns");
+  constexpr int kQStages = kResident ? 2 : 1;     // pairs of Q tiles in flight
+  constexpr int kKvStages = kResident ? 2 : kStages2;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
-  uint8_t* sm_q = smem;                                   // 2 tiles x 16 KB (head dim <= 64: one atom)
-  uint8_t* sm_k = sm_q + 2 * kQAtomBytes;                 // kStages2 x 8 KB
-  uint8_t* sm_v = sm_k + kStages2 * kKvAtomBytes;         // kStages2 x 8 KB
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sm_v + kStages2 * kKvAtomBytes);
-  uint64_t* q_full = bars;
-  uint64_t* k_full = bars + 1;                    // [kStages2]
+  uint8_t* sm_q = smem;                                   // kQStages x 2 tiles x 16 KB (head dim <= 64: one atom)
+  uint8_t* sm_k = sm_q + kQStages * 2 * kQAtomBytes;      // kKvStages x 8 KB
+  uint8_t* sm_v = sm_k + kKvStages * kKvAtomBytes;        // kKvStages x 8 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm_v + kKvStages * kKvAtomBytes);
+  uint64_t* q_full = bars;                        // [2]
+  uint64_t* q_empty = bars + 2;                   // [2] every S product of the pair in this Q stage is complete
+  uint64_t* k_full = bars + 4;                    // [kStages2]
   uint64_t* k_empty = k_full + kStages2;          // [kStages2]
   uint64_t* v_full = k_empty + kStages2;          // [kStages2]
   uint64_t* v_empty = v_full + kStages2;          // [kStages2]
   uint64_t* s_full = v_empty + kStages2;          // [2] S_q(t) complete (and every earlier MMA, incl. PV_q(t-1))
   uint64_t* p_full = s_full + 2;                  // [2] P_q(t) written over S_q(t), O_q rescaled if it had to be
-  uint64_t* o_done = p_full + 2;                  // every PV complete
+  uint64_t* o_done = p_full + 2;                  // every PV of the current pair complete
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_done + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * (2 * kBlockQ);
   const int head = blockIdx.y;
   const int batch = blockIdx.z;
   const int n_sub = (p.seq_k + kSub - 1) / kSub;
   const int k_steps_s = (p.head_dim + 15) / 16;
-  const int nq = q0 + kBlockQ < p.seq_q ? 2 : 1;  // the last CTA of an odd tile count owns one tile
+  const int total_pairs = (p.seq_q + 2 * kBlockQ - 1) / (2 * kBlockQ);
+  const int pair0 = kResident ? 0 : blockIdx.x;                  // this CTA's pairs: pair0, pair0 + 1, ... (n_pairs)
+  const int n_pairs = kResident ? total_pairs : 1;
+  auto tiles_of = [&](int pair) { return pair * 2 * kBlockQ + kBlockQ < p.seq_q ? 2 : 1; };   // an odd tile count ends in a half pair
 
   if (threadIdx.x == 0) {
-    mbar_init(q_full, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1); }
     for (int i = 0; i < kStages2; ++i) {
       mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1);
       mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1);
@@ -374,19 +386,26 @@ attention2_kernel(const __grid_constant__ AttParams p) {
   if (warp == kWarpTma) {
     if (lane == 0) {
       tma_prefetch_desc(&p.tm_q); tma_prefetch_desc(&p.tm_k); tma_prefetch_desc(&p.tm_v);
-      mbar_expect_tx(q_full, nq * kQAtomBytes);
-      for (int q = 0; q < nq; ++q)
-        tma_load_4d(sm_q + q * kQAtomBytes, &p.tm_q, q_full, 0, head, q0 + q * kBlockQ, batch);
+      auto load_q = [&](int i) {                   // pair pair0 + i into Q stage i % kQStages
+        const int qs = i % kQStages;
+        const int nq = tiles_of(pair0 + i);
+        if (kResident) mbar_wait<256>(&q_empty[qs], ((i / kQStages) & 1) ^ 1);
+        mbar_expect_tx(&q_full[qs], nq * kQAtomBytes);
+        for (int q = 0; q < nq; ++q)
+          tma_load_4d(sm_q + (qs * 2 + q) * kQAtomBytes, &p.tm_q, &q_full[qs], 0, head,
+                      (pair0 + i) * 2 * kBlockQ + q * kBlockQ, batch);
+      };
+      load_q(0);
       for (int t = 0; t < n_sub; ++t) {
-        const int st = t % kStages2;
-        const uint32_t ph = ((t / kStages2) & 1) ^ 1;
-        mbar_wait<512>(&k_empty[st], ph);
+        const int st = t % kKvStages;
+        if (!kResident) mbar_wait<512>(&k_empty[st], ((t / kKvStages) & 1) ^ 1);
         mbar_expect_tx(&k_full[st], kKvAtomBytes);
         tma_load_4d(sm_k + st * kKvAtomBytes, &p.tm_k, &k_full[st], 0, head, t * kSub, batch);
-        mbar_wait<512>(&v_empty[st], ph);
+        if (!kResident) mbar_wait<512>(&v_empty[st], ((t / kKvStages) & 1) ^ 1);
         mbar_expect_tx(&v_full[st], kKvAtomBytes);
         tma_load_4d(sm_v + st * kKvAtomBytes, &p.tm_v, &v_full[st], 0, head, t * kSub, batch);
       }
+      for (int i = 1; i < n_pairs; ++i) load_q(i);
     }
   } else if (warp == kWarpMma) {
     // Warp-uniform control flow, one elected lane issues (see attention_kernel).
@@ -395,8 +414,8 @@ attention2_kernel(const __grid_constant__ AttParams p) {
     const uint64_t k_desc0 = make_sw128_desc(smem_u32(sm_k), 16, 1024);
     const uint64_t v_desc0 = make_sw128_desc(smem_u32(sm_v), kKvAtomBytes, 1024);
     constexpr int kMaxKS = (kDPV + 15) / 16;
-    auto issue_s = [&](int q, int st) {            // S_q = Q_q K^T of the K tile in stage st
-      const uint64_t qd = q_desc0 + static_cast<uint64_t>((q * kQAtomBytes) >> 4);
+    auto issue_s = [&](int qs, int q, int st) {    // S_q = Q_q K^T of the K tile in stage st
+      const uint64_t qd = q_desc0 + static_cast<uint64_t>(((qs * 2 + q) * kQAtomBytes) >> 4);
       const uint64_t kd = k_desc0 + static_cast<uint64_t>((st * kKvAtomBytes) >> 4);
       if (leader) {
 #pragma unroll
@@ -406,36 +425,47 @@ attention2_kernel(const __grid_constant__ AttParams p) {
       }
       __syncwarp();
     };
-    mbar_wait(q_full, 0);
-    mbar_wait(&k_full[0], 0);
-    tc_fence_after();
-    for (int q = 0; q < nq; ++q) issue_s(q, 0);
-    if (leader) umma_commit(&k_empty[0]);
-    __syncwarp();
-    for (int t = 0; t < n_sub; ++t) {
-      const int st = t % kStages2;
-      const int st1 = (t + 1) % kStages2;
-      const bool more = t + 1 < n_sub;
-      for (int q = 0; q < nq; ++q) {
-        mbar_wait<64>(&p_full[q], t & 1);
-        if (q == 0) mbar_wait(&v_full[st], (t / kStages2) & 1);
-        tc_fence_after();
-        const uint32_t ts = tmem_base + q * 128;
-        const uint64_t vd = v_desc0 + static_cast<uint64_t>((st * kKvAtomBytes) >> 4);
-        if (leader) {
+    uint32_t n_item = 0;                           // (pair, sub-tile) items so far: the phase of s_full / p_full
+    for (int i = 0; i < n_pairs; ++i) {
+      const int qs = i % kQStages;
+      const int nq = tiles_of(pair0 + i);
+      mbar_wait(&q_full[qs], (i / kQStages) & 1);
+      mbar_wait(&k_full[0], 0);
+      tc_fence_after();
+      for (int q = 0; q < nq; ++q) issue_s(qs, q, 0);
+      if (leader) {
+        if (!kResident) umma_commit(&k_empty[0]);
+        if (n_sub == 1) umma_commit(&q_empty[qs]);
+      }
+      __syncwarp();
+      for (int t = 0; t < n_sub; ++t, ++n_item) {
+        const int st = t % kKvStages;
+        const int st1 = (t + 1) % kKvStages;
+        const bool more = t + 1 < n_sub;
+        for (int q = 0; q < nq; ++q) {
+          mbar_wait<64>(&p_full[q], n_item & 1);
+          if (q == 0) mbar_wait(&v_full[st], kResident ? 0 : (t / kKvStages) & 1);
+          tc_fence_after();
+          const uint32_t ts = tmem_base + q * 128;
+          const uint64_t vd = v_desc0 + static_cast<uint64_t>((st * kKvAtomBytes) >> 4);
+          if (leader) {
 #pragma unroll
-          for (int ks = 0; ks < kSub / 16; ++ks)
-            umma_bf16_ts(ts + kSub, ts + ks * 8, vd + ks * (2048 >> 4), p.idesc_pv, (t | ks) != 0);
-          if (q == nq - 1) umma_commit(&v_empty[st]);
-          if (!more && q == nq - 1) umma_commit(o_done);
-        }
-        __syncwarp();
-        if (more) {
-          if (q == 0) { mbar_wait(&k_full[st1], ((t + 1) / kStages2) & 1); tc_fence_after(); }
-          issue_s(q, st1);
-          if (q == nq - 1) {
-            if (leader) umma_commit(&k_empty[st1]);
-            __syncwarp();
+            for (int ks = 0; ks < kSub / 16; ++ks)
+              umma_bf16_ts(ts + kSub, ts + ks * 8, vd + ks * (2048 >> 4), p.idesc_pv, (t | ks) != 0);
+            if (!kResident && q == nq - 1) umma_commit(&v_empty[st]);
+            if (!more && q == nq - 1) umma_commit(o_done);
+          }
+          __syncwarp();
+          if (more) {
+            if (q == 0) { mbar_wait(&k_full[st1], kResident ? 0 : ((t + 1) / kKvStages) & 1); tc_fence_after(); }
+            issue_s(qs, q, st1);
+            if (q == nq - 1) {
+              if (leader) {
+                if (!kResident) umma_commit(&k_empty[st1]);
+                if (t + 2 == n_sub) umma_commit(&q_empty[qs]);      // the pair's last S product
+              }
+              __syncwarp();
+            }
           }
         }
       }
@@ -443,7 +473,6 @@ attention2_kernel(const __grid_constant__ AttParams p) {
   } else {
     const int row = warp * 32 + lane;
     const uint32_t lane_addr = static_cast<uint32_t>(warp * 32) << 16;
-    float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
     const float lazy_raw = kLazyLog2 / p.scale_log2;
 
     auto softmax_sub = [&](float& m_r, float& l_r, uint32_t t_s, int t, auto mask_tag, int valid) {
@@ -491,53 +520,61 @@ attention2_kernel(const __grid_constant__ AttParams p) {
       l_r += (ps[0] + ps[1]) + (ps[2] + ps[3]);
     };
 
-    for (int t = 0; t < n_sub; ++t) {
+    uint32_t n_item = 0;
+    for (int i = 0; i < n_pairs; ++i) {
+      const int q0 = (pair0 + i) * 2 * kBlockQ;
+      const int nq = tiles_of(pair0 + i);
+      float m_run[2] = {-INFINITY, -INFINITY}, l_run[2] = {0.f, 0.f};
+      for (int t = 0; t < n_sub; ++t, ++n_item) {
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          if (q < nq) {
+            int valid = p.seq_k - t * kSub;
+            if (p.causal) valid = min(valid, q0 + q * kBlockQ + row - t * kSub + 1);
+            const uint32_t t_s = tmem_base + q * 128 + lane_addr;
+            mbar_wait<64>(&s_full[q], n_item & 1);
+            tc_fence_after();
+            if (__all_sync(0xffffffffu, valid >= kSub)) softmax_sub(m_run[q], l_run[q], t_s, t, std::false_type{}, kSub);
+            else softmax_sub(m_run[q], l_run[q], t_s, t, std::true_type{}, valid);
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&p_full[q]);
+          }
+        }
+      }
+      // O of this pair: its last PV is complete; the next pair's first PV waits for p_full, which these warps only
+      // arrive on after the reads below, so the accumulators are not overwritten early.
+      mbar_wait<64>(o_done, i & 1);
+      tc_fence_after();
 #pragma unroll
       for (int q = 0; q < 2; ++q) {
         if (q < nq) {
-          int valid = p.seq_k - t * kSub;
-          if (p.causal) valid = min(valid, q0 + q * kBlockQ + row - t * kSub + 1);
-          const uint32_t t_s = tmem_base + q * 128 + lane_addr;
-          mbar_wait<64>(&s_full[q], t & 1);
-          tc_fence_after();
-          if (__all_sync(0xffffffffu, valid >= kSub)) softmax_sub(m_run[q], l_run[q], t_s, t, std::false_type{}, kSub);
-          else softmax_sub(m_run[q], l_run[q], t_s, t, std::true_type{}, valid);
-          tmem_st_wait();
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&p_full[q]);
-        }
-      }
-    }
-    mbar_wait<64>(o_done, 0);
-    tc_fence_after();
-
+          const int s_idx = q0 + q * kBlockQ + row;
+          const float inv = 1.0f / l_run[q];
+          __nv_bfloat16* orow = p.o + (static_cast<size_t>(batch) * p.seq_q + s_idx) * p.ld_o + head * p.head_dim;
+          const uint32_t t_o = tmem_base + q * 128 + kSub + lane_addr;
 #pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      if (q < nq) {
-        const int s_idx = q0 + q * kBlockQ + row;
-        const float inv = 1.0f / l_run[q];
-        __nv_bfloat16* orow = p.o + (static_cast<size_t>(batch) * p.seq_q + s_idx) * p.ld_o + head * p.head_dim;
-        const uint32_t t_o = tmem_base + q * 128 + kSub + lane_addr;
+          for (int c = 0; c < kDPV; c += 16) {
+            uint32_t v[16];
+            tmem_ld16(t_o + c, v);
+            tmem_ld_wait();
+            if (s_idx < p.seq_q) {
 #pragma unroll
-        for (int c = 0; c < kDPV; c += 16) {
-          uint32_t v[16];
-          tmem_ld16(t_o + c, v);
-          tmem_ld_wait();
-          if (s_idx < p.seq_q) {
-#pragma unroll
-            for (int h = 0; h < 16; h += 8) {
-              if (c + h < p.head_dim) {
-                uint4 u = make_uint4(pack_bf16(__uint_as_float(v[h]) * inv, __uint_as_float(v[h + 1]) * inv),
-                                     pack_bf16(__uint_as_float(v[h + 2]) * inv, __uint_as_float(v[h + 3]) * inv),
-                                     pack_bf16(__uint_as_float(v[h + 4]) * inv, __uint_as_float(v[h + 5]) * inv),
-                                     pack_bf16(__uint_as_float(v[h + 6]) * inv, __uint_as_float(v[h + 7]) * inv));
-                *reinterpret_cast<uint4*>(orow + c + h) = u;
+              for (int h = 0; h < 16; h += 8) {
+                if (c + h < p.head_dim) {
+                  uint4 u = make_uint4(pack_bf16(__uint_as_float(v[h]) * inv, __uint_as_float(v[h + 1]) * inv),
+                                       pack_bf16(__uint_as_float(v[h + 2]) * inv, __uint_as_float(v[h + 3]) * inv),
+                                       pack_bf16(__uint_as_float(v[h + 4]) * inv, __uint_as_float(v[h + 5]) * inv),
+                                       pack_bf16(__uint_as_float(v[h + 6]) * inv, __uint_as_float(v[h + 7]) * inv));
+                  *reinterpret_cast<uint4*>(orow + c + h) = u;
+                }
               }
             }
           }
         }
       }
+      tc_fence_before();                           // the reads above precede this thread's next p_full arrive
     }
   }
 
@@ -549,18 +586,18 @@ attention2_kernel(const __grid_constant__ AttParams p) {
   }
 }
 
-template <int kDPV>
+template <int kDPV, bool kResident>
 int launch_att2(const AttentionPlan* pl, const AttParams& prm, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    SONIC_CUDA(cudaFuncSetAttribute(attention2_kernel<kDPV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    SONIC_CUDA(cudaFuncSetAttribute(attention2_kernel<kDPV, kResident>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    227 * 1024));
     attr_set = true;
   }
-  attention2_kernel<kDPV><<<pl->grid, kAttThreads, pl->smem, stream>>>(prm);
+  attention2_kernel<kDPV, kResident><<<pl->grid, kAttThreads, pl->smem, stream>>>(prm);
   SONIC_CUDA(cudaGetLastError());
   return 0;
 }
-
 
 template <int kDPV>
 int launch_att(const AttentionPlan* pl, const AttParams& prm, cudaStream_t stream) {
@@ -619,7 +656,9 @@ int attention_plan(const AttentionOp& op, AttentionPlan** out) {
     pl->smem = 2 * kQAtomBytes + 2 * kStages2 * kKvAtomBytes + 1024 + 256;
   else
     pl->smem = static_cast<size_t>(pl->atoms) * (kQAtomBytes + 4 * kKvAtomBytes) + 1024 + 256;
-  pl->grid = dim3((op.seq_q + kBlockQ * pl->qt - 1) / (kBlockQ * pl->qt), op.heads, op.batch);
+  // <= 128 keys and at least four query-tile pairs per head: one CTA per (batch, head) keeps K / V resident
+  pl->resident = pl->qt == 2 && op.seq_k <= 2 * kSub && op.seq_q >= 8 * kBlockQ;
+  pl->grid = dim3(pl->resident ? 1 : (op.seq_q + kBlockQ * pl->qt - 1) / (kBlockQ * pl->qt), op.heads, op.batch);
   *out = pl;
   return 0;
 }
@@ -639,7 +678,10 @@ int attention_launch(const AttentionPlan* pl, cudaStream_t stream) {
   prm.scale_log2 = op.scale * 1.4426950408889634f;
   prm.idesc_s = make_idesc_bf16(kBlockQ, kSub, false);
   prm.idesc_pv = make_idesc_bf16(kBlockQ, pl->dpv, true);
-  if (pl->qt == 2) return pl->dpv == 48 ? launch_att2<48>(pl, prm, stream) : launch_att2<64>(pl, prm, stream);
+  if (pl->qt == 2) {
+    if (pl->resident) return pl->dpv == 48 ? launch_att2<48, true>(pl, prm, stream) : launch_att2<64, true>(pl, prm, stream);
+    return pl->dpv == 48 ? launch_att2<48, false>(pl, prm, stream) : launch_att2<64, false>(pl, prm, stream);
+  }
   switch (pl->dpv) {
     case 48: return launch_att<48>(pl, prm, stream);
     case 64: return launch_att<64>(pl, prm, stream);

@@ -21,7 +21,10 @@ def _rel(got, ref):
                                           # two-tile kernel (d <= 64, more than 128 queries): odd tile counts, ragged
                                           # last tile / last key sub-tile, one key sub-tile, exactly two tiles
                                           (1, 2, 384, 320, 64), (2, 3, 197, 197, 64), (1, 2, 300, 77, 40),
-                                          (1, 1, 256, 1024, 48), (1, 1, 640, 640, 40), (1, 3, 129, 64, 16)])
+                                          (1, 1, 256, 1024, 48), (1, 1, 640, 640, 40), (1, 3, 129, 64, 16),
+                                          # resident-K/V form (<= 128 keys, >= 8 query tiles): odd tile count, one / two
+                                          # full key sub-tiles, ragged keys
+                                          (1, 2, 1152, 100, 64), (1, 1, 1024, 64, 40), (2, 3, 2048, 128, 48)])
 def test_attention(cuda, B, H, Sq, Sk, d):
     from sonicdiffusionbayeslab_b200 import kernels as k
 
