@@ -135,6 +135,11 @@ int sonic_upsample2x(const void* x, void* y, int32_t n_img, int32_t H, int32_t W
                      sonic_stream_t stream);
 int sonic_im2col_s2(const void* x, void* y, int32_t n_img, int32_t H, int32_t W, int32_t C,
                     sonic_stream_t stream);
+/* y[n_img*(H/stride)*(W/stride), 9*C] = 3x3 patches (tap-major, zero padding 1) of NHWC x; stride 1 or 2.  Stride 1
+ * feeds conv_in (4 -> 8 padded input channels: nine 16-byte TMA rows per pixel would be row-rate-bound, one
+ * 144-byte row is not); reference call site src/models.py:227-235 -> UNet2DConditionModel.conv_in. */
+int sonic_im2col3x3(const void* x, void* y, int32_t n_img, int32_t H, int32_t W, int32_t C, int32_t stride,
+                    sonic_stream_t stream);
 /* In-place row softmax of bf16 scores: x[r, :cols] = softmax(scale * x[r, :cols]); rows of pitch ld elements.
  * With two sonic_conv_gemm calls this is the single-head d=512 attention of the VAE decoder
  * (reference call site src/models.py:288-302 -> AutoencoderKL.decode). */
@@ -170,6 +175,8 @@ int sonic_plan_add_upsample2x(sonic_plan_t plan, const void* x, void* y, int32_t
                               int32_t W, int32_t C);
 int sonic_plan_add_im2col_s2(sonic_plan_t plan, const void* x, void* y, int32_t n_img, int32_t H,
                              int32_t W, int32_t C);
+int sonic_plan_add_im2col3x3(sonic_plan_t plan, const void* x, void* y, int32_t n_img, int32_t H,
+                             int32_t W, int32_t C, int32_t stride);
 /* out[dim] = [cos(t f_j) | sin(t f_j)], t read from DEVICE memory at run time (graph-safe). */
 int sonic_plan_add_timestep_embedding(sonic_plan_t plan, const float* t_dev, int32_t dim, float* out);
 /* Batched M=1 GEMV: y_j = bias_j + add_j + W_j[N_j x K] * act(x), act = SiLU if silu_in.

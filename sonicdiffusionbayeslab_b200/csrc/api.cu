@@ -98,7 +98,12 @@ int sonic_upsample2x(const void* x, void* y, int32_t n_img, int32_t H, int32_t W
 }
 int sonic_im2col_s2(const void* x, void* y, int32_t n_img, int32_t H, int32_t W, int32_t C,
                     sonic_stream_t stream) {
-  return im2col_s2_launch(x, y, n_img, H, W, C, static_cast<cudaStream_t>(stream));
+  return im2col3x3_launch(x, y, n_img, H, W, C, 2, static_cast<cudaStream_t>(stream));
+}
+
+int sonic_im2col3x3(const void* x, void* y, int32_t n_img, int32_t H, int32_t W, int32_t C, int32_t stride,
+                    sonic_stream_t stream) {
+  return im2col3x3_launch(x, y, n_img, H, W, C, stride, static_cast<cudaStream_t>(stream));
 }
 
 int sonic_softmax_rows(void* x, int32_t rows, int32_t cols, int64_t ld, float scale, sonic_stream_t stream) {

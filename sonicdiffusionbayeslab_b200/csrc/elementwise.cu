@@ -4,7 +4,7 @@
 //                     + history write, one pass, fp32 math, one rounding per output.
 //     Replaces /root/reference/src/models.py:238-242 + :253-255 (scheduler.step) and the
 //     10-25 tiny ATen launches per step they cause.
-//   * layout helpers (NCHW<->NHWC, nearest 2x upsample, stride-2 im2col) and the M=1 GEMVs of
+//   * layout helpers (NCHW<->NHWC, nearest 2x upsample, 3x3 im2col for the stride-2 and the 8-channel input convolutions) and the M=1 GEMVs of
 //     the timestep-embedding path.
 #include "ops.cuh"
 
@@ -157,9 +157,9 @@ __global__ void upsample2x_kernel(const uint4* __restrict__ x, uint4* __restrict
   }
 }
 
-__global__ void im2col_s2_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int n_img, int H, int W,
-                                 int vpp) {
-  const int Ho = H / 2, Wo = W / 2;
+__global__ void im2col3x3_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int n_img, int H, int W,
+                                 int vpp, int stride) {
+  const int Ho = H / stride, Wo = W / stride;
   const long total = static_cast<long>(n_img) * Ho * Wo * 9 * vpp;
   for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < total;
        i += static_cast<long>(gridDim.x) * blockDim.x) {
@@ -169,7 +169,7 @@ __global__ void im2col_s2_kernel(const uint4* __restrict__ x, uint4* __restrict_
     const int wo = static_cast<int>(r % Wo); r /= Wo;
     const int ho = static_cast<int>(r % Ho);
     const int img = static_cast<int>(r / Ho);
-    const int hi = 2 * ho + tap / 3 - 1, wi = 2 * wo + tap % 3 - 1;
+    const int hi = stride * ho + tap / 3 - 1, wi = stride * wo + tap % 3 - 1;
     uint4 u = make_uint4(0, 0, 0, 0);
     if (hi >= 0 && hi < H && wi >= 0 && wi < W)
       u = __ldg(x + ((static_cast<long>(img) * H + hi) * W + wi) * vpp + v);
@@ -337,12 +337,13 @@ int upsample2x_launch(const void* x, void* y, int n_img, int H, int W, int C, cu
   return 0;
 }
 
-int im2col_s2_launch(const void* x, void* y, int n_img, int H, int W, int C, cudaStream_t stream) {
-  SONIC_REQUIRE(C % 8 == 0 && H % 2 == 0 && W % 2 == 0, "im2col_s2: bad shape");
-  const long total = static_cast<long>(n_img) * (H / 2) * (W / 2) * 9 * (C / 8);
+int im2col3x3_launch(const void* x, void* y, int n_img, int H, int W, int C, int stride, cudaStream_t stream) {
+  SONIC_REQUIRE(C % 8 == 0 && (stride == 1 || stride == 2) && H % stride == 0 && W % stride == 0,
+                "im2col3x3: bad shape / stride");
+  const long total = static_cast<long>(n_img) * (H / stride) * (W / stride) * 9 * (C / 8);
   const int blocks = static_cast<int>(std::min<long>((total + 255) / 256, 148L * 16));
-  im2col_s2_kernel<<<blocks, 256, 0, stream>>>(static_cast<const uint4*>(x), static_cast<uint4*>(y), n_img, H, W,
-                                               C / 8);
+  im2col3x3_kernel<<<blocks, 256, 0, stream>>>(static_cast<const uint4*>(x), static_cast<uint4*>(y), n_img, H, W,
+                                               C / 8, stride);
   SONIC_CUDA(cudaGetLastError());
   return 0;
 }

@@ -52,7 +52,7 @@ int upsample2x_launch(const void* x, void* y, int n_img, int H, int W, int C, cu
 // in place: x[r, :cols] = softmax(scale * x[r, :cols]) over bf16 rows of pitch ld
 int softmax_rows_launch(void* x, int rows, int cols, long ld, float scale, cudaStream_t stream);
 // stride-2, pad-1 3x3 patches: y[n][ho][wo][tap*C + c]  (Ho = H/2, Wo = W/2)
-int im2col_s2_launch(const void* x, void* y, int n_img, int H, int W, int C, cudaStream_t stream);
+int im2col3x3_launch(const void* x, void* y, int n_img, int H, int W, int C, int stride, cudaStream_t stream);
 
 // Batched GEMV for the timestep path: for every job j, y_j[n] = b_j[n] + add_j[n] + sum_k W_j[n][k]*act(x[k]).
 struct GemvJob {

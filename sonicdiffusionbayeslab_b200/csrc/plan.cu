@@ -58,7 +58,7 @@ static int run_ops(const Plan& plan, cudaStream_t s) {
       case PlanOp::kToNhwc8: rc = nchw_to_nhwc8_launch(op.src, op.i0, op.i1, op.i2, op.i3, op.i4, op.dst, s); break;
       case PlanOp::kToNchw: rc = nhwc_to_nchw_launch(op.src, op.i0, op.i1, op.i2, op.i3, op.dst, op.i4, s); break;
       case PlanOp::kUpsample: rc = upsample2x_launch(op.src, op.dst, op.i0, op.i1, op.i2, op.i3, s); break;
-      case PlanOp::kIm2col: rc = im2col_s2_launch(op.src, op.dst, op.i0, op.i1, op.i2, op.i3, s); break;
+      case PlanOp::kIm2col: rc = im2col3x3_launch(op.src, op.dst, op.i0, op.i1, op.i2, op.i3, op.i4, s); break;
       case PlanOp::kTimeEmb: rc = timestep_embedding_launch(op.f0, op.i0, static_cast<float*>(op.dst), s); break;
       case PlanOp::kGemv: rc = gemv_batched_launch(op.jobs_dev, op.i0, op.i1, op.f0, op.i2, op.i3, s); break;
       case PlanOp::kSoftmaxRows: rc = softmax_rows_launch(op.dst, op.i0, op.i1, op.l0, op.eps, s); break;
@@ -200,12 +200,23 @@ int sonic_plan_add_upsample2x(sonic_plan_t h, const void* x, void* y, int32_t n_
   return 0;
 }
 
+int sonic_plan_add_im2col3x3(sonic_plan_t h, const void* x, void* y, int32_t n_img, int32_t H, int32_t W,
+                             int32_t C, int32_t stride) {
+  SONIC_REQUIRE(h && x && y && (stride == 1 || stride == 2), "sonic_plan_add_im2col3x3: bad argument");
+  PlanOp p;
+  p.kind = PlanOp::kIm2col;
+  p.src = x; p.dst = y; p.i0 = n_img; p.i1 = H; p.i2 = W; p.i3 = C; p.i4 = stride;
+  static_cast<Plan*>(h)->launches += 1;
+  static_cast<Plan*>(h)->ops.push_back(p);
+  return 0;
+}
+
 int sonic_plan_add_im2col_s2(sonic_plan_t h, const void* x, void* y, int32_t n_img, int32_t H, int32_t W,
                              int32_t C) {
   SONIC_REQUIRE(h && x && y, "sonic_plan_add_im2col_s2: null argument");
   PlanOp p;
   p.kind = PlanOp::kIm2col;
-  p.src = x; p.dst = y; p.i0 = n_img; p.i1 = H; p.i2 = W; p.i3 = C;
+  p.src = x; p.dst = y; p.i0 = n_img; p.i1 = H; p.i2 = W; p.i3 = C; p.i4 = 2;
   static_cast<Plan*>(h)->launches += 1;
   static_cast<Plan*>(h)->ops.push_back(p);
   return 0;
