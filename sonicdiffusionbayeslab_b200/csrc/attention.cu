@@ -61,6 +61,8 @@ struct AttParams {
   int ld_o, seq_q, seq_k, head_dim, atoms, causal;
   float scale_log2;
   uint32_t idesc_s, idesc_pv;
+  int tail_w;              // keys of the last sub-tile rounded up to 16 / 32 / 64: its S, softmax and PV only span these
+  uint32_t idesc_s_tail;   // S product of the last sub-tile (N = tail_w)
 };
 
 #ifdef SONIC_ATT_TRACE
@@ -332,7 +334,9 @@ constexpr int kStages2 = 4;
 // (TMEM allocation, barrier set-up, the first Q / K / V loads from HBM, the output stores): 126 us for 0.1 ms of
 // arithmetic-free work.  Here those costs are paid once per head and the next pair's Q is in flight while the
 // current one is processed.
-template <int kDPV, bool kResident>
+// kNarrow: the last key sub-tile is ragged and spans only 16 or 32 columns (77 keys: 64 + 16).  A template flag because
+// the extra selects cost the full-width instantiation 4.7 % (1.433 -> 1.500 ms on the 4096-token self-attention).
+template <int kDPV, bool kResident, bool kNarrow>
 __global__ void __launch_bounds__(kAttThreads, 2)
 attention2_kernel(const __grid_constant__ AttParams p) {
   static_assert(kSub + kDPV <= 128, "S/P + O of one query tile must fit 128 TMEM columns");
@@ -414,13 +418,14 @@ attention2_kernel(const __grid_constant__ AttParams p) {
     const uint64_t k_desc0 = make_sw128_desc(smem_u32(sm_k), 16, 1024);
     const uint64_t v_desc0 = make_sw128_desc(smem_u32(sm_v), kKvAtomBytes, 1024);
     constexpr int kMaxKS = (kDPV + 15) / 16;
-    auto issue_s = [&](int qs, int q, int st) {    // S_q = Q_q K^T of the K tile in stage st
+    auto issue_s = [&](int qs, int q, int st, bool last) {   // S_q = Q_q K^T of the K tile in stage st
       const uint64_t qd = q_desc0 + static_cast<uint64_t>(((qs * 2 + q) * kQAtomBytes) >> 4);
       const uint64_t kd = k_desc0 + static_cast<uint64_t>((st * kKvAtomBytes) >> 4);
+      const uint32_t idesc = kNarrow && last ? p.idesc_s_tail : p.idesc_s;   // a ragged last sub-tile only spans tail_w keys
       if (leader) {
 #pragma unroll
         for (int ks = 0; ks < kMaxKS; ++ks)
-          if (ks < k_steps_s) umma_bf16_ss(tmem_base + q * 128, qd + ((ks * 32) >> 4), kd + ((ks * 32) >> 4), p.idesc_s, ks != 0);
+          if (ks < k_steps_s) umma_bf16_ss(tmem_base + q * 128, qd + ((ks * 32) >> 4), kd + ((ks * 32) >> 4), idesc, ks != 0);
         umma_commit(&s_full[q]);
       }
       __syncwarp();
@@ -432,7 +437,7 @@ attention2_kernel(const __grid_constant__ AttParams p) {
       mbar_wait(&q_full[qs], (i / kQStages) & 1);
       mbar_wait(&k_full[0], 0);
       tc_fence_after();
-      for (int q = 0; q < nq; ++q) issue_s(qs, q, 0);
+      for (int q = 0; q < nq; ++q) issue_s(qs, q, 0, n_sub == 1);
       if (leader) {
         if (!kResident) umma_commit(&k_empty[0]);
         if (n_sub == 1) umma_commit(&q_empty[qs]);
@@ -448,17 +453,18 @@ attention2_kernel(const __grid_constant__ AttParams p) {
           tc_fence_after();
           const uint32_t ts = tmem_base + q * 128;
           const uint64_t vd = v_desc0 + static_cast<uint64_t>((st * kKvAtomBytes) >> 4);
+          const int pv_steps = !kNarrow || more ? kSub / 16 : p.tail_w / 16;
           if (leader) {
 #pragma unroll
             for (int ks = 0; ks < kSub / 16; ++ks)
-              umma_bf16_ts(ts + kSub, ts + ks * 8, vd + ks * (2048 >> 4), p.idesc_pv, (t | ks) != 0);
+              if (!kNarrow || ks < pv_steps) umma_bf16_ts(ts + kSub, ts + ks * 8, vd + ks * (2048 >> 4), p.idesc_pv, (t | ks) != 0);
             if (!kResident && q == nq - 1) umma_commit(&v_empty[st]);
             if (!more && q == nq - 1) umma_commit(o_done);
           }
           __syncwarp();
           if (more) {
             if (q == 0) { mbar_wait(&k_full[st1], kResident ? 0 : ((t + 1) / kKvStages) & 1); tc_fence_after(); }
-            issue_s(qs, q, st1);
+            issue_s(qs, q, st1, t + 2 == n_sub);
             if (q == nq - 1) {
               if (leader) {
                 if (!kResident) umma_commit(&k_empty[st1]);
@@ -475,14 +481,17 @@ attention2_kernel(const __grid_constant__ AttParams p) {
     const uint32_t lane_addr = static_cast<uint32_t>(warp * 32) << 16;
     const float lazy_raw = kLazyLog2 / p.scale_log2;
 
-    auto softmax_sub = [&](float& m_r, float& l_r, uint32_t t_s, int t, auto mask_tag, int valid) {
+    auto softmax_sub = [&](float& m_r, float& l_r, uint32_t t_s, int t, auto mask_tag, auto width_tag, int valid) {
       constexpr bool kMask = decltype(mask_tag)::value;
-      uint32_t v[kSub];
-      tmem_ld64(t_s, v);
+      constexpr int kW = decltype(width_tag)::value;     // score columns of this sub-tile: 64, or a ragged tail's 16 / 32
+      uint32_t v[kW];
+      if constexpr (kW == 64) tmem_ld64(t_s, v);
+      else if constexpr (kW == 32) tmem_ld32(t_s, v);
+      else tmem_ld16(t_s, v);
       tmem_ld_wait();
       float tm[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-      for (int i = 0; i < kSub; ++i)
+      for (int i = 0; i < kW; ++i)
         if (!kMask || i < valid) tm[i & 3] = fmaxf(tm[i & 3], __uint_as_float(v[i]));
       const float tmax = fmaxf(fmaxf(tm[0], tm[1]), fmaxf(tm[2], tm[3]));
       if (__any_sync(0xffffffffu, tmax > m_r + lazy_raw)) {
@@ -506,9 +515,9 @@ attention2_kernel(const __grid_constant__ AttParams p) {
       }
       const float m_scaled = m_r * p.scale_log2;
       float ps[4] = {0.f, 0.f, 0.f, 0.f};
-      uint32_t pk[kSub / 2];
+      uint32_t pk[kW / 2];
 #pragma unroll
-      for (int i = 0; i < kSub; i += 2) {
+      for (int i = 0; i < kW; i += 2) {
         float e0 = fast_exp2(fmaf(__uint_as_float(v[i]), p.scale_log2, -m_scaled));
         float e1 = fast_exp2(fmaf(__uint_as_float(v[i + 1]), p.scale_log2, -m_scaled));
         if (kMask && i >= valid) e0 = 0.f;
@@ -516,7 +525,9 @@ attention2_kernel(const __grid_constant__ AttParams p) {
         ps[(i >> 1) & 3] += e0 + e1;
         pk[i >> 1] = pack_bf16(e0, e1);
       }
-      tmem_st32(t_s, pk);
+      if constexpr (kW == 64) tmem_st32(t_s, pk);
+      else if constexpr (kW == 32) tmem_st16(t_s, pk);
+      else tmem_st8(t_s, pk);
       l_r += (ps[0] + ps[1]) + (ps[2] + ps[3]);
     };
 
@@ -534,8 +545,12 @@ attention2_kernel(const __grid_constant__ AttParams p) {
             const uint32_t t_s = tmem_base + q * 128 + lane_addr;
             mbar_wait<64>(&s_full[q], n_item & 1);
             tc_fence_after();
-            if (__all_sync(0xffffffffu, valid >= kSub)) softmax_sub(m_run[q], l_run[q], t_s, t, std::false_type{}, kSub);
-            else softmax_sub(m_run[q], l_run[q], t_s, t, std::true_type{}, valid);
+            using W64 = std::integral_constant<int, 64>;
+            const int w = kNarrow && t + 1 == n_sub ? p.tail_w : kSub;
+            if (kNarrow && w == 16) softmax_sub(m_run[q], l_run[q], t_s, t, std::true_type{}, std::integral_constant<int, 16>{}, valid);
+            else if (kNarrow && w == 32) softmax_sub(m_run[q], l_run[q], t_s, t, std::true_type{}, std::integral_constant<int, 32>{}, valid);
+            else if (__all_sync(0xffffffffu, valid >= kSub)) softmax_sub(m_run[q], l_run[q], t_s, t, std::false_type{}, W64{}, kSub);
+            else softmax_sub(m_run[q], l_run[q], t_s, t, std::true_type{}, W64{}, valid);
             tmem_st_wait();
             tc_fence_before();
             __syncwarp();
@@ -586,17 +601,24 @@ attention2_kernel(const __grid_constant__ AttParams p) {
   }
 }
 
-template <int kDPV, bool kResident>
+template <int kDPV, bool kResident, bool kNarrow>
 int launch_att2(const AttentionPlan* pl, const AttParams& prm, cudaStream_t stream) {
   static bool attr_set = false;
   if (!attr_set) {
-    SONIC_CUDA(cudaFuncSetAttribute(attention2_kernel<kDPV, kResident>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    227 * 1024));
+    SONIC_CUDA(cudaFuncSetAttribute(attention2_kernel<kDPV, kResident, kNarrow>,
+                                    cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  attention2_kernel<kDPV, kResident><<<pl->grid, kAttThreads, pl->smem, stream>>>(prm);
+  attention2_kernel<kDPV, kResident, kNarrow><<<pl->grid, kAttThreads, pl->smem, stream>>>(prm);
   SONIC_CUDA(cudaGetLastError());
   return 0;
+}
+
+template <int kDPV>
+int dispatch_att2(const AttentionPlan* pl, const AttParams& prm, cudaStream_t stream) {
+  const bool narrow = prm.tail_w < kSub;
+  if (pl->resident) return narrow ? launch_att2<kDPV, true, true>(pl, prm, stream) : launch_att2<kDPV, true, false>(pl, prm, stream);
+  return narrow ? launch_att2<kDPV, false, true>(pl, prm, stream) : launch_att2<kDPV, false, false>(pl, prm, stream);
 }
 
 template <int kDPV>
@@ -677,11 +699,11 @@ int attention_launch(const AttentionPlan* pl, cudaStream_t stream) {
   prm.causal = op.causal;
   prm.scale_log2 = op.scale * 1.4426950408889634f;
   prm.idesc_s = make_idesc_bf16(kBlockQ, kSub, false);
+  const int tail = op.seq_k - (op.seq_k - 1) / kSub * kSub;          // 1 .. 64 keys in the last sub-tile
+  prm.tail_w = tail <= 16 ? 16 : tail <= 32 ? 32 : kSub;
+  prm.idesc_s_tail = make_idesc_bf16(kBlockQ, prm.tail_w, false);
   prm.idesc_pv = make_idesc_bf16(kBlockQ, pl->dpv, true);
-  if (pl->qt == 2) {
-    if (pl->resident) return pl->dpv == 48 ? launch_att2<48, true>(pl, prm, stream) : launch_att2<64, true>(pl, prm, stream);
-    return pl->dpv == 48 ? launch_att2<48, false>(pl, prm, stream) : launch_att2<64, false>(pl, prm, stream);
-  }
+  if (pl->qt == 2) return pl->dpv == 48 ? dispatch_att2<48>(pl, prm, stream) : dispatch_att2<64>(pl, prm, stream);
   switch (pl->dpv) {
     case 48: return launch_att<48>(pl, prm, stream);
     case 64: return launch_att<64>(pl, prm, stream);

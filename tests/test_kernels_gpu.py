@@ -24,7 +24,9 @@ def _rel(got, ref):
                                           (1, 1, 256, 1024, 48), (1, 1, 640, 640, 40), (1, 3, 129, 64, 16),
                                           # resident-K/V form (<= 128 keys, >= 8 query tiles): odd tile count, one / two
                                           # full key sub-tiles, ragged keys
-                                          (1, 2, 1152, 100, 64), (1, 1, 1024, 64, 40), (2, 3, 2048, 128, 48)])
+                                          (1, 2, 1152, 100, 64), (1, 1, 1024, 64, 40), (2, 3, 2048, 128, 48),
+                                          # ragged last key sub-tile narrowed to 16 / 32 columns
+                                          (1, 1, 256, 80, 40), (1, 2, 256, 96, 64), (1, 1, 1024, 90, 40)])
 def test_attention(cuda, B, H, Sq, Sk, d):
     from sonicdiffusionbayeslab_b200 import kernels as k
 

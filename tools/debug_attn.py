@@ -39,7 +39,7 @@ for cfg in [(1, 1, 128, 128, 64), (1, 1, 128, 128, 40), (1, 1, 128, 256, 64), (1
             (2, 8, 1024, 1024, 80), (1, 1, 256, 256, 40), (1, 2, 384, 320, 64), (2, 3, 197, 197, 64),
             (1, 2, 300, 77, 40), (2, 8, 4096, 4096, 40), (2, 8, 4096, 77, 40), (1, 1, 256, 1024, 48)]:
     run(*cfg)
-for cfg in [(1, 2, 1152, 100, 64), (1, 1, 1024, 64, 40), (2, 3, 2048, 128, 48), (1, 1, 1280, 77, 16)]:
+for cfg in [(1, 1, 256, 80, 40), (1, 2, 256, 96, 64), (1, 1, 1024, 90, 40), (1, 2, 1152, 100, 64), (1, 1, 1024, 64, 40), (2, 3, 2048, 128, 48), (1, 1, 1280, 77, 16)]:
     run(*cfg)
 run(2, 4, 200, 200, 64, causal=True)
 run(1, 2, 512, 512, 40, causal=True)
