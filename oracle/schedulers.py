@@ -226,7 +226,7 @@ class DPMSolverScheduler(_SchedulerBase):
             else:
                 ratio = T / num_inference_steps
                 ts = np.arange(last, 0, -ratio).round().copy().astype(np.int64) - 1
-        sig = np.array(((1 - self.alphas_cumprod) / self.alphas_cumprod) ** 0.5)
+        sig = (((1 - self.alphas_cumprod) / self.alphas_cumprod) ** 0.5).numpy()
         sig = np.interp(ts, np.arange(0, len(sig)), sig)
         if self.config.final_sigmas_type == "sigma_min":
             last_sigma = float(((1 - self.alphas_cumprod[0]) / self.alphas_cumprod[0]) ** 0.5)

@@ -269,7 +269,7 @@ class DPMSolverScheduler(FusedScheduler):
                 ts = np.arange(last, 0, -T / num_inference_steps).round().copy().astype(np.int64) - 1
             else:
                 raise ValueError(f"{cfg.timestep_spacing} is not supported")
-        sig = np.array(((1 - self.alphas_cumprod) / self.alphas_cumprod) ** 0.5)
+        sig = (((1 - self.alphas_cumprod) / self.alphas_cumprod) ** 0.5).numpy()
         sig = np.interp(ts, np.arange(0, len(sig)), sig)
         if cfg.final_sigmas_type == "sigma_min":
             sigma_last = float(((1 - self.alphas_cumprod[0]) / self.alphas_cumprod[0]) ** 0.5)
