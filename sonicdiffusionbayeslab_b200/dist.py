@@ -83,6 +83,11 @@ def all_reduce_metric(metric):
     if not dist.is_initialized() or dist.get_world_size() == 1:
         return metric
     t = metric.state_tensor()
-    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    if dist.get_backend() == "nccl" and not t.is_cuda:           # NCCL reduces device tensors only (host-side metrics)
+        t_dev = t.to(torch.device("cuda", torch.cuda.current_device()))
+        dist.all_reduce(t_dev, op=dist.ReduceOp.SUM)
+        t = t_dev.to(t.device)
+    else:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
     metric.load_state_tensor(t)
     return metric
