@@ -4,8 +4,11 @@
 // h*D) through strided 4-D TMA tensor maps; head dims that are not a multiple of 64 (40, 80,
 // 160) are zero-filled by the TMA unit, never padded in HBM.
 //
-// One CTA = one 128-row query tile of one (batch, head).  Keys are consumed in sub-tiles of 64 and
-// everything between the two GEMMs lives in tensor memory:
+// Two kernels share the scheme below.  attention_kernel: one CTA = one 128-row query tile of one (batch, head)
+// (head dims 80 / 160, or at most 128 queries).  attention2_kernel (head dims <= 64, further down): one CTA owns TWO
+// query tiles and ping-pongs between them, optionally with K / V resident in shared memory for short key sequences;
+// it is the one the 64x64 UNet level and the CLIP towers run on.
+// Keys are consumed in sub-tiles of 64 and everything between the two GEMMs lives in tensor memory:
 //   TMEM columns  [0, 64)        S = Q K^T scores of a sub-tile, fp32; once a thread has read its row it
 //                                overwrites columns [0, 32) with P = exp2(...) as bf16 pairs -- the A operand
 //                                of the PV product, read by the tensor core straight from TMEM (".ts" MMA)
