@@ -6,7 +6,7 @@
 Same op order and dtypes as the reference: latents duplicated with ``torch.cat``, UNet call,
 ``uncond + g * (text - uncond)`` in the model dtype, ``scheduler.step``.  Optional DeepCache via
 ``oracle.deepcache.DeepCacheOracle`` and teacher forcing (``forced_latents``) for parity tests.
-PARITY UNPINNED (see oracle/__init__.py).
+Pinned against the reference's own source where it has one (oracle/refexec.py; see oracle/__init__.py).
 """
 from __future__ import annotations
 
@@ -38,10 +38,15 @@ def _extra(scheduler, generator, eta):
 
 @torch.no_grad()
 def denoise(unet, scheduler, prompt_embeds, negative_prompt_embeds, latents, num_inference_steps,
-            guidance_scale=7.5, generator=None, eta=0.0, deepcache=None, forced_latents=None):
-    """Returns dict(latents=final, per_step=[latents after each step], x0=[x0 preds], timesteps=[...]).
+            guidance_scale=7.5, generator=None, eta=0.0, deepcache=None, forced_latents=None, skip_timesteps=None):
+    """Returns dict(latents=final, per_step=[latents after each EXECUTED step], x0=[x0 preds], timesteps=[...],
+    timesteps_run=[timesteps of the executed steps]).
 
-    ``forced_latents[i]`` (if given) replaces the loop's latents before step i (teacher forcing)."""
+    ``forced_latents[i]`` (if given) replaces the loop's latents before step i (teacher forcing).
+    ``skip_timesteps``: loop INDICES that are skipped entirely -- no UNet call, no scheduler step, so a multistep
+    scheduler's own step counter falls behind the grid exactly as in the reference
+    (/root/reference/src/models.py:1220-1223,1338-1340, ``StableDiffusionModelSkipTimesteps``)."""
+    skip = set(skip_timesteps) if skip_timesteps is not None else set()
     do_cfg = guidance_scale > 1
     ctx = torch.cat([negative_prompt_embeds, prompt_embeds]) if do_cfg else prompt_embeds
     device = latents.device
@@ -50,10 +55,13 @@ def denoise(unet, scheduler, prompt_embeds, negative_prompt_embeds, latents, num
     t_list = [int(t) for t in timesteps.tolist()]
     latents = latents * scheduler.init_noise_sigma
     extra = _extra(scheduler, generator, eta)
-    per_step, x0s = [], []
+    per_step, x0s, ran = [], [], []
     if deepcache is not None:
         deepcache.reset()
     for i, t in enumerate(timesteps):
+        if i in skip:
+            continue
+        ran.append(int(t))
         if forced_latents is not None:
             latents = forced_latents[i]
         x_in = torch.cat([latents] * 2) if do_cfg else latents
@@ -70,7 +78,7 @@ def denoise(unet, scheduler, prompt_embeds, negative_prompt_embeds, latents, num
         if len(step) == 2:
             x0s.append(step[1][0].unsqueeze(0))
         per_step.append(latents)
-    return dict(latents=latents, per_step=per_step, x0=x0s, timesteps=t_list)
+    return dict(latents=latents, per_step=per_step, x0=x0s, timesteps=t_list, timesteps_run=ran)
 
 
 def switch_timestamp(timesteps_first, timesteps_second, num_step_switch, type_switch="closest"):

@@ -12,7 +12,7 @@ diffusers 0.32.1 (absent from /root/reference; pinned at poetry.lock:454-455):
 Every tensor op is kept as a separate ATen op in the same order and dtype as the
 published algorithm, so per-op rounding (model dtype for DDIM/LCM/PNDM, the fp32
 upcast of schedulers.py:133 for DPM) is reproduced.  Scalars are 0-dim float32 CPU
-tensors exactly as diffusers holds them.  PARITY UNPINNED (see oracle/__init__.py).
+tensors exactly as diffusers holds them.  Pinned against the reference's own source where it has one (oracle/refexec.py; see oracle/__init__.py).
 """
 from __future__ import annotations
 

@@ -1,0 +1,44 @@
+"""The product's fused scheduler step (ONE ``sonic_latent_update`` launch per step, through the C ABI) against
+the fixtures that executing the REFERENCE'S OWN ``DPMSolverScheduler.step`` / ``convert_model_output`` produced
+(/root/reference/src/schedulers.py:14-187 via oracle/refexec.py; tests/golden/make_reference_pins.py).
+
+Tolerance (BASELINE.json north_star): fp32 I/O max-abs <= 1e-4; bf16 I/O max-abs <= 2e-2 relative to
+max(1, |x|max) of the tensor (the synthetic trajectory reaches |x0| ~ 20, where one bf16 ulp is 0.125).
+Teacher-forced from the fixture after every step, so kernel error does not compound through the recursion.
+"""
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+
+import refpin_cases as RC  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+PINS = np.load(os.path.join(HERE, "golden", "reference_pins.npz"))
+META = json.load(open(os.path.join(HERE, "golden", "reference_pins.json")))
+
+
+@pytest.mark.parametrize("name", list(RC.SCHEDULER_CASES))
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-4), (torch.bfloat16, 2e-2)])
+def test_fused_step_matches_reference_source(cuda, name, dtype, tol):
+    from sonicdiffusionbayeslab_b200 import schedulers as S
+
+    kind, over, n, patch, seed = RC.SCHEDULER_CASES[name]
+    want_prev = torch.from_numpy(PINS[f"sched/{name}/prev"])
+    want_x0 = torch.from_numpy(PINS[f"sched/{name}/x0"])
+    sched = RC.make_scheduler(kind, over, module=S)
+    prevs, x0s, ts = RC.run_scheduler_case(sched, n, seed, device=cuda, dtype=dtype, teacher=list(want_prev))
+    assert ts == META["scheduler_timesteps"][name]                 # integer schedule: bit-exact
+    worst = 0.0
+    for got, want in list(zip(prevs, want_prev)) + list(zip(x0s, want_x0)):
+        scale = max(1.0, want.abs().max().item()) if dtype == torch.bfloat16 else 1.0
+        worst = max(worst, (got.float().cpu() - want).abs().max().item() / scale)
+    print(f"\n[{name} {dtype}] fused step vs reference source: max-abs {worst:.3e}")
+    assert worst <= tol, (name, dtype, worst)
