@@ -125,6 +125,13 @@ int sonic_latent_update(const sonic_update_coeffs* k, const void* eps_uncond, co
                         const void* sample, const void* h1, const void* h2, const void* h3,
                         const void* noise, void* out_sample, void* out_m0, void* out_x0, int64_t n,
                         int32_t dtype, sonic_stream_t stream);
+/* Same launch, but only the first n_x0 elements of x0 are written (n_x0 a multiple of 8): the reference keeps
+ * x0_pred[0] only (src/models.py:257-261 `x0_preds.append(x0_pred[0].unsqueeze(0))`), so the pipelines pass one
+ * image's worth and save the other B-1 writes. */
+int sonic_latent_update_x0n(const sonic_update_coeffs* k, const void* eps_uncond, const void* eps_text,
+                            const void* sample, const void* h1, const void* h2, const void* h3,
+                            const void* noise, void* out_sample, void* out_m0, void* out_x0, int64_t n,
+                            int64_t n_x0, int32_t dtype, sonic_stream_t stream);
 
 /* Layout helpers used around the UNet (exposed for tests). */
 int sonic_nchw_to_nhwc8(const void* x, int32_t dtype, int32_t n_img, int32_t C, int32_t hw,

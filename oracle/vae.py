@@ -1,9 +1,11 @@
-"""VAE decoder used after the denoising loop (/root/reference/src/models.py:288-302).
+"""Oracle VAE decoder: PyTorch restatement of diffusers ``AutoencoderKL.decode`` (SD-v1 config).
 
-The decode is OUTSIDE the reference's timed region (models.py:208,284-285) and is row (f)-1
-("next") of SURVEY.md section 8: it stays a plain PyTorch module for now (library kernels, bf16),
-with diffusers' ``AutoencoderKL`` state-dict key names so a real SD-v1.5 ``vae`` checkpoint
-loads unchanged.  Architecture: SURVEY.md appendix A.8.
+TEST INFRASTRUCTURE ONLY (see oracle/__init__.py): the checker of the native decoder
+(sonicdiffusionbayeslab_b200/vae_engine.py) and the stock-PyTorch (cuDNN) timing baseline.  The
+reference calls ``self.vae.decode`` at /root/reference/src/models.py:288-302; the module lives in
+diffusers 0.32.1 (absent), so the published architecture is restated with
+diffusers' state-dict key names -- the same names ``sonicdiffusionbayeslab_b200/vae_spec.py`` lists,
+so one state dict feeds both.  UNPINNED (third-party layer).
 """
 from __future__ import annotations
 

@@ -12,6 +12,8 @@ import yaml
 # keys read by attribute in the reference drivers but absent from configs/*.yaml
 DEFAULTS = {
     "dpm_solver": {"experiment_params": {"algorithm_type": "dpmsolver++", "final_sigmas_type": "zero"}},
+    "skip_steps": {"experiment_params": {"solver_order": 2, "algorithm_type": "dpmsolver++",
+                                         "final_sigmas_type": "zero"}},
 }
 
 

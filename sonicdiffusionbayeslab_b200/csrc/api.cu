@@ -81,7 +81,19 @@ int sonic_latent_update(const sonic_update_coeffs* k, const void* eps_uncond, co
   UpdateCoeffs c{k->guidance, k->m_x, k->m_e, k->x0_x, k->x0_e, k->c_x, k->c_e, k->c_m0, k->c_h1, k->c_h2,
                  k->c_h3, k->c_z};
   return latent_update_launch(c, eps_uncond, eps_text, sample, h1, h2, h3, noise, out_sample, out_m0, out_x0,
-                              static_cast<long>(n), dtype, static_cast<cudaStream_t>(stream));
+                              static_cast<long>(n), static_cast<long>(n), dtype, static_cast<cudaStream_t>(stream));
+}
+
+int sonic_latent_update_x0n(const sonic_update_coeffs* k, const void* eps_uncond, const void* eps_text,
+                            const void* sample, const void* h1, const void* h2, const void* h3, const void* noise,
+                            void* out_sample, void* out_m0, void* out_x0, int64_t n, int64_t n_x0, int32_t dtype,
+                            sonic_stream_t stream) {
+  SONIC_REQUIRE(k != nullptr, "sonic_latent_update_x0n: null coefficients");
+  UpdateCoeffs c{k->guidance, k->m_x, k->m_e, k->x0_x, k->x0_e, k->c_x, k->c_e, k->c_m0, k->c_h1, k->c_h2,
+                 k->c_h3, k->c_z};
+  return latent_update_launch(c, eps_uncond, eps_text, sample, h1, h2, h3, noise, out_sample, out_m0, out_x0,
+                              static_cast<long>(n), static_cast<long>(n_x0), dtype,
+                              static_cast<cudaStream_t>(stream));
 }
 
 int sonic_nchw_to_nhwc8(const void* x, int32_t dtype, int32_t n_img, int32_t C, int32_t hw, int32_t dup, void* y,

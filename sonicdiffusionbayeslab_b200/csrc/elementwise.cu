@@ -19,17 +19,30 @@ template <> struct Vec8<float> {
     const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
     f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
   }
+  // plain (coherent) load: for tensors an OUTPUT of the same launch may alias (sample / history / noise).  The
+  // non-coherent path (ld.global.nc) is only defined for data no thread writes during the kernel.
+  static __device__ __forceinline__ void loadc(const float* p, float (&f)[8]) {
+    const float4 a = *reinterpret_cast<const float4*>(p);
+    const float4 b = *(reinterpret_cast<const float4*>(p) + 1);
+    f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+  }
   static __device__ __forceinline__ void store(float* p, const float (&f)[8]) {
     reinterpret_cast<float4*>(p)[0] = make_float4(f[0], f[1], f[2], f[3]);
     reinterpret_cast<float4*>(p)[1] = make_float4(f[4], f[5], f[6], f[7]);
   }
   static __device__ __forceinline__ float round(float x) { return x; }
-  static __device__ __forceinline__ float ld1(const float* p) { return __ldg(p); }
+  static __device__ __forceinline__ float ld1(const float* p) { return *p; }
   static __device__ __forceinline__ void st1(float* p, float v) { *p = v; }
 };
 template <> struct Vec8<__nv_bfloat16> {
   static __device__ __forceinline__ void load(const __nv_bfloat16* p, float (&f)[8]) {
     const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+    const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { f[2 * j] = bf16_lo(w[j]); f[2 * j + 1] = bf16_hi(w[j]); }
+  }
+  static __device__ __forceinline__ void loadc(const __nv_bfloat16* p, float (&f)[8]) {
+    const uint4 u = *reinterpret_cast<const uint4*>(p);
     const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
     for (int j = 0; j < 4; ++j) { f[2 * j] = bf16_lo(w[j]); f[2 * j + 1] = bf16_hi(w[j]); }
@@ -63,7 +76,7 @@ __device__ __forceinline__ void update_math(const UpdateCoeffs& k, bool cfg, flo
 
 template <typename T>
 __global__ void __launch_bounds__(256)
-latent_update_kernel(const UpdateCoeffs k, const UpdatePtrs<T> p, long n) {
+latent_update_kernel(const UpdateCoeffs k, const UpdatePtrs<T> p, long n, long n_x0) {
   const long nvec = n / 8;
   const bool cfg = p.et != nullptr;
   for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < nvec;
@@ -72,11 +85,11 @@ latent_update_kernel(const UpdateCoeffs k, const UpdatePtrs<T> p, long n) {
     float eu[8], et[8], x[8], h1[8], h2[8], h3[8], z[8];
     Vec8<T>::load(p.eu + o, eu);
     if (cfg) Vec8<T>::load(p.et + o, et);
-    Vec8<T>::load(p.x + o, x);
-    if (p.h1) Vec8<T>::load(p.h1 + o, h1);
-    if (p.h2) Vec8<T>::load(p.h2 + o, h2);
-    if (p.h3) Vec8<T>::load(p.h3 + o, h3);
-    if (p.z) Vec8<T>::load(p.z + o, z);
+    Vec8<T>::loadc(p.x + o, x);                    // may alias out_sample / out_m0: coherent loads
+    if (p.h1) Vec8<T>::loadc(p.h1 + o, h1);
+    if (p.h2) Vec8<T>::loadc(p.h2 + o, h2);
+    if (p.h3) Vec8<T>::loadc(p.h3 + o, h3);
+    if (p.z) Vec8<T>::loadc(p.z + o, z);
     float ox[8], om[8], o0[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j)
@@ -85,7 +98,7 @@ latent_update_kernel(const UpdateCoeffs k, const UpdatePtrs<T> p, long n) {
     // all loads of this vector precede the stores, so out_sample may alias sample / history
     if (p.ox) Vec8<T>::store(p.ox + o, ox);
     if (p.om) Vec8<T>::store(p.om + o, om);
-    if (p.o0) Vec8<T>::store(p.o0 + o, o0);
+    if (p.o0 && o < n_x0) Vec8<T>::store(p.o0 + o, o0);      // n_x0: multiple of 8 or >= n (checked by the launcher)
   }
   // scalar tail (n not a multiple of 8)
   for (long i = nvec * 8 + blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < n;
@@ -96,13 +109,13 @@ latent_update_kernel(const UpdateCoeffs k, const UpdatePtrs<T> p, long n) {
                    p.h3 ? Vec8<T>::ld1(p.h3 + i) : 0.f, p.z ? Vec8<T>::ld1(p.z + i) : 0.f, ox, om, o0);
     if (p.ox) Vec8<T>::st1(p.ox + i, ox);
     if (p.om) Vec8<T>::st1(p.om + i, om);
-    if (p.o0) Vec8<T>::st1(p.o0 + i, o0);
+    if (p.o0 && i < n_x0) Vec8<T>::st1(p.o0 + i, o0);
   }
 }
 
 template <typename T>
 int launch_update(const UpdateCoeffs& k, const void* eu, const void* et, const void* x, const void* h1,
-                  const void* h2, const void* h3, const void* z, void* ox, void* om, void* o0, long n,
+                  const void* h2, const void* h3, const void* z, void* ox, void* om, void* o0, long n, long n_x0,
                   cudaStream_t stream) {
   UpdatePtrs<T> p{static_cast<const T*>(eu), static_cast<const T*>(et), static_cast<const T*>(x),
                   static_cast<const T*>(h1), static_cast<const T*>(h2), static_cast<const T*>(h3),
@@ -111,7 +124,7 @@ int launch_update(const UpdateCoeffs& k, const void* eu, const void* et, const v
   const long nvec = std::max<long>(1, n / 8);
   // multiples of the SM count; two resident 256-thread CTAs per SM cover the small latents
   const int blocks = static_cast<int>(std::min<long>((nvec + 255) / 256, 148L * 8));
-  latent_update_kernel<T><<<std::max(blocks, 1), 256, 0, stream>>>(k, p, n);
+  latent_update_kernel<T><<<std::max(blocks, 1), 256, 0, stream>>>(k, p, n, n_x0);
   SONIC_CUDA(cudaGetLastError());
   return 0;
 }
@@ -225,15 +238,17 @@ gemv_batched_kernel(const GemvJob* __restrict__ jobs, int n_jobs, int total_rows
 
 int latent_update_launch(const UpdateCoeffs& k, const void* eps_uncond, const void* eps_text, const void* sample,
                          const void* h1, const void* h2, const void* h3, const void* noise, void* out_sample,
-                         void* out_m0, void* out_x0, long n, int dtype, cudaStream_t stream) {
+                         void* out_m0, void* out_x0, long n, long n_x0, int dtype, cudaStream_t stream) {
   SONIC_REQUIRE(eps_uncond && sample, "latent_update: eps and sample are required");
   SONIC_REQUIRE(n > 0, "latent_update: n=%ld", n);
+  if (n_x0 < 0 || n_x0 > n) n_x0 = n;
+  SONIC_REQUIRE(n_x0 == n || n_x0 % 8 == 0, "latent_update: n_x0=%ld must be a multiple of 8 (or n)", n_x0);
   if (dtype == kF32)
     return launch_update<float>(k, eps_uncond, eps_text, sample, h1, h2, h3, noise, out_sample, out_m0, out_x0, n,
-                                stream);
+                                n_x0, stream);
   if (dtype == kBF16)
     return launch_update<__nv_bfloat16>(k, eps_uncond, eps_text, sample, h1, h2, h3, noise, out_sample, out_m0,
-                                        out_x0, n, stream);
+                                        out_x0, n, n_x0, stream);
   SONIC_REQUIRE(false, "latent_update: unknown dtype %d", dtype);
 }
 

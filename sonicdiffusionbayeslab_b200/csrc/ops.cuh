@@ -39,7 +39,7 @@ struct UpdateCoeffs {
 int latent_update_launch(const UpdateCoeffs& k, const void* eps_uncond, const void* eps_text,
                          const void* sample, const void* h1, const void* h2, const void* h3,
                          const void* noise, void* out_sample, void* out_m0, void* out_x0, long n,
-                         int dtype, cudaStream_t stream);
+                         long n_x0, int dtype, cudaStream_t stream);   // n_x0: leading elements of x0 to write
 
 // NCHW (fp32 or bf16) latents -> NHWC bf16 padded to 8 channels; `dup` writes each image twice
 // (image i and image i + n_img) for the classifier-free-guidance batch.

@@ -21,7 +21,8 @@ def init_from_env(device=None):
     world = int(os.environ.get("WORLD_SIZE", 1))
     rank = int(os.environ.get("RANK", 0))
     if world > 1 and not dist.is_initialized():
-        backend = "nccl" if torch.cuda.is_available() else "gloo"
+        # SONIC_DIST_BACKEND=gloo: several ranks on ONE GPU (NCCL refuses duplicate devices) -- used by the tests
+        backend = os.environ.get("SONIC_DIST_BACKEND") or ("nccl" if torch.cuda.is_available() else "gloo")
         kw = {"device_id": device} if (backend == "nccl" and device is not None) else {}
         dist.init_process_group(backend, **kw)
     return rank, world
@@ -50,6 +51,8 @@ def all_gather_cat(t: torch.Tensor) -> torch.Tensor:
     """Concatenate equally- or unequally-sized row blocks from every rank in rank order."""
     if not dist.is_initialized() or dist.get_world_size() == 1:
         return t
+    if dist.get_backend() == "gloo" and t.is_cuda:               # several ranks on one GPU (tests): gather on the host
+        return all_gather_cat(t.cpu()).to(t.device)
     n = torch.tensor([t.shape[0]], device=t.device, dtype=torch.long)
     counts = [torch.zeros_like(n) for _ in range(dist.get_world_size())]
     dist.all_gather(counts, n)
@@ -83,7 +86,11 @@ def all_reduce_metric(metric):
     if not dist.is_initialized() or dist.get_world_size() == 1:
         return metric
     t = metric.state_tensor()
-    if dist.get_backend() == "nccl" and not t.is_cuda:           # NCCL reduces device tensors only (host-side metrics)
+    if dist.get_backend() == "gloo" and t.is_cuda:
+        t_host = t.cpu()
+        dist.all_reduce(t_host, op=dist.ReduceOp.SUM)
+        t = t_host.to(t.device)
+    elif dist.get_backend() == "nccl" and not t.is_cuda:         # NCCL reduces device tensors only (host-side metrics)
         t_dev = t.to(torch.device("cuda", torch.cuda.current_device()))
         dist.all_reduce(t_dev, op=dist.ReduceOp.SUM)
         t = t_dev.to(t.device)

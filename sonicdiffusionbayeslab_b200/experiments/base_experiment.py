@@ -6,7 +6,9 @@ Same hook structure (``setup_exp_params`` .. ``setup_loggers``, ``generate``, ``
 method classes read like the reference's.  Differences, all forced by the deployment or by reference
 defects: bf16 instead of fp16 (C-11), synthetic prompts when the COCO files
 are absent, null logger offline (C-14), true image counts in the time metric (C-9), prompts sharded
-across ranks when launched under torchrun with the CLIP-score states all-reduced over NCCL.
+across ranks when launched under torchrun (whole batches per rank, the shared generator replayed over the
+batches of other ranks so every image equals the single-process run's) with the CLIP-score states
+all-reduced over NCCL.
 """
 from __future__ import annotations
 
@@ -30,7 +32,7 @@ class BaseMethod(ABC):
         self.config = config
         self.device = "cuda" if torch.cuda.is_available() else "cpu"
         if self.device == "cuda":
-            local = int(os.environ.get("LOCAL_RANK", 0))
+            local = int(os.environ.get("LOCAL_RANK", 0)) % torch.cuda.device_count()   # ranks may share one GPU in tests
             torch.cuda.set_device(local)
             self.device = f"cuda:{local}"
         self.rank, self.world = D.init_from_env(torch.device(self.device) if "cuda" in self.device else None)
@@ -100,22 +102,44 @@ class BaseMethod(ABC):
                              run_id=lg.get("run_id", None))
 
     # ---------------------------------------------------------------- data sharding
-    def _local_dataloader(self, batch_size):
-        """This rank's contiguous block of whole batches, in dataloader order (shuffle=False)."""
+    def _global_batches(self, batch_size):
+        """Every batch of the sweep point in dataloader order (shuffle=False; ``inference.batch_count`` caps it,
+        base_experiment.py:130-131) as (start, stop) item ranges."""
         n = len(self.test_dataset)
         count = self.config.inference.get("batch_count", None)
         if count is not None:
             n = min(n, count * batch_size)
-        blocks = D.shard_batches(n, batch_size, self.rank, self.world)
+        return [(s, min(n, s + batch_size)) for s in range(0, n, batch_size)]
+
+    def _local_dataloader(self, batch_size):
+        """This rank's contiguous block of whole batches, in dataloader order (shuffle=False)."""
+        blocks = self._my_batches(batch_size)
         idx = [i for a, b in blocks for i in range(a, b)]
         return DataLoader(Subset(self.test_dataset, idx), batch_size=batch_size, shuffle=False)
 
+    def _my_batches(self, batch_size):
+        batches = self._global_batches(batch_size)
+        return D.shard_batches(batches[-1][1] if batches else 0, batch_size, self.rank, self.world)
+
     # ---------------------------------------------------------------- generation (the hot-path caller)
     def generate(self, test_dataloader, steps, batch_size=1, guidance_scale=7.5, **call_kwargs):
+        """base_experiment.py:122-163.  ONE generator serves every batch (and every noisy scheduler step) of the
+        whole experiment (:51-53,149), so under sharding each rank walks the GLOBAL batch list in order: the
+        batches it owns run on the engine, the others are *replayed* (``rng_only=True``: the pipeline draws the
+        initial latents and the per-step noise it would have drawn and advances the generator, nothing else).
+        Rank r's images are therefore bit-identical to images [its block] of the single-process run."""
         gen_images_list, x0_preds = [], []
-        for batch in test_dataloader:
-            prompts = list(batch["prompt"])
+        mine = set(self._my_batches(batch_size))
+        local = iter(test_dataloader)
+        for start, stop in self._global_batches(batch_size):
             kw = dict(num_inference_steps=steps) if steps is not None else {}
+            if (start, stop) not in mine:
+                self.model([""] * (stop - start), guidance_scale=guidance_scale, generator=self.generator,
+                           output_type="pt", rng_only=True, **kw, **call_kwargs)
+                continue
+            batch = next(local)
+            prompts = list(batch["prompt"])
+            assert len(prompts) == stop - start
             out, inference_time, x0_preds = self.model(prompts, guidance_scale=guidance_scale,
                                                        generator=self.generator, output_type="pt", **kw, **call_kwargs)
             imgs = out.images.float().cpu()
@@ -150,6 +174,9 @@ class BaseMethod(ABC):
         self.metric_dict["image_reward"].append(self.image_reward_metric.compute().item())
         self.metric_dict["fid"].append(self.fid_metric.compute().item())
         self.metric_dict["time_metric"].append(self.time_metric.compute().item())
+        # a run on random-init stand-ins must be recognisable in its own metric table
+        self.metric_dict["weights"].append(f"model:{getattr(self.model, 'weights_source', 'provided')},"
+                                           f"clip:{getattr(self.clip_score_gen_metric.model, 'source', 'provided')}")
         if self.rank == 0:
             if self.config.logger.save:
                 import pandas as pd

@@ -145,16 +145,34 @@ class TwoSchedulerMethod(BaseMethod):
 
 @methods_registry.add_to_registry("skip_steps")
 class SkipStepsMethod(BaseMethod):
+    """skip_steps_exp.py:10-144: ``experiment_params.skip_steps`` is a list of lists of LOOP INDICES, zipped with
+    ``num_inference_steps`` (one sweep point per pair); the DPM-Solver scheduler is built with
+    ``solver_order`` / ``algorithm_type`` / ``final_sigmas_type`` like ``dpm_solver``."""
+
     def setup_exp_params(self):
         p = self.config.experiment_params
+        self.skip_steps = p.skip_steps
         self.num_inference_steps = p.num_inference_steps
-        self.skip_timesteps = p.get("skip_timesteps", [])
+        self.solver_order = p.solver_order
+        self.algorithm_type = p.algorithm_type
+        self.final_sigmas_type = p.final_sigmas_type
+        self.batch_size = self.config.inference.get("batch_size", 1)
+        if len(self.skip_steps) != len(self.num_inference_steps):
+            raise ValueError(f"skip_steps ({len(self.skip_steps)} lists) and num_inference_steps "
+                             f"({len(self.num_inference_steps)}) are zipped: they must have the same length")
+
+    def setup_scheduler(self, **kwargs):
+        return super().setup_scheduler(solver_order=self.solver_order, algorithm_type=self.algorithm_type,
+                                       final_sigmas_type=self.final_sigmas_type)
 
     def run_experiment(self):
-        bs = self.config.inference.get("batch_size", 1)
-        for steps in self.num_inference_steps:
-            self._sweep_point(bs, steps, f"{self.config.experiment_name}, Inference steps: {steps}",
-                              skip_timesteps=tuple(self.skip_timesteps))
+        for steps, skip in zip(self.num_inference_steps, self.skip_steps):
+            skip = [int(v) for v in skip]
+            label = " ".join(map(str, skip))
+            self._sweep_point(self.batch_size, steps,
+                              f"{self.config.experiment_name}, Step main: {steps}, Skip steps:{label}",
+                              additional_values={"num_inference_steps": steps, "skip_steps": label},
+                              skip_timesteps=tuple(skip))
 
 
 @methods_registry.add_to_registry("interliving_schedulers")

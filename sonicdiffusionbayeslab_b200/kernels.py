@@ -191,9 +191,10 @@ def latent_update(coeffs: dict, eps, sample, *, eps_text=None, h1=None, h2=None,
     for t in (eps, eps_text, h1, h2, h3, noise, out_sample, out_m0, out_x0):
         assert t is None or (t.dtype == sample.dtype and t.is_cuda and t.is_contiguous())
     n = sample.numel()
-    check(lib().sonic_latent_update(C.byref(k), ptr(eps), ptr(eps_text), ptr(sample), ptr(h1), ptr(h2), ptr(h3),
-                                    ptr(noise), ptr(out_sample), ptr(out_m0), ptr(out_x0), C.c_int64(n), code,
-                                    stream_ptr()), "sonic_latent_update")
+    n_x0 = n if out_x0 is None else min(n, out_x0.numel())      # a shorter out_x0 receives the leading images only
+    check(lib().sonic_latent_update_x0n(C.byref(k), ptr(eps), ptr(eps_text), ptr(sample), ptr(h1), ptr(h2), ptr(h3),
+                                        ptr(noise), ptr(out_sample), ptr(out_m0), ptr(out_x0), C.c_int64(n),
+                                        C.c_int64(n_x0), code, stream_ptr()), "sonic_latent_update_x0n")
     return out_sample, out_m0, out_x0
 
 

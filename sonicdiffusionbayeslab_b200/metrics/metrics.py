@@ -12,7 +12,9 @@ registered so ``BaseMethod.setup_metrics`` works, and report NaN.
 """
 from __future__ import annotations
 
+import logging
 import os
+import warnings
 
 import torch
 import torch.nn.functional as F
@@ -72,25 +74,47 @@ def clip_preprocess(images: torch.Tensor, size: int = 224) -> torch.Tensor:
     return (x - mean) / std
 
 
+class ClipWeights:
+    """State dict + config of a ``transformers.CLIPModel`` (ViT-B/16): the towers run on the native engine
+    (clip_engine.py), the module that produced the weights is discarded."""
+
+    def __init__(self, state_dict, config, source):
+        self._sd, self.config, self.source = state_dict, config, source
+
+    def state_dict(self):
+        return self._sd
+
+
 def make_clip_model(model_name_or_path=None, seed=29):
-    """CLIP ViT-B/16 from a local directory, else seeded random-init of that architecture."""
+    """CLIP ViT-B/16 weights from a local directory, else seeded random-init of that architecture (with a loud
+    warning: the score of a random-init CLIP is a synthetic-workload number).  Returns (ClipWeights, tokenizer)."""
     from transformers import CLIPConfig, CLIPModel
 
     if model_name_or_path and os.path.isdir(model_name_or_path):
-        return CLIPModel.from_pretrained(model_name_or_path).eval(), load_tokenizer(model_name_or_path)
-    cfg = CLIPConfig(text_config=dict(vocab_size=49408, hidden_size=512, intermediate_size=2048,
-                                      num_hidden_layers=12, num_attention_heads=8, max_position_embeddings=77,
-                                      bos_token_id=49406, eos_token_id=49407, pad_token_id=1),
-                     vision_config=dict(hidden_size=768, intermediate_size=3072, num_hidden_layers=12,
-                                        num_attention_heads=12, image_size=224, patch_size=16),
-                     projection_dim=512)
-    state = torch.random.get_rng_state()
-    torch.manual_seed(seed + 3)
-    try:
-        model = CLIPModel(cfg)
-    finally:
-        torch.random.set_rng_state(state)
-    return model.eval(), HashTokenizer()
+        model, tok, source = CLIPModel.from_pretrained(model_name_or_path).eval(), load_tokenizer(model_name_or_path), \
+            "provided"
+    else:
+        msg = (f"clip_score: no local weights at {model_name_or_path!r} and no network -- RANDOM-INIT CLIP ViT-B/16 and a "
+               "CRC32 hash tokenizer are used; the reported CLIP score is a synthetic-workload number")
+        if os.environ.get("SONIC_REQUIRE_WEIGHTS") == "1":
+            raise FileNotFoundError(msg)
+        logging.getLogger("sonicdiffusionbayeslab_b200").warning(msg)
+        warnings.warn(msg, RuntimeWarning, stacklevel=2)
+        cfg = CLIPConfig(text_config=dict(vocab_size=49408, hidden_size=512, intermediate_size=2048,
+                                          num_hidden_layers=12, num_attention_heads=8, max_position_embeddings=77,
+                                          bos_token_id=49406, eos_token_id=49407, pad_token_id=1),
+                         vision_config=dict(hidden_size=768, intermediate_size=3072, num_hidden_layers=12,
+                                            num_attention_heads=12, image_size=224, patch_size=16),
+                         projection_dim=512)
+        state = torch.random.get_rng_state()
+        torch.manual_seed(seed + 3)
+        try:
+            model = CLIPModel(cfg)
+        finally:
+            torch.random.set_rng_state(state)
+        tok, source = HashTokenizer(), "random-init"
+    sd = {k: v.detach().clone() for k, v in model.state_dict().items()}
+    return ClipWeights(sd, model.config, source), tok
 
 
 @metrics_registry.add_to_registry("clip_score")
@@ -102,16 +126,13 @@ class ClipScoreMetric(Metric):
         self.add_state("n_samples", torch.tensor(0, dtype=torch.long))
         self.keep_features = False
         self._feats = []
-        self.use_native_towers = True           # clip_engine.py on a CUDA device; False = transformers modules
         self._engines = {}
-
-    def to(self, device):
-        super().to(device)
-        self.model.to(self.device)
-        return self
 
     @torch.no_grad()
     def features(self, images, text):
+        """L2-normalised (image, text) features of the native towers; uint8 images (n,3,H,W)."""
+        if self.device.type != "cuda":
+            raise RuntimeError("clip_score runs on the B200 engine (clip_engine.py): call .to('cuda') first")
         if isinstance(images, (list, tuple)):
             images = torch.stack(list(images))
         if images.dim() == 3:
@@ -120,26 +141,19 @@ class ClipScoreMetric(Metric):
         if len(text) != images.shape[0]:
             raise ValueError("Expected the number of images and text examples to be the same")
         pixel = clip_preprocess(images.to(self.device))
-        ids, mask = self.tokenizer(text)
-        ids, mask = ids.to(self.device), mask.to(self.device)
-        if self.use_native_towers and self.device.type == "cuda":
-            vis, txt = self._native(len(text))
-            fi, ft = vis.image_features(pixel).float(), txt.text_features(ids).float()
-        else:
-            fi = self.model.get_image_features(pixel_values=pixel.to(self.model.dtype))
-            ft = self.model.get_text_features(input_ids=ids, attention_mask=mask)
-            fi = getattr(fi, "pooler_output", fi)
-            ft = getattr(ft, "pooler_output", ft)
+        ids, _ = self.tokenizer(text)
+        vis, txt = self._native(len(text))
+        fi, ft = vis.image_features(pixel).float(), txt.text_features(ids.to(self.device)).float()
         fi = fi / fi.norm(p=2, dim=-1, keepdim=True)
         ft = ft / ft.norm(p=2, dim=-1, keepdim=True)
-        return fi.float(), ft.float()
+        return fi, ft
 
     def _native(self, n):
-        """Native towers for a batch of n (built on first use from the transformers state dict)."""
+        """Native towers for a batch of n (built on first use from the transformers-layout state dict)."""
         if n not in self._engines:
             from ..clip_engine import ClipTextEngine, ClipVisionEngine
 
-            sd = {k: v.detach() for k, v in self.model.state_dict().items()}
+            sd = self.model.state_dict()
             vc, tc = self.model.config.vision_config, self.model.config.text_config
             self._engines[n] = (
                 ClipVisionEngine(sd, n=n, image_size=vc.image_size, patch=vc.patch_size, width=vc.hidden_size,

@@ -17,8 +17,10 @@ timestep / index schedule is computed on the host exactly as diffusers does (bit
 from __future__ import annotations
 
 import inspect
+import logging
 import os
 import time
+import warnings
 from types import SimpleNamespace
 
 import numpy as np
@@ -26,10 +28,18 @@ import torch
 
 from . import schedulers as S
 from .registry import models_registry
-from .text import encode_prompts, load_tokenizer, make_text_encoder
+from .text import load_tokenizer, make_text_encoder
 from .unet_engine import PackedWeights, UNetArch, UNetEngine
 from .unet_spec import random_unet_state_dict, validate_state_dict
-from .vae import make_vae
+from .vae_spec import VaeWeights, random_vae_state_dict, validate_vae_state_dict
+
+log = logging.getLogger("sonicdiffusionbayeslab_b200")
+
+
+def _loud(msg):
+    """Random-init / synthetic stand-ins must never pass for a real run: warn on both channels."""
+    log.warning(msg)
+    warnings.warn(msg, RuntimeWarning, stacklevel=3)
 
 # runwayml/stable-diffusion-v1-5 scheduler/scheduler_config.json + instantiated defaults (SURVEY A.0)
 SD15_SCHEDULER_CONFIG = dict(
@@ -83,9 +93,8 @@ class _PipelineBase:
         self._num_timesteps = 0
         self._deepcache = None                      # set by DeepCacheSDHelper.enable()
         self.use_cuda_graphs = True
-        self.use_native_vae = True
-        self.use_native_text = True
         self.decode_x0_preds = True
+        self.weights_source = "provided"            # or "random-init": reported in the experiments' metric tables
         self.unet = SimpleNamespace(config=SimpleNamespace(
             in_channels=arch.in_channels, sample_size=latent_size, time_cond_proj_dim=None))
         self.last_step_kinds = []                   # "full"/"cached" per UNet call of the last run
@@ -94,28 +103,49 @@ class _PipelineBase:
     @classmethod
     def from_pretrained(cls, pretrained_model, timestamps=None, safety_checker=None,
                         requires_safety_checker=False, torch_dtype=torch.bfloat16, seed=29, **kwargs):
-        """``pretrained_model``: a local diffusers-layout directory (unet/, vae/, text_encoder/,
-        tokenizer/) is loaded; any other id (e.g. "runwayml/stable-diffusion-v1-5" without network)
-        yields seeded random-init weights of the SD-v1.5 architecture."""
+        """``pretrained_model``: a local diffusers-layout directory (unet/, vae/, text_encoder/, tokenizer/) is
+        loaded.  Any other id (e.g. "runwayml/stable-diffusion-v1-5": there is no network) yields seeded
+        RANDOM-INIT weights of the SD-v1.5 architecture and a hash tokenizer -- the synthetic workload of
+        BASELINE.json -- with a loud warning; ``SONIC_REQUIRE_WEIGHTS=1`` turns that into an error."""
         if torch_dtype == torch.float16:
             torch_dtype = torch.bfloat16            # the engine computes in bf16 (SURVEY C-11)
         arch = UNetArch()
         root = pretrained_model if isinstance(pretrained_model, str) and os.path.isdir(pretrained_model) else None
         sub = (lambda *p: os.path.join(root, *p)) if root else None
+        random_parts = []
         unet_file = sub("unet", "diffusion_pytorch_model.safetensors") if root else None
         if unet_file and os.path.exists(unet_file):
             sd = _load_safetensors(unet_file)
             validate_state_dict(sd, arch)
         else:
             sd = random_unet_state_dict(seed, arch)
-        vae = make_vae(seed, dtype=torch_dtype)
+            random_parts.append("UNet")
         vae_file = sub("vae", "diffusion_pytorch_model.safetensors") if root else None
         if vae_file and os.path.exists(vae_file):
-            vae.load_diffusers_state_dict(_load_safetensors(vae_file))
-        text = make_text_encoder(seed, sub("text_encoder") if root else None, dtype=torch_dtype)
-        tok = load_tokenizer(sub("tokenizer") if root else None)
+            vae_sd = validate_vae_state_dict(_load_safetensors(vae_file))
+        else:
+            vae_sd = random_vae_state_dict(seed)
+            random_parts.append("VAE decoder")
+        text_dir = sub("text_encoder") if root else None
+        if not (text_dir and os.path.isdir(text_dir)):
+            random_parts.append("text encoder")
+        tok_dir = sub("tokenizer") if root else None
+        if not (tok_dir and os.path.isdir(tok_dir)):
+            random_parts.append("tokenizer (CRC32 hash tokenizer)")
+        if random_parts:
+            msg = (f"from_pretrained({pretrained_model!r}): no local weights for {', '.join(random_parts)} -- using "
+                   f"seeded RANDOM-INIT stand-ins (seed {seed}); images and quality metrics of this run are "
+                   "synthetic-workload numbers, not Stable Diffusion outputs")
+            if os.environ.get("SONIC_REQUIRE_WEIGHTS") == "1":
+                raise FileNotFoundError(msg)
+            _loud(msg)
+        text = make_text_encoder(seed, text_dir, dtype=torch_dtype)
+        tok = load_tokenizer(tok_dir)
         sched = S.PNDMScheduler.from_config(SD15_SCHEDULER_CONFIG)
-        return cls(sd, vae, text, tok, sched, arch=arch, torch_dtype=torch_dtype, timestamps=timestamps, seed=seed)
+        pipe = cls(sd, VaeWeights(vae_sd), text, tok, sched, arch=arch, torch_dtype=torch_dtype, timestamps=timestamps,
+                   seed=seed)
+        pipe.weights_source = "random-init" if random_parts else "provided"
+        return pipe
 
     def to(self, device):
         """Weights are packed into HBM on the first move to a CUDA device and stay resident; moving
@@ -124,8 +154,6 @@ class _PipelineBase:
         dev = torch.device(device)
         if dev.type == "cuda":
             self.device = dev
-            self.vae.to(dev)
-            self.text_encoder.to(dev)
         return self
 
     @property
@@ -141,26 +169,49 @@ class _PipelineBase:
         return self._guidance_scale > 1 and self.unet.config.time_cond_proj_dim is None
 
     def load_lora_weights(self, adapter, adapter_scale=1.0, **_):
-        """Offline LoRA merge source (consistency_model.py:20-21): a local .safetensors with
-        ``<key>.lora_A/.lora_B(.alpha)`` tensors; unknown ids (no network) leave weights unchanged."""
+        """LoRA merge source (consistency_model.py:20-21): a local ``.safetensors`` in either the diffusers/PEFT
+        layout (``<module>.lora_A.weight`` / ``.lora_B.weight``) or the kohya layout the LCM-LoRA ships in
+        (``lora_unet_<module with _>.lora_down.weight`` / ``.lora_up.weight`` / ``.alpha``).  A hub id cannot be
+        fetched (no network): that is reported loudly and the base weights stay as they are."""
         self._lora = None
-        if isinstance(adapter, str) and os.path.exists(adapter):
-            self._lora = (_load_safetensors(adapter), adapter_scale)
+        if isinstance(adapter, str) and os.path.isfile(adapter):
+            self._lora = (_load_safetensors(adapter), adapter_scale, adapter)
+        else:
+            _loud(f"load_lora_weights({adapter!r}): not a local file and there is no network -- NO adapter is "
+                  "applied; the consistency-model method then runs the LCM scheduler on non-LCM weights")
 
     def fuse_lora(self, lora_scale=1.0):
         lora = getattr(self, "_lora", None)
         if not lora:
             return
-        tensors, scale = lora
-        for k in [k for k in tensors if k.endswith("lora_A.weight")]:
-            base = k[: -len(".lora_A.weight")]
-            target = base.replace("unet.", "", 1) + ".weight"
-            if target not in self._unet_sd:
+        tensors, scale, path = lora
+        flat = {k[: -len(".weight")].replace(".", "_"): k for k in self._unet_sd if k.endswith(".weight")}
+        pairs = []                                   # (target key, down/A, up/B, alpha or None)
+        for k in tensors:
+            if k.endswith(".lora_A.weight"):
+                base = k[: -len(".lora_A.weight")]
+                target = base.replace("unet.", "", 1) + ".weight"
+                pairs.append((target, tensors[k], tensors[base + ".lora_B.weight"], tensors.get(base + ".alpha")))
+            elif k.endswith(".lora_down.weight"):
+                base = k[: -len(".lora_down.weight")]
+                if not base.startswith("lora_unet_"):
+                    continue                          # text-encoder adapters (lora_te_*) are not applied
+                target = flat.get(base[len("lora_unet_"):])
+                pairs.append((target, tensors[k], tensors[base + ".lora_up.weight"], tensors.get(base + ".alpha")))
+        merged = 0
+        for target, A, B, alpha in pairs:
+            if target is None or target not in self._unet_sd:
                 continue
-            A, B = tensors[k].float(), tensors[base + ".lora_B.weight"].float()
-            alpha = float(tensors.get(base + ".alpha", torch.tensor(float(A.shape[0]))))
-            delta = (B.flatten(1) @ A.flatten(1)) * (alpha / A.shape[0]) * scale * lora_scale
-            self._unet_sd[target] = self._unet_sd[target].float() + delta.reshape(self._unet_sd[target].shape)
+            A, B = A.float(), B.float()
+            rank = A.shape[0]
+            a = float(alpha) if alpha is not None else float(rank)
+            delta = (B.flatten(1) @ A.flatten(1)) * (a / rank) * scale * lora_scale
+            w = self._unet_sd[target].float()
+            self._unet_sd[target] = w + delta.reshape(w.shape)
+            merged += 1
+        if merged == 0:
+            raise ValueError(f"fuse_lora: none of the {len(tensors)} tensors in {path} matched a UNet weight "
+                             "(expected diffusers `lora_A/lora_B` or kohya `lora_unet_*.lora_down/lora_up` keys)")
         self._weights = None
         self._engines = {}
 
@@ -171,27 +222,28 @@ class _PipelineBase:
                                "(there is no CPU fallback)")
         if self._weights is None:
             self._weights = PackedWeights(self._unet_sd, self.device)
-        key = (n_latents, bool(cfg_dup), self.dtype)
+        branch = self._deepcache["branch"] if self._deepcache else 0
+        key = (n_latents, bool(cfg_dup), self.dtype, branch)
         if key not in self._engines:
             eng = UNetEngine(self._weights, n_latents=n_latents, cfg_dup=cfg_dup, arch=self.arch,
                              height=self.latent_size, width=self.latent_size, io_dtype=self.dtype,
-                             device=self.device)
+                             device=self.device, cache_branch=branch)
             if self.use_cuda_graphs:
                 eng.capture_graphs()
             self._engines[key] = eng
         return self._engines[key]
 
     def _encode(self, prompts):
-        """CLIP text tower (models.py:139-149) on the native engine (clip_engine.ClipTextEngine)."""
-        if not (self.use_native_text and self.device.type == "cuda"):
-            return encode_prompts(self.tokenizer, self.text_encoder, prompts, self.device)
+        """CLIP text tower (models.py:139-149) on the native engine (clip_engine.ClipTextEngine); no library path."""
+        if self.device.type != "cuda":
+            raise RuntimeError("the prompt encoder runs on the B200 engine: call .to('cuda') first")
         from .clip_engine import ClipTextEngine
 
         key = ("text", len(prompts))
         if key not in self._engines:
             c = self.text_encoder.config
-            sd = {k: v.detach() for k, v in self.text_encoder.state_dict().items()}
-            self._engines[key] = ClipTextEngine(sd, n=len(prompts), seq=c.max_position_embeddings, width=c.hidden_size,
+            self._engines[key] = ClipTextEngine(self.text_encoder.state_dict(), n=len(prompts),
+                                                seq=c.max_position_embeddings, width=c.hidden_size,
                                                 heads=c.num_attention_heads, layers=c.num_hidden_layers,
                                                 mlp=c.intermediate_size, device=self.device)
         ids, _ = self.tokenizer(list(prompts))
@@ -211,13 +263,34 @@ class _PipelineBase:
             negative_prompt_embeds = negative_prompt_embeds.to(device=self.device, dtype=torch.bfloat16)
         return prompt_embeds, negative_prompt_embeds
 
-    def prepare_latents(self, batch, generator, latents, init_noise_sigma):
+    def prepare_latents(self, batch, generator, latents, init_noise_sigma, rng_rows=None):
+        """``prepare_latents`` / ``randn_tensor`` of models.py:172-182.  ``rng_rows = (lo, hi, total)``: this call
+        computes rows lo:hi of a GLOBAL batch of ``total`` prompts -- the full tensor is drawn (what a single
+        process would draw) and sliced, so a sharded run reproduces the single-GPU noise."""
         shape = (batch, self.arch.in_channels, self.latent_size, self.latent_size)
         if latents is None:
-            latents = S.randn_tensor(shape, generator=generator, device=self.device, dtype=self.dtype)
+            if rng_rows is not None:
+                lo, hi, total = rng_rows
+                assert hi - lo == batch, (rng_rows, batch)
+                latents = S.randn_tensor((total,) + shape[1:], generator=generator, device=self.device,
+                                         dtype=self.dtype)[lo:hi]
+            else:
+                latents = S.randn_tensor(shape, generator=generator, device=self.device, dtype=self.dtype)
         else:
             latents = latents.to(device=self.device, dtype=self.dtype)
         return latents * init_noise_sigma
+
+    def _replay_rng(self, plan, batch, latents, generator, init_noise_sigma):
+        """``rng_only=True``: consume from ``generator`` exactly what the call would -- the initial latents and
+        every noisy step's draw, in order -- with no text encoding, no engine and no kernel launch.  This is how
+        a rank walks over the batches other ranks compute (experiments/base_experiment.py ``generate``)."""
+        if self.device.type != "cuda" and generator is not None and generator.device.type == "cuda":
+            raise RuntimeError("replaying a CUDA generator needs the pipeline on that device: call .to('cuda')")
+        self.prepare_latents(batch, generator, latents, init_noise_sigma)
+        shape = (batch, self.arch.in_channels, self.latent_size, self.latent_size)
+        for sched, t, extra in plan:
+            sched.replay(t, shape, self.dtype, self.device, **extra)
+        return None, 0.0, []
 
     @staticmethod
     def _extra_step_kwargs(scheduler, generator, eta):
@@ -247,6 +320,17 @@ class _PipelineBase:
             return scheduler.step_cfg(eps[:B], eps[B:], guidance_scale, t, eng.x_in, out=eng.x_in, **extra)
         return scheduler._step(eps, None, 0.0, t, eng.x_in, out=eng.x_in, **extra)
 
+    def _x0_mode(self, schedulers, output_type):
+        """The loop keeps ``x0_pred[0]`` only (models.py:257-261) and ``output_type="latent"`` never decodes it:
+        tell the fused step to write one image's x0, or none."""
+        for s_ in schedulers:
+            s_.x0_rows, s_.skip_x0 = 1, (output_type == "latent" or not self.decode_x0_preds)
+
+    @staticmethod
+    def _x0_reset(schedulers):
+        for s_ in schedulers:
+            s_.x0_rows, s_.skip_x0, s_.rng_rows = None, False, None
+
     def _run_callback(self, callback, eng, i, t):
         """``callback_on_step_end(pipe, i, t, {"latents": ...})`` as at models.py:263-273; a returned
         ``{"latents": tensor}`` replaces the resident latents (used for teacher-forced parity runs)."""
@@ -263,16 +347,15 @@ class _PipelineBase:
 
         key = ("vae", n_img, self.dtype)
         if key not in self._engines:
-            self._engines[key] = VaeEngine({k: v.detach() for k, v in self.vae.state_dict().items()}, n_img=n_img,
+            self._engines[key] = VaeEngine(dict(self.vae.state_dict()), n_img=n_img,
                                            latent=self.latent_size, io_dtype=self.dtype, device=self.device)
         return self._engines[key]
 
     def _decode(self, z):
-        """``vae.decode`` (models.py:288-302) on the native engine; ``use_native_vae = False`` keeps the
-        PyTorch module (library kernels)."""
-        if self.use_native_vae and self.device.type == "cuda":
-            return self.vae_engine(z.shape[0]).decode(z.to(self.dtype)).clone()
-        return self.vae.decode(z)[0]
+        """``vae.decode`` (models.py:288-302) on the native engine (vae_engine.VaeEngine); no library path."""
+        if self.device.type != "cuda":
+            raise RuntimeError("the VAE decoder runs on the B200 engine: call .to('cuda') first")
+        return self.vae_engine(z.shape[0]).decode(z.to(self.dtype)).clone()
 
     def _finish(self, eng, x0_preds, output_type, exec_time):
         latents = eng.x_in.clone()
@@ -307,15 +390,21 @@ class StableDiffusionModel(_PipelineBase):
             raise NotImplementedError("guidance_rescale is 0 in every reference config and is not fused")
         if output_type not in ("pt", "latent"):
             raise NotImplementedError("output_type must be 'pt' (as the experiments use) or 'latent'")
+        rng_only, rng_rows = kwargs.pop("rng_only", False), kwargs.pop("rng_rows", None)
         self._guidance_scale = guidance_scale
         batch = (1 if isinstance(prompt, str) else len(prompt)) if prompt is not None else prompt_embeds.shape[0]
         do_cfg = self.do_classifier_free_guidance
-        pe, ne = self.encode_prompt(prompt, do_cfg, prompt_embeds, negative_prompt_embeds, negative_prompt)
-        ctx = torch.cat([ne, pe]) if do_cfg else pe
         ts, num_inference_steps = retrieve_timesteps(self.scheduler, num_inference_steps, self.device, timesteps)
         t_list = [int(t) for t in ts.tolist()]
-        latents = self.prepare_latents(batch, generator, latents, self.scheduler.init_noise_sigma)
+        skip = set(skip_timesteps or ())            # loop INDICES, models.py:1220-1223,1338-1340
         extra = self._extra_step_kwargs(self.scheduler, generator, eta)
+        self.scheduler.rng_rows = rng_rows
+        if rng_only:
+            plan = [(self.scheduler, t, extra) for i, t in enumerate(t_list) if i not in skip]
+            return self._replay_rng(plan, batch, latents, generator, self.scheduler.init_noise_sigma)
+        pe, ne = self.encode_prompt(prompt, do_cfg, prompt_embeds, negative_prompt_embeds, negative_prompt)
+        ctx = torch.cat([ne, pe]) if do_cfg else pe
+        latents = self.prepare_latents(batch, generator, latents, self.scheduler.init_noise_sigma, rng_rows)
         eng = self.engine(batch, do_cfg)
         eng.set_context(ctx)
         eng.x_in.copy_(latents)
@@ -324,19 +413,21 @@ class StableDiffusionModel(_PipelineBase):
         self._num_timesteps = len(t_list)
         self.last_step_kinds = []
         x0_preds = []
+        self._x0_mode([self.scheduler], output_type)
         torch.cuda.synchronize(self.device)
         start = time.perf_counter()
         for i, t in enumerate(t_list):
-            if i in skip_timesteps:                 # skip-steps variant, models.py:1338-1340
+            if i in skip:                           # skip-steps variant, models.py:1338-1340
                 continue
             cached = self._is_cached_step(t_list, i)
             self.last_step_kinds.append("cached" if cached else "full")
             step = self._denoise_step(eng, self.scheduler, t, do_cfg, guidance_scale, cached, extra)
-            if len(step) == 2:
+            if len(step) == 2 and step[1] is not None:
                 x0_preds.append(step[1][0:1])
             self._run_callback(callback_on_step_end, eng, i, t)
         torch.cuda.synchronize(self.device)
         exec_time = time.perf_counter() - start
+        self._x0_reset([self.scheduler])
         return self._finish(eng, x0_preds, output_type, exec_time)
 
 
@@ -345,8 +436,8 @@ class StableDiffusionModelSkipTimesteps(StableDiffusionModel):
     """models.py:1138-1467: the single-scheduler loop with ``if i in skip_timesteps: continue``."""
 
     def call(self, *args, skip_timesteps=None, **kwargs):
-        skip = self.timestamps if skip_timesteps is None else skip_timesteps
-        return super().call(*args, skip_timesteps=tuple(skip or ()), **kwargs)
+        # models.py:1220-1223: ``None`` -> nothing skipped; entries are loop indices, not timestep values
+        return super().call(*args, skip_timesteps=tuple(skip_timesteps or ()), **kwargs)
 
 
 @models_registry.add_to_registry("stable_diffusion_model_two_schedulers")
@@ -363,35 +454,46 @@ class StableDiffusionModelTwoSchedulers(_PipelineBase):
              callback_on_step_end=None, **kwargs):
         if output_type not in ("pt", "latent"):
             raise NotImplementedError("output_type must be 'pt' or 'latent'")
+        rng_only, rng_rows = kwargs.pop("rng_only", False), kwargs.pop("rng_rows", None)
         self._guidance_scale = guidance_scale
         batch = (1 if isinstance(prompt, str) else len(prompt)) if prompt is not None else prompt_embeds.shape[0]
         do_cfg = self.do_classifier_free_guidance
-        pe, ne = self.encode_prompt(prompt, do_cfg, prompt_embeds, negative_prompt_embeds, negative_prompt)
-        ctx = torch.cat([ne, pe]) if do_cfg else pe
         # models.py:487-494: the second scheduler runs on the FIRST scheduler's grid (N2 unused)
         ts1, _ = retrieve_timesteps(self.scheduler_first, num_inference_steps_first, self.device, timesteps)
         ts2, _ = retrieve_timesteps(self.scheduler_second, device=self.device, timesteps=ts1.cpu().numpy())
         first, second = self.switch_timestamp(ts1, ts2, num_step_switch, type_switch)
-        latents = self.prepare_latents(batch, generator, latents, self.scheduler_first.init_noise_sigma)
-        extra1 = self._extra_step_kwargs(self.scheduler_first, generator, eta)
-        extra2 = self._extra_step_kwargs(self.scheduler_second, generator, eta)
+        # models.py:520: ONE extra_step_kwargs, derived from ``self.scheduler`` (the pipeline's default), serves
+        # both phases; a keyword the phase's scheduler does not take is dropped instead of raising TypeError
+        extra = self._extra_step_kwargs(self.scheduler, generator, eta)
+        extra1 = {k: v for k, v in extra.items() if k in inspect.signature(self.scheduler_first._step).parameters}
+        extra2 = {k: v for k, v in extra.items() if k in inspect.signature(self.scheduler_second._step).parameters}
+        self.scheduler_first.rng_rows = self.scheduler_second.rng_rows = rng_rows
+        if rng_only:
+            plan = [(self.scheduler_first, int(t), extra1) for t in first] + \
+                   [(self.scheduler_second, int(t), extra2) for t in second]
+            return self._replay_rng(plan, batch, latents, generator, self.scheduler_first.init_noise_sigma)
+        pe, ne = self.encode_prompt(prompt, do_cfg, prompt_embeds, negative_prompt_embeds, negative_prompt)
+        ctx = torch.cat([ne, pe]) if do_cfg else pe
+        latents = self.prepare_latents(batch, generator, latents, self.scheduler_first.init_noise_sigma, rng_rows)
         eng = self.engine(batch, do_cfg)
         eng.set_context(ctx)
         eng.x_in.copy_(latents)
         self._num_timesteps = len(first) + len(second)
         self.last_timesteps = (list(first), list(second))
         x0_preds = []
+        self._x0_mode([self.scheduler_first, self.scheduler_second], output_type)
         torch.cuda.synchronize(self.device)
         start = time.perf_counter()
         for i, t in enumerate(first + second):     # models.py:545-621 (history seeding :603-611 is a
             in_first = i < len(first)              # no-op for solver_order <= 2, SURVEY C-4)
             sched, extra = (self.scheduler_first, extra1) if in_first else (self.scheduler_second, extra2)
             step = self._denoise_step(eng, sched, int(t), do_cfg, guidance_scale, False, extra)
-            if len(step) == 2:
+            if len(step) == 2 and step[1] is not None:
                 x0_preds.append(step[1][0:1])
             self._run_callback(callback_on_step_end, eng, i, int(t))
         torch.cuda.synchronize(self.device)
         exec_time = time.perf_counter() - start
+        self._x0_reset([self.scheduler_first, self.scheduler_second])
         return self._finish(eng, x0_preds, output_type, exec_time)
 
     def switch_timestamp(self, timesteps_first, timesteps_second, num_step_switch, type_switch="closest"):
@@ -444,26 +546,33 @@ class StableDiffusionModelInterlivingSchedulers(_PipelineBase):
         if main is None or inter_s is None:
             raise ValueError("scheduler_main / scheduler_inter must be set (interliving_exp.py:40-62)")
         interliving_steps = list(interliving_steps or [])
+        rng_only, rng_rows = kwargs.pop("rng_only", False), kwargs.pop("rng_rows", None)
         self._guidance_scale = guidance_scale
         batch = (1 if isinstance(prompt, str) else len(prompt)) if prompt is not None else prompt_embeds.shape[0]
         do_cfg = self.do_classifier_free_guidance
-        pe, ne = self.encode_prompt(prompt, do_cfg, prompt_embeds, negative_prompt_embeds, negative_prompt)
-        ctx = torch.cat([ne, pe]) if do_cfg else pe
         order = main.config.solver_order
         ts_main, _ = retrieve_timesteps(main, num_inference_steps, self.device, timesteps)        # models.py:880-886
         retrieve_timesteps(inter_s, num_inference_steps // order, self.device, timesteps)         # models.py:888-894
         kept, t_inter = self.partition(ts_main.tolist(), order, interliving_steps)
         self._num_timesteps = len(ts_main) - len(interliving_steps)                               # models.py:939
         self.last_timesteps = (kept, t_inter)
-        latents = self.prepare_latents(batch, generator, latents, self.scheduler.init_noise_sigma)
-        extra_main = self._extra_step_kwargs(main, generator, eta)
-        extra_inter = self._extra_step_kwargs(inter_s, generator, eta)
+        extra = self._extra_step_kwargs(self.scheduler, generator, eta)                           # models.py:911
+        extra_main = {k: v for k, v in extra.items() if k in inspect.signature(main._step).parameters}
+        extra_inter = {k: v for k, v in extra.items() if k in inspect.signature(inter_s._step).parameters}
+        main.rng_rows = inter_s.rng_rows = rng_rows
+        if rng_only:
+            plan = [(inter_s, t, extra_inter) if t in t_inter else (main, t, extra_main) for t in kept]
+            return self._replay_rng(plan, batch, latents, generator, self.scheduler.init_noise_sigma)
+        pe, ne = self.encode_prompt(prompt, do_cfg, prompt_embeds, negative_prompt_embeds, negative_prompt)
+        ctx = torch.cat([ne, pe]) if do_cfg else pe
+        latents = self.prepare_latents(batch, generator, latents, self.scheduler.init_noise_sigma, rng_rows)
         feed_inter = isinstance(inter_s, S.DPMSolverScheduler)                                    # models.py:1045
         eng = self.engine(batch, do_cfg)
         eng.set_context(ctx)
         eng.x_in.copy_(latents)
         B = eng.n_lat
         x0_preds = []
+        self._x0_mode([main, inter_s], output_type)
         torch.cuda.synchronize(self.device)
         start = time.perf_counter()
         for i, t in enumerate(kept):
@@ -472,11 +581,12 @@ class StableDiffusionModelInterlivingSchedulers(_PipelineBase):
             eps = eng.forward(float(t))
             eps_u, eps_c, g = (eps[:B], eps[B:], guidance_scale) if do_cfg else (eps, None, 0.0)
             step = stepper._step(eps_u, eps_c, g, t, eng.x_in, out=eng.x_in, **extra)
-            if len(step) == 2:
+            if len(step) == 2 and step[1] is not None:
                 x0_preds.append(step[1][0:1])
             if other is not None:
                 other.feed_history(eps_u, eps_c, g, eng.x_in)       # post-step latents, pre-step noise: as written
             self._run_callback(callback_on_step_end, eng, i, t)
         torch.cuda.synchronize(self.device)
         exec_time = time.perf_counter() - start
+        self._x0_reset([main, inter_s])
         return self._finish(eng, x0_preds, output_type, exec_time)

@@ -96,6 +96,11 @@ class FusedScheduler:
         self.timesteps = None
         self._timesteps_host = None
         self._step_index = None
+        self._replay_device = None          # set by replay(): steps draw their noise and advance, no launches
+        self.rng_rows = None                # (row_start, row_stop, global_rows): draw the global tensor, keep rows
+        self.x0_rows = None                 # pipelines: write x0 for the leading images only (models.py:257-261)
+        self.skip_x0 = False                # pipelines with output_type="latent": x0 predictions are never decoded
+        self._ring, self._ring_pos = {}, 0  # history buffers (m0) are recycled, not allocated per step
 
     # -- construction as in base_experiment.py:69-72: unknown keys are dropped silently
     @classmethod
@@ -124,18 +129,59 @@ class FusedScheduler:
             return len(self._timesteps_host) - 1
         return hits[1] if len(hits) > 1 else hits[0]
 
+    # -- RNG parity: ONE generator is consumed, in order, by every batch
+    # and every noisy step (base_experiment.py:51-53,149; schedulers.py:134-147).
+    def _draw(self, sample, generator, dtype):
+        """The per-step noise draw of this scheduler, shaped like ``sample``.  Under ``rng_rows`` the GLOBAL
+        batch is drawn and this shard's rows are kept (Philox output depends on the tensor shape, so a
+        shard-shaped draw would not reproduce the single-process stream)."""
+        device = self._replay_device if self._replay_device is not None else sample.device
+        shape = tuple(sample.shape)
+        if self.rng_rows is None:
+            return randn_tensor(shape, generator=generator, device=device, dtype=dtype)
+        lo, hi, total = self.rng_rows
+        return randn_tensor((total,) + shape[1:], generator=generator, device=device, dtype=dtype)[lo:hi]
+
+    def replay(self, timestep, shape, dtype, device, **step_kwargs):
+        """Advance exactly like ``step`` -- same step-index bookkeeping, same draws from ``generator`` -- without
+        touching the GPU: how a rank keeps the shared generator aligned over batches another rank computes."""
+        meta = torch.empty(shape, dtype=dtype, device="meta")
+        self._replay_device = torch.device(device)
+        try:
+            self._step(meta, None, 0.0, timestep, meta, **step_kwargs)
+        finally:
+            self._replay_device = None
+
     # -- the device step
-    def _launch(self, coeffs, eps, eps_text, sample, hist=(), noise=None, want_m0=False, want_x0=True, out=None):
+    def _launch(self, coeffs, eps, eps_text, sample, hist=(), noise=None, want_m0=False, want_x0=True, out=None,
+                ring=True):
+        if self._replay_device is not None:
+            return sample, (sample if want_m0 else None), (sample if want_x0 else None)
         if not sample.is_cuda:
             raise RuntimeError(f"{type(self).__name__}.step needs CUDA tensors: the B200 engine has no CPU path")
         sample = sample.contiguous()
         out_sample = torch.empty_like(sample) if out is None else out
-        out_m0 = torch.empty_like(sample) if want_m0 else None
-        out_x0 = torch.empty_like(sample) if want_x0 else None
+        out_m0 = (self._history_buffer(sample) if ring else torch.empty_like(sample)) if want_m0 else None
+        out_x0 = None
+        if want_x0 and not self.skip_x0:
+            rows = sample.shape[0] if self.x0_rows is None else min(self.x0_rows, sample.shape[0])
+            out_x0 = torch.empty((rows,) + tuple(sample.shape[1:]), dtype=sample.dtype, device=sample.device)
         h = list(hist) + [None] * (3 - len(hist))
         K.latent_update(coeffs, eps.contiguous(), sample, eps_text=eps_text, h1=h[0], h2=h[1], h3=h[2], noise=noise,
                         out_sample=out_sample, out_m0=out_m0, out_x0=out_x0)
         return out_sample, out_m0, out_x0
+
+    _RING = 6            # > the longest history any scheduler keeps alive (PNDM: 4 ets + the one being written)
+
+    def _history_buffer(self, like):
+        """Next slot of a small ring of latent-shaped buffers: the converted model outputs kept as multistep
+        history live for at most ``solver_order`` (DPM) / 4 (PLMS) steps, so nothing is allocated per step."""
+        key = (tuple(like.shape), like.dtype, like.device)
+        ring = self._ring.get(key)
+        if ring is None:
+            ring = self._ring[key] = [torch.empty_like(like) for _ in range(self._RING)]
+        self._ring_pos = (self._ring_pos + 1) % self._RING
+        return ring[self._ring_pos]
 
     def step(self, model_output, timestep, sample, return_dict=False, **kw):
         return self._step(model_output, None, 0.0, timestep, sample, **kw)
@@ -198,7 +244,7 @@ class DDIMSchedulerMy(FusedScheduler):
         c["x0_x"], c["x0_e"] = c["m_x"], c["m_e"]
         noise = None
         if eta > 0:
-            noise = randn_tensor(sample.shape, generator=generator, device=sample.device, dtype=sample.dtype)
+            noise = self._draw(sample, generator, sample.dtype)
             c["c_z"] = _f(std)
         prev, _, x0 = self._launch(c, eps, eps_text, sample, noise=noise, out=out)
         return (prev, x0)
@@ -310,7 +356,7 @@ class DPMSolverScheduler(FusedScheduler):
             raise ValueError("convert_model_output needs an initialised step index (call step first)")
         c = self._convert_coeffs()
         c["c_x"] = 1.0                                            # out_sample is a scratch copy of x
-        _, m0, x0 = self._launch(c, model_output, None, sample, want_m0=True)
+        _, m0, x0 = self._launch(c, model_output, None, sample, want_m0=True, ring=False)   # caller owns the result
         return m0, x0
 
     def feed_history(self, eps, eps_text, guidance, sample):
@@ -420,7 +466,7 @@ class DPMSolverScheduler(FusedScheduler):
         noise = None
         if cfg.algorithm_type in ("sde-dpmsolver", "sde-dpmsolver++"):
             if variance_noise is None:
-                noise = randn_tensor(sample.shape, generator=generator, device=sample.device, dtype=torch.float32)
+                noise = self._draw(sample, generator, torch.float32)
             else:
                 noise = variance_noise.to(device=sample.device, dtype=torch.float32)
             noise = noise.to(sample.dtype)
@@ -493,7 +539,7 @@ class LCMScheduler(FusedScheduler):
         last = self.step_index == self.num_inference_steps - 1
         noise = None
         if not last:
-            noise = randn_tensor(sample.shape, generator=generator, device=sample.device, dtype=sample.dtype)
+            noise = self._draw(sample, generator, sample.dtype)
             s = _f(ap.sqrt())
             c.update(c_m0=s * _f(c_out), c_x=s * _f(c_skip), c_z=_f((1 - ap).sqrt()))
         else:

@@ -1,10 +1,11 @@
 """Prompt conditioning for the pipelines (``encode_prompt``, /root/reference/src/models.py:139-149).
 
-Once per batch and outside the timed region; SURVEY.md section 8(f) row 3 ("next"), so it stays
-on library code: ``transformers.CLIPTextModel`` (CLIP-L/14 text tower, 77 tokens, final
-LayerNorm).  No CLIP BPE vocabulary exists offline, so unless a local tokenizer directory is
-given prompts are tokenised by a deterministic hash tokenizer with CLIP's framing
-(BOS 49406, EOS/pad 49407, length 77, ids in [0, 49405]).
+Once per batch and outside the timed region; SURVEY.md section 8(f) row 3.  The tower itself runs on the
+native engine (``clip_engine.ClipTextEngine``); this module only supplies its WEIGHTS -- the state dict of a
+``transformers.CLIPTextModel`` (CLIP-L/14 text tower, 77 tokens, final LayerNorm), loaded from a local
+diffusers ``text_encoder`` directory or random-initialised -- and the tokenizer.  No CLIP BPE vocabulary
+exists offline, so unless a local tokenizer directory is given prompts are tokenised by a deterministic
+hash tokenizer with CLIP's framing (BOS 49406, EOS/pad 49407, length 77, ids in [0, 49405]).
 """
 from __future__ import annotations
 
@@ -49,9 +50,24 @@ def load_tokenizer(path=None):
     return HashTokenizer()
 
 
+class TextWeights:
+    """What the pipelines keep in ``pipe.text_encoder``: the CLIP text tower's state dict and config
+    (transformers key names); the module that produced them is discarded -- there is no library forward path."""
+
+    def __init__(self, state_dict, config):
+        self._sd = state_dict
+        self.config = config
+
+    def state_dict(self):
+        return self._sd
+
+    def to(self, *_a, **_k):
+        return self
+
+
 def make_text_encoder(seed: int = 29, path=None, dtype=torch.bfloat16, device="cpu", hidden=768, layers=12,
-                      heads=12):
-    """CLIP-L text tower; weights from ``path`` (diffusers ``text_encoder`` dir) or random-init."""
+                      heads=12) -> TextWeights:
+    """CLIP-L text tower weights from ``path`` (diffusers ``text_encoder`` dir) or seeded random-init."""
     from transformers import CLIPTextConfig, CLIPTextModel
 
     if path and os.path.isdir(path):
@@ -67,11 +83,5 @@ def make_text_encoder(seed: int = 29, path=None, dtype=torch.bfloat16, device="c
             model = CLIPTextModel(cfg)
         finally:
             torch.random.set_rng_state(state)
-    return model.to(device=device, dtype=dtype).eval()
-
-
-@torch.no_grad()
-def encode_prompts(tokenizer, text_encoder, prompts, device):
-    ids, _ = tokenizer(list(prompts))
-    out = text_encoder(ids.to(device))
-    return out[0]
+    sd = {k: v.detach().to(dtype).clone() for k, v in model.state_dict().items()}
+    return TextWeights(sd, model.config)

@@ -40,6 +40,23 @@ class UNetArch:
     norm_eps: float = 1e-5
 
 
+def deepcache_runs(branch: int, n_blocks: int, layers: int):
+    """Which layers a DeepCache non-refresh step recomputes for ``cache_branch_id = branch`` (SURVEY appendix A.4,
+    ``DeepCacheSDHelper.is_skip_step``): returns ``(down_runs(b, j), up_runs(b, j), first_up)`` with b / j in
+    FORWARD order (a down-sampler is layer ``layers``); ``first_up`` = the (up block, layer) whose input is the
+    cached feature."""
+    bid, lid = divmod(branch, 3)
+
+    def down_runs(b, j):
+        return b < bid or (b == bid and j < lid)
+
+    def up_runs(b, j):
+        bi, li = n_blocks - 1 - b, layers - j               # DeepCache indexes the up path in reverse
+        return bi < bid or (bi == bid and li <= lid)
+
+    return down_runs, up_runs, (n_blocks - 1 - bid, layers - lid)
+
+
 class Arena:
     """Exact-size free lists over torch-owned device memory (pointers stay valid for the plan)."""
 
@@ -134,7 +151,7 @@ class UNetEngine:
 
     def __init__(self, weights, *, n_latents: int, cfg_dup: bool, arch: UNetArch = UNetArch(),
                  height: int = 64, width: int = 64, ctx_len: int = 77, io_dtype=torch.bfloat16,
-                 device="cuda", build_cached: bool = True):
+                 device="cuda", build_cached: bool = True, cache_branch: int = 0):
         if not isinstance(weights, PackedWeights):
             weights = PackedWeights(weights, device)
         state_dict = weights.sd
@@ -143,6 +160,9 @@ class UNetEngine:
         self.dev = torch.device(device)
         self.n_lat = n_latents
         self.n = n_latents * (2 if cfg_dup else 1)          # UNet batch
+        if not 0 <= cache_branch < 3 * len(arch.block_out_channels):
+            raise ValueError(f"cache_branch_id {cache_branch} out of range for {len(arch.block_out_channels)} blocks")
+        self.cache_branch = cache_branch                     # DeepCache branch the ``cached`` plan is recorded for
         self.cfg_dup = cfg_dup
         self.H, self.W, self.ctx_len = height, width, ctx_len
         self.io_dtype = io_dtype
@@ -172,25 +192,30 @@ class UNetEngine:
     def _p(self, name):
         return self.sd[name].detach().to(self.dev)
 
+    def _src(self, name):
+        """The checkpoint tensor WHERE IT LIVES: repacking (cast / permute / cat) runs on the source device and only
+        the packed result is copied to HBM -- a CPU-resident state dict costs no device launches to pack."""
+        return self.sd[name].detach()
+
     def _f32(self, name):
         key = ("f32", name)
         if key not in self._w:
-            self._w[key] = self._p(name).float().contiguous()
+            self._w[key] = self._src(name).float().contiguous().to(self.dev)
         return self._w[key]
 
     def _lin(self, name):
         key = ("lin", name)
         if key not in self._w:
-            w = self._p(name)
+            w = self._src(name)
             if w.dim() == 4:                                  # 1x1 conv
                 w = w.reshape(w.shape[0], w.shape[1])
-            self._w[key] = w.to(torch.bfloat16).contiguous()
+            self._w[key] = w.to(torch.bfloat16).contiguous().to(self.dev)
         return self._w[key]
 
     def _conv3(self, name):
         key = ("c3", name)
         if key not in self._w:
-            self._w[key] = K.pack_conv3x3_weight(self._p(name))
+            self._w[key] = K.pack_conv3x3_weight(self._src(name)).to(self.dev)
         return self._w[key]
 
     # ------------------------------------------------------------------ op recording helpers
@@ -310,8 +335,8 @@ class UNetEngine:
         ln = self._ln(plan, h, tb + ".norm1")
         key = ("qkv", tb)
         if key not in self._w:
-            self._w[key] = torch.cat([self._p(tb + f".attn1.to_{n}.weight") for n in "qkv"], 0) \
-                .to(torch.bfloat16).contiguous()
+            self._w[key] = torch.cat([self._src(tb + f".attn1.to_{n}.weight") for n in "qkv"], 0) \
+                .to(torch.bfloat16).contiguous().to(self.dev)
         qkv = self._gemm(plan, ln, self._w[key], 3 * Cc)
         self.arena.release(ln)
         ao = self._attn(plan, qkv[:, :Cc], qkv[:, Cc:2 * Cc], qkv[:, 2 * Cc:], hw, hw, d)
@@ -334,9 +359,9 @@ class UNetEngine:
         bn = K.gemm_block_n(8 * Cc, 1, 1, ln.shape[0], K.EPI_GEGLU)
         key = ("geglu", tb, bn)
         if key not in self._w:
-            wp, bp = K.pack_geglu(self._p(tb + ".ff.net.0.proj.weight").to(torch.bfloat16),
-                                  self._p(tb + ".ff.net.0.proj.bias").float(), bn)
-            self._w[key] = (wp, bp, bn)
+            wp, bp = K.pack_geglu(self._src(tb + ".ff.net.0.proj.weight").to(torch.bfloat16),
+                                  self._src(tb + ".ff.net.0.proj.bias").float(), bn)
+            self._w[key] = (wp.to(self.dev), bp.to(self.dev), bn)
         wp, bp, bn = self._w[key]
         ff = self._gemm(plan, ln, wp, 8 * Cc, bias=bp, epilogue=K.EPI_GEGLU, block_n=bn)
         self.arena.release(ln)
@@ -371,13 +396,28 @@ class UNetEngine:
             out += [f"up_blocks.{b}.resnets.{j}" for j in range(a.layers_per_block + 1)]
         return out
 
+    def _downsample(self, plan, b, h, H, W, cout):
+        """Stride-2 3x3 convolution of ``down_blocks[b].downsamplers[0]``; returns (out, H/2, W/2)."""
+        n = self.n
+        col = self.arena.alloc((n * (H // 2) * (W // 2), 9 * cout))
+        check(lib().sonic_plan_add_im2col_s2(plan.h, K.ptr(h), K.ptr(col), n, H, W, cout), "sonic_plan_add_im2col_s2")
+        plan.log.append(f"im2col_s2 {n}x{H}x{W}x{cout}")
+        key = ("down", b)
+        if key not in self._w:
+            w = self._src(f"down_blocks.{b}.downsamplers.0.conv.weight")
+            self._w[key] = w.permute(0, 2, 3, 1).reshape(w.shape[0], -1).to(torch.bfloat16).contiguous().to(self.dev)
+        out = self._gemm(plan, col, self._w[key], cout, bias=self._f32(f"down_blocks.{b}.downsamplers.0.conv.bias"),
+                         gn_stats=True)
+        self.arena.release(col)
+        return out, H // 2, W // 2
+
     def _build_ctx_plan(self):
         plan = _Plan()
         for pfx in self._attn_prefixes():
             tb = pfx + ".transformer_blocks.0"
             if ("kv", tb) not in self._w:
-                wk, wv = self._p(tb + ".attn2.to_k.weight"), self._p(tb + ".attn2.to_v.weight")
-                self._w[("kv", tb)] = torch.cat([wk, wv], 0).to(torch.bfloat16).contiguous()
+                wk, wv = self._src(tb + ".attn2.to_k.weight"), self._src(tb + ".attn2.to_v.weight")
+                self._w[("kv", tb)] = torch.cat([wk, wv], 0).to(torch.bfloat16).contiguous().to(self.dev)
             w = self._w[("kv", tb)]
             kv = self.arena.alloc((self.n * self.ctx_len, w.shape[0]))
             self._ctx_kv[tb] = kv                              # persistent: never released
@@ -419,15 +459,34 @@ class UNetEngine:
         return gemv
 
     def _build_unet_plan(self, cached: bool):
+        """One walk over the network serves both plans.  ``cached`` = a DeepCache non-refresh step for
+        ``self.cache_branch`` (appendix A.4: ``block_id, layer_id = divmod(branch, 3)``): down layer (b, j) runs iff
+        ``b < block_id or (b == block_id and j < layer_id)`` (a down-sampler is layer ``layers_per_block``), the mid
+        block never, up layer (b, j) -- DeepCache indexes the up path in reverse, ``bi = nb-1-b``,
+        ``li = layers-1-j`` -- iff ``bi < block_id or (bi == block_id and li <= layer_id)``; the first up layer that
+        runs takes as input the feature the last FULL step left resident in HBM (``self.cache_feature``).  The skip
+        connections a cached step consumes are exactly the ones it recomputes."""
         a = self.arch
         plan = _Plan()
         n, H, W = self.n, self.H, self.W
         boc = a.block_out_channels
+        nb, L = len(boc), a.layers_per_block
+        d_runs, u_runs, first_up = deepcache_runs(self.cache_branch, nb, L)
+
+        def down_runs(b, j):
+            return not cached or d_runs(b, j)
+
+        def up_runs(b, j):
+            return not cached or u_runs(b, j)
+
         gemv = self._record_time_path(plan)
-        if cached:
-            prefixes = [f"up_blocks.{len(boc) - 1}.resnets.{a.layers_per_block}"]
-        else:
-            prefixes = self._resnet_prefixes()
+        prefixes = []
+        for b in range(nb):
+            prefixes += [f"down_blocks.{b}.resnets.{j}" for j in range(L) if down_runs(b, j)]
+        if not cached:
+            prefixes += ["mid_block.resnets.0", "mid_block.resnets.1"]
+        for b in range(nb):
+            prefixes += [f"up_blocks.{b}.resnets.{j}" for j in range(L + 1) if up_runs(b, j)]
         gemv([(self._lin(p + ".time_emb_proj.weight"), self._f32(p + ".time_emb_proj.bias"),
                self._f32(p + ".conv1.bias"), self._temb_bias[p]) for p in prefixes], self._t_e2, 4 * boc[0], True)
 
@@ -441,10 +500,10 @@ class UNetEngine:
         # TMA taps the A operand arrives in 16-byte rows and the copy engine's row rate made this 154 us (38 TFLOP/s).
         key = ("conv_in",)
         if key not in self._w:
-            w = self._p("conv_in.weight")
-            wp = torch.zeros(w.shape[0], 8, 3, 3, device=self.dev, dtype=w.dtype)
+            w = self._src("conv_in.weight")
+            wp = torch.zeros(w.shape[0], 8, 3, 3, device=w.device, dtype=w.dtype)
             wp[:, : w.shape[1]] = w
-            self._w[key] = wp.permute(0, 2, 3, 1).reshape(w.shape[0], -1).to(torch.bfloat16).contiguous()
+            self._w[key] = wp.permute(0, 2, 3, 1).reshape(w.shape[0], -1).to(torch.bfloat16).contiguous().to(self.dev)
         col = self.arena.alloc((n * H * W, 72))
         check(lib().sonic_plan_add_im2col3x3(plan.h, K.ptr(x8), K.ptr(col), n, H, W, 8, 1), "sonic_plan_add_im2col3x3")
         plan.log.append(f"im2col3x3 {n}x{H}x{W}x8")
@@ -452,86 +511,88 @@ class UNetEngine:
         h = self._gemm(plan, col, self._w[key], boc[0], bias=self._f32("conv_in.bias"), gn_stats=True)
         self.arena.release(col)
 
-        last_up = len(boc) - 1
         if cached:
             assert self.cache_feature is not None, "build the full plan first"
-            pfx = f"up_blocks.{last_up}"
-            j = a.layers_per_block
-            out = self._resnet(plan, f"{pfx}.resnets.{j}", self.cache_feature, h, H, W, boc[0])
-            self.arena.release(h)
-            if a.attn_blocks[0]:
-                out = self._transformer(plan, f"{pfx}.attentions.{j}", out, H, W)
-            h = out
-        else:
-            skips = [(h, H, W)]
-            # ---- down path
-            for b, cout in enumerate(boc):
-                for j in range(a.layers_per_block):
+        # ---- down path; ``skips`` holds (tensor or None for a layer this plan does not run, H, W)
+        skips = [(h, H, W)]
+        alive = True                                        # False once the walk passes the last layer that runs
+        for b, cout in enumerate(boc):
+            for j in range(L):
+                if alive and down_runs(b, j):
                     r = self._resnet(plan, f"down_blocks.{b}.resnets.{j}", h, None, H, W, cout)
                     if a.attn_blocks[b]:
                         r = self._transformer(plan, f"down_blocks.{b}.attentions.{j}", r, H, W)
                     h = r
                     skips.append((h, H, W))
-                if b != len(boc) - 1:
-                    col = self.arena.alloc((n * (H // 2) * (W // 2), 9 * cout))
-                    check(lib().sonic_plan_add_im2col_s2(plan.h, K.ptr(h), K.ptr(col), n, H, W, cout),
-                          "sonic_plan_add_im2col_s2")
-                    plan.log.append(f"im2col_s2 {n}x{H}x{W}x{cout}")
-                    key = ("down", b)
-                    if key not in self._w:
-                        w = self._p(f"down_blocks.{b}.downsamplers.0.conv.weight")
-                        self._w[key] = w.permute(0, 2, 3, 1).reshape(w.shape[0], -1).to(torch.bfloat16).contiguous()
-                    H, W = H // 2, W // 2
-                    h = self._gemm(plan, col, self._w[key], cout,
-                                   bias=self._f32(f"down_blocks.{b}.downsamplers.0.conv.bias"), gn_stats=True)
-                    self.arena.release(col)
+                else:
+                    alive = False
+                    skips.append((None, H, W))
+            if b != nb - 1:
+                if alive and down_runs(b, L):
+                    h, H, W = self._downsample(plan, b, h, H, W, cout)
                     skips.append((h, H, W))
-            # ---- mid
+                else:
+                    alive = False
+                    H, W = H // 2, W // 2
+                    skips.append((None, H, W))
+        # ---- mid
+        if not cached:
             c = boc[-1]
             r = self._resnet(plan, "mid_block.resnets.0", h, None, H, W, c)
             r = self._transformer(plan, "mid_block.attentions.0", r, H, W)
             h = self._resnet(plan, "mid_block.resnets.1", r, None, H, W, c)
             self.arena.release(r)
-            # ---- up path
-            rev = list(reversed(boc))
-            rev_attn = list(reversed(a.attn_blocks))
-            for b, cout in enumerate(rev):
-                for j in range(a.layers_per_block + 1):
-                    skip, sh, sw = skips.pop()
-                    assert (sh, sw) == (H, W)
-                    r = self._resnet(plan, f"up_blocks.{b}.resnets.{j}", h, skip, H, W, cout)
-                    keep_h = b == last_up and j == a.layers_per_block and h is self.cache_feature
-                    if not keep_h:
-                        self.arena.release(h)
-                    self.arena.release(skip)
-                    if rev_attn[b]:
-                        r = self._transformer(plan, f"up_blocks.{b}.attentions.{j}", r, H, W)
-                    h = r
-                    if b == last_up and j == a.layers_per_block - 1:
-                        self.cache_feature = h               # DeepCache branch-0 feature: stays in HBM
-                if b != last_up:
-                    up = self.arena.alloc((n * 4 * H * W, cout))
-                    check(lib().sonic_plan_add_upsample2x(plan.h, K.ptr(h), K.ptr(up), n, H, W, cout),
-                          "sonic_plan_add_upsample2x")
-                    plan.log.append(f"upsample2x {n}x{H}x{W}x{cout}")
+        else:
+            h = None
+        # ---- up path
+        rev = list(reversed(boc))
+        rev_attn = list(reversed(a.attn_blocks))
+        for b, cout in enumerate(rev):
+            for j in range(L + 1):
+                skip, sh, sw = skips.pop()
+                if (b, j) == first_up:
+                    if cached:
+                        h = self.cache_feature              # left resident by the last full step
+                    else:
+                        self.cache_feature = h              # never released: stays in HBM between steps
+                if not up_runs(b, j):
+                    assert skip is None, "a cached step recomputed a skip connection it does not consume"
+                    continue
+                assert (sh, sw) == (H, W) and skip is not None and h is not None
+                r = self._resnet(plan, f"up_blocks.{b}.resnets.{j}", h, skip, H, W, cout)
+                if h is not self.cache_feature:
                     self.arena.release(h)
+                self.arena.release(skip)
+                if rev_attn[b]:
+                    r = self._transformer(plan, f"up_blocks.{b}.attentions.{j}", r, H, W)
+                h = r
+            if b != nb - 1:
+                if h is None:                               # cached plan: this block did not run at all
                     H, W = 2 * H, 2 * W
-                    h = self._gemm(plan, up, self._conv3(f"up_blocks.{b}.upsamplers.0.conv.weight"), cout, n_img=n,
-                                   H=H, W=W, taps=9, bias=self._f32(f"up_blocks.{b}.upsamplers.0.conv.bias"),
-                                   gn_stats=True)
-                    self.arena.release(up)
-            assert not skips
+                    continue
+                up = self.arena.alloc((n * 4 * H * W, cout))
+                check(lib().sonic_plan_add_upsample2x(plan.h, K.ptr(h), K.ptr(up), n, H, W, cout),
+                      "sonic_plan_add_upsample2x")
+                plan.log.append(f"upsample2x {n}x{H}x{W}x{cout}")
+                if h is not self.cache_feature:
+                    self.arena.release(h)
+                H, W = 2 * H, 2 * W
+                h = self._gemm(plan, up, self._conv3(f"up_blocks.{b}.upsamplers.0.conv.weight"), cout, n_img=n,
+                               H=H, W=W, taps=9, bias=self._f32(f"up_blocks.{b}.upsamplers.0.conv.bias"),
+                               gn_stats=True)
+                self.arena.release(up)
+        assert not skips
         # ---- out: GroupNorm+SiLU -> conv3x3 (4 output channels padded to one 16-wide MMA tile) -> NCHW
         g = self._gn(plan, h, None, "conv_norm_out", self.H * self.W, a.norm_eps, True)
         self.arena.release(h)
         key = ("conv_out",)
         if key not in self._w:
-            w = self._p("conv_out.weight")
-            wp = torch.zeros(16, w.shape[1], 3, 3, device=self.dev, dtype=w.dtype)
+            w = self._src("conv_out.weight")
+            wp = torch.zeros(16, w.shape[1], 3, 3, device=w.device, dtype=w.dtype)
             wp[: w.shape[0]] = w
-            bp = torch.zeros(16, device=self.dev, dtype=torch.float32)
-            bp[: w.shape[0]] = self._p("conv_out.bias").float()
-            self._w[key] = (K.pack_conv3x3_weight(wp), bp)
+            bp = torch.zeros(16, device=w.device, dtype=torch.float32)
+            bp[: w.shape[0]] = self._src("conv_out.bias").float()
+            self._w[key] = (K.pack_conv3x3_weight(wp).to(self.dev), bp.to(self.dev))
         wp, bp = self._w[key]
         o16 = self._gemm(plan, g, wp, 16, n_img=n, H=self.H, W=self.W, taps=9, bias=bp, block_n=16)
         self.arena.release(g)

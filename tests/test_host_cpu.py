@@ -252,3 +252,49 @@ def test_step_requires_cuda():
     x = torch.zeros(1, 4, 8, 8)
     with pytest.raises(RuntimeError, match="no CPU path"):
         s.step(x, s.timesteps[0], x)
+
+
+@pytest.mark.parametrize("branch", list(range(12)))
+def test_deepcache_branch_layer_sets_match_the_oracle(branch):
+    """The engine's cached-plan walk (which layers a non-refresh step recomputes, which feature it reads) against
+    the oracle's restatement of ``DeepCacheSDHelper.is_skip_step`` executed on a tiny UNet, for every branch."""
+    import sys
+
+    sys.path.insert(0, os.path.dirname(__file__))
+    import refpin_cases as RC
+    from oracle.deepcache import DeepCacheOracle
+    from sonicdiffusionbayeslab_b200.unet_engine import deepcache_runs
+
+    net = RC.tiny_unet()
+    dc = DeepCacheOracle(net)
+    dc.set_params(cache_interval=5, cache_branch_id=branch)
+    pe, ne, lat = RC.pipeline_inputs()
+    x = torch.cat([lat, lat])
+    ctx = torch.cat([ne, pe])
+    ran = []
+    orig = dc._wrap
+
+    def spy(key, block_i, layer_i, blocktype, fn):
+        def fn2():
+            ran.append(key)
+            return fn()
+        return orig(key, block_i, layer_i, blocktype, fn2)
+
+    dc._wrap = spy
+    with torch.no_grad():
+        dc.forward(x, torch.tensor(500), ctx, 0)          # refresh step
+        ran.clear()
+        dc.forward(x, torch.tensor(400), ctx, 1)          # cached step
+    nb, L = 4, 2
+    down_runs, up_runs, first_up = deepcache_runs(branch, nb, L)
+    want_down = {(b, j) for b in range(nb) for j in range(L) if down_runs(b, j)}
+    want_ds = {b for b in range(nb - 1) if down_runs(b, L)}
+    want_up = {(b, j) for b in range(nb) for j in range(L + 1) if up_runs(b, j)}
+    got_down = {(k[2], k[3]) for k in ran if k[:2] == ("down", "resnet")}
+    got_ds = {k[2] for k in ran if k[:2] == ("down", "downsampler")}
+    got_up = {(nb - 1 - k[2], L - k[3]) for k in ran if k[:2] == ("up", "resnet")}       # reversed -> forward indices
+    assert (got_down, got_ds, got_up) == (want_down, want_ds, want_up)
+    assert not any(k[0] == "mid" for k in ran)
+    assert min(want_up) == first_up
+    got_us = {nb - 1 - k[2] for k in ran if k[:2] == ("up", "upsampler")}
+    assert got_us == {b for b in range(nb - 1) if any(up_runs(b, j) for j in range(L + 1))}

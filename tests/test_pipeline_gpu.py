@@ -219,6 +219,42 @@ def test_deepcache_pattern_and_parity(world):
     assert max(errs) <= TF_TOL, errs
 
 
+@pytest.mark.parametrize("branch", [1, 2, 3, 5])
+def test_deepcache_other_branches(world, branch):
+    """``cache_branch_id`` != 0 (DeepCacheSDHelper.set_params): the engine records a cached plan
+    whose cut follows ``divmod(branch, 3)``; teacher-forced against the oracle's DeepCache restatement."""
+    from oracle.deepcache import DeepCacheOracle
+    from oracle.pipeline import denoise
+    from oracle.schedulers import SD15_SCHEDULER_CONFIG, DDIMScheduler
+    from sonicdiffusionbayeslab_b200 import schedulers as S
+    from sonicdiffusionbayeslab_b200.deepcache import DeepCacheSDHelper
+
+    n, interval = 4, 2
+    dc = DeepCacheOracle(world["net"])
+    dc.set_params(cache_interval=interval, cache_branch_id=branch)
+    ref = denoise(world["net"], DDIMScheduler.from_config(SD15_SCHEDULER_CONFIG), world["pe"], world["ne"],
+                  world["lat"], n, deepcache=dc)
+    model = world["make"]()
+    model.scheduler = S.DDIMSchedulerMy.from_config(SD15_SCHEDULER_CONFIG)
+    helper = DeepCacheSDHelper(pipe=model)
+    helper.set_params(cache_interval=interval, cache_branch_id=branch)
+    helper.enable()
+    errs = []
+
+    def cb(pipe, i, t, kwargs):
+        errs.append(_rel(kwargs["latents"], ref["per_step"][i]))
+        return {"latents": ref["per_step"][i].to(kwargs["latents"].dtype)}
+
+    model(prompt_embeds=world["pe"], negative_prompt_embeds=world["ne"], latents=world["lat"], num_inference_steps=n,
+          guidance_scale=7.5, output_type="latent", callback_on_step_end=cb)
+    helper.disable()
+    assert model.last_step_kinds == ["full", "cached", "full", "cached"]
+    full_n, _ = model.engine(world["B"], True).stats("full")
+    cached_n, _ = model.engine(world["B"], True).stats("cached")
+    print(f"\n[deepcache branch {branch}] teacher-forced per-step max-abs {max(errs):.3e}; launches full {full_n} cached {cached_n}")
+    assert cached_n < full_n and max(errs) <= TF_TOL, errs
+
+
 def test_two_schedulers_switch(world):
     from oracle import schedulers as O
     from oracle.pipeline import denoise_two
@@ -314,15 +350,17 @@ def test_main_py_runs_a_config_end_to_end(tmp_path):
     rows = tables[-1].read_text().strip().splitlines()
     assert rows[0].split("\t")[:2] == ["nfe", "clip_score_gen_image"]
     assert [r.split("\t")[0] for r in rows[1:]] == ["3", "5"]      # nfe = number of UNet evaluations
-    assert all(float(r.split("\t")[-1]) > 0 for r in rows[1:])     # seconds per image, loop only
+    cols = rows[0].split("\t")
+    assert all(float(r.split("\t")[cols.index("time_metric")]) > 0 for r in rows[1:])     # seconds per image, loop only
+    assert all(r.split("\t")[cols.index("weights")] == "model:random-init,clip:random-init" for r in rows[1:])
     assert len(list(tmp_path.rglob("*.png"))) == 16                # 2 batches x 4 prompts x 2 sweep points
 
 
 @pytest.mark.parametrize("n_img,latent", [(2, 32), (1, 64)])
 def test_native_vae_decoder_matches_torch_module(cuda, n_img, latent):
-    """VaeEngine (tcgen05 convs, fused GroupNorm, GEMM + row-softmax attention) against the PyTorch
-    AutoencoderKL decoder (vae.py, fp32) on the same seeded weights; output is an image in roughly [-1, 1]."""
-    from sonicdiffusionbayeslab_b200.vae import make_vae
+    """VaeEngine (tcgen05 convs, fused GroupNorm, GEMM + row-softmax attention) against the oracle's PyTorch
+    AutoencoderKL decoder (oracle/vae.py, fp32) on the same seeded weights; output is an image in roughly [-1, 1]."""
+    from oracle.vae import make_vae
     from sonicdiffusionbayeslab_b200.vae_engine import VaeEngine
 
     ref_mod = make_vae(29, dtype=torch.float32, device=cuda)
@@ -348,8 +386,12 @@ def test_native_clip_towers_match_transformers(cuda):
     from sonicdiffusionbayeslab_b200.clip_engine import ClipTextEngine, ClipVisionEngine
     from sonicdiffusionbayeslab_b200.metrics.metrics import make_clip_model
 
-    model, tok = make_clip_model(None)
-    model = model.to(cuda).float()
+    from transformers import CLIPModel
+
+    weights, tok = make_clip_model(None)
+    model = CLIPModel(weights.config)
+    model.load_state_dict(weights.state_dict())
+    model = model.to(cuda).float().eval()
     sd = {k: v.detach() for k, v in model.state_dict().items()}
     n = 4
     g = torch.Generator(device="cuda").manual_seed(3)
@@ -378,13 +420,21 @@ def test_native_clip_towers_match_transformers(cuda):
 def test_native_prompt_encoder_matches_transformers(cuda):
     """encode_prompt (models.py:139-149) through ClipTextEngine (CLIP-L text tower, causal attention, final LayerNorm)
     against transformers.CLIPTextModel fp32 on the same seeded weights."""
-    from sonicdiffusionbayeslab_b200 import models as M
-    from sonicdiffusionbayeslab_b200.text import encode_prompts
+    from transformers import CLIPTextModel
 
-    model = M.StableDiffusionModel.from_pretrained("runwayml/stable-diffusion-v1-5", torch_dtype=torch.bfloat16).to(cuda)
+    from sonicdiffusionbayeslab_b200 import models as M
+
+    with pytest.warns(RuntimeWarning, match="RANDOM-INIT"):
+        model = M.StableDiffusionModel.from_pretrained("runwayml/stable-diffusion-v1-5",
+                                                       torch_dtype=torch.bfloat16).to(cuda)
+    assert model.weights_source == "random-init"
     prompts = ["a photo of an astronaut riding a horse", "", "sunset over mountains, oil painting"]
     got = model._encode(prompts).float()
-    ref = encode_prompts(model.tokenizer, model.text_encoder.float(), prompts, cuda).float()
+    ref_mod = CLIPTextModel(model.text_encoder.config)
+    ref_mod.load_state_dict(model.text_encoder.state_dict())
+    ids, _ = model.tokenizer(prompts)
+    with torch.no_grad():
+        ref = ref_mod.to(cuda).float().eval()(ids.to(cuda))[0].float()
     torch.cuda.synchronize()
     assert got.shape == ref.shape == (3, 77, 768)
     assert (got - ref).abs().max().item() < 3e-2 * ref.abs().max().item()

@@ -5,7 +5,7 @@ import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 
-from sonicdiffusionbayeslab_b200.vae import make_vae
+from oracle.vae import make_vae
 from sonicdiffusionbayeslab_b200.vae_engine import VaeEngine
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 16
