@@ -1,25 +1,34 @@
 #!/usr/bin/env python
 """Headline benchmark: images/sec of the SD-v1.5 denoising loop on B200 (BASELINE.json metric).
 
-Workload (configs[1]): SD-v1.5 UNet, DPM-Solver++ (2M) 25 steps, 512x512 (latent 64x64), batch 16,
-classifier-free guidance 7.5 (UNet batch 32), bf16, random-init weights, synthetic prompt
-embeddings.  One bench "step" = one pass of the hot path over one batch: 25 x (UNet plan replay +
-fused CFG/scheduler update) for 16 images.
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--config NAME]
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+Default workload = BASELINE configs[1] (``dpm_solver``): SD-v1.5 UNet, DPM-Solver++ (2M) 25 steps, 512x512
+(latent 64x64), batch 16 per GPU, classifier-free guidance 7.5 (UNet batch 32), bf16, random-init weights,
+synthetic prompt embeddings.  One bench "step" = one pass of the hot path over one batch.  The other BASELINE
+configurations are selected with ``--config`` (the driver's contract run never passes it):
 
-Own arm (default): prints ONE JSON line with
+    deep_cache          configs[2]: DDIM 50 steps + DeepCache interval 3, global batch 64 sharded over the ranks
+    consistency_model   configs[3]: LCM 4 steps, guidance 0 (no CFG), global batch 128 sharded over the ranks
+    two_schedulers      configs[4]: DDIM -> DPM-Solver++ switch (N1 = 20, k = 10), 125 prompts per rank (1 000 on
+                        8 GPUs) -> native VAE decode -> uint8 -> native CLIP towers -> NCCL all-gather of the
+                        uint8 images and CLIP features -> CLIP score, collective INSIDE the timed e2e region
+
+Own arm: ONE JSON line with
   value      images/s, whole job, inputs (latents, prompt embeddings) resident in HBM, loop only
              (the reference's time_metric scope, /root/reference/src/models.py:208,284-285)
-  e2e        the same loop through the plugin call ``model(prompt_embeds=, latents=, ...)`` with
-             PINNED HOST inputs copied H2D and the final latents copied D2H inside the timed region
-  roofline   dominant kernel (conv_gemm_kernel: every conv / linear of the UNet) vs the measured
-             dense-bf16 tensor peak, from per-operator CUDA-event times of the same plan
-  cpu_baseline  the oracle (CPU restatement of the reference path) on this box's host cores, on a
-             bounded sample (rank 0, N=1 only)
-Reference arm (--impl reference): the oracle's CPU path (there is no runnable reference: its
-arithmetic lives in diffusers, absent here) timed on all host threads; each step is a bounded
-sample (one CFG denoising step at batch 1) extrapolated to the 25-step workload.
+  e2e        the same through the plugin call with PINNED HOST inputs copied H2D and the result copied D2H inside
+             the timed region (two_schedulers: prompts as strings, images + features gathered, score read back)
+  e2e_with_vae   prompts as strings -> tokenise -> text tower -> loop -> VAE decode -> uint8 images on the host
+  roofline   dominant kernel (conv_gemm_kernel: every conv / linear of the UNet) vs the measured dense-bf16
+             tensor peak, from per-operator CUDA-event times of the same plan; roofline_hbm: the HBM-bound
+             kernels (GroupNorm, LayerNorm, fused latent update) vs the measured copy bandwidth
+  gpu_library_baseline   the oracle UNet through stock PyTorch eager (cuDNN / cuBLASLt / flash-SDPA, bf16) on
+             the same GPU at the same UNet batch -- the "existing Blackwell kernels" bar (rank 0, N=1 only)
+  cpu_baseline  the oracle (CPU restatement of the reference path) on this box's host cores, bounded sample
+Reference arm (--impl reference): the oracle's CPU path (there is no runnable reference: its arithmetic lives in
+diffusers, absent here) on all host threads; each step is a bounded sample (ONE CFG denoising step at batch 1,
+fp32) extrapolated to the workload -- the line's ``config`` says so.
 """
 from __future__ import annotations
 
@@ -37,17 +46,36 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-STEPS_PER_IMAGE = 25
-BATCH = 16
 GUIDANCE = 7.5
 FLOP_PER_SAMPLE_FWD = 803.27e9
-CONFIG = {"workload": "configs/dpm_solver_config.yaml: SD-v1.5 UNet, DPM-Solver++(2M) 25 steps, 512x512, "
-                      "batch 16 per GPU, CFG 7.5 (UNet batch 32), bf16",
-          "per_gpu_batch": BATCH, "l2": "working set larger than L2 (weights 1.7 GB + streamed activations)"}
+
+WORKLOADS = {
+    "dpm_solver": dict(
+        text="configs/dpm_solver_config.yaml: SD-v1.5 UNet, DPM-Solver++(2M) 25 steps, 512x512, batch 16 per GPU, "
+             "CFG 7.5 (UNet batch 32), bf16",
+        metric="images/sec (512x512, 25 steps DPM-Solver++, CFG 7.5)", scaling="weak", per_gpu=lambda w: 16,
+        steps=25, guidance=7.5),
+    "deep_cache": dict(
+        text="configs/deep_cache_config.yaml: SD-v1.5 UNet, DDIM 50 steps + DeepCache interval 3 (branch 0), 512x512, "
+             "global batch 64 sharded over the GPUs, CFG 7.5, bf16",
+        metric="images/sec (512x512, DDIM 50 steps + DeepCache interval 3, CFG 7.5)", scaling="strong",
+        per_gpu=lambda w: 64 // w, steps=50, guidance=7.5),
+    "consistency_model": dict(
+        text="configs/consistency_model_config.yaml: latent consistency model (LCM scheduler) 4 steps, 512x512, "
+             "global batch 128 sharded over the GPUs, guidance 0 (no CFG), bf16",
+        metric="images/sec (512x512, LCM 4 steps, no CFG)", scaling="strong", per_gpu=lambda w: 128 // w, steps=4,
+        guidance=0.0),
+    "two_schedulers": dict(
+        text="configs/two_schedulers_config.yaml: DDIM -> DPM-Solver++ switch (N1=20, k=10: 21 UNet calls), 512x512, "
+             "125 prompts per GPU in batches of <=32 (1 000 prompts on 8 GPUs), CFG 7.5, bf16; e2e adds VAE decode, "
+             "uint8 quantise, CLIP towers, NCCL all-gather of images + features, CLIP score",
+        metric="images/sec (512x512, DDIM->DPM-Solver++ 21 UNet calls, CFG 7.5)", scaling="weak",
+        per_gpu=lambda w: 125, steps=21, guidance=7.5),
+}
 
 
 def _traffic():
-    """DRAM bytes per conv_gemm_kernel launch (mean over the 194 launches of one UNet step) from the committed ncu
+    """DRAM bytes per conv_gemm_kernel launch (mean over the launches of one UNet step) from the committed ncu
     launch list (profiles/traffic.json, written by the round's profiling pass); None if absent."""
     path = os.path.join(ROOT, "profiles", "traffic.json")
     try:
@@ -106,18 +134,123 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def build_model(device, seed=29):
+# ----------------------------------------------------------------------------------------- model construction
+def build_model(device, workload, seed=29):
+    import warnings
+
     from sonicdiffusionbayeslab_b200 import models as M
     from sonicdiffusionbayeslab_b200 import schedulers as S
+    from sonicdiffusionbayeslab_b200.deepcache import DeepCacheSDHelper
 
-    model = M.StableDiffusionModel.from_pretrained("runwayml/stable-diffusion-v1-5", torch_dtype=torch.bfloat16,
-                                                   seed=seed)
+    cfg = M.SD15_SCHEDULER_CONFIG
+    cls = M.StableDiffusionModelTwoSchedulers if workload == "two_schedulers" else M.StableDiffusionModel
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")          # random-init weights ARE the benchmark's declared data
+        model = cls.from_pretrained("runwayml/stable-diffusion-v1-5", torch_dtype=torch.bfloat16, seed=seed)
     model.to(device)
-    model.scheduler = S.DPMSolverScheduler.from_config(M.SD15_SCHEDULER_CONFIG, solver_order=2,
-                                                       algorithm_type="dpmsolver++", final_sigmas_type="zero")
+    dpmpp = dict(solver_order=2, algorithm_type="dpmsolver++", final_sigmas_type="zero")
+    if workload == "dpm_solver":
+        model.scheduler = S.DPMSolverScheduler.from_config(cfg, **dpmpp)
+    elif workload == "deep_cache":
+        model.scheduler = S.DDIMSchedulerMy.from_config(cfg)
+        h = DeepCacheSDHelper(pipe=model)
+        h.set_params(cache_interval=3, cache_branch_id=0)
+        h.enable()
+    elif workload == "consistency_model":
+        model.scheduler = S.LCMScheduler.from_config(cfg)
+    else:
+        model.scheduler_first = S.DDIMSchedulerMy.from_config(cfg)
+        model.scheduler_second = S.DPMSolverScheduler.from_config(cfg, **dpmpp)
     return model
 
 
+def call_kwargs(workload):
+    w = WORKLOADS[workload]
+    if workload == "two_schedulers":
+        return dict(num_inference_steps_first=20, num_inference_steps_second=20, num_step_switch=10,
+                    guidance_scale=w["guidance"])
+    return dict(num_inference_steps=w["steps"], guidance_scale=w["guidance"])
+
+
+def _events():
+    return torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+
+# ----------------------------------------------------------------------------------------- same-box library baseline
+def gpu_library_baseline(dev, unet_batch, engine_step_ms, profile_rows):
+    """The oracle UNet in bf16 through stock PyTorch eager on the SAME GPU (cuDNN / cuBLASLt / flash SDPA, TF32 off)
+    at the benchmarked UNet batch, plus four operator classes at the 64x64 level, each with this repo's kernel
+    time for the same shape beside it (from the per-operator plan profile)."""
+    import torch.nn.functional as F
+
+    from oracle.unet import make_unet
+
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.benchmark = True
+    net = make_unet(29).to(torch.bfloat16).to(dev).to(memory_format=torch.channels_last)
+    g = torch.Generator(device=dev).manual_seed(1)
+    x = torch.randn(unet_batch, 4, 64, 64, device=dev, generator=g).bfloat16()
+    ctx = torch.randn(unet_batch, 77, 768, device=dev, generator=g).bfloat16()
+    t = torch.tensor(481, device=dev)
+
+    def timed(fn, reps, warm=3):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        a, b = _events()
+        a.record()
+        for _ in range(reps):
+            fn()
+        b.record()
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / reps
+
+    with torch.no_grad():
+        unet_ms = timed(lambda: net(x, t, encoder_hidden_states=ctx), 5)
+    del net
+    torch.cuda.empty_cache()
+    n = unet_batch
+    ops = {}
+    with torch.no_grad():
+        xc = torch.randn(n, 320, 64, 64, device=dev).bfloat16().to(memory_format=torch.channels_last)
+        w = torch.randn(320, 320, 3, 3, device=dev).bfloat16().to(memory_format=torch.channels_last)
+        ms = timed(lambda: F.conv2d(xc, w, padding=1), 20)
+        ops["conv3x3 320->320 @64x64"] = {"torch_us": round(ms * 1e3, 1),
+                                         "torch_tflops": round(2 * n * 4096 * 320 * 2880 / ms / 1e9, 1)}
+        q = torch.randn(n, 8, 4096, 40, device=dev).bfloat16()
+        ms = timed(lambda: F.scaled_dot_product_attention(q, q, q), 10)
+        ops["self-attention 4096 tokens, 8 heads, d=40"] = {
+            "torch_us": round(ms * 1e3, 1), "torch_tflops": round(4 * n * 8 * 4096 * 4096 * 40 / ms / 1e9, 1)}
+        gw, gb = torch.ones(320, device=dev).bfloat16(), torch.zeros(320, device=dev).bfloat16()
+        ms = timed(lambda: F.silu(F.group_norm(xc, 32, gw, gb, 1e-5)), 20)
+        ops["GroupNorm(32)+SiLU 320ch @64x64"] = {"torch_us": round(ms * 1e3, 1),
+                                                 "torch_gbs": round(2 * xc.numel() * 2 / ms / 1e6, 1)}
+        xl = torch.randn(n * 4096, 320, device=dev).bfloat16()
+        ms = timed(lambda: F.layer_norm(xl, (320,), gw, gb, 1e-5), 20)
+        ops["LayerNorm 320 over 64x64 tokens"] = {"torch_us": round(ms * 1e3, 1),
+                                                 "torch_gbs": round(2 * xl.numel() * 2 / ms / 1e6, 1)}
+    rows = n * 4096
+    mine = {
+        "conv3x3 320->320 @64x64": f"gemm M={rows} N=320 K=320x9",
+        "self-attention 4096 tokens, 8 heads, d=40": f"attention B={n} H=8 Sq=4096 Sk=4096 d=40",
+        "GroupNorm(32)+SiLU 320ch @64x64": f"groupnorm rows={rows} C=320 silu=1",
+        "LayerNorm 320 over 64x64 tokens": f"layernorm rows={rows} C=320",
+    }
+    for k, prefix in mine.items():
+        hits = [ms for line, ms in profile_rows if line.startswith(prefix)]
+        if hits:
+            ops[k]["sonic_us"] = round(1e3 * statistics.mean(hits), 1)
+            ops[k]["speedup"] = round(ops[k]["torch_us"] / ops[k]["sonic_us"], 2)
+        else:
+            ops[k]["sonic_us"] = None          # e.g. LayerNorm: folded into the consumer GEMM, no kernel left
+    return {"what": f"oracle UNet (same architecture / weights layout) in bf16 through stock PyTorch "
+                    f"{torch.__version__} eager, channels_last, cudnn.benchmark, TF32 off, UNet batch {unet_batch}",
+            "unet_step_ms": round(unet_ms, 2), "sonic_unet_step_ms": round(engine_step_ms, 2),
+            "speedup": round(unet_ms / engine_step_ms, 2), "ops": ops}
+
+
+# ----------------------------------------------------------------------------------------- own arm
 def run_own(args):
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -132,34 +265,65 @@ def run_own(args):
 
         if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
             os.environ["NCCL_DEBUG"] = "WARN"          # NCCL prints its version banner on stdout otherwise
-
         dist = dist_mod
         dist.init_process_group("nccl", device_id=dev)
 
-    model = build_model(dev)
-    g = torch.Generator(device="cpu").manual_seed(29 + rank)
-    pe_host = torch.randn(BATCH, 77, 768, generator=g).to(torch.bfloat16).pin_memory()
-    ne_host = torch.randn(BATCH, 77, 768, generator=g).to(torch.bfloat16).pin_memory()
-    lat_host = torch.randn(BATCH, 4, 64, 64, generator=g).to(torch.bfloat16).pin_memory()
-    out_host = torch.empty(BATCH, 4, 64, 64, dtype=torch.bfloat16).pin_memory()
+    wl = args.config
+    W = WORKLOADS[wl]
+    B = W["per_gpu"](world)
+    if B < 1:
+        raise SystemExit(f"bench.py: workload {wl} does not shard over {world} GPUs")
+    model = build_model(dev, wl)
+    kw = call_kwargs(wl)
+    if wl == "two_schedulers":
+        line = run_two_schedulers(args, model, kw, B, rank, world, local, dev, dist)
+    else:
+        line = run_loop_workload(args, model, kw, wl, B, rank, world, local, dev, dist)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    if line is not None:
+        print(json.dumps(line), flush=True)
+
+
+def _barrier(dist):
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+def run_loop_workload(args, model, kw, wl, B, rank, world, local, dev, dist):
+    W = WORKLOADS[wl]
+    # Strong-scaling workloads (one GLOBAL batch sharded over the ranks) draw the global tensors and keep this
+    # rank's rows -- the single-GPU noise (rng_rows); the weak one gives every rank its own seeded batch.
+    g = torch.Generator(device="cpu").manual_seed(29 + (rank if W["scaling"] == "weak" else 0))
+    total = B * world if W["scaling"] == "strong" else B
+    lo = rank * B if W["scaling"] == "strong" else 0
+    pe_host = torch.randn(total, 77, 768, generator=g).to(torch.bfloat16)[lo:lo + B].contiguous().pin_memory()
+    ne_host = torch.randn(total, 77, 768, generator=g).to(torch.bfloat16)[lo:lo + B].contiguous().pin_memory()
+    lat_host = torch.randn(total, 4, 64, 64, generator=g).to(torch.bfloat16)[lo:lo + B].contiguous().pin_memory()
+    out_host = torch.empty(B, 4, 64, 64, dtype=torch.bfloat16).pin_memory()
     pe, ne, lat = pe_host.to(dev), ne_host.to(dev), lat_host.to(dev)
+    cfg_on = W["guidance"] > 1
+    noise_gen = torch.Generator(device=dev)          # on the device, like base_experiment.py:51-53
+    rows = (lo, lo + B, total) if W["scaling"] == "strong" else None
+
+    def extra():
+        if wl != "consistency_model":
+            return {}
+        noise_gen.manual_seed(7)                      # LCM draws fresh noise every step from this generator
+        return {"generator": noise_gen, "rng_rows": rows}
 
     def step_resident():
-        _, secs, _ = model(prompt_embeds=pe, negative_prompt_embeds=ne, latents=lat,
-                           num_inference_steps=STEPS_PER_IMAGE, guidance_scale=GUIDANCE, output_type="latent")
+        _, secs, _ = model(prompt_embeds=pe, negative_prompt_embeds=ne if cfg_on else None, latents=lat,
+                           output_type="latent", **kw, **extra())
         return secs
 
     def step_e2e():
         o, _, _ = model(prompt_embeds=pe_host.to(dev, non_blocking=True),
-                        negative_prompt_embeds=ne_host.to(dev, non_blocking=True),
-                        latents=lat_host.to(dev, non_blocking=True), num_inference_steps=STEPS_PER_IMAGE,
-                        guidance_scale=GUIDANCE, output_type="latent")
+                        negative_prompt_embeds=ne_host.to(dev, non_blocking=True) if cfg_on else None,
+                        latents=lat_host.to(dev, non_blocking=True), output_type="latent", **kw, **extra())
         out_host.copy_(o.images, non_blocking=True)
-        torch.cuda.synchronize()
-
-    def barrier():
-        if dist is not None:
-            dist.barrier()
         torch.cuda.synchronize()
 
     for _ in range(max(args.warmup, 3)):
@@ -170,93 +334,287 @@ def run_own(args):
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    barrier()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    _barrier(dist)
+    ev0, ev1 = _events()
     ev0.record()
     for _ in range(args.steps):
         step_resident()
     ev1.record()
-    barrier()
+    _barrier(dist)
     ms_total = ev0.elapsed_time(ev1)
     # ---- timed region 2: end to end through the plugin call with pinned host buffers
-    barrier()
+    _barrier(dist)
     t0 = time.perf_counter()
     for _ in range(args.steps):
         step_e2e()
-    barrier()
+    _barrier(dist)
     e2e_s = time.perf_counter() - t0
+    # ---- timed region 3 (default workload): strings in, uint8 images out -- text tower + loop + VAE decode
+    vae_s = None
+    if wl == "dpm_solver":
+        from sonicdiffusionbayeslab_b200.dataset.dataset import synthetic_prompts
+
+        prompts = synthetic_prompts(B, seed=29 + rank)
+        img_host = torch.empty(B, 3, 512, 512, dtype=torch.uint8).pin_memory()
+        model.decode_x0_preds = False                 # per-step x0 previews (models.py:295-302) are not decoded
+
+        def step_vae():
+            o, _, _ = model(prompts, latents=lat_host.to(dev, non_blocking=True), output_type="pt", **kw)
+            img_host.copy_((o.images * 255).to(torch.uint8), non_blocking=True)
+            torch.cuda.synchronize()
+
+        step_vae()
+        _barrier(dist)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step_vae()
+        _barrier(dist)
+        vae_s = time.perf_counter() - t0
     clocks = sampler.stop() if rank == 0 else None
     if dist is not None:
-        t = torch.tensor([ms_total, e2e_s], device=dev, dtype=torch.float64)
+        t = torch.tensor([ms_total, e2e_s, vae_s or 0.0], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_total, e2e_s = t.tolist()
+        ms_total, e2e_s, vae_s = t.tolist()
+        vae_s = vae_s or None
 
-    images = BATCH * args.steps * world
+    images = B * args.steps * world
     value = images / (ms_total / 1e3)
-    e2e_value = images / e2e_s
+    if rank != 0:
+        return None
+    # ---- rooflines from per-operator CUDA-event times of the recorded plan (rank 0)
+    import ctypes
 
-    # ---- roofline of the dominant kernel from per-operator CUDA-event times (rank 0)
-    line = None
+    eng = model.engine(B, cfg_on)
+    side = torch.cuda.Stream(device=dev)                    # kernels are timed on the stream they run on
+    with torch.cuda.stream(side):
+        eng.plans["full"].profile(ctypes.c_void_p(side.cuda_stream))          # warm
+        prof = eng.plans["full"].profile(ctypes.c_void_p(side.cuda_stream))
+    torch.cuda.synchronize()
+    log = eng.plans["full"].log
+    names = {0: "conv_gemm_kernel", 1: "attention kernels", 2: "groupnorm (finalize+apply)", 3: "layernorm_kernel",
+             4: "layout kernels", 5: "timestep gemv"}
+    agg, hbm = {}, {2: [0.0, 0.0], 3: [0.0, 0.0]}
+    for (kind, ms, fl), text in zip(prof, log):
+        a = agg.setdefault(kind, [0, 0.0, 0.0])
+        a[0] += 1
+        a[1] += ms
+        a[2] += fl
+        if kind in hbm:                                     # "groupnorm rows=R C=C ..." / "layernorm rows=R C=C"
+            f = dict(p.split("=") for p in text.split()[1:] if "=" in p)
+            hbm[kind][0] += 2.0 * int(f["rows"]) * int(f["C"]) * 2       # read once + write once, bf16
+            hbm[kind][1] += ms
+    tot_ms = sum(a[1] for a in agg.values())
+    burst, sustained, hbm_peak, how = _peaks()
+    kernels = [{"kernel": names[k], "ops": c, "ms": round(ms, 3), "share": round(ms / tot_ms, 4),
+                "tflops": round(fl / ms / 1e9, 1) if fl else None}
+               for k, (c, ms, fl) in sorted(agg.items(), key=lambda kv: -kv[1][1])]
+    gemm = agg[0]
+    achieved = gemm[2] / gemm[1] / 1e9
+    n_launch, plan_flops = eng.stats("full")
+    n_unet = len(model.last_step_kinds) or W["steps"]
+    unet_ms = ms_total / args.steps / n_unet
+    # fused latent update: one launch per step; timed alone (CUDA events around 200 launches at this batch)
+    upd = time_latent_update(dev, B, cfg_on)
+    roof_hbm = {}
+    for kind, label in ((2, "groupnorm"), (3, "layernorm")):
+        by, ms = hbm[kind]
+        if ms > 0:
+            roof_hbm[label] = {"bound": "hbm", "achieved": round(by / ms / 1e6, 1), "peak": hbm_peak, "unit": "GB/s",
+                               "frac": round(by / ms / 1e6 / hbm_peak, 4), "ops": agg[kind][0],
+                               "bytes_per_step": int(by), "ms_per_step": round(ms, 3)}
+        else:
+            roof_hbm[label] = {"ops": 0, "note": "no such kernel in the plan (folded into the consumer GEMM)"}
+    roof_hbm["latent_update_kernel"] = upd | {"peak": hbm_peak, "frac": round(upd["achieved"] / hbm_peak, 4)}
+    n_cached = model.last_step_kinds.count("cached")
+    launches_per_image_loop = (n_unet - n_cached) * (n_launch + 1) + n_cached * (
+        (eng.stats("cached")[0] if "cached" in eng.plans else 0) + 1)
+    line = {
+        "metric": W["metric"], "value": round(value, 3), "unit": "images/s", "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": round(ms_total / args.steps, 3),
+        "higher_is_better": True, "scaling": W["scaling"], "vs_baseline": None, "dtype": "bf16",
+        "data": "synthetic (random-init SD-v1.5 weights, N(0,1) prompt embeddings and latents, seed 29)",
+        "config": {"workload": W["text"], "per_gpu_batch": B, "global_batch": B * world,
+                   "l2": "working set larger than L2 (weights 1.7 GB + streamed activations)"},
+        "e2e": {"value": round(images / e2e_s, 3), "unit": "images/s",
+                "h2d_bytes_per_step": int(pe_host.numel() * 2 * (2 if cfg_on else 1) + lat_host.numel() * 2),
+                "d2h_bytes_per_step": int(out_host.numel() * 2)},
+        "gpu_launches": int(args.steps * 2 * (eng.stats("ctx")[0] + launches_per_image_loop)),
+        "unet_step_ms": round(unet_ms, 3),
+        "unet_calls_per_image": n_unet, "deepcache_cached_steps": n_cached or None,
+        "roofline": {"kernel": "conv_gemm_kernel (all conv3x3/conv1x1/linear launches of one UNet forward)",
+                     "bound": "tensor", "achieved": round(achieved, 1), "peak": sustained, "unit": "TFLOP/s",
+                     "frac": round(achieved / sustained, 4), "peak_kind": f"bf16_tflops_sustained ({how})",
+                     "frac_of_burst": round(achieved / burst, 4), "traffic": _traffic(),
+                     "algorithmic_per_launch": round(gemm[2] / gemm[0]), "launches_per_step": gemm[0],
+                     "note": "achieved = sum of 2*M*N*K over the step's conv/linear launches / sum of their CUDA-event "
+                             "durations (same stream); traffic = mean DRAM bytes per launch from the committed ncu "
+                             "launch list (cold cache per launch)"},
+        "roofline_hbm": roof_hbm,
+        "kernels": kernels,
+        "clocks": clocks,
+    }
+    if wl == "dpm_solver":
+        line["unet_tflops"] = round(2 * B * FLOP_PER_SAMPLE_FWD / unet_ms / 1e9, 1)
+    if vae_s:
+        line["e2e_with_vae"] = {
+            "value": round(images / vae_s, 3), "unit": "images/s",
+            "includes": "hash tokenise + native CLIP-L text tower (prompt and empty negative prompt) + denoising loop "
+                        "+ native VAE decode + uint8 quantise + D2H of the images; x0 previews not decoded",
+            "h2d_bytes_per_step": int(lat_host.numel() * 2 + 2 * B * 77 * 8),
+            "d2h_bytes_per_step": int(B * 3 * 512 * 512)}
+    if world == 1 and wl == "dpm_solver" and not args.no_library_baseline:
+        rows_ = [(text, ms) for (kind, ms, fl), text in zip(prof, log)]
+        try:
+            line["gpu_library_baseline"] = gpu_library_baseline(dev, 2 * B if cfg_on else B, unet_ms, rows_)
+        except Exception as e:                              # noqa: BLE001  (an OOM here must not lose the bench line)
+            line["gpu_library_baseline"] = {"error": f"{type(e).__name__}: {e}"[:300]}
+    if world == 1 and not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(sample_steps=1)
+    return line
+
+
+def time_latent_update(dev, B, cfg_on):
+    """The fused CFG + DPM-Solver++ 2nd-order update alone: CUDA events around 200 launches at this batch."""
+    from sonicdiffusionbayeslab_b200 import models as M
+    from sonicdiffusionbayeslab_b200 import schedulers as S
+
+    s = S.DPMSolverScheduler.from_config(M.SD15_SCHEDULER_CONFIG, solver_order=2, algorithm_type="dpmsolver++",
+                                         final_sigmas_type="zero")
+    s.set_timesteps(25, device=dev)
+    x = torch.randn(B, 4, 64, 64, device=dev).bfloat16()
+    eu, et = torch.randn_like(x), torch.randn_like(x)
+    t0, t1 = int(s.timesteps[0]), int(s.timesteps[1])
+    s.x0_rows = 1
+    s.step_cfg(eu, et if cfg_on else None, GUIDANCE, t0, x, out=x)         # order-1 warm-up fills the history
+    reps = 200
+    a, b = _events()
+    torch.cuda.synchronize()
+    a.record()
+    for _ in range(reps):
+        s._step_index = 1
+        s.step_cfg(eu, et if cfg_on else None, GUIDANCE, t1, x, out=x)
+    b.record()
+    torch.cuda.synchronize()
+    us = a.elapsed_time(b) / reps * 1e3
+    per_image = (6 if cfg_on else 5) * 32768                # eps_u, eps_c, x, m1 read; x', m0 written (+ x0 of image 0)
+    by = per_image * B + 32768
+    return {"bound": "hbm (launch-latency-bound at this size)", "achieved": round(by / us / 1e3, 1), "unit": "GB/s",
+            "us_per_launch": round(us, 2), "bytes_per_launch": by,
+            "note": f"{by} algorithmic bytes per launch: host launch overhead of back-to-back launches, not "
+                    "bandwidth, sets the time"}
+
+
+def run_two_schedulers(args, model, kw, n_prompts, rank, world, local, dev, dist):
+    """BASELINE configs[4]: each rank generates its contiguous block of the global prompt list (125 prompts,
+    batches of <= 32), decodes, scores with the CLIP towers, and the uint8 images + features are all-gathered."""
+    from sonicdiffusionbayeslab_b200 import dist as D
+    from sonicdiffusionbayeslab_b200.dataset.dataset import synthetic_prompts
+    from sonicdiffusionbayeslab_b200.metrics.metrics import ClipScoreMetric
+    import warnings
+
+    W = WORKLOADS["two_schedulers"]
+    prompts_all = synthetic_prompts(n_prompts * world, seed=29)
+    mine = prompts_all[rank * n_prompts:(rank + 1) * n_prompts]
+    batches = [mine[i:i + 32] for i in range(0, len(mine), 32)]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        clip = ClipScoreMetric().to(dev)
+    model.decode_x0_preds = False
+    gen = torch.Generator(device="cpu")
+    state = {}
+
+    def job(loop_only):
+        """One pass over this rank's prompts.  Returns (loop seconds, score or None)."""
+        gen.manual_seed(29)
+        loop_s, imgs, fi, ft = 0.0, [], [], []
+        done = 0
+        for b in batches:
+            # the shared generator is replayed over the batches of lower ranks once, then consumed in order
+            if done == 0:
+                for r in range(rank):
+                    for i in range(0, n_prompts, 32):
+                        model([""] * min(32, n_prompts - i), generator=gen, output_type="pt", rng_only=True, **kw)
+            o, secs, _ = model(b, generator=gen, output_type="latent" if loop_only else "pt", **kw)
+            loop_s += secs
+            done += len(b)
+            if not loop_only:
+                u8 = D.quantise_uint8(o.images.float())
+                a, t_ = clip.features(u8, b)
+                imgs.append(u8)
+                fi.append(a)
+                ft.append(t_)
+        if loop_only:
+            return loop_s, None
+        gi, gf, gt = D.gather_images_and_features(torch.cat(imgs), torch.cat(fi), torch.cat(ft))
+        score = D.clip_score_from_features(gf, gt)
+        state["gathered"] = (gi.shape[0], gi.numel() + (gf.numel() + gt.numel()) * 4)
+        return loop_s, float(score.item())               # D2H of the metric
+
+    warm = max(args.warmup, 3)
+    for i in range(warm):
+        job(loop_only=i < warm - 1)                       # the last warm-up pass exercises decode + CLIP + gather
+    sampler = ClockSampler(local)
     if rank == 0:
-        eng = model.engine(BATCH, True)
-        import ctypes
-
-        side = torch.cuda.Stream(device=dev)                    # kernels are timed on the stream they run on
-        with torch.cuda.stream(side):
-            eng.plans["full"].profile(ctypes.c_void_p(side.cuda_stream))          # warm
-            prof = eng.plans["full"].profile(ctypes.c_void_p(side.cuda_stream))
-        torch.cuda.synchronize()
-        names = {0: "conv_gemm_kernel", 1: "attention_kernel", 2: "groupnorm(stats+apply)", 3: "layernorm_kernel",
-                 4: "layout kernels", 5: "timestep gemv"}
-        agg = {}
-        for kind, ms, fl in prof:
-            a = agg.setdefault(kind, [0, 0.0, 0.0])
-            a[0] += 1
-            a[1] += ms
-            a[2] += fl
-        tot_ms = sum(a[1] for a in agg.values())
-        burst, sustained, hbm, how = _peaks()
-        kernels = []
-        for kind, (cnt, ms, fl) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
-            kernels.append({"kernel": names[kind], "ops": cnt, "ms": round(ms, 3), "share": round(ms / tot_ms, 4),
-                            "tflops": round(fl / ms / 1e9, 1) if fl else None})
-        gemm = agg[0]
-        achieved = gemm[2] / gemm[1] / 1e9                      # TFLOP/s over all conv/linear launches
-        n_launch, plan_flops = eng.stats("full")
-        unet_ms = ms_total / args.steps / STEPS_PER_IMAGE
-        line = {
-            "metric": "images/sec (512x512, 25 steps DPM-Solver++, CFG 7.5)",
-            "value": round(value, 3), "unit": "images/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": round(ms_total / args.steps, 3),
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
-            "data": "synthetic (random-init SD-v1.5 weights, N(0,1) prompt embeddings and latents, seed 29)",
-            "config": dict(CONFIG),
-            "e2e": {"value": round(e2e_value, 3), "unit": "images/s",
-                    "h2d_bytes_per_step": int(pe_host.numel() * 2 * 2 + lat_host.numel() * 2),
-                    "d2h_bytes_per_step": int(out_host.numel() * 2)},
-            "gpu_launches": int(args.steps * 2 * (eng.stats("ctx")[0] + STEPS_PER_IMAGE * (n_launch + 1))),
-            "unet_step_ms": round(unet_ms, 3),
-            "unet_tflops": round(2 * BATCH * FLOP_PER_SAMPLE_FWD / unet_ms / 1e9, 1),
-            "roofline": {"kernel": "conv_gemm_kernel (all conv3x3/conv1x1/linear launches of one UNet forward)",
-                         "bound": "tensor", "achieved": round(achieved, 1), "peak": sustained, "unit": "TFLOP/s",
-                         "frac": round(achieved / sustained, 4), "peak_kind": f"bf16_tflops_sustained ({how})",
-                         "frac_of_burst": round(achieved / burst, 4), "traffic": _traffic(),
-                         "algorithmic_per_launch": round(gemm[2] / gemm[0]), "launches_per_step": gemm[0],
-                         "note": "achieved = sum of 2*M*N*K over the step's conv/linear launches / sum of their CUDA-event "
-                                 "durations (same stream); traffic = mean DRAM bytes per launch from the committed ncu "
-                                 "launch list (cold cache per launch)"},
-            "kernels": kernels,
-            "clocks": clocks,
-        }
-        if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline(sample_steps=1)
+        sampler.start()
+    _barrier(dist)
+    ev0, ev1 = _events()
+    ev0.record()
+    loop_s = sum(job(True)[0] for _ in range(args.steps))
+    ev1.record()
+    _barrier(dist)
+    ms_total = ev0.elapsed_time(ev1)
+    _barrier(dist)
+    t0 = time.perf_counter()
+    score = None
+    for _ in range(args.steps):
+        _, score = job(False)
+    _barrier(dist)
+    e2e_s = time.perf_counter() - t0
+    # the collective alone, for its share of the e2e region
+    n_img, gathered = state["gathered"]
+    u8 = torch.zeros(n_prompts, 3, 512, 512, dtype=torch.uint8, device=dev)
+    f = torch.zeros(n_prompts, 512, device=dev)
+    _barrier(dist)
+    a, b = _events()
+    a.record()
+    D.gather_images_and_features(u8, f, f)
+    b.record()
+    _barrier(dist)
+    gather_ms = a.elapsed_time(b)
+    clocks = sampler.stop() if rank == 0 else None
     if dist is not None:
-        dist.barrier()
-        dist.destroy_process_group()
-    if line is not None:
-        print(json.dumps(line), flush=True)
+        t = torch.tensor([ms_total, e2e_s, gather_ms, loop_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total, e2e_s, gather_ms, loop_s = t.tolist()
+    if rank != 0:
+        return None
+    images = n_prompts * world * args.steps
+    unet_launches = 0
+    for b in batches:
+        eng = model.engine(len(b), True)
+        unet_launches += eng.stats("ctx")[0] + W["steps"] * (eng.stats("full")[0] + 1)
+    return {
+        "metric": W["metric"], "value": round(images / (ms_total / 1e3), 3), "unit": "images/s", "n_gpus": world,
+        "steps": args.steps, "warmup": warm, "ms_per_step": round(ms_total / args.steps, 3), "higher_is_better": True,
+        "scaling": W["scaling"], "vs_baseline": None, "dtype": "bf16",
+        "data": "synthetic (random-init SD-v1.5 / VAE / CLIP weights, seeded synthetic captions, seed 29)",
+        "config": {"workload": W["text"], "per_gpu_prompts": n_prompts, "global_prompts": n_prompts * world,
+                   "l2": "working set larger than L2 (weights 1.7 GB + streamed activations)"},
+        "e2e": {"value": round(images / e2e_s, 3), "unit": "images/s",
+                "h2d_bytes_per_step": int(n_prompts * 2 * 77 * 8),
+                "d2h_bytes_per_step": 4,
+                "includes": "hash tokenise + text tower + loop + VAE decode + uint8 + CLIP towers + all-gather + score"},
+        "loop_seconds_per_step": round(loop_s / args.steps, 3),
+        "collective": {"op": "all_gather (uint8 images + fp32 image/text features)", "backend": "nccl" if world > 1 else "none",
+                       "bytes_gathered_per_rank": int(gathered), "images_gathered": int(n_img),
+                       "ms": round(gather_ms, 3), "share_of_e2e": round(gather_ms / (e2e_s / args.steps * 1e3), 5)},
+        "clip_score": score,
+        "gpu_launches": int(2 * args.steps * unet_launches),     # UNet plans + fused updates of both timed regions;
+        "clocks": clocks,                                        # the text / VAE / CLIP plans of e2e come on top
+    }
 
 
+# ----------------------------------------------------------------------------------------- CPU oracle arms
 def _oracle_cfg_step_seconds(n_steps, threads):
     """Times the oracle (reference restatement) on CPU: batch 1, CFG 7.5, DPM-Solver++ steps."""
     from oracle.pipeline import denoise
@@ -277,7 +635,7 @@ def _oracle_cfg_step_seconds(n_steps, threads):
     sched = Trunc.from_config(SD15_SCHEDULER_CONFIG, solver_order=2, algorithm_type="dpmsolver++",
                               final_sigmas_type="zero")
     t0 = time.perf_counter()
-    denoise(net, sched, pe, ne, lat, STEPS_PER_IMAGE, guidance_scale=GUIDANCE)
+    denoise(net, sched, pe, ne, lat, 25, guidance_scale=GUIDANCE)
     return (time.perf_counter() - t0) / n_steps
 
 
@@ -285,7 +643,7 @@ def cpu_baseline(sample_steps=1):
     threads = len(os.sched_getaffinity(0))
     _oracle_cfg_step_seconds(1, threads)                       # warm-up (allocations, thread pool)
     s = _oracle_cfg_step_seconds(sample_steps, threads)
-    return {"value": round(1.0 / (s * STEPS_PER_IMAGE), 6), "unit": "images/s", "cores": threads, "kind": "port",
+    return {"value": round(1.0 / (s * 25), 6), "unit": "images/s", "cores": threads, "kind": "port",
             "sample": f"{sample_steps} CFG denoising step(s) at batch 1 (2 UNet sample-forwards each, fp32) of the "
                       f"25-step DPM-Solver++ schedule, {s:.2f} s/step, extrapolated x25",
             "gflops": round(2 * FLOP_PER_SAMPLE_FWD / s / 1e9, 1)}
@@ -295,18 +653,29 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return
+    if args.config != "dpm_solver":
+        print(json.dumps({"impl": "reference", "unavailable": "the CPU oracle arm is defined for the default "
+                                                               "workload (dpm_solver) only"}), flush=True)
+        return
     threads = len(os.sched_getaffinity(0))
     for _ in range(min(args.warmup, 1)):
         _oracle_cfg_step_seconds(1, threads)
     times = [_oracle_cfg_step_seconds(1, threads) for _ in range(max(1, min(args.steps, 3)))]
     s = statistics.mean(times)
-    value = 1.0 / (s * STEPS_PER_IMAGE)
+    value = 1.0 / (s * 25)
+    W = WORKLOADS["dpm_solver"]
     line = {
-        "impl": "reference", "metric": "images/sec (512x512, 25 steps DPM-Solver++, CFG 7.5)",
+        "impl": "reference", "metric": W["metric"],
         "value": round(value, 6), "unit": "images/s", "n_gpus": int(os.environ.get("WORLD_SIZE", 1)),
-        "steps": len(times), "warmup": min(args.warmup, 1), "ms_per_step": round(s * 1e3 * STEPS_PER_IMAGE, 1),
+        "steps": len(times), "warmup": min(args.warmup, 1), "ms_per_step": round(s * 1e3 * 25, 1),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": dict(CONFIG),
+        # what THIS arm really ran -- not the GPU arm's batch-16 bf16 workload
+        "config": {"workload": "bounded CPU sample of configs/dpm_solver_config.yaml: the oracle restatement of the "
+                               "reference loop, ONE classifier-free-guidance denoising step (2 UNet sample-forwards) of "
+                               "the 25-step DPM-Solver++ schedule at batch 1, fp32, all host threads; images/s = "
+                               "1 / (25 x seconds per step)",
+                   "per_gpu_batch": 1, "dtype": "f32", "extrapolated": True, "sampled_steps": len(times),
+                   "steps_per_image": 25, "gpu_arm_workload": W["text"]},
         "cpu_baseline": {"value": round(value, 6), "unit": "images/s", "cores": threads, "kind": "port",
                          "sample": f"oracle restatement of the reference path (diffusers is not installable here), fp32, "
                                    f"all host threads: {len(times)} x 1 CFG denoising step at batch 1 (2 UNet "
@@ -323,7 +692,9 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="own", choices=["own", "reference"])
+    ap.add_argument("--config", default="dpm_solver", choices=list(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-library-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

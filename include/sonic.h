@@ -152,6 +152,23 @@ int sonic_im2col3x3(const void* x, void* y, int32_t n_img, int32_t H, int32_t W,
  * (reference call site src/models.py:288-302 -> AutoencoderKL.decode). */
 int sonic_softmax_rows(void* x, int32_t rows, int32_t cols, int64_t ld, float scale, sonic_stream_t stream);
 
+/* CLIP image preprocessing of the CLIP-score metric (reference: src/metrics/metrics.py:25-41 -> torchmetrics
+ * CLIPScore -> HF CLIPImageProcessor on PIL, the host-side hot spot of SURVEY.md row a12; images produced at
+ * src/experiments/base_experiment.py:198-201).  ONE kernel: [quantise x*255 -> uint8] -> PIL's two-pass antialiased
+ * bicubic resize (uint8 intermediate, 22-bit fixed-point coefficients: bit-identical to Pillow) -> centre crop ->
+ * * 1/255 -> (x - mean) / std.
+ *   images   [n_img][3][H][W], dtype 0 = fp32 in [0,1], 1 = bf16 in [0,1], 2 = uint8
+ *   hb / hk  horizontal bounds [nw][2] (first input column, count) and coefficients [nw][hks] of the resized width
+ *   vb / vk  the same for the resized height; max_rows >= input rows any 16-output-row tile needs
+ *   top/left centre-crop offset in the resized image; S = output size (224)
+ *   mean3 / std3  HOST pointers to 3 floats
+ *   out      out_mode 0: fp32 [n_img][3][S][S];  out_mode 1: bf16 [n_img*(S/patch)^2][3*patch*patch], the A operand
+ *            of the ViT patch-embedding GEMM (row = image, patch row, patch column; column = channel, y, x). */
+int sonic_clip_preprocess(const void* images, int32_t dtype, int32_t n_img, int32_t H, int32_t W, const int32_t* hb,
+                          const int32_t* hk, int32_t hks, const int32_t* vb, const int32_t* vk, int32_t vks,
+                          int32_t max_rows, int32_t top, int32_t left, int32_t S, const float* mean3,
+                          const float* std3, void* out, int32_t out_mode, int32_t patch, sonic_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------
  * Launch plans: the native runtime under the engine.  The host records every operator of a
  * network once (TMA descriptors and tile shapes are resolved at record time); running the plan

@@ -99,7 +99,7 @@ def switch_timestamp(timesteps_first, timesteps_second, num_step_switch, type_sw
 @torch.no_grad()
 def denoise_two(unet, scheduler_first, scheduler_second, prompt_embeds, negative_prompt_embeds, latents,
                 num_inference_steps_first, num_step_switch, type_switch="closest", guidance_scale=7.5,
-                generator=None, eta=0.0):
+                generator=None, eta=0.0, forced_latents=None):
     do_cfg = guidance_scale > 1
     ctx = torch.cat([negative_prompt_embeds, prompt_embeds]) if do_cfg else prompt_embeds
     device = latents.device
@@ -113,6 +113,8 @@ def denoise_two(unet, scheduler_first, scheduler_second, prompt_embeds, negative
     per_step = []
     for i, t in enumerate(first + second):
         sched, extra = (scheduler_first, e1) if i < len(first) else (scheduler_second, e2)
+        if forced_latents is not None:
+            latents = forced_latents[i]
         x_in = torch.cat([latents] * 2) if do_cfg else latents
         noise_pred = unet(x_in, torch.as_tensor(t, device=device), encoder_hidden_states=ctx)[0]
         if do_cfg:

@@ -83,10 +83,15 @@ class _SchedulerBase:
 
     @classmethod
     def from_config(cls, config, **overrides):
-        """ConfigMixin.from_config: copy accepted keys, silently drop the rest."""
+        """ConfigMixin.from_config: accepted keys go to ``__init__``; the rest stay in ``.config`` as hidden
+        entries (so ``Other.from_config(this.config)`` still sees them)."""
         merged = dict(config)
         merged.update(overrides)
-        return cls(**{k: v for k, v in merged.items() if k in cls._defaults})
+        obj = cls(**{k: v for k, v in merged.items() if k in cls._defaults})
+        for k, v in merged.items():
+            if k not in cls._defaults:
+                obj.config[k] = v
+        return obj
 
     @property
     def step_index(self):

@@ -105,10 +105,23 @@ class ClipVisionEngine(ClipEncoderEngine):
 
     @torch.no_grad()
     def image_features(self, pixel_values):
+        """Already-normalised pixel values (n, 3, S, S) -> projected image embeddings."""
         n, g, p_ = self.n, self.grid, self.patch
         assert pixel_values.shape == (n, 3, g * p_, g * p_), pixel_values.shape
         x = pixel_values.to(self.dev).view(n, 3, g, p_, g, p_).permute(0, 2, 4, 1, 3, 5).reshape(n * g * g, -1)
         self.patches.copy_(x)
+        return self.features_from_patches()
+
+    @torch.no_grad()
+    def image_features_from_images(self, images):
+        """uint8 (or float [0,1]) images (n, 3, H, W) -> embeddings: the fused preprocessing kernel
+        (``sonic_clip_preprocess``) writes the patch rows of the embedding GEMM directly."""
+        K.clip_preprocess(images.contiguous(), size=self.grid * self.patch, patches_out=self.patches, patch=self.patch)
+        return self.features_from_patches()
+
+    @torch.no_grad()
+    def features_from_patches(self):
+        n = self.n
         self.x.view(n, self.seq, self.width)[:, 0] = self.cls_pos
         self.pre_plan.run(K.stream_ptr())
         out = self.run()

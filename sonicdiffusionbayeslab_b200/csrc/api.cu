@@ -118,6 +118,14 @@ int sonic_im2col3x3(const void* x, void* y, int32_t n_img, int32_t H, int32_t W,
   return im2col3x3_launch(x, y, n_img, H, W, C, stride, static_cast<cudaStream_t>(stream));
 }
 
+int sonic_clip_preprocess(const void* images, int32_t dtype, int32_t n_img, int32_t H, int32_t W, const int32_t* hb,
+                          const int32_t* hk, int32_t hks, const int32_t* vb, const int32_t* vk, int32_t vks,
+                          int32_t max_rows, int32_t top, int32_t left, int32_t S, const float* mean3,
+                          const float* std3, void* out, int32_t out_mode, int32_t patch, sonic_stream_t stream) {
+  return clip_preprocess_launch(images, dtype, n_img, H, W, hb, hk, hks, vb, vk, vks, max_rows, top, left, S, mean3,
+                                std3, out, out_mode, patch, static_cast<cudaStream_t>(stream));
+}
+
 int sonic_softmax_rows(void* x, int32_t rows, int32_t cols, int64_t ld, float scale, sonic_stream_t stream) {
   SONIC_REQUIRE(x != nullptr, "sonic_softmax_rows: null operand");
   return softmax_rows_launch(x, rows, cols, static_cast<long>(ld), scale, static_cast<cudaStream_t>(stream));

@@ -68,6 +68,13 @@ int gemv_batched_launch(const GemvJob* jobs_dev, int n_jobs, int total_rows, con
 // t -> [cos(t f_j) | sin(t f_j)] (flip_sin_to_cos, freq_shift 0), fp32 out[dim]
 int timestep_embedding_launch(const float* t_dev, int dim, float* out, cudaStream_t stream);
 
+// CLIP image preprocessing (preprocess.cu): uint8 / float[0,1] images -> PIL-exact bicubic resize + centre crop +
+// normalise.  dtype: 0 fp32, 1 bf16 (both quantised with x*255 -> uint8 first), 2 uint8.  mean3 / std3: HOST arrays.
+int clip_preprocess_launch(const void* images, int dtype, int n_img, int H, int W, const int* hb, const int* hk, int hks,
+                           const int* vb, const int* vk, int vks, int max_rows, int top, int left, int S,
+                           const float* mean3, const float* std3, void* out, int out_mode, int patch,
+                           cudaStream_t stream);
+
 struct AttentionOp {
   const void* q; const void* k; const void* v;   // bf16; element (b, s, h, d) at ((b*S + s)*ld + h*D + d)
   int ld_q = 0, ld_k = 0, ld_v = 0;

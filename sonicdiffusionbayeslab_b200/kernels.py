@@ -225,3 +225,92 @@ def im2col_s2(x):
     y = torch.empty((n, h // 2, w // 2, 9 * c), device=x.device, dtype=torch.bfloat16)
     check(lib().sonic_im2col_s2(ptr(_bf16c(x)), ptr(y), n, h, w, c, stream_ptr()), "sonic_im2col_s2")
     return y
+
+
+# ------------------------------------------------------------------------------------------ CLIP preprocessing
+CLIP_MEAN = (0.48145466, 0.4578275, 0.40821073)
+CLIP_STD = (0.26862954, 0.26130258, 0.27577711)
+_PRECISION_BITS = 32 - 8 - 2
+_resample_cache = {}
+
+
+def _bicubic(x: float) -> float:
+    """Pillow's ``bicubic_filter`` (a = -0.5), same expression order."""
+    a = -0.5
+    if x < 0.0:
+        x = -x
+    if x < 1.0:
+        return ((a + 2.0) * x - (a + 3.0)) * x * x + 1
+    if x < 2.0:
+        return (((x - 5) * x + 8) * x - 4) * a
+    return 0.0
+
+
+def pil_bicubic_coeffs(in_size: int, out_size: int):
+    """Pillow ``precompute_coeffs`` + ``normalize_coeffs_8bpc`` for a full-image resize (box = whole image):
+    returns (bounds [out][2] int32, coefficients [out][ksize] int32, ksize).  Double arithmetic, C truncation."""
+    import math
+
+    scale = in_size / out_size
+    filterscale = max(scale, 1.0)
+    support = 2.0 * filterscale
+    ksize = int(math.ceil(support)) * 2 + 1
+    bounds, coeffs = [], []
+    ss = 1.0 / filterscale
+    for xx in range(out_size):
+        center = (xx + 0.5) * scale
+        xmin = max(int(center - support + 0.5), 0)
+        xmax = min(int(center + support + 0.5), in_size) - xmin
+        k = [_bicubic((x + xmin - center + 0.5) * ss) for x in range(xmax)]
+        ww = 0.0
+        for w in k:
+            ww += w
+        if ww != 0.0:
+            k = [w / ww for w in k]
+        k += [0.0] * (ksize - xmax)
+        bounds.append((xmin, xmax))
+        coeffs.append([int(-0.5 + w * (1 << _PRECISION_BITS)) if w < 0 else int(0.5 + w * (1 << _PRECISION_BITS))
+                       for w in k])
+    return bounds, coeffs, ksize
+
+
+def _resample_tables(H, W, size, device):
+    """Resize-shortest-edge-to-``size`` + centre-crop geometry of HF ``CLIPImageProcessor`` and PIL's tables."""
+    key = (H, W, size, str(device))
+    if key not in _resample_cache:
+        short, long_ = (H, W) if H <= W else (W, H)
+        new_long = int(size * long_ / short)
+        nh, nw = (size, new_long) if H <= W else (new_long, size)
+        hb, hk, hks = pil_bicubic_coeffs(W, nw)
+        vb, vk, vks = pil_bicubic_coeffs(H, nh)
+        top, left = (nh - size) // 2, (nw - size) // 2
+        max_rows = 0
+        for oy0 in range(0, size, 16):
+            last = min(oy0 + 16, size) - 1 + top
+            max_rows = max(max_rows, vb[last][0] + vb[last][1] - vb[oy0 + top][0])
+        t = lambda v: torch.tensor(v, dtype=torch.int32, device=device).contiguous()   # noqa: E731
+        _resample_cache[key] = dict(hb=t(hb), hk=t(hk), hks=hks, vb=t(vb), vk=t(vk), vks=vks, top=top, left=left,
+                                    max_rows=max_rows)
+    return _resample_cache[key]
+
+
+def clip_preprocess(images: torch.Tensor, size: int = 224, patches_out: torch.Tensor = None, patch: int = 16):
+    """uint8 (n,3,H,W) -- or float / bf16 in [0,1], quantised in the kernel like base_experiment.py:198-199 -- ->
+    normalised fp32 (n,3,size,size), bit-identical to HF ``CLIPImageProcessor`` on PIL; with ``patches_out`` the
+    bf16 patch rows of the ViT patch-embedding GEMM are written instead (one launch, no torch ops)."""
+    assert images.is_cuda and images.dim() == 4 and images.shape[1] == 3 and images.is_contiguous()
+    code = {torch.float32: 0, torch.bfloat16: 1, torch.uint8: 2}[images.dtype]
+    n, _, H, W = images.shape
+    tb = _resample_tables(H, W, size, images.device)
+    mean, std = (C.c_float * 3)(*CLIP_MEAN), (C.c_float * 3)(*CLIP_STD)
+    if patches_out is None:
+        out, mode = torch.empty((n, 3, size, size), device=images.device, dtype=torch.float32), 0
+    else:
+        g = size // patch
+        assert patches_out.dtype == torch.bfloat16 and patches_out.is_contiguous() and \
+            tuple(patches_out.shape) == (n * g * g, 3 * patch * patch)
+        out, mode = patches_out, 1
+    check(lib().sonic_clip_preprocess(ptr(images), code, n, H, W, ptr(tb["hb"]), ptr(tb["hk"]), tb["hks"], ptr(tb["vb"]),
+                                      ptr(tb["vk"]), tb["vks"], tb["max_rows"], tb["top"], tb["left"], size, mean, std,
+                                      ptr(out), mode, patch, stream_ptr()), "sonic_clip_preprocess")
+    return out

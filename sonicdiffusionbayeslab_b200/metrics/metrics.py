@@ -5,8 +5,9 @@ torchmetrics is not installable here, so a minimal ``Metric`` base provides the 
 use (``update`` / ``compute`` / ``reset`` / ``to``; sum-reduced states).  ``ClipScoreMetric`` restates
 torchmetrics 1.6.1 ``CLIPScore`` on ``transformers.CLIPModel``:
 ``max(0, mean_i 100 * cos(f_img(i), f_txt(i)))`` -- with the image preprocessing (resize shortest side
-to 224 bicubic + antialias, centre crop, 1/255, CLIP mean/std) done on the GPU instead of PIL on
-the host, which is where the reference spends its metric time.
+to 224 with PIL's antialiased bicubic resampler, centre crop, 1/255, CLIP mean/std) done by ONE native kernel
+(csrc/preprocess.cu, bit-identical to PIL) instead of PIL on the host, which is where the reference spends its
+metric time, and both towers on the native engine (clip_engine.py).
 ImageReward and FID need downloaded networks and the real COCO images (no network): they stay
 registered so ``BaseMethod.setup_metrics`` works, and report NaN.
 """
@@ -17,13 +18,11 @@ import os
 import warnings
 
 import torch
-import torch.nn.functional as F
 
 from ..registry import metrics_registry
 from ..text import HashTokenizer, load_tokenizer
 
-CLIP_MEAN = (0.48145466, 0.4578275, 0.40821073)
-CLIP_STD = (0.26862954, 0.26130258, 0.27577711)
+from ..kernels import CLIP_MEAN, CLIP_STD  # noqa: E402,F401
 
 
 class Metric:
@@ -56,22 +55,15 @@ class Metric:
 
 
 def clip_preprocess(images: torch.Tensor, size: int = 224) -> torch.Tensor:
-    """uint8 (n,3,H,W) -> normalised float (n,3,size,size); HF CLIPImageProcessor semantics on device."""
+    """uint8 (n,3,H,W) -> normalised float (n,3,size,size): HF ``CLIPImageProcessor`` semantics (PIL bicubic with
+    antialiasing, centre crop, 1/255, CLIP mean/std) in ONE native kernel, bit-identical to PIL's uint8 resize
+    (``kernels.clip_preprocess`` / csrc/preprocess.cu)."""
     if images.dtype != torch.uint8:
         raise TypeError("CLIP score expects uint8 images (the in-pipeline path, base_experiment.py:198-201); "
                         "float [0,1] inputs are the calc_clip_score.py defect (SURVEY C-8)")
-    x = images.float()
-    h, w = x.shape[-2:]
-    s = size / min(h, w)
-    nh, nw = max(size, round(h * s)), max(size, round(w * s))
-    if (nh, nw) != (h, w):
-        x = F.interpolate(x, size=(nh, nw), mode="bicubic", antialias=True, align_corners=False)
-        x = x.round().clamp(0, 255)                        # PIL resize returns uint8
-    top, left = (nh - size) // 2, (nw - size) // 2
-    x = x[..., top:top + size, left:left + size] / 255.0
-    mean = torch.tensor(CLIP_MEAN, device=x.device).view(1, 3, 1, 1)
-    std = torch.tensor(CLIP_STD, device=x.device).view(1, 3, 1, 1)
-    return (x - mean) / std
+    from .. import kernels as K
+
+    return K.clip_preprocess(images.contiguous(), size=size)
 
 
 class ClipWeights:
@@ -140,10 +132,13 @@ class ClipScoreMetric(Metric):
         text = [text] if isinstance(text, str) else list(text)
         if len(text) != images.shape[0]:
             raise ValueError("Expected the number of images and text examples to be the same")
-        pixel = clip_preprocess(images.to(self.device))
+        if images.dtype != torch.uint8:
+            raise TypeError("CLIP score expects uint8 images (the in-pipeline path, base_experiment.py:198-201); "
+                            "float [0,1] inputs are the calc_clip_score.py defect (SURVEY C-8)")
         ids, _ = self.tokenizer(text)
         vis, txt = self._native(len(text))
-        fi, ft = vis.image_features(pixel).float(), txt.text_features(ids.to(self.device)).float()
+        fi = vis.image_features_from_images(images.to(self.device)).float()      # fused preprocess -> patch rows
+        ft = txt.text_features(ids.to(self.device)).float()
         fi = fi / fi.norm(p=2, dim=-1, keepdim=True)
         ft = ft / ft.norm(p=2, dim=-1, keepdim=True)
         return fi, ft

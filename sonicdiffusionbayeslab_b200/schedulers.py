@@ -105,9 +105,17 @@ class FusedScheduler:
     # -- construction as in base_experiment.py:69-72: unknown keys are dropped silently
     @classmethod
     def from_config(cls, config, **overrides):
+        """diffusers ``ConfigMixin.from_config``: keys this class does not take are not passed to ``__init__`` but
+        stay in ``.config`` as hidden entries, so the scheduler-swap idiom of the reference
+        (``Other.from_config(pipe.scheduler.config)``, base_experiment.py:69-72) still sees e.g. ``clip_sample=False``
+        of the SD-v1.5 scheduler_config.json after a trip through a scheduler that has no such field."""
         merged = dict(config)
         merged.update(overrides)
-        return cls(**{k: v for k, v in merged.items() if k in cls._defaults})
+        obj = cls(**{k: v for k, v in merged.items() if k in cls._defaults})
+        for k, v in merged.items():
+            if k not in cls._defaults:
+                obj.config[k] = v
+        return obj
 
     @property
     def step_index(self):

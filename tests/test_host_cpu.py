@@ -298,3 +298,49 @@ def test_deepcache_branch_layer_sets_match_the_oracle(branch):
     assert min(want_up) == first_up
     got_us = {nb - 1 - k[2] for k in ran if k[:2] == ("up", "upsampler")}
     assert got_us == {b for b in range(nb - 1) if any(up_runs(b, j) for j in range(L + 1))}
+
+
+def test_scheduler_swap_keeps_hidden_config_keys():
+    """``Other.from_config(pipe.scheduler.config)`` (base_experiment.py:69-72): keys a scheduler does not take
+    survive in its config, so DDIM built from the stock PNDM scheduler still sees ``clip_sample=False``."""
+    from sonicdiffusionbayeslab_b200 import models as M
+    from sonicdiffusionbayeslab_b200 import schedulers as S
+
+    pndm = S.PNDMScheduler.from_config(M.SD15_SCHEDULER_CONFIG)
+    assert "clip_sample" not in S.PNDMScheduler._defaults and pndm.config.clip_sample is False
+    ddim = S.DDIMSchedulerMy.from_config(pndm.config)
+    assert ddim.config.clip_sample is False and ddim.config.steps_offset == 1
+    lcm = S.LCMScheduler.from_config(S.DPMSolverScheduler.from_config(pndm.config, solver_order=3).config)
+    assert lcm.config.clip_sample is False and lcm.config.solver_order == 3
+
+
+@pytest.mark.parametrize("hw", [(512, 512), (480, 640), (224, 224)])
+def test_pil_resample_tables_are_bit_exact(hw):
+    """The coefficient tables the native CLIP-preprocess kernel consumes (kernels.pil_bicubic_coeffs: Pillow's
+    precompute_coeffs + normalize_coeffs_8bpc restated) and the kernel's two-pass integer arithmetic, emulated in
+    numpy, against PIL itself -- bit-exact uint8 images."""
+    import numpy as np
+    from PIL import Image
+
+    from sonicdiffusionbayeslab_b200.kernels import pil_bicubic_coeffs
+
+    H, W = hw
+    short, long_ = min(H, W), max(H, W)
+    nh, nw = (224, int(224 * long_ / short)) if H <= W else (int(224 * long_ / short), 224)
+    rng = np.random.default_rng(0)
+    img = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+    want = np.asarray(Image.fromarray(img).resize((nw, nh), resample=Image.BICUBIC))
+    hb, hk, _ = pil_bicubic_coeffs(W, nw)
+    vb, vk, _ = pil_bicubic_coeffs(H, nh)
+    got = np.zeros((nh, nw, 3), np.uint8)
+    for c in range(3):
+        tmp = np.zeros((H, nw), np.uint8)
+        for ox in range(nw):
+            xmin, cnt = hb[ox]
+            ss = (1 << 21) + (img[:, xmin:xmin + cnt, c].astype(np.int64) * np.array(hk[ox][:cnt], np.int64)).sum(1)
+            tmp[:, ox] = np.clip(ss >> 22, 0, 255)
+        for oy in range(nh):
+            ymin, cnt = vb[oy]
+            ss = (1 << 21) + (tmp[ymin:ymin + cnt].astype(np.int64) * np.array(vk[oy][:cnt], np.int64)[:, None]).sum(0)
+            got[oy, :, c] = np.clip(ss >> 22, 0, 255)
+    assert np.array_equal(got, want)

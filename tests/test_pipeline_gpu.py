@@ -438,3 +438,110 @@ def test_native_prompt_encoder_matches_transformers(cuda):
     torch.cuda.synchronize()
     assert got.shape == ref.shape == (3, 77, 768)
     assert (got - ref).abs().max().item() < 3e-2 * ref.abs().max().item()
+
+
+def _test_images(n=4, H=512, W=512):
+    g = torch.Generator().manual_seed(0)
+    yy, xx = torch.meshgrid(torch.arange(H), torch.arange(W), indexing="ij")
+    imgs = [torch.randint(0, 256, (3, H, W), generator=g, dtype=torch.uint8)]
+    for k in range(1, n):                                    # smooth, image-like content
+        imgs.append(torch.stack([(127 + 120 * torch.sin(xx / (17.0 + 9 * k) + c) * torch.cos(yy / (11.0 + 5 * k)))
+                                 .clamp(0, 255) for c in range(3)]).to(torch.uint8))
+    return torch.stack(imgs)
+
+
+@pytest.mark.parametrize("hw", [(512, 512), (480, 640)])
+def test_clip_preprocess_kernel_matches_hf_processor(cuda, hw):
+    """``sonic_clip_preprocess`` (one kernel: PIL-exact antialiased bicubic resize, centre crop, rescale, normalise)
+    against transformers' CLIPImageProcessor: the PIL-backed one -- what the reference's pinned transformers 4.48 /
+    torchmetrics CLIPScore run (/root/reference/src/metrics/metrics.py:25-41) -- to float rounding, the default
+    (torchvision-backed) one to one uint8 level."""
+    from transformers import CLIPImageProcessor
+
+    from sonicdiffusionbayeslab_b200 import kernels as K
+
+    imgs = _test_images(4, *hw)
+    got = K.clip_preprocess(imgs.to(cuda)).cpu()
+    assert got.shape == (4, 3, 224, 224)
+    level = 1.0 / 255.0 / min(K.CLIP_STD)                     # one uint8 level in normalised units
+    try:
+        from transformers import CLIPImageProcessorPil
+
+        want = CLIPImageProcessorPil()(images=[im for im in imgs], return_tensors="pt")["pixel_values"]
+        assert (got - want).abs().max().item() <= 1e-6, (got - want).abs().max().item()
+    except ImportError:
+        pass
+    want = CLIPImageProcessor()(images=[im for im in imgs], return_tensors="pt")["pixel_values"]
+    assert (got - want).abs().max().item() <= 1.05 * level
+    # fused quantise: float [0,1] images -> (x * 255).to(uint8) inside the kernel (base_experiment.py:198-199)
+    f = torch.rand(2, 3, *hw, generator=torch.Generator().manual_seed(1))
+    a = K.clip_preprocess(f.to(cuda))
+    b = K.clip_preprocess((f * 255).to(torch.uint8).to(cuda))
+    assert torch.equal(a, b)
+    # fused patch cut: bf16 rows of the ViT patch-embedding GEMM
+    patches = torch.zeros(4 * 196, 768, device=cuda, dtype=torch.bfloat16)
+    K.clip_preprocess(imgs.to(cuda), patches_out=patches)
+    ref = got.view(4, 3, 14, 16, 14, 16).permute(0, 2, 4, 1, 3, 5).reshape(4 * 196, 768).bfloat16()
+    assert torch.equal(patches.cpu(), ref)
+
+
+def test_clip_score_end_to_end_matches_transformers(cuda):
+    """uint8 512x512 images + prompts -> CLIP score through the product metric (native preprocess kernel + native
+    towers) against transformers.CLIPModel fed by HF's CLIPImageProcessor (the torchmetrics CLIPScore recipe,
+    SURVEY appendix A.5) on the same seeded weights: per-image and mean score within the north_star's +-0.2."""
+    from transformers import CLIPImageProcessor, CLIPModel
+
+    from sonicdiffusionbayeslab_b200.metrics.metrics import ClipScoreMetric
+
+    with pytest.warns(RuntimeWarning, match="RANDOM-INIT"):
+        metric = ClipScoreMetric().to(cuda)
+    imgs = _test_images(4)
+    text = ["a photo of a cat", "two dogs running on the beach at sunset", "x", "a " * 60]
+    fi, ft = metric.features(imgs.to(cuda), text)
+    got = 100 * (fi * ft).sum(-1)
+    model = CLIPModel(metric.model.config)
+    model.load_state_dict(metric.model.state_dict())
+    model = model.to(cuda).float().eval()
+    pixel = CLIPImageProcessor()(images=[im for im in imgs], return_tensors="pt")["pixel_values"].to(cuda)
+    ids, mask = metric.tokenizer(text)
+    with torch.no_grad():
+        a = model.get_image_features(pixel_values=pixel)
+        b = model.get_text_features(input_ids=ids.to(cuda), attention_mask=mask.to(cuda))
+    a, b = getattr(a, "pooler_output", a), getattr(b, "pooler_output", b)
+    want = 100 * torch.nn.functional.cosine_similarity(a, b, dim=-1)
+    metric.update(imgs.to(cuda), text)
+    mean_want = torch.clamp(want.mean(), min=0)
+    print(f"\n[clip score e2e] per-image delta {(got - want).abs().max().item():.4f}, "
+          f"mean {metric.compute().item():.4f} vs {mean_want.item():.4f}")
+    assert (got - want).abs().max().item() < 0.2
+    assert abs(metric.compute().item() - mean_want.item()) < 0.2
+
+
+def test_calc_clip_score_script_sharded_equals_single(tmp_path):
+    """``calc_clip_score.py`` (reference: /root/reference/calc_clip_score.py) on seeded synthetic images: one process
+    vs two ranks with the feature all-gather (gloo here: two ranks share the one GPU)."""
+    import os
+    import re
+    import socket
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+    def run(nproc):
+        env = dict(os.environ, PYTHONWARNINGS="ignore")
+        cmd = [sys.executable]
+        if nproc > 1:
+            with socket.socket() as s_:
+                s_.bind(("127.0.0.1", 0))
+                port = s_.getsockname()[1]
+            env["SONIC_DIST_BACKEND"] = "gloo"
+            cmd += ["-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}", "--master-addr", "127.0.0.1",
+                    "--master-port", str(port)]
+        cmd += [os.path.join(root, "calc_clip_score.py"), "--synthetic", "10", "--batch_size", "4", "--gather_images"]
+        r = subprocess.run(cmd, cwd=root, env=env, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        return float(re.search(r"CLIP Score: ([-0-9.e]+)", r.stdout).group(1))
+
+    one, two = run(1), run(2)
+    assert abs(one - two) < 1e-4, (one, two)

@@ -19,10 +19,12 @@ dev = torch.device("cuda:0")
 net, net16, scale = PL.unit_variance_unet(dev)
 sd = dict(net.state_dict())
 print(f"unit-variance fixture: conv_out scaled by {scale:.4f}")
+r = PL.teacher_forced("dpmpp25", net, None, sd, dev, io_dtype=torch.bfloat16, B=16, max_steps=3)
+print(f"batch 16 (UNet batch 32) dpmpp25 steps 1-3 vs fp32 oracle: engine max-abs {r['engine']}  |x|max {max(r['xmax']):.2f}")
 for name in PL.CASES:
     for io in (torch.bfloat16, torch.float32):
         r = PL.teacher_forced(name, net, net16, sd, dev, io_dtype=io)
-        e, f = r["engine"], r.get("torch_bf16")
+        e, f = r["engine"], r["torch_bf16"]
         print(f"{name:22s} io={str(io).split('.')[-1]:8s} steps={len(e):2d} |x|max={max(r['xmax']):5.2f}  "
               f"engine max-abs: worst {max(e):.3e} median {sorted(e)[len(e) // 2]:.3e}"
               + (f"  | torch-bf16: worst {max(f):.3e} median {sorted(f)[len(f) // 2]:.3e}" if f else ""))
