@@ -60,6 +60,18 @@ typedef struct sonic_gemm_args {
    * bf16-rounded output over each block of 32 consecutive rows, per channel.  sonic_groupnorm_fused turns
    * these into group statistics, so the separate statistics pass over the tensor disappears. */
   float* gn_partial;
+  /* LayerNorm folded into the GEMMs around it -- the 48 LayerNorms of the UNet's transformer blocks
+   * (BasicTransformerBlock.norm1/2/3, reached from src/models.py:227-235) launch no kernel of their own:
+   *   LN(x) W^T + b = rstd_row * (x (gamma .* W)^T - mean_row * s) + b',   s_n = sum_k gamma_k W_nk,  b' = W beta + b.
+   * PRODUCER of x: ln_stats_out = [M][2 * ceil(N / block_n)][2] fp32 per-row (sum, sumsq) partials of its
+   *   bf16-rounded output, one slot per (n-tile, column half): fixed-order, no atomics.  Pass block_n explicitly.
+   * CONSUMER (a plain [M][K] product, taps == 1, no concat): w = bf16(gamma .* W), bias = b', ln_stats_in = the
+   *   producer's buffer with ln_parts slots per row, ln_colsum = s (fp32 [N], summed over the bf16 w), ln_eps. */
+  float* ln_stats_out;
+  const float* ln_stats_in;
+  const float* ln_colsum;
+  int32_t ln_parts;
+  float ln_eps;
 } sonic_gemm_args;
 int sonic_conv_gemm(const sonic_gemm_args* args, sonic_stream_t stream);
 /* Tile width the library would choose for (N, M) -- needed to pack GEGLU weights. */

@@ -196,6 +196,25 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
       const int ocol0 = n_tile * out_cols;                   // output column base
       int my_n = 0;                                          // chunks col_half, col_half + 2, ... inside the matrix
       for (int c = col_half; c < n_chunks && ocol0 + c * kChunkCols < p.n_out_total; c += 2) ++my_n;
+      // Folded LayerNorm, consumer side: this lane's row of A is normalised AFTER the product --
+      // out = ln_a * acc + ln_b * s[n] + bias'[n] with ln_a = rstd, ln_b = -rstd * mean -- from the per-row
+      // (sum, sumsq) partials A's producer left (fixed summation order: bit-reproducible).
+      float ln_a = 1.f, ln_b = 0.f;
+      if (p.ln_stats_in) {
+        const float2* st = reinterpret_cast<const float2*>(p.ln_stats_in) +
+                           static_cast<size_t>(min(row0 + lane, p.M - 1)) * p.ln_parts;
+        float sa = 0.f, sq = 0.f;
+        for (int i = 0; i < p.ln_parts; ++i) {
+          const float2 v = __ldcg(st + i);
+          sa += v.x;
+          sq += v.y;
+        }
+        const float mean = sa * p.ln_inv_k;
+        const float var = fmaxf(sq * p.ln_inv_k - mean * mean, 0.f);
+        ln_a = rsqrtf(var + p.ln_eps);
+        ln_b = -ln_a * mean;
+      }
+      float rs_sum = 0.f, rs_sq = 0.f;                       // producer side: statistics of this lane's output row
       if (has_res && lane == 0) {
         // residual of the NEXT tile into L2 now; this tile's first chunk into the staging buffer
         const int tile2 = tile + gridDim.x;
@@ -236,6 +255,23 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
           uint32_t gt[32];
           tmem_ld32(t_row + out_cols + c * kChunkCols, gt);
           tmem_ld_wait();
+          if (p.ln_stats_in) {
+            const float4* sv = reinterpret_cast<const float4*>(p.ln_colsum + ncol0 + c * kChunkCols);
+            const float4* sg = reinterpret_cast<const float4*>(p.ln_colsum + ncol0 + out_cols + c * kChunkCols);
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 bv = __ldg(bias_v + (j >> 2)), bg = __ldg(bias_g + (j >> 2));
+              const float4 cv = __ldg(sv + (j >> 2)), cg = __ldg(sg + (j >> 2));
+              f[j] = fmaf(ln_a, __uint_as_float(v[j]), fmaf(ln_b, cv.x, bv.x)) *
+                     gelu_erf(fmaf(ln_a, __uint_as_float(gt[j]), fmaf(ln_b, cg.x, bg.x)));
+              f[j + 1] = fmaf(ln_a, __uint_as_float(v[j + 1]), fmaf(ln_b, cv.y, bv.y)) *
+                         gelu_erf(fmaf(ln_a, __uint_as_float(gt[j + 1]), fmaf(ln_b, cg.y, bg.y)));
+              f[j + 2] = fmaf(ln_a, __uint_as_float(v[j + 2]), fmaf(ln_b, cv.z, bv.z)) *
+                         gelu_erf(fmaf(ln_a, __uint_as_float(gt[j + 2]), fmaf(ln_b, cg.z, bg.z)));
+              f[j + 3] = fmaf(ln_a, __uint_as_float(v[j + 3]), fmaf(ln_b, cv.w, bv.w)) *
+                         gelu_erf(fmaf(ln_a, __uint_as_float(gt[j + 3]), fmaf(ln_b, cg.w, bg.w)));
+            }
+          } else {
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
             const float4 bv = __ldg(bias_v + (j >> 2)), bg = __ldg(bias_g + (j >> 2));
@@ -243,6 +279,18 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
             f[j + 1] = (__uint_as_float(v[j + 1]) + bv.y) * gelu_erf(__uint_as_float(gt[j + 1]) + bg.y);
             f[j + 2] = (__uint_as_float(v[j + 2]) + bv.z) * gelu_erf(__uint_as_float(gt[j + 2]) + bg.z);
             f[j + 3] = (__uint_as_float(v[j + 3]) + bv.w) * gelu_erf(__uint_as_float(gt[j + 3]) + bg.w);
+          }
+          }
+        } else if (p.ln_stats_in) {
+          tmem_ld_wait();
+          const float4* sv = reinterpret_cast<const float4*>(p.ln_colsum + ncol0 + c * kChunkCols);
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 bv = __ldg(bias_v + (j >> 2)), cv = __ldg(sv + (j >> 2));
+            f[j] = fmaf(ln_a, __uint_as_float(v[j]), fmaf(ln_b, cv.x, bv.x));
+            f[j + 1] = fmaf(ln_a, __uint_as_float(v[j + 1]), fmaf(ln_b, cv.y, bv.y));
+            f[j + 2] = fmaf(ln_a, __uint_as_float(v[j + 2]), fmaf(ln_b, cv.z, bv.z));
+            f[j + 3] = fmaf(ln_a, __uint_as_float(v[j + 3]), fmaf(ln_b, cv.w, bv.w));
           }
         } else {
           tmem_ld_wait();
@@ -290,11 +338,23 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
           if (lane == 0) bulk_wait_read<1>();                // the store that last used this buffer has read it
           __syncwarp();
         }
+        uint32_t pk[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) pk[j] = pack_bf16(f[2 * j], f[2 * j + 1]);
 #pragma unroll
         for (int q = 0; q < 4; ++q)
-          *reinterpret_cast<uint4*>(my_row + ((q ^ sw) << 4)) =
-              make_uint4(pack_bf16(f[8 * q], f[8 * q + 1]), pack_bf16(f[8 * q + 2], f[8 * q + 3]),
-                         pack_bf16(f[8 * q + 4], f[8 * q + 5]), pack_bf16(f[8 * q + 6], f[8 * q + 7]));
+          *reinterpret_cast<uint4*>(my_row + ((q ^ sw) << 4)) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+        if (p.ln_stats_out) {                                // of the bf16-ROUNDED values: what the consumer multiplies
+          float a0 = 0.f, a1 = 0.f, q0 = 0.f, q1 = 0.f;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float lo = bf16_lo(pk[j]), hi = bf16_hi(pk[j]);
+            a0 += lo; a1 += hi;
+            q0 = fmaf(lo, lo, q0); q1 = fmaf(hi, hi, q1);
+          }
+          rs_sum += a0 + a1;
+          rs_sq += q0 + q1;
+        }
         if (i == 0 && threadIdx.x == 64) GEMM_TRACE(3, ti, 2);
         fence_proxy_async_smem();
         __syncwarp();
@@ -329,6 +389,9 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
         if (i == 0 && threadIdx.x == 64) GEMM_TRACE(3, ti, 3);
         ++slot;
       }
+      if (p.ln_stats_out && row0 + lane < p.M)               // one slot per (row, n_tile, column half): no atomics
+        reinterpret_cast<float2*>(p.ln_stats_out)[(static_cast<size_t>(row0 + lane) * p.n_tiles + n_tile) * 2 + col_half] =
+            make_float2(rs_sum, rs_sq);
       if (threadIdx.x == 64) GEMM_TRACE(2, ti, 3);
       acc ^= 1;
       if (acc == 0) acc_phase ^= 1;
@@ -468,7 +531,7 @@ int gemm_choose_block_n(int N, int n_img, int H, int W, int epilogue) {
       g_num_sms = 148;
   }
   int m_tiles;
-  if (W >= kTileM) {
+  if (W >= kTileM || (H == 1 && n_img == 1)) {
     m_tiles = ((W + kTileM - 1) / kTileM) * H * n_img;
   } else {
     const int th = std::min(H, kTileM / W);
@@ -501,7 +564,9 @@ int gemm_plan(const GemmOp& op, GemmPlan* plan) {
   p.k_chunks1 = op.a1 ? (op.c1 + kTileK - 1) / kTileK : 0;
   p.taps = op.taps;
   p.H = op.H; p.W = op.W; p.n_img = op.n_img;
-  if (op.W >= kTileM) {
+  if (op.W >= kTileM || (op.H == 1 && op.n_img == 1)) {
+    // rows of an image row (or of a plain [M][K] matrix, however short: the part of the 128-row box beyond the
+    // tensor is zero-filled by the TMA unit and its output rows are clipped by the tile store)
     p.tile_w = kTileM; p.tile_h = 1; p.tile_n = 1;
   } else {
     SONIC_REQUIRE(kTileM % op.W == 0, "gemm: W=%d must divide 128", op.W);
@@ -527,6 +592,16 @@ int gemm_plan(const GemmOp& op, GemmPlan* plan) {
   const bool flat = op.W < kTileM || op.W % kTileM == 0 || (op.H == 1 && op.n_img == 1);
   p.tma_epilogue = (out_cols % kChunkCols == 0 && flat) ? 1 : 0;
   p.gn_partial = op.gn_partial;
+  p.ln_stats_out = op.ln_stats_out;
+  p.ln_stats_in = op.ln_stats_in;
+  p.ln_colsum = op.ln_colsum;
+  p.ln_parts = op.ln_parts;
+  p.ln_eps = op.ln_eps;
+  p.ln_inv_k = 1.0f / static_cast<float>(K);
+  SONIC_REQUIRE((op.ln_stats_out == nullptr && op.ln_stats_in == nullptr) || p.tma_epilogue,
+                "gemm: folded LayerNorm needs the staged epilogue (block_n %% 32 == 0, contiguous 128-row tiles)");
+  SONIC_REQUIRE(op.ln_stats_in == nullptr || (op.ln_colsum != nullptr && op.ln_parts > 0 && op.taps == 1 && !op.a1),
+                "gemm: folded LayerNorm needs ln_colsum, ln_parts > 0 and a plain [M][K] A operand");
   SONIC_REQUIRE(op.epilogue != kEpiQuickGelu || p.tma_epilogue, "gemm: QuickGELU needs the staged epilogue");
   SONIC_REQUIRE(op.gn_partial == nullptr || p.tma_epilogue,
                 "gemm: gn_partial needs the staged epilogue (block_n %% 32 == 0, contiguous 128-row tiles)");

@@ -31,6 +31,12 @@ struct GemmParams {
   int n_out_total;               // output columns (N, or N/2 for GEGLU)
   int tma_epilogue;              // 1: smem-staged TMA-store epilogue, 0: direct stores
   float* gn_partial;             // optional [ceil(M/32)][n_out_total][2] GroupNorm pre-reduction of the output
+  // LayerNorm folded into the GEMMs around it (LN(x) W^T = rstd_row (x (gamma.W)^T - mu_row s) + b'):
+  float* ln_stats_out;           // producer: optional [M][2 * n_tiles][2] per-row (sum, sumsq) partials of the OUTPUT
+  const float* ln_stats_in;      // consumer: [M][ln_parts][2] partials of the rows of A (written by A's producer)
+  const float* ln_colsum;        // consumer: s[n] = sum_k (gamma_k W_nk as bf16), same order as the B rows
+  int ln_parts;                  // consumer: partials per row
+  float ln_eps, ln_inv_k;        // consumer: epsilon, 1 / (LayerNorm width)
 };
 
 struct GemmOp {                  // host-side description; pointers are borrowed
@@ -45,6 +51,8 @@ struct GemmOp {                  // host-side description; pointers are borrowed
   int epilogue = kEpiNone;
   int block_n = 0;               // 0 = choose
   float* gn_partial = nullptr;
+  float* ln_stats_out = nullptr;           // see GemmParams
+  const float* ln_stats_in = nullptr; const float* ln_colsum = nullptr; int ln_parts = 0; float ln_eps = 1e-5f;
 };
 
 struct GemmPlan {

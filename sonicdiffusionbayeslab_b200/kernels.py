@@ -51,8 +51,28 @@ def gemm_block_n(N: int, n_img: int, H: int, W: int, epilogue: int = EPI_NONE) -
     return lib().sonic_gemm_block_n(N, n_img, H, W, epilogue)
 
 
+def fold_layernorm(w, b, gamma, beta):
+    """LayerNorm folded into the Linear that follows it: returns (w', s, b') with
+    ``LN(x) w^T + b == rstd * (x w'^T - mean * s) + b'`` -- w' = bf16(gamma .* w), s_n = sum_k w'_nk (summed over the
+    ROUNDED w', so the mean subtraction is exact for the product the tensor cores compute), b' = w beta + b."""
+    wf = w.float()
+    wp = (wf * gamma.float()[None, :]).to(torch.bfloat16)
+    s = wp.float().sum(dim=1)
+    bp = wf @ beta.float()
+    if b is not None:
+        bp = bp + b.float()
+    return wp.contiguous(), s.contiguous(), bp.contiguous()
+
+
+def ln_stats_buffer(rows, N, block_n, device):
+    """Per-row (sum, sumsq) partial buffer a producer GEMM of width N / tile ``block_n`` fills; (buffer, parts)."""
+    parts = 2 * ((N + block_n - 1) // block_n)
+    return torch.zeros(rows, parts, 2, device=device, dtype=torch.float32), parts
+
+
 def conv_gemm(a0, w, N, *, taps=1, n_img=1, H=1, W=None, c0=None, a1=None, c1=0, bias=None,
-              row_bias=None, residual=None, out=None, epilogue=EPI_NONE, block_n=0, gn_partial=None):
+              row_bias=None, residual=None, out=None, epilogue=EPI_NONE, block_n=0, gn_partial=None,
+              ln_stats_out=None, ln_fold=None):
     """out[M, N'] = epilogue(implicit_gemm(A, w)); see ``sonic_conv_gemm`` in include/sonic.h.
 
     ``a0`` / ``a1`` are NHWC bf16 tensors whose last dim is the pixel pitch; a Linear over
@@ -88,6 +108,14 @@ def conv_gemm(a0, w, N, *, taps=1, n_img=1, H=1, W=None, c0=None, a1=None, c1=0,
         assert gn_partial.dtype == torch.float32 and gn_partial.is_contiguous() and \
             gn_partial.numel() >= (M + 31) // 32 * n_out * 2
         args.gn_partial = gn_partial.data_ptr()
+    if ln_stats_out is not None:                                     # producer of a LayerNorm input
+        assert block_n and ln_stats_out.dtype == torch.float32 and ln_stats_out.is_contiguous() and \
+            ln_stats_out.numel() == M * 2 * ((N + block_n - 1) // block_n) * 2
+        args.ln_stats_out = ln_stats_out.data_ptr()
+    if ln_fold is not None:                                          # consumer: (stats buffer, parts, colsum, eps)
+        stats, parts, colsum, eps = ln_fold
+        assert stats.dtype == colsum.dtype == torch.float32 and colsum.numel() == N and stats.numel() == M * parts * 2
+        args.ln_stats_in, args.ln_parts, args.ln_colsum, args.ln_eps = stats.data_ptr(), parts, colsum.data_ptr(), eps
     check(lib().sonic_conv_gemm(C.byref(args), stream_ptr()), "sonic_conv_gemm")
     return out
 

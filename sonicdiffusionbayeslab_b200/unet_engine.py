@@ -84,10 +84,11 @@ class Arena:
         return t
 
     def release(self, t):
-        part = getattr(t, "_gn_part", None)
-        if part is not None:                      # GroupNorm pre-reduction buffer travels with its tensor
-            t._gn_part = None
-            self.release(part)
+        for attr in ("_gn_part", "_ln_part"):     # GroupNorm / LayerNorm pre-reduction buffers travel with their tensor
+            part = getattr(t, attr, None)
+            if part is not None:
+                setattr(t, attr, None)
+                self.release(part)
         raw = t._arena_raw
         self.free.setdefault(raw.numel(), []).append(raw)
 
@@ -168,6 +169,7 @@ class UNetEngine:
         self.io_dtype = io_dtype
         self.arena = Arena(self.dev)
         self.fuse_gn_stats = True                            # GroupNorm statistics from the producers' epilogues
+        self.fold_layernorm = True                           # LayerNorms folded into the GEMMs around them
         self._keep = []                                      # packed weights
         self.sd = state_dict
         a = arch
@@ -212,6 +214,15 @@ class UNetEngine:
             self._w[key] = w.to(torch.bfloat16).contiguous().to(self.dev)
         return self._w[key]
 
+    def _folded(self, key, weight_names, bias_name, norm_prefix):
+        """(w', s, b') of ``K.fold_layernorm`` for the (row-concatenated) Linear behind LayerNorm ``norm_prefix``."""
+        if key + ("ln",) not in self._w:
+            w = torch.cat([self._src(n) for n in weight_names], 0)
+            b = self._src(bias_name) if bias_name else None
+            wp, s_, bp = K.fold_layernorm(w, b, self._src(norm_prefix + ".weight"), self._src(norm_prefix + ".bias"))
+            self._w[key + ("ln",)] = (wp.to(self.dev), s_.to(self.dev), bp.to(self.dev))
+        return self._w[key + ("ln",)]
+
     def _conv3(self, name):
         key = ("c3", name)
         if key not in self._w:
@@ -220,7 +231,7 @@ class UNetEngine:
 
     # ------------------------------------------------------------------ op recording helpers
     def _gemm(self, plan, a0, w, N, *, n_img=1, H=1, W=None, taps=1, c0=None, a1=None, bias=None,
-              residual=None, out=None, epilogue=K.EPI_NONE, block_n=0, gn_stats=False):
+              residual=None, out=None, epilogue=K.EPI_NONE, block_n=0, gn_stats=False, ln_stats=False, ln_fold=None):
         ld0 = a0.shape[-1]
         M = a0.numel() // ld0
         if W is None:
@@ -241,6 +252,20 @@ class UNetEngine:
             g.residual, g.ld_res = residual.data_ptr(), residual.shape[-1]
         g.out, g.ld_out = out.data_ptr(), out.shape[-1]
         g.epilogue, g.block_n = epilogue, block_n
+        if ln_stats:
+            # producer of a LayerNorm input: per-row (sum, sumsq) partials of the output ride along with the tensor
+            bn = block_n or K.gemm_block_n(N, n_img, H, W, epilogue)
+            g.block_n = bn
+            parts = 2 * ((N + bn - 1) // bn)
+            buf = getattr(out, "_ln_part", None)
+            if buf is None or buf.shape[1] != parts:
+                buf = self.arena.alloc((M, parts, 2), torch.float32)
+                out._ln_part = buf
+            g.ln_stats_out = buf.data_ptr()
+        if ln_fold is not None:
+            stats, colsum, eps = ln_fold                     # consumer: A's row partials, s[n], epsilon
+            assert stats.shape[0] == M and colsum.numel() == N
+            g.ln_stats_in, g.ln_parts, g.ln_colsum, g.ln_eps = stats.data_ptr(), stats.shape[1], colsum.data_ptr(), eps
         if gn_stats and self.fuse_gn_stats:
             # the epilogue also writes per-32-row (sum, sumsq) of the output: the consumer GroupNorm needs no
             # statistics pass over the tensor
@@ -252,7 +277,8 @@ class UNetEngine:
         check(lib().sonic_plan_add_conv_gemm(plan.h, C.byref(g)), "sonic_plan_add_conv_gemm")
         kk = g.c0 + (g.c1 if a1 is not None else 0)
         plan.log.append(f"gemm M={M} N={N} K={kk}x{taps} img={n_img}x{H}x{W} epi={epilogue}"
-                        f"{' +res' if residual is not None else ''}")
+                        f"{' +res' if residual is not None else ''}{' +lnfold' if ln_fold is not None else ''}"
+                        f"{' +lnstats' if ln_stats else ''}")
         return out
 
     def _gn(self, plan, x0, x1, prefix, hw, eps, silu):
@@ -329,42 +355,66 @@ class UNetEngine:
         d = Cc // a.num_heads
         tb = prefix + ".transformer_blocks.0"
         g = self._gn(plan, x, None, prefix + ".norm", hw, 1e-6, False)
-        h = self._gemm(plan, g, self._lin(prefix + ".proj_in.weight"), Cc, bias=self._f32(prefix + ".proj_in.bias"))
+        fold = self.fold_layernorm
+        h = self._gemm(plan, g, self._lin(prefix + ".proj_in.weight"), Cc, bias=self._f32(prefix + ".proj_in.bias"),
+                       ln_stats=fold)
         self.arena.release(g)
+        # The three LayerNorms of the block launch nothing: the producer of ``h`` leaves per-row (sum, sumsq) in its
+        # epilogue and the consuming projection applies rstd / mean after the product (``K.fold_layernorm``).
         # self-attention: fused QKV projection, heads read in place by the attention kernel
-        ln = self._ln(plan, h, tb + ".norm1")
-        key = ("qkv", tb)
-        if key not in self._w:
-            self._w[key] = torch.cat([self._src(tb + f".attn1.to_{n}.weight") for n in "qkv"], 0) \
-                .to(torch.bfloat16).contiguous().to(self.dev)
-        qkv = self._gemm(plan, ln, self._w[key], 3 * Cc)
-        self.arena.release(ln)
+        if fold:
+            wq, sq_, bq = self._folded(("qkv", tb), [tb + f".attn1.to_{n}.weight" for n in "qkv"], None, tb + ".norm1")
+            qkv = self._gemm(plan, h, wq, 3 * Cc, bias=bq, ln_fold=(h._ln_part, sq_, 1e-5))
+        else:
+            ln = self._ln(plan, h, tb + ".norm1")
+            key = ("qkv", tb)
+            if key not in self._w:
+                self._w[key] = torch.cat([self._src(tb + f".attn1.to_{n}.weight") for n in "qkv"], 0) \
+                    .to(torch.bfloat16).contiguous().to(self.dev)
+            qkv = self._gemm(plan, ln, self._w[key], 3 * Cc)
+            self.arena.release(ln)
         ao = self._attn(plan, qkv[:, :Cc], qkv[:, Cc:2 * Cc], qkv[:, 2 * Cc:], hw, hw, d)
         self.arena.release(qkv)
         self._gemm(plan, ao, self._lin(tb + ".attn1.to_out.0.weight"), Cc, bias=self._f32(tb + ".attn1.to_out.0.bias"),
-                   residual=h, out=h)
+                   residual=h, out=h, ln_stats=fold)
         self.arena.release(ao)
         # cross-attention: K/V come from the per-call ctx plan
-        ln = self._ln(plan, h, tb + ".norm2")
-        q = self._gemm(plan, ln, self._lin(tb + ".attn2.to_q.weight"), Cc)
-        self.arena.release(ln)
+        if fold:
+            wq, sq_, bq = self._folded(("xq", tb), [tb + ".attn2.to_q.weight"], None, tb + ".norm2")
+            q = self._gemm(plan, h, wq, Cc, bias=bq, ln_fold=(h._ln_part, sq_, 1e-5))
+        else:
+            ln = self._ln(plan, h, tb + ".norm2")
+            q = self._gemm(plan, ln, self._lin(tb + ".attn2.to_q.weight"), Cc)
+            self.arena.release(ln)
         kv = self._ctx_kv[tb]
         ao = self._attn(plan, q, kv[:, :Cc], kv[:, Cc:], hw, self.ctx_len, d)
         self.arena.release(q)
         self._gemm(plan, ao, self._lin(tb + ".attn2.to_out.0.weight"), Cc, bias=self._f32(tb + ".attn2.to_out.0.bias"),
-                   residual=h, out=h)
+                   residual=h, out=h, ln_stats=fold)
         self.arena.release(ao)
         # feed-forward: GEGLU fused into the first GEMM's epilogue
-        ln = self._ln(plan, h, tb + ".norm3")
-        bn = K.gemm_block_n(8 * Cc, 1, 1, ln.shape[0], K.EPI_GEGLU)
-        key = ("geglu", tb, bn)
-        if key not in self._w:
-            wp, bp = K.pack_geglu(self._src(tb + ".ff.net.0.proj.weight").to(torch.bfloat16),
-                                  self._src(tb + ".ff.net.0.proj.bias").float(), bn)
-            self._w[key] = (wp.to(self.dev), bp.to(self.dev), bn)
-        wp, bp, bn = self._w[key]
-        ff = self._gemm(plan, ln, wp, 8 * Cc, bias=bp, epilogue=K.EPI_GEGLU, block_n=bn)
-        self.arena.release(ln)
+        bn = K.gemm_block_n(8 * Cc, 1, 1, h.shape[0], K.EPI_GEGLU)
+        if fold:
+            key = ("geglu_ln", tb, bn)
+            if key not in self._w:
+                wf, sf, bf = K.fold_layernorm(self._src(tb + ".ff.net.0.proj.weight"), self._src(tb + ".ff.net.0.proj.bias"),
+                                              self._src(tb + ".norm3.weight"), self._src(tb + ".norm3.bias"))
+                wp, bp = K.pack_geglu(wf, bf, bn)
+                _, sp = K.pack_geglu(wf, sf, bn)
+                self._w[key] = (wp.to(self.dev), bp.to(self.dev), sp.to(self.dev))
+            wp, bp, sp = self._w[key]
+            ff = self._gemm(plan, h, wp, 8 * Cc, bias=bp, epilogue=K.EPI_GEGLU, block_n=bn,
+                            ln_fold=(h._ln_part, sp, 1e-5))
+        else:
+            ln = self._ln(plan, h, tb + ".norm3")
+            key = ("geglu", tb, bn)
+            if key not in self._w:
+                wp, bp = K.pack_geglu(self._src(tb + ".ff.net.0.proj.weight").to(torch.bfloat16),
+                                      self._src(tb + ".ff.net.0.proj.bias").float(), bn)
+                self._w[key] = (wp.to(self.dev), bp.to(self.dev), bn)
+            wp, bp, bn = self._w[key]
+            ff = self._gemm(plan, ln, wp, 8 * Cc, bias=bp, epilogue=K.EPI_GEGLU, block_n=bn)
+            self.arena.release(ln)
         self._gemm(plan, ff, self._lin(tb + ".ff.net.2.weight"), Cc, bias=self._f32(tb + ".ff.net.2.bias"),
                    residual=h, out=h)
         self.arena.release(ff)

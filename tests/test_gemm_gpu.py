@@ -20,7 +20,7 @@ def _bf(x):
 
 
 @pytest.mark.parametrize("M,N,K", [(128, 64, 64), (256, 320, 320), (77 * 2, 640, 768), (1000, 1280, 1280),
-                                    (4096, 960, 320)])
+                                    (4096, 960, 320), (77, 512, 512), (29, 512, 512), (1, 768, 512)])
 def test_linear(cuda, M, N, K):
     from sonicdiffusionbayeslab_b200 import kernels as k
 
@@ -123,3 +123,49 @@ def test_narrow_and_strided_outputs(cuda):
         ref = a.float() @ w.float().t()
         assert _rel_err(out, ref) < 1e-2, (M, N, K)
         assert wide[:, :32].abs().max().item() == 0 and wide[:, 32 + N:].abs().max().item() == 0, (M, N, K)
+
+
+@pytest.mark.parametrize("M,C,N,geglu", [(4096, 320, 960, False), (1000, 640, 640, False), (512, 1280, 3840, False),
+                                          (4096, 320, 2560, True), (300, 1280, 10240, True)])
+def test_layernorm_folded_into_gemm(cuda, M, C, N, geglu):
+    """The LayerNorms of the transformer blocks launch no kernel: the PRODUCER GEMM (here a +residual projection
+    of width C) leaves per-row (sum, sumsq) partials of its output, the CONSUMER (a plain / GEGLU projection)
+    applies rstd and mean after the product.  Reference: fp32 LayerNorm -> Linear (-> GEGLU) of the same
+    bf16-rounded tensors, as oracle/unet.py BasicTransformerBlock computes them."""
+    from sonicdiffusionbayeslab_b200 import kernels as k
+
+    g = torch.Generator(device="cuda").manual_seed(M + C + N)
+    a = _bf(torch.randn(M, C, device=cuda, generator=g))
+    wp_ = _bf(torch.randn(C, C, device=cuda, generator=g) / C ** 0.5)
+    res = _bf(3.0 + 2.0 * torch.randn(M, C, device=cuda, generator=g))     # rows with a large mean: the hard case
+    bn = k.gemm_block_n(C, 1, 1, M)
+    stats, parts = k.ln_stats_buffer(M, C, bn, cuda)
+    h = k.conv_gemm(a, wp_, C, residual=res, block_n=bn, ln_stats_out=stats)           # producer
+    # the partials are the row sums of the bf16 output, whatever the tiling
+    assert torch.allclose(stats[..., 0].sum(1), h.float().sum(1), rtol=1e-4, atol=1e-2)
+    assert torch.allclose(stats[..., 1].sum(1), (h.float() ** 2).sum(1), rtol=1e-4, atol=1e-2)
+    gamma = 1.0 + 0.2 * torch.randn(C, device=cuda, generator=g)
+    beta = 0.3 * torch.randn(C, device=cuda, generator=g)
+    w = torch.randn(N, C, device=cuda, generator=g) / C ** 0.5
+    b = torch.randn(N, device=cuda, generator=g)
+    wf, s, bf_ = k.fold_layernorm(w, b, gamma, beta)
+    ln = F.layer_norm(h.float(), (C,), gamma, beta, 1e-5)
+    ref = ln @ _bf(w).float().t() + b
+    if geglu:
+        bnc = k.gemm_block_n(N, 1, 1, M, k.EPI_GEGLU)
+        wpk, bpk = k.pack_geglu(wf, bf_, bnc)
+        _, spk = k.pack_geglu(wf, s, bnc)
+        out = k.conv_gemm(h, wpk, N, bias=bpk, epilogue=k.EPI_GEGLU, block_n=bnc, ln_fold=(stats, parts, spk, 1e-5))
+        v, gate = ref.chunk(2, dim=-1)
+        ref = v * F.gelu(gate)
+    else:
+        out = k.conv_gemm(h, wf, N, bias=bf_, ln_fold=(stats, parts, s, 1e-5))
+    # what the unfused path (LayerNorm kernel -> bf16 -> GEMM) loses on the same data
+    ln16 = _bf(ln)
+    unf = ln16.float() @ _bf(w).float().t() + b
+    if geglu:
+        v, gate = unf.chunk(2, dim=-1)
+        unf = v * F.gelu(gate)
+    torch.cuda.synchronize()
+    err, floor = _rel_err(out, ref), _rel_err(_bf(unf), ref)
+    assert err < 1e-2 and err < 1.5 * floor + 2e-3, (err, floor)

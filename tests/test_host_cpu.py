@@ -344,3 +344,22 @@ def test_pil_resample_tables_are_bit_exact(hw):
             ss = (1 << 21) + (tmp[ymin:ymin + cnt].astype(np.int64) * np.array(vk[oy][:cnt], np.int64)[:, None]).sum(0)
             got[oy, :, c] = np.clip(ss >> 22, 0, 255)
     assert np.array_equal(got, want)
+
+
+def test_fold_layernorm_algebra():
+    """``kernels.fold_layernorm``: LN(x) W^T + b == rstd (x W'^T - mean s) + b' (fp32, CPU)."""
+    from sonicdiffusionbayeslab_b200 import kernels as K
+
+    g = torch.Generator().manual_seed(0)
+    x = (2.0 + 3.0 * torch.randn(64, 320, generator=g)).bfloat16().float()
+    w, b = torch.randn(96, 320, generator=g) / 18, torch.randn(96, generator=g)
+    gamma, beta = 1 + 0.2 * torch.randn(320, generator=g), 0.3 * torch.randn(320, generator=g)
+    wp, s, bp = K.fold_layernorm(w, b, gamma, beta)
+    mean, var = x.mean(1, keepdim=True), x.var(1, unbiased=False, keepdim=True)
+    rstd = (var + 1e-5).rsqrt()
+    got = rstd * (x @ wp.float().t() - mean * s) + bp
+    want = torch.nn.functional.layer_norm(x, (320,), gamma, beta, 1e-5) @ w.t() + b
+    assert wp.dtype == torch.bfloat16
+    assert (got - want).abs().max().item() < 2e-2 * want.abs().max().item()      # only the bf16 rounding of W'
+    exact = torch.nn.functional.layer_norm(x, (320,), torch.ones(320), torch.zeros(320), 1e-5) @ wp.float().t() + bp
+    assert (got - exact).abs().max().item() < 1e-4 * exact.abs().max().item()    # the identity itself

