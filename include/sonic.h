@@ -72,6 +72,16 @@ typedef struct sonic_gemm_args {
   const float* ln_colsum;
   int32_t ln_parts;
   float ln_eps;
+  /* Strided / upsampled 3x3 convolutions without a materialised im2col or upsampled tensor (taps = 9, one source,
+   * no residual / row_bias / GEGLU):
+   *   stride = 2   : Downsample2D (stride 2, pad 1).  H, W are the OUTPUT extents, a0 is the 2H x 2W input; the nine
+   *                  taps are TMA boxes of four parity views of the input.  w: [9][N][K] as for stride 1.
+   *   upsample = 1 : Upsample2D (nearest 2x, then 3x3).  H, W are the SOURCE extents, out is the 2H x 2W result.
+   *                  Each output phase (y & 1, x & 1) is a 2x2 convolution of the source with taps summed from the
+   *                  3x3 kernel (4/9 of the multiply-adds): w = [16][N][K], phase-major (sonic kernels.py
+   *                  pack_upsample_conv_weight); the epilogue stores through four strided views of the output. */
+  int32_t stride;        /* 0 / 1 = unit stride */
+  int32_t upsample;
 } sonic_gemm_args;
 int sonic_conv_gemm(const sonic_gemm_args* args, sonic_stream_t stream);
 /* Tile width the library would choose for (N, M) -- needed to pack GEGLU weights. */

@@ -29,6 +29,7 @@ class GemmArgs(C.Structure):
         ("gn_partial", C.c_void_p),
         ("ln_stats_out", C.c_void_p), ("ln_stats_in", C.c_void_p), ("ln_colsum", C.c_void_p),
         ("ln_parts", C.c_int32), ("ln_eps", C.c_float),
+        ("stride", C.c_int32), ("upsample", C.c_int32),
     ]
 
 

@@ -25,6 +25,7 @@ int sonic_conv_gemm(const sonic_gemm_args* a, sonic_stream_t stream) {
   op.epilogue = a->epilogue; op.block_n = a->block_n; op.gn_partial = a->gn_partial;
   op.ln_stats_out = a->ln_stats_out; op.ln_stats_in = a->ln_stats_in; op.ln_colsum = a->ln_colsum;
   op.ln_parts = a->ln_parts; op.ln_eps = a->ln_eps;
+  op.stride = a->stride == 2 ? 2 : 1; op.upsample = a->upsample;
   GemmPlan plan;
   if (int rc = gemm_plan(op, &plan)) return rc;
   return gemm_launch(plan, static_cast<cudaStream_t>(stream));

@@ -32,6 +32,7 @@ constexpr int kMaxGranules = 8;            // 16-column granules per epilogue wa
 constexpr int kEpiWarps = 8;
 constexpr int kChunkCols = 32;             // output columns per staged chunk (64 B of bf16: one swizzle-64B row)
 constexpr int kStgBufBytes = 32 * kChunkCols * 2;       // 32 rows x 64 B
+constexpr int kMaxLnPairs = 8;             // folded LayerNorm: at most 16 per-row partials (2 per n-tile of the producer)
 constexpr int kStgBufs = 2;                // staging buffers per epilogue warp
 constexpr int kStgBytes = kEpiWarps * kStgBufs * kStgBufBytes;   // 32 KB
 
@@ -102,30 +103,50 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
       tma_prefetch_desc(&p.tm_a0);
       tma_prefetch_desc(&p.tm_b);
       if (p.k_chunks1) tma_prefetch_desc(&p.tm_a1);
+      if (p.mode == kModeStride2)
+        for (int i = 0; i < 3; ++i) tma_prefetch_desc(&p.tm_x[i]);
       int stage = 0;
       uint32_t phase = 0;
       int ti = 0;
       for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
         GEMM_TRACE(0, ti, 0);
         const int n_tile = tile % p.n_tiles;
-        const int m_tile = tile / p.n_tiles;
+        int m_tile = tile / p.n_tiles;
+        int phase_a = 0, phase_b = 0, b_tap0 = 0;
+        if (p.mode == kModeUpsample) {                       // tiles are phase-major: (phase, source-pixel tile)
+          const int ph = m_tile / p.m_tiles_src;
+          m_tile -= ph * p.m_tiles_src;
+          phase_a = ph >> 1; phase_b = ph & 1; b_tap0 = ph * 4;
+        }
         const int w0 = (m_tile % p.tiles_w) * p.tile_w;
         const int h0 = ((m_tile / p.tiles_w) % p.tiles_h) * p.tile_h;
         const int i0 = (m_tile / (p.tiles_w * p.tiles_h)) * p.tile_n;
         const int ncol0 = n_tile * p.block_n;
         for (int tap = 0; tap < p.taps; ++tap) {
-          const int dy = p.taps == 9 ? tap / 3 - 1 : 0;
-          const int dx = p.taps == 9 ? tap % 3 - 1 : 0;
+          int dy = 0, dx = 0;
+          const CUtensorMap* ma = &p.tm_a0;
+          if (p.mode == kModeStride2) {
+            // input row 2h + ky - 1: ky = 0 -> odd row of pair h - 1, ky = 1 -> even row of pair h, ky = 2 -> odd row
+            // of pair h; the parity views make each of them an ordinary (zero-filled at -1) TMA box
+            const int ky = tap / 3, kx = tap % 3;
+            dy = ky == 0 ? -1 : 0; dx = kx == 0 ? -1 : 0;
+            const int par = (ky != 1 ? 2 : 0) + (kx != 1 ? 1 : 0);
+            ma = par == 0 ? &p.tm_a0 : &p.tm_x[par - 1];
+          } else if (p.mode == kModeUpsample) {
+            dy = (tap >> 1) - 1 + phase_a; dx = (tap & 1) - 1 + phase_b;
+          } else if (p.taps == 9) {
+            dy = tap / 3 - 1; dx = tap % 3 - 1;
+          }
           for (int ch = 0; ch < k_chunks; ++ch) {
             mbar_wait<512>(&empty_bar[stage], phase ^ 1);
             mbar_expect_tx(&full_bar[stage], stage_bytes);
             uint8_t* sa = smem + stage * stage_bytes;
             if (ch < p.k_chunks0)
-              tma_load_4d(sa, &p.tm_a0, &full_bar[stage], ch * kTileK, w0 + dx, h0 + dy, i0);
+              tma_load_4d(sa, ma, &full_bar[stage], ch * kTileK, w0 + dx, h0 + dy, i0);
             else
               tma_load_4d(sa, &p.tm_a1, &full_bar[stage], (ch - p.k_chunks0) * kTileK, w0 + dx,
                           h0 + dy, i0);
-            tma_load_3d(sa + kABytes, &p.tm_b, &full_bar[stage], ch * kTileK, ncol0, tap);
+            tma_load_3d(sa + kABytes, &p.tm_b, &full_bar[stage], ch * kTileK, ncol0, b_tap0 + tap);
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
           }
         }
@@ -186,11 +207,27 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
     if (lane == 0) {
       tma_prefetch_desc(&p.tm_out);
       if (has_res) tma_prefetch_desc(&p.tm_res);
+      if (p.mode == kModeUpsample)
+        for (int i = 0; i < 3; ++i) tma_prefetch_desc(&p.tm_x[i]);
+    }
+    float4 ln_nx[kMaxLnPairs];                   // (sum, sumsq) partial pairs of the tile about to be processed
+    if (p.ln_stats_in && static_cast<int>(blockIdx.x) < total_tiles) {
+      const int r1 = (static_cast<int>(blockIdx.x) / p.n_tiles) * kTileM + quarter * 32 + lane;
+      const float4* st = reinterpret_cast<const float4*>(p.ln_stats_in) +
+                         static_cast<size_t>(min(r1, p.M - 1)) * (p.ln_parts >> 1);
+#pragma unroll
+      for (int i = 0; i < kMaxLnPairs; ++i)
+        if (2 * i < p.ln_parts) ln_nx[i] = __ldcg(st + i);
     }
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
       if (threadIdx.x == 64) GEMM_TRACE(2, ti, 0);
       const int n_tile = tile % p.n_tiles;
-      const int m_tile = tile / p.n_tiles;
+      int m_tile = tile / p.n_tiles;
+      int up_phase = 0;
+      if (p.mode == kModeUpsample) {                         // phase-major tiles over the SOURCE pixels
+        up_phase = m_tile / p.m_tiles_src;
+        m_tile -= up_phase * p.m_tiles_src;
+      }
       const int row0 = m_tile * kTileM + quarter * 32;       // tiles are 128 consecutive rows of [M][N]
       const int ncol0 = n_tile * p.block_n;                  // B-row / bias index base
       const int ocol0 = n_tile * out_cols;                   // output column base
@@ -198,21 +235,28 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
       for (int c = col_half; c < n_chunks && ocol0 + c * kChunkCols < p.n_out_total; c += 2) ++my_n;
       // Folded LayerNorm, consumer side: this lane's row of A is normalised AFTER the product --
       // out = ln_a * acc + ln_b * s[n] + bias'[n] with ln_a = rstd, ln_b = -rstd * mean -- from the per-row
-      // (sum, sumsq) partials A's producer left (fixed summation order: bit-reproducible).
+      // (sum, sumsq) partials A's producer left (fixed summation order: bit-reproducible).  The partials of the
+      // NEXT tile are requested now and reduced one iteration later, so their L2 latency (~700 cycles per load,
+      // measured as +25 % on the K = 320 projections when it sat in front of every tile) hides behind this tile.
       float ln_a = 1.f, ln_b = 0.f;
       if (p.ln_stats_in) {
-        const float2* st = reinterpret_cast<const float2*>(p.ln_stats_in) +
-                           static_cast<size_t>(min(row0 + lane, p.M - 1)) * p.ln_parts;
         float sa = 0.f, sq = 0.f;
-        for (int i = 0; i < p.ln_parts; ++i) {
-          const float2 v = __ldcg(st + i);
-          sa += v.x;
-          sq += v.y;
-        }
+#pragma unroll
+        for (int i = 0; i < kMaxLnPairs; ++i)
+          if (2 * i < p.ln_parts) { sa += ln_nx[i].x + ln_nx[i].z; sq += ln_nx[i].y + ln_nx[i].w; }
         const float mean = sa * p.ln_inv_k;
         const float var = fmaxf(sq * p.ln_inv_k - mean * mean, 0.f);
         ln_a = rsqrtf(var + p.ln_eps);
         ln_b = -ln_a * mean;
+        const int tile2 = tile + gridDim.x;
+        if (tile2 < total_tiles) {
+          const int r2 = (tile2 / p.n_tiles) * kTileM + quarter * 32 + lane;
+          const float4* st = reinterpret_cast<const float4*>(p.ln_stats_in) +
+                             static_cast<size_t>(min(r2, p.M - 1)) * (p.ln_parts >> 1);
+#pragma unroll
+          for (int i = 0; i < kMaxLnPairs; ++i)
+            if (2 * i < p.ln_parts) ln_nx[i] = __ldcg(st + i);
+        }
       }
       float rs_sum = 0.f, rs_sq = 0.f;                       // producer side: statistics of this lane's output row
       if (has_res && lane == 0) {
@@ -372,12 +416,24 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
             sq[r & 1] = fmaf(x, x, sq[r & 1]);
           }
           const int col = ocol0 + c * kChunkCols + lane;
+          // slot of this 32-row block among the per-image partials of the OUTPUT tensor (any order inside an image)
+          size_t blk = static_cast<size_t>(row0 >> 5);
+          if (p.mode == kModeUpsample) {
+            const int hw = p.H * p.W, img = row0 / hw;
+            blk = static_cast<size_t>(img) * (hw >> 3) + up_phase * (hw >> 5) + ((row0 - img * hw) >> 5);
+          }
           if (col < p.n_out_total && rmax > 0)
-            *reinterpret_cast<float2*>(p.gn_partial + (static_cast<size_t>(row0 >> 5) * p.n_out_total + col) * 2) =
+            *reinterpret_cast<float2*>(p.gn_partial + (blk * p.n_out_total + col) * 2) =
                 make_float2(sa[0] + sa[1], sq[0] + sq[1]);
         }
         if (lane == 0) {
-          tma_store_2d(&p.tm_out, buf, ocol0 + c * kChunkCols, row0);
+          if (p.mode == kModeUpsample) {                     // 32 source pixels -> pixels (2h + a, 2w + b) of the output
+            const int hw = p.H * p.W, img = row0 / hw, rem = row0 - img * hw;
+            tma_store_4d(up_phase == 0 ? &p.tm_out : &p.tm_x[up_phase - 1], buf, ocol0 + c * kChunkCols, rem % p.W,
+                         rem / p.W, img);
+          } else {
+            tma_store_2d(&p.tm_out, buf, ocol0 + c * kChunkCols, row0);
+          }
           bulk_commit();
           if (has_res && i + 1 < my_n) {                     // next chunk's residual into the other buffer
             const uint32_t nb = b ^ 1;
@@ -544,6 +600,12 @@ int gemm_choose_block_n(int N, int n_img, int H, int W, int epilogue) {
 int gemm_plan(const GemmOp& op, GemmPlan* plan) {
   SONIC_REQUIRE(op.a0 && op.w && op.out, "gemm: null operand");
   SONIC_REQUIRE(op.taps == 1 || op.taps == 9, "gemm: taps must be 1 or 9 (got %d)", op.taps);
+  SONIC_REQUIRE(op.stride == 1 || op.stride == 2, "gemm: stride must be 1 or 2");
+  SONIC_REQUIRE(!(op.stride == 2 && op.upsample), "gemm: stride 2 and upsample are exclusive");
+  SONIC_REQUIRE((op.stride == 1 && !op.upsample) || (op.taps == 9 && op.a1 == nullptr && op.residual == nullptr &&
+                                                      op.row_bias == nullptr && op.epilogue == kEpiNone),
+                "gemm: stride-2 / upsample convolutions are plain 3x3 convolutions of one tensor");
+  const int mode = op.stride == 2 ? kModeStride2 : op.upsample ? kModeUpsample : kModeNormal;
   SONIC_REQUIRE(op.N % 16 == 0, "gemm: N=%d must be a multiple of 16", op.N);
   SONIC_REQUIRE(op.c0 % 8 == 0 && op.c1 % 8 == 0 && op.ld0 % 8 == 0 && op.ld1 % 8 == 0,
                 "gemm: channel counts / strides must be multiples of 8");
@@ -562,7 +624,8 @@ int gemm_plan(const GemmOp& op, GemmPlan* plan) {
   p.N = op.N;
   p.k_chunks0 = (op.c0 + kTileK - 1) / kTileK;
   p.k_chunks1 = op.a1 ? (op.c1 + kTileK - 1) / kTileK : 0;
-  p.taps = op.taps;
+  p.taps = mode == kModeUpsample ? 4 : op.taps;
+  p.mode = mode;
   p.H = op.H; p.W = op.W; p.n_img = op.n_img;
   if (op.W >= kTileM || (op.H == 1 && op.n_img == 1)) {
     // rows of an image row (or of a plain [M][K] matrix, however short: the part of the 128-row box beyond the
@@ -579,7 +642,8 @@ int gemm_plan(const GemmOp& op, GemmPlan* plan) {
   p.tiles_w = (op.W + p.tile_w - 1) / p.tile_w;
   p.tiles_h = (op.H + p.tile_h - 1) / p.tile_h;
   p.tiles_img = (op.n_img + p.tile_n - 1) / p.tile_n;
-  p.m_tiles = p.tiles_w * p.tiles_h * p.tiles_img;
+  p.m_tiles_src = p.tiles_w * p.tiles_h * p.tiles_img;
+  p.m_tiles = p.m_tiles_src * (mode == kModeUpsample ? 4 : 1);
   const bool geglu = op.epilogue == kEpiGeglu;
   p.block_n = op.block_n ? op.block_n : pick_block_n(op.N, p.m_tiles, geglu, g_num_sms);
   SONIC_REQUIRE(p.block_n % 16 == 0 && p.block_n >= 16 && p.block_n <= 256, "gemm: bad block_n %d",
@@ -602,6 +666,10 @@ int gemm_plan(const GemmOp& op, GemmPlan* plan) {
                 "gemm: folded LayerNorm needs the staged epilogue (block_n %% 32 == 0, contiguous 128-row tiles)");
   SONIC_REQUIRE(op.ln_stats_in == nullptr || (op.ln_colsum != nullptr && op.ln_parts > 0 && op.taps == 1 && !op.a1),
                 "gemm: folded LayerNorm needs ln_colsum, ln_parts > 0 and a plain [M][K] A operand");
+  SONIC_REQUIRE(op.ln_stats_in == nullptr || (op.ln_parts % 2 == 0 && op.ln_parts <= 2 * kMaxLnPairs &&
+                                               (reinterpret_cast<uintptr_t>(op.ln_stats_in) & 15) == 0),
+                "gemm: folded LayerNorm takes an even number of at most %d partials per row, 16-byte aligned",
+                2 * kMaxLnPairs);
   SONIC_REQUIRE(op.epilogue != kEpiQuickGelu || p.tma_epilogue, "gemm: QuickGELU needs the staged epilogue");
   SONIC_REQUIRE(op.gn_partial == nullptr || p.tma_epilogue,
                 "gemm: gn_partial needs the staged epilogue (block_n %% 32 == 0, contiguous 128-row tiles)");
@@ -632,7 +700,17 @@ int gemm_plan(const GemmOp& op, GemmPlan* plan) {
                        static_cast<uint64_t>(op.H) * op.W * op.ld0 * 2};
     uint32_t box[4] = {kTileK, static_cast<uint32_t>(p.tile_w), static_cast<uint32_t>(p.tile_h),
                        static_cast<uint32_t>(p.tile_n)};
-    if (int rc = encode_tensor_map(&p.tm_a0, op.a0, 4, dims, str, box, 128)) return rc;
+    if (mode == kModeStride2) {
+      // four parity views of the 2H x 2W input: view (a, b) element (n, h, w) = input pixel (2h + a, 2w + b)
+      const uint64_t ld = static_cast<uint64_t>(op.ld0), Wi = 2ull * op.W, Hi = 2ull * op.H;
+      uint64_t st2[3] = {2 * ld * 2, 2 * Wi * ld * 2, Hi * Wi * ld * 2};
+      for (int par = 0; par < 4; ++par) {
+        const char* base = static_cast<const char*>(op.a0) + ((par >> 1) * Wi + (par & 1)) * ld * 2;
+        if (int rc = encode_tensor_map(par == 0 ? &p.tm_a0 : &p.tm_x[par - 1], base, 4, dims, st2, box, 128)) return rc;
+      }
+    } else if (int rc = encode_tensor_map(&p.tm_a0, op.a0, 4, dims, str, box, 128)) {
+      return rc;
+    }
     if (op.a1) {
       dims[0] = op.c1;
       str[0] = static_cast<uint64_t>(op.ld1) * 2;
@@ -648,14 +726,30 @@ int gemm_plan(const GemmOp& op, GemmPlan* plan) {
     SONIC_REQUIRE(Kp == static_cast<uint64_t>(K) || op.a1 == nullptr,
                   "gemm: concat operands must be multiples of 64 channels");
     uint64_t dims[3] = {static_cast<uint64_t>(K), static_cast<uint64_t>(op.N),
-                        static_cast<uint64_t>(op.taps)};
+                        static_cast<uint64_t>(mode == kModeUpsample ? 16 : op.taps)};
     uint64_t str[2] = {static_cast<uint64_t>(K) * 2, static_cast<uint64_t>(op.N) * K * 2};
     uint32_t box[3] = {kTileK, static_cast<uint32_t>(p.block_n), 1};
     if (int rc = encode_tensor_map(&p.tm_b, op.w, 3, dims, str, box, 128)) return rc;
   }
   p.tm_out = p.tm_b;
   p.tm_res = p.tm_b;
-  if (p.tma_epilogue) {
+  if (mode == kModeUpsample) {
+    // four phase views of the 2H x 2W output: view (a, b) element (n, h, w) = output pixel (2h + a, 2w + b); a staged
+    // chunk of 32 consecutive source pixels is a (32 / tw) x tw patch of the view
+    SONIC_REQUIRE(p.tma_epilogue, "gemm: the upsample convolution needs the staged epilogue (N %% 32 == 0)");
+    const int tw = std::min(32, op.W), th = 32 / tw;
+    SONIC_REQUIRE(32 % tw == 0 && op.W % tw == 0 && (op.H * op.W) % 32 == 0 && op.H % th == 0,
+                  "gemm: upsample convolution needs 32-pixel chunks that tile the %dx%d source", op.H, op.W);
+    const uint64_t ld = static_cast<uint64_t>(op.ld_out), Wo = 2ull * op.W, Ho = 2ull * op.H;
+    uint64_t dims[4] = {static_cast<uint64_t>(p.n_out_total), static_cast<uint64_t>(op.W), static_cast<uint64_t>(op.H),
+                        static_cast<uint64_t>(op.n_img)};
+    uint64_t str[3] = {2 * ld * 2, 2 * Wo * ld * 2, Ho * Wo * ld * 2};
+    uint32_t box[4] = {kChunkCols, static_cast<uint32_t>(tw), static_cast<uint32_t>(th), 1};
+    for (int ph = 0; ph < 4; ++ph) {
+      char* base = static_cast<char*>(op.out) + ((ph >> 1) * Wo + (ph & 1)) * ld * 2;
+      if (int rc = encode_tensor_map(ph == 0 ? &p.tm_out : &p.tm_x[ph - 1], base, 4, dims, str, box, 64)) return rc;
+    }
+  } else if (p.tma_epilogue) {
     uint64_t dims[2] = {static_cast<uint64_t>(p.n_out_total), static_cast<uint64_t>(p.M)};
     uint64_t str[1] = {static_cast<uint64_t>(op.ld_out) * 2};
     uint32_t box[2] = {kChunkCols, 32};
@@ -667,7 +761,9 @@ int gemm_plan(const GemmOp& op, GemmPlan* plan) {
   }
   plan->grid = std::min(p.m_tiles * p.n_tiles, g_num_sms);
   plan->smem = static_cast<size_t>(p.stages) * stage_bytes + kStgBytes + 1024 /*align*/ + 512 /*barriers*/;
-  plan->flops = 2.0 * p.M * static_cast<double>(op.N) * K * op.taps;
+  // algorithmic work of the operator (a 9-tap convolution of every OUTPUT pixel), whatever the kernel executes: the
+  // phase form of the upsample convolution runs 4/9 of it
+  plan->flops = 2.0 * p.M * (mode == kModeUpsample ? 4.0 : 1.0) * static_cast<double>(op.N) * K * op.taps;
   return 0;
 }
 

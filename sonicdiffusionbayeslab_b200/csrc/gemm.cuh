@@ -11,9 +11,18 @@ namespace sonic {
 
 enum GemmEpilogue { kEpiNone = 0, kEpiGeglu = 1, kEpiQuickGelu = 2 };
 
+enum GemmMode {
+  kModeNormal = 0,
+  kModeStride2 = 1,              // 3x3, stride 2, pad 1: the nine taps read four PARITY views of the input
+  kModeUpsample = 2,             // 3x3 over a nearest-2x upsampled input, as four 2x2 convolutions (one per phase)
+};
+
 struct GemmParams {
   CUtensorMap tm_a0, tm_a1, tm_b;
   CUtensorMap tm_out, tm_res;    // [M][n_out] output / residual, 32x32 boxes (staged epilogue)
+  CUtensorMap tm_x[3];           // mode 1: parity views (0,1) (1,0) (1,1) of A (tm_a0 is (0,0));
+                                 // mode 2: output views of phases (0,1) (1,0) (1,1) (tm_out is phase (0,0))
+  int mode;
   int M, N;                      // GEMM rows (= n_img*H*W) and B rows (= out channels before GEGLU)
   int k_chunks0, k_chunks1;      // 64-wide K chunks taken from source 0 / source 1
   int taps;                      // 1 or 9
@@ -21,6 +30,7 @@ struct GemmParams {
   int tile_w, tile_h, tile_n;    // tile_w*tile_h*tile_n == 128 rows of one M tile
   int tiles_w, tiles_h, tiles_img;
   int m_tiles, n_tiles, block_n, stages;
+  int m_tiles_src;               // mode 2: M tiles of ONE phase (m_tiles = 4 * m_tiles_src)
   uint32_t idesc;
   const float* bias;             // [N] or null
   const float* row_bias;         // [n_img][N] or null
@@ -50,6 +60,9 @@ struct GemmOp {                  // host-side description; pointers are borrowed
   void* out = nullptr; int ld_out = 0;
   int epilogue = kEpiNone;
   int block_n = 0;               // 0 = choose
+  int stride = 1;                // 2: 3x3 stride-2 pad-1 convolution; H, W are the OUTPUT extents, the input is 2H x 2W
+  int upsample = 0;              // 1: 3x3 convolution of the nearest-2x upsampled input; H, W are the SOURCE extents,
+                                 //    the output is 2H x 2W and w holds the 16 phase-combined 2x2 taps [16][N][K]
   float* gn_partial = nullptr;
   float* ln_stats_out = nullptr;           // see GemmParams
   const float* ln_stats_in = nullptr; const float* ln_colsum = nullptr; int ln_parts = 0; float ln_eps = 1e-5f;

@@ -99,6 +99,7 @@ int sonic_plan_add_conv_gemm(sonic_plan_t h, const sonic_gemm_args* a) {
   op.epilogue = a->epilogue; op.block_n = a->block_n; op.gn_partial = a->gn_partial;
   op.ln_stats_out = a->ln_stats_out; op.ln_stats_in = a->ln_stats_in; op.ln_colsum = a->ln_colsum;
   op.ln_parts = a->ln_parts; op.ln_eps = a->ln_eps;
+  op.stride = a->stride == 2 ? 2 : 1; op.upsample = a->upsample;
   PlanOp p;
   p.kind = PlanOp::kGemm;
   if (int rc = gemm_plan(op, &p.gemm)) return rc;

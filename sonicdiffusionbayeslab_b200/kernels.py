@@ -35,6 +35,28 @@ def pack_conv3x3_weight(w_oihw: torch.Tensor) -> torch.Tensor:
     return w_oihw.permute(2, 3, 0, 1).reshape(kh * kw, O, I).contiguous().to(torch.bfloat16)
 
 
+def pack_upsample_conv_weight(w_oihw: torch.Tensor) -> torch.Tensor:
+    """3x3 kernel applied to a nearest-2x upsampled image == four 2x2 kernels applied to the source, one per output
+    phase (a, b) = (y & 1, x & 1): source row offset a - 1 + ty collects the kernel rows that land on it
+    (a = 0: {0} | {1, 2};  a = 1: {0, 1} | {2}), likewise for columns.  OIHW -> [phase = 2a + b][tap = 2ty + tx][O][I]
+    flattened to [16][O][I] bf16; the sums are formed in fp32 and rounded once."""
+    O, I, kh, kw = w_oihw.shape
+    assert (kh, kw) == (3, 3)
+    w = w_oihw.float()
+    rows = {0: ([0], [1, 2]), 1: ([0, 1], [2])}
+    out = torch.zeros(4, 4, O, I, dtype=torch.float32, device=w.device)
+    for a in (0, 1):
+        for b in (0, 1):
+            for ty in (0, 1):
+                for tx in (0, 1):
+                    acc = 0
+                    for ky in rows[a][ty]:
+                        for kx in rows[b][tx]:
+                            acc = acc + w[:, :, ky, kx]
+                    out[2 * a + b, 2 * ty + tx] = acc
+    return out.reshape(16, O, I).to(torch.bfloat16).contiguous()
+
+
 def pack_geglu(w: torch.Tensor, b: torch.Tensor, block_n: int):
     """Interleave the value / gate halves of ff.net.0.proj per ``block_n`` tile."""
     n2, K = w.shape
@@ -72,7 +94,7 @@ def ln_stats_buffer(rows, N, block_n, device):
 
 def conv_gemm(a0, w, N, *, taps=1, n_img=1, H=1, W=None, c0=None, a1=None, c1=0, bias=None,
               row_bias=None, residual=None, out=None, epilogue=EPI_NONE, block_n=0, gn_partial=None,
-              ln_stats_out=None, ln_fold=None):
+              ln_stats_out=None, ln_fold=None, stride=1, upsample=False):
     """out[M, N'] = epilogue(implicit_gemm(A, w)); see ``sonic_conv_gemm`` in include/sonic.h.
 
     ``a0`` / ``a1`` are NHWC bf16 tensors whose last dim is the pixel pitch; a Linear over
@@ -83,11 +105,12 @@ def conv_gemm(a0, w, N, *, taps=1, n_img=1, H=1, W=None, c0=None, a1=None, c1=0,
     c0 = ld0 if c0 is None else c0
     if W is None:
         W = a0.numel() // ld0
-    M = n_img * H * W
+    M = n_img * H * W * (4 if upsample else 1)      # stride 2: H, W = output extents; upsample: H, W = source extents
     n_out = N // 2 if epilogue == EPI_GEGLU else N
     if out is None:
         out = torch.empty((M, n_out), device=a0.device, dtype=torch.bfloat16)
     args = GemmArgs()
+    args.stride, args.upsample = stride, int(upsample)
     args.a0, args.c0, args.ld0 = a0.data_ptr(), c0, ld0
     if a1 is not None:
         _bf16c(a1)

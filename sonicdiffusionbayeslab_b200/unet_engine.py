@@ -231,9 +231,14 @@ class UNetEngine:
 
     # ------------------------------------------------------------------ op recording helpers
     def _gemm(self, plan, a0, w, N, *, n_img=1, H=1, W=None, taps=1, c0=None, a1=None, bias=None,
-              residual=None, out=None, epilogue=K.EPI_NONE, block_n=0, gn_stats=False, ln_stats=False, ln_fold=None):
+              residual=None, out=None, epilogue=K.EPI_NONE, block_n=0, gn_stats=False, ln_stats=False, ln_fold=None,
+              stride=1, upsample=False):
         ld0 = a0.shape[-1]
         M = a0.numel() // ld0
+        if stride == 2:                                       # H, W are the output extents; A is the 2H x 2W input
+            M //= 4
+        elif upsample:                                        # H, W are the source extents; the output is 2H x 2W
+            M *= 4
         if W is None:
             W = M
         n_out = N // 2 if epilogue == K.EPI_GEGLU else N
@@ -252,6 +257,7 @@ class UNetEngine:
             g.residual, g.ld_res = residual.data_ptr(), residual.shape[-1]
         g.out, g.ld_out = out.data_ptr(), out.shape[-1]
         g.epilogue, g.block_n = epilogue, block_n
+        g.stride, g.upsample = stride, int(upsample)
         if ln_stats:
             # producer of a LayerNorm input: per-row (sum, sumsq) partials of the output ride along with the tensor
             bn = block_n or K.gemm_block_n(N, n_img, H, W, epilogue)
@@ -276,7 +282,8 @@ class UNetEngine:
             g.gn_partial = part.data_ptr()
         check(lib().sonic_plan_add_conv_gemm(plan.h, C.byref(g)), "sonic_plan_add_conv_gemm")
         kk = g.c0 + (g.c1 if a1 is not None else 0)
-        plan.log.append(f"gemm M={M} N={N} K={kk}x{taps} img={n_img}x{H}x{W} epi={epilogue}"
+        plan.log.append(f"gemm M={M} N={N} K={kk}x{taps}{'s2' if stride == 2 else 'up' if upsample else ''} "
+                        f"img={n_img}x{H}x{W} epi={epilogue}"
                         f"{' +res' if residual is not None else ''}{' +lnfold' if ln_fold is not None else ''}"
                         f"{' +lnstats' if ln_stats else ''}")
         return out
@@ -447,19 +454,25 @@ class UNetEngine:
         return out
 
     def _downsample(self, plan, b, h, H, W, cout):
-        """Stride-2 3x3 convolution of ``down_blocks[b].downsamplers[0]``; returns (out, H/2, W/2)."""
-        n = self.n
-        col = self.arena.alloc((n * (H // 2) * (W // 2), 9 * cout))
-        check(lib().sonic_plan_add_im2col_s2(plan.h, K.ptr(h), K.ptr(col), n, H, W, cout), "sonic_plan_add_im2col_s2")
-        plan.log.append(f"im2col_s2 {n}x{H}x{W}x{cout}")
-        key = ("down", b)
-        if key not in self._w:
-            w = self._src(f"down_blocks.{b}.downsamplers.0.conv.weight")
-            self._w[key] = w.permute(0, 2, 3, 1).reshape(w.shape[0], -1).to(torch.bfloat16).contiguous().to(self.dev)
-        out = self._gemm(plan, col, self._w[key], cout, bias=self._f32(f"down_blocks.{b}.downsamplers.0.conv.bias"),
-                         gn_stats=True)
-        self.arena.release(col)
+        """Stride-2 3x3 convolution of ``down_blocks[b].downsamplers[0]``: nine taps over four parity views of the
+        input straight from the TMA unit (no im2col buffer); returns (out, H/2, W/2)."""
+        out = self._gemm(plan, h, self._conv3(f"down_blocks.{b}.downsamplers.0.conv.weight"), cout, n_img=self.n,
+                         H=H // 2, W=W // 2, taps=9, stride=2,
+                         bias=self._f32(f"down_blocks.{b}.downsamplers.0.conv.bias"), gn_stats=True)
         return out, H // 2, W // 2
+
+    def _up3(self, name):
+        key = ("up3", name)
+        if key not in self._w:
+            self._w[key] = K.pack_upsample_conv_weight(self._src(name)).to(self.dev)
+        return self._w[key]
+
+    def _upsample_conv(self, plan, prefix, h, H, W, cout):
+        """``Upsample2D``: nearest 2x + 3x3 convolution as four phase-wise 2x2 convolutions of the SOURCE (4/9 of the
+        multiply-adds, no upsampled tensor); returns (out, 2H, 2W)."""
+        out = self._gemm(plan, h, self._up3(prefix + ".conv.weight"), cout, n_img=self.n, H=H, W=W, taps=9,
+                         upsample=True, bias=self._f32(prefix + ".conv.bias"), gn_stats=True)
+        return out, 2 * H, 2 * W
 
     def _build_ctx_plan(self):
         plan = _Plan()
@@ -620,17 +633,10 @@ class UNetEngine:
                 if h is None:                               # cached plan: this block did not run at all
                     H, W = 2 * H, 2 * W
                     continue
-                up = self.arena.alloc((n * 4 * H * W, cout))
-                check(lib().sonic_plan_add_upsample2x(plan.h, K.ptr(h), K.ptr(up), n, H, W, cout),
-                      "sonic_plan_add_upsample2x")
-                plan.log.append(f"upsample2x {n}x{H}x{W}x{cout}")
-                if h is not self.cache_feature:
-                    self.arena.release(h)
-                H, W = 2 * H, 2 * W
-                h = self._gemm(plan, up, self._conv3(f"up_blocks.{b}.upsamplers.0.conv.weight"), cout, n_img=n,
-                               H=H, W=W, taps=9, bias=self._f32(f"up_blocks.{b}.upsamplers.0.conv.bias"),
-                               gn_stats=True)
-                self.arena.release(up)
+                src = h
+                h, H, W = self._upsample_conv(plan, f"up_blocks.{b}.upsamplers.0", src, H, W, cout)
+                if src is not self.cache_feature:
+                    self.arena.release(src)
         assert not skips
         # ---- out: GroupNorm+SiLU -> conv3x3 (4 output channels padded to one 16-wide MMA tile) -> NCHW
         g = self._gn(plan, h, None, "conv_norm_out", self.H * self.W, a.norm_eps, True)

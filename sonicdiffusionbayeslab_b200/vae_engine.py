@@ -132,16 +132,9 @@ class VaeEngine(UNetEngine):
                 self.arena.release(h)
                 h = r
             if i != len(rev) - 1:
-                up = self.arena.alloc((n * 4 * H * W, cout))
-                check(lib().sonic_plan_add_upsample2x(plan.h, K.ptr(h), K.ptr(up), n, H, W, cout),
-                      "sonic_plan_add_upsample2x")
-                plan.log.append(f"upsample2x {n}x{H}x{W}x{cout}")
-                self.arena.release(h)
-                H, W = 2 * H, 2 * W
-                h = self._gemm(plan, up, self._conv3(f"decoder.up_blocks.{i}.upsamplers.0.conv.weight"), cout, n_img=n,
-                               H=H, W=W, taps=9, bias=self._f32(f"decoder.up_blocks.{i}.upsamplers.0.conv.bias"),
-                               gn_stats=True)
-                self.arena.release(up)
+                src = h                       # nearest 2x + 3x3 as four phase-wise 2x2 convolutions of the source
+                h, H, W = self._upsample_conv(plan, f"decoder.up_blocks.{i}.upsamplers.0", src, H, W, cout)
+                self.arena.release(src)
         # out: GroupNorm + SiLU -> conv3x3 (3 output channels padded to one 16-wide MMA tile) -> NCHW
         g = self._gn(plan, h, None, "decoder.conv_norm_out", H * W, 1e-6, True)
         self.arena.release(h)

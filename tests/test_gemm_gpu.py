@@ -169,3 +169,48 @@ def test_layernorm_folded_into_gemm(cuda, M, C, N, geglu):
     torch.cuda.synchronize()
     err, floor = _rel_err(out, ref), _rel_err(_bf(unf), ref)
     assert err < 1e-2 and err < 1.5 * floor + 2e-3, (err, floor)
+
+
+@pytest.mark.parametrize("B,H,W,C,Cout", [(2, 64, 64, 320, 320), (3, 32, 32, 640, 640), (2, 16, 16, 1280, 1280),
+                                           (1, 128, 128, 128, 128)])
+def test_conv3x3_stride2_parity_views(cuda, B, H, W, C, Cout):
+    """Downsample2D (3x3, stride 2, pad 1) straight from four parity views of the input -- no im2col buffer."""
+    from sonicdiffusionbayeslab_b200 import kernels as k
+
+    g = torch.Generator(device="cuda").manual_seed(H + C)
+    x = _bf(torch.randn(B, H, W, C, device=cuda, generator=g))
+    w = _bf(torch.randn(Cout, C, 3, 3, device=cuda, generator=g) / (9 * C) ** 0.5)
+    b = torch.randn(Cout, device=cuda, generator=g)
+    part = k.gn_partial_buffer(B * H * W // 4, Cout, cuda)
+    out = k.conv_gemm(x, k.pack_conv3x3_weight(w), Cout, taps=9, n_img=B, H=H // 2, W=W // 2, bias=b, stride=2,
+                      gn_partial=part)
+    ref = F.conv2d(x.float().permute(0, 3, 1, 2), w.float(), b, stride=2, padding=1)
+    ref = ref.permute(0, 2, 3, 1).reshape(B * H * W // 4, Cout)
+    torch.cuda.synchronize()
+    assert out.shape == ref.shape and _rel_err(out, ref) < 1e-2
+    assert torch.allclose(part[..., 0].sum(0), out.float().sum(0), rtol=1e-3, atol=0.5)
+
+
+@pytest.mark.parametrize("B,H,W,C,Cout", [(2, 32, 32, 640, 640), (3, 16, 16, 1280, 1280), (2, 8, 8, 1280, 1280),
+                                           (1, 64, 64, 512, 512), (1, 256, 256, 128, 128)])
+def test_upsample_conv_phase_form(cuda, B, H, W, C, Cout):
+    """Upsample2D (nearest 2x, then 3x3) as four phase-wise 2x2 convolutions of the SOURCE with summed taps:
+    no upsampled tensor, 4/9 of the multiply-adds, output written through four strided TMA views; the GroupNorm
+    partials of the epilogue must still add up to the per-image channel sums."""
+    from sonicdiffusionbayeslab_b200 import kernels as k
+
+    g = torch.Generator(device="cuda").manual_seed(H + C + 1)
+    x = _bf(torch.randn(B, H, W, C, device=cuda, generator=g))
+    w = _bf(torch.randn(Cout, C, 3, 3, device=cuda, generator=g) / (9 * C) ** 0.5)
+    b = torch.randn(Cout, device=cuda, generator=g)
+    part = k.gn_partial_buffer(B * 4 * H * W, Cout, cuda)
+    out = k.conv_gemm(x, k.pack_upsample_conv_weight(w), Cout, taps=9, n_img=B, H=H, W=W, bias=b, upsample=True,
+                      gn_partial=part)
+    up = F.interpolate(x.float().permute(0, 3, 1, 2), scale_factor=2.0, mode="nearest")
+    ref = F.conv2d(up, w.float(), b, padding=1).permute(0, 2, 3, 1).reshape(B * 4 * H * W, Cout)
+    torch.cuda.synchronize()
+    assert out.shape == ref.shape and _rel_err(out, ref) < 1.2e-2
+    per_img = part.view(B, -1, Cout, 2)
+    got = out.float().view(B, 4 * H * W, Cout)
+    assert torch.allclose(per_img[..., 0].sum(1), got.sum(1), rtol=1e-3, atol=0.5)
+    assert torch.allclose(per_img[..., 1].sum(1), (got ** 2).sum(1), rtol=1e-3, atol=0.5)
