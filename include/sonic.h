@@ -61,17 +61,16 @@ typedef struct sonic_gemm_args {
    * these into group statistics, so the separate statistics pass over the tensor disappears. */
   float* gn_partial;
   /* LayerNorm folded into the GEMMs around it -- the 48 LayerNorms of the UNet's transformer blocks
-   * (BasicTransformerBlock.norm1/2/3, reached from src/models.py:227-235) launch no kernel of their own:
-   *   LN(x) W^T + b = rstd_row * (x (gamma .* W)^T - mean_row * s) + b',   s_n = sum_k gamma_k W_nk,  b' = W beta + b.
+   * (BasicTransformerBlock.norm1/2/3, reached from src/models.py:227-235) make no pass over the activations:
+   *   LN(x) W^T + b = rstd_row * (x (gamma .* W)^T - mean_row * s + std_row * b'),  s_n = sum_k gamma_k W_nk, b' = W beta + b.
    * PRODUCER of x: ln_stats_out = [M][2 * ceil(N / block_n)][2] fp32 per-row (sum, sumsq) partials of its
    *   bf16-rounded output, one slot per (n-tile, column half): fixed-order, no atomics.  Pass block_n explicitly.
-   * CONSUMER (a plain [M][K] product, taps == 1, no concat): w = bf16(gamma .* W), bias = b', ln_stats_in = the
-   *   producer's buffer with ln_parts slots per row, ln_colsum = s (fp32 [N], summed over the bf16 w), ln_eps. */
+   * sonic_ln_side() turns the partials into rstd[M] and a bf16 side tensor [M][64] holding (-mean, std) as hi/lo pairs.
+   * CONSUMER: a0 = x, a1 = the side tensor (c1 = 64), w = [N][K + 64] = (bf16(gamma .* W) | s, b' as hi/lo pairs, zeros)
+   *   (kernels.py fold_layernorm), bias = NULL, row_scale = rstd: the two rank-1 terms ride through the tensor core
+   *   as one extra K chunk and the epilogue only multiplies each row by rstd. */
   float* ln_stats_out;
-  const float* ln_stats_in;
-  const float* ln_colsum;
-  int32_t ln_parts;
-  float ln_eps;
+  const float* row_scale;
   /* Strided / upsampled 3x3 convolutions without a materialised im2col or upsampled tensor (taps = 9, one source,
    * no residual / row_bias / GEGLU):
    *   stride = 2   : Downsample2D (stride 2, pad 1).  H, W are the OUTPUT extents, a0 is the 2H x 2W input; the nine
@@ -125,6 +124,11 @@ int sonic_groupnorm_fused(const void* x0, int32_t c0, const float* part0, const 
                           sonic_stream_t stream);
 int sonic_layernorm(const void* x, void* y, int32_t rows, int32_t C, float eps, const float* gamma,
                     const float* beta, sonic_stream_t stream);
+/* Folded LayerNorm, the step between producer and consumer GEMM (see sonic_gemm_args): partials [M][parts][2] ->
+ * rstd[M] (fp32) and bytes 0..15 of every 128-byte row of `side` ([M][64] bf16, ZERO-INITIALISED by the caller:
+ * columns 8..63 are never written).  K = LayerNorm width. */
+int sonic_ln_side(const float* partials, int32_t parts, int32_t M, int32_t K, float eps, void* side, float* rstd,
+                  sonic_stream_t stream);
 
 /* Fused classifier-free-guidance combine + scheduler update + x0 prediction + history write:
  * one kernel for the whole of src/models.py:238-242 and :253-255 (scheduler.step of
@@ -224,6 +228,8 @@ int sonic_plan_add_im2col_s2(sonic_plan_t plan, const void* x, void* y, int32_t 
 int sonic_plan_add_im2col3x3(sonic_plan_t plan, const void* x, void* y, int32_t n_img, int32_t H,
                              int32_t W, int32_t C, int32_t stride);
 /* out[dim] = [cos(t f_j) | sin(t f_j)], t read from DEVICE memory at run time (graph-safe). */
+int sonic_plan_add_ln_side(sonic_plan_t plan, const float* partials, int32_t parts, int32_t M, int32_t K, float eps,
+                           void* side, float* rstd);
 int sonic_plan_add_timestep_embedding(sonic_plan_t plan, const float* t_dev, int32_t dim, float* out);
 /* Batched M=1 GEMV: y_j = bias_j + add_j + W_j[N_j x K] * act(x), act = SiLU if silu_in.
  * The pointer tables are HOST arrays of n_jobs device pointers (bias/add tables may be NULL). */

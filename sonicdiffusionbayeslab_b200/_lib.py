@@ -27,8 +27,7 @@ class GemmArgs(C.Structure):
         ("out", C.c_void_p), ("ld_out", C.c_int32),
         ("epilogue", C.c_int32), ("block_n", C.c_int32),
         ("gn_partial", C.c_void_p),
-        ("ln_stats_out", C.c_void_p), ("ln_stats_in", C.c_void_p), ("ln_colsum", C.c_void_p),
-        ("ln_parts", C.c_int32), ("ln_eps", C.c_float),
+        ("ln_stats_out", C.c_void_p), ("row_scale", C.c_void_p),
         ("stride", C.c_int32), ("upsample", C.c_int32),
     ]
 

@@ -23,8 +23,7 @@ int sonic_conv_gemm(const sonic_gemm_args* a, sonic_stream_t stream) {
   op.residual = a->residual; op.ld_res = a->ld_res;
   op.out = a->out; op.ld_out = a->ld_out;
   op.epilogue = a->epilogue; op.block_n = a->block_n; op.gn_partial = a->gn_partial;
-  op.ln_stats_out = a->ln_stats_out; op.ln_stats_in = a->ln_stats_in; op.ln_colsum = a->ln_colsum;
-  op.ln_parts = a->ln_parts; op.ln_eps = a->ln_eps;
+  op.ln_stats_out = a->ln_stats_out; op.row_scale = a->row_scale;
   op.stride = a->stride == 2 ? 2 : 1; op.upsample = a->upsample;
   GemmPlan plan;
   if (int rc = gemm_plan(op, &plan)) return rc;
@@ -74,6 +73,11 @@ int sonic_groupnorm_fused(const void* x0, int32_t c0, const float* part0, const 
 int sonic_layernorm(const void* x, void* y, int32_t rows, int32_t C, float eps, const float* gamma,
                     const float* beta, sonic_stream_t stream) {
   return layernorm_launch(x, y, rows, C, eps, gamma, beta, static_cast<cudaStream_t>(stream));
+}
+
+int sonic_ln_side(const float* partials, int32_t parts, int32_t M, int32_t K, float eps, void* side, float* rstd,
+                  sonic_stream_t stream) {
+  return ln_side_launch(partials, parts, M, K, eps, side, rstd, static_cast<cudaStream_t>(stream));
 }
 
 int sonic_latent_update(const sonic_update_coeffs* k, const void* eps_uncond, const void* eps_text,

@@ -32,7 +32,6 @@ constexpr int kMaxGranules = 8;            // 16-column granules per epilogue wa
 constexpr int kEpiWarps = 8;
 constexpr int kChunkCols = 32;             // output columns per staged chunk (64 B of bf16: one swizzle-64B row)
 constexpr int kStgBufBytes = 32 * kChunkCols * 2;       // 32 rows x 64 B
-constexpr int kMaxLnPairs = 8;             // folded LayerNorm: at most 16 per-row partials (2 per n-tile of the producer)
 constexpr int kStgBufs = 2;                // staging buffers per epilogue warp
 constexpr int kStgBytes = kEpiWarps * kStgBufs * kStgBufBytes;   // 32 KB
 
@@ -210,15 +209,12 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
       if (p.mode == kModeUpsample)
         for (int i = 0; i < 3; ++i) tma_prefetch_desc(&p.tm_x[i]);
     }
-    float4 ln_nx[kMaxLnPairs];                   // (sum, sumsq) partial pairs of the tile about to be processed
-    if (p.ln_stats_in && static_cast<int>(blockIdx.x) < total_tiles) {
-      const int r1 = (static_cast<int>(blockIdx.x) / p.n_tiles) * kTileM + quarter * 32 + lane;
-      const float4* st = reinterpret_cast<const float4*>(p.ln_stats_in) +
-                         static_cast<size_t>(min(r1, p.M - 1)) * (p.ln_parts >> 1);
-#pragma unroll
-      for (int i = 0; i < kMaxLnPairs; ++i)
-        if (2 * i < p.ln_parts) ln_nx[i] = __ldcg(st + i);
-    }
+    // Folded LayerNorm, consumer side: the mean / bias terms arrive THROUGH THE TENSOR CORE (an extra K chunk, see
+    // gemm.cuh), so all that is left here is one multiply by this lane's row scale (rstd).  The scale of the NEXT tile
+    // is requested a tile ahead: its L2 latency hides behind the current tile.
+    float rs_next = 1.f;
+    if (p.row_scale && static_cast<int>(blockIdx.x) < total_tiles)
+      rs_next = __ldcg(p.row_scale + min((static_cast<int>(blockIdx.x) / p.n_tiles) * kTileM + quarter * 32 + lane, p.M - 1));
     for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
       if (threadIdx.x == 64) GEMM_TRACE(2, ti, 0);
       const int n_tile = tile % p.n_tiles;
@@ -233,30 +229,11 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
       const int ocol0 = n_tile * out_cols;                   // output column base
       int my_n = 0;                                          // chunks col_half, col_half + 2, ... inside the matrix
       for (int c = col_half; c < n_chunks && ocol0 + c * kChunkCols < p.n_out_total; c += 2) ++my_n;
-      // Folded LayerNorm, consumer side: this lane's row of A is normalised AFTER the product --
-      // out = ln_a * acc + ln_b * s[n] + bias'[n] with ln_a = rstd, ln_b = -rstd * mean -- from the per-row
-      // (sum, sumsq) partials A's producer left (fixed summation order: bit-reproducible).  The partials of the
-      // NEXT tile are requested now and reduced one iteration later, so their L2 latency (~700 cycles per load,
-      // measured as +25 % on the K = 320 projections when it sat in front of every tile) hides behind this tile.
-      float ln_a = 1.f, ln_b = 0.f;
-      if (p.ln_stats_in) {
-        float sa = 0.f, sq = 0.f;
-#pragma unroll
-        for (int i = 0; i < kMaxLnPairs; ++i)
-          if (2 * i < p.ln_parts) { sa += ln_nx[i].x + ln_nx[i].z; sq += ln_nx[i].y + ln_nx[i].w; }
-        const float mean = sa * p.ln_inv_k;
-        const float var = fmaxf(sq * p.ln_inv_k - mean * mean, 0.f);
-        ln_a = rsqrtf(var + p.ln_eps);
-        ln_b = -ln_a * mean;
+      const float rs = rs_next;
+      if (p.row_scale) {
         const int tile2 = tile + gridDim.x;
-        if (tile2 < total_tiles) {
-          const int r2 = (tile2 / p.n_tiles) * kTileM + quarter * 32 + lane;
-          const float4* st = reinterpret_cast<const float4*>(p.ln_stats_in) +
-                             static_cast<size_t>(min(r2, p.M - 1)) * (p.ln_parts >> 1);
-#pragma unroll
-          for (int i = 0; i < kMaxLnPairs; ++i)
-            if (2 * i < p.ln_parts) ln_nx[i] = __ldcg(st + i);
-        }
+        if (tile2 < total_tiles)
+          rs_next = __ldcg(p.row_scale + min((tile2 / p.n_tiles) * kTileM + quarter * 32 + lane, p.M - 1));
       }
       float rs_sum = 0.f, rs_sq = 0.f;                       // producer side: statistics of this lane's output row
       if (has_res && lane == 0) {
@@ -299,22 +276,10 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
           uint32_t gt[32];
           tmem_ld32(t_row + out_cols + c * kChunkCols, gt);
           tmem_ld_wait();
-          if (p.ln_stats_in) {
-            const float4* sv = reinterpret_cast<const float4*>(p.ln_colsum + ncol0 + c * kChunkCols);
-            const float4* sg = reinterpret_cast<const float4*>(p.ln_colsum + ncol0 + out_cols + c * kChunkCols);
+          if (p.row_scale) {                                   // bias already inside the accumulator
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 bv = __ldg(bias_v + (j >> 2)), bg = __ldg(bias_g + (j >> 2));
-              const float4 cv = __ldg(sv + (j >> 2)), cg = __ldg(sg + (j >> 2));
-              f[j] = fmaf(ln_a, __uint_as_float(v[j]), fmaf(ln_b, cv.x, bv.x)) *
-                     gelu_erf(fmaf(ln_a, __uint_as_float(gt[j]), fmaf(ln_b, cg.x, bg.x)));
-              f[j + 1] = fmaf(ln_a, __uint_as_float(v[j + 1]), fmaf(ln_b, cv.y, bv.y)) *
-                         gelu_erf(fmaf(ln_a, __uint_as_float(gt[j + 1]), fmaf(ln_b, cg.y, bg.y)));
-              f[j + 2] = fmaf(ln_a, __uint_as_float(v[j + 2]), fmaf(ln_b, cv.z, bv.z)) *
-                         gelu_erf(fmaf(ln_a, __uint_as_float(gt[j + 2]), fmaf(ln_b, cg.z, bg.z)));
-              f[j + 3] = fmaf(ln_a, __uint_as_float(v[j + 3]), fmaf(ln_b, cv.w, bv.w)) *
-                         gelu_erf(fmaf(ln_a, __uint_as_float(gt[j + 3]), fmaf(ln_b, cg.w, bg.w)));
-            }
+            for (int j = 0; j < 32; ++j)
+              f[j] = (rs * __uint_as_float(v[j])) * gelu_erf(rs * __uint_as_float(gt[j]));
           } else {
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
@@ -325,17 +290,10 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
             f[j + 3] = (__uint_as_float(v[j + 3]) + bv.w) * gelu_erf(__uint_as_float(gt[j + 3]) + bg.w);
           }
           }
-        } else if (p.ln_stats_in) {
+        } else if (p.row_scale) {
           tmem_ld_wait();
-          const float4* sv = reinterpret_cast<const float4*>(p.ln_colsum + ncol0 + c * kChunkCols);
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 bv = __ldg(bias_v + (j >> 2)), cv = __ldg(sv + (j >> 2));
-            f[j] = fmaf(ln_a, __uint_as_float(v[j]), fmaf(ln_b, cv.x, bv.x));
-            f[j + 1] = fmaf(ln_a, __uint_as_float(v[j + 1]), fmaf(ln_b, cv.y, bv.y));
-            f[j + 2] = fmaf(ln_a, __uint_as_float(v[j + 2]), fmaf(ln_b, cv.z, bv.z));
-            f[j + 3] = fmaf(ln_a, __uint_as_float(v[j + 3]), fmaf(ln_b, cv.w, bv.w));
-          }
+          for (int j = 0; j < 32; ++j) f[j] = rs * __uint_as_float(v[j]);
         } else {
           tmem_ld_wait();
 #pragma unroll
@@ -657,19 +615,11 @@ int gemm_plan(const GemmOp& op, GemmPlan* plan) {
   p.tma_epilogue = (out_cols % kChunkCols == 0 && flat) ? 1 : 0;
   p.gn_partial = op.gn_partial;
   p.ln_stats_out = op.ln_stats_out;
-  p.ln_stats_in = op.ln_stats_in;
-  p.ln_colsum = op.ln_colsum;
-  p.ln_parts = op.ln_parts;
-  p.ln_eps = op.ln_eps;
-  p.ln_inv_k = 1.0f / static_cast<float>(K);
-  SONIC_REQUIRE((op.ln_stats_out == nullptr && op.ln_stats_in == nullptr) || p.tma_epilogue,
+  p.row_scale = op.row_scale;
+  SONIC_REQUIRE((op.ln_stats_out == nullptr && op.row_scale == nullptr) || p.tma_epilogue,
                 "gemm: folded LayerNorm needs the staged epilogue (block_n %% 32 == 0, contiguous 128-row tiles)");
-  SONIC_REQUIRE(op.ln_stats_in == nullptr || (op.ln_colsum != nullptr && op.ln_parts > 0 && op.taps == 1 && !op.a1),
-                "gemm: folded LayerNorm needs ln_colsum, ln_parts > 0 and a plain [M][K] A operand");
-  SONIC_REQUIRE(op.ln_stats_in == nullptr || (op.ln_parts % 2 == 0 && op.ln_parts <= 2 * kMaxLnPairs &&
-                                               (reinterpret_cast<uintptr_t>(op.ln_stats_in) & 15) == 0),
-                "gemm: folded LayerNorm takes an even number of at most %d partials per row, 16-byte aligned",
-                2 * kMaxLnPairs);
+  SONIC_REQUIRE(op.row_scale == nullptr || (op.bias == nullptr && op.residual == nullptr && op.row_bias == nullptr),
+                "gemm: row_scale (folded LayerNorm) carries its bias inside the product: no bias / residual / row_bias");
   SONIC_REQUIRE(op.epilogue != kEpiQuickGelu || p.tma_epilogue, "gemm: QuickGELU needs the staged epilogue");
   SONIC_REQUIRE(op.gn_partial == nullptr || p.tma_epilogue,
                 "gemm: gn_partial needs the staged epilogue (block_n %% 32 == 0, contiguous 128-row tiles)");
@@ -763,7 +713,9 @@ int gemm_plan(const GemmOp& op, GemmPlan* plan) {
   plan->smem = static_cast<size_t>(p.stages) * stage_bytes + kStgBytes + 1024 /*align*/ + 512 /*barriers*/;
   // algorithmic work of the operator (a 9-tap convolution of every OUTPUT pixel), whatever the kernel executes: the
   // phase form of the upsample convolution runs 4/9 of it
-  plan->flops = 2.0 * p.M * (mode == kModeUpsample ? 4.0 : 1.0) * static_cast<double>(op.N) * K * op.taps;
+  // (likewise the side-tensor K chunk of a folded LayerNorm is not algorithmic work)
+  plan->flops = 2.0 * p.M * (mode == kModeUpsample ? 4.0 : 1.0) * static_cast<double>(op.N) *
+                (op.row_scale ? op.c0 : K) * op.taps;
   return 0;
 }
 

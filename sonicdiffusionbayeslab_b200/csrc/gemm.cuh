@@ -41,12 +41,12 @@ struct GemmParams {
   int n_out_total;               // output columns (N, or N/2 for GEGLU)
   int tma_epilogue;              // 1: smem-staged TMA-store epilogue, 0: direct stores
   float* gn_partial;             // optional [ceil(M/32)][n_out_total][2] GroupNorm pre-reduction of the output
-  // LayerNorm folded into the GEMMs around it (LN(x) W^T = rstd_row (x (gamma.W)^T - mu_row s) + b'):
+  // LayerNorm folded into the GEMMs around it:  LN(x) W^T + b = rstd_row * (x (gamma.W)^T - mu_row s + std_row b'),
+  // s_n = sum_k gamma_k W_nk, b' = W beta + b.  The two rank-1 terms ride through the tensor core as ONE extra K chunk:
+  // A gets a side tensor [M][64] holding (-mu, std) as bf16 hi/lo pairs (ln_side_kernel, norm.cu), B gets 64 extra
+  // columns holding (s, b') the same way, so the epilogue only multiplies by rstd_row.
   float* ln_stats_out;           // producer: optional [M][2 * n_tiles][2] per-row (sum, sumsq) partials of the OUTPUT
-  const float* ln_stats_in;      // consumer: [M][ln_parts][2] partials of the rows of A (written by A's producer)
-  const float* ln_colsum;        // consumer: s[n] = sum_k (gamma_k W_nk as bf16), same order as the B rows
-  int ln_parts;                  // consumer: partials per row
-  float ln_eps, ln_inv_k;        // consumer: epsilon, 1 / (LayerNorm width)
+  const float* row_scale;        // consumer: optional [M] per-row factor applied to the accumulator (no bias added)
 };
 
 struct GemmOp {                  // host-side description; pointers are borrowed
@@ -65,7 +65,7 @@ struct GemmOp {                  // host-side description; pointers are borrowed
                                  //    the output is 2H x 2W and w holds the 16 phase-combined 2x2 taps [16][N][K]
   float* gn_partial = nullptr;
   float* ln_stats_out = nullptr;           // see GemmParams
-  const float* ln_stats_in = nullptr; const float* ln_colsum = nullptr; int ln_parts = 0; float ln_eps = 1e-5f;
+  const float* row_scale = nullptr;
 };
 
 struct GemmPlan {

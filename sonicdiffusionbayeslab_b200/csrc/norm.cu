@@ -378,7 +378,50 @@ layernorm40_kernel(const __nv_bfloat16* __restrict__ x, int rows, float eps, con
   }
 }
 
+// Folded LayerNorm, between producer and consumer GEMM (gemm.cuh): per row, fold the producer's (sum, sumsq)
+// partials in a fixed order and emit (i) rstd, the consumer's per-row epilogue scale, and (ii) the 16 bytes of the
+// side tensor row that carry -mean and std = 1 / rstd through the tensor core as bf16 hi / lo pairs:
+//   side[row][0..7] = (-mu_hi, -mu_hi, -mu_lo, -mu_lo, std_hi, std_hi, std_lo, std_lo)   (columns 8..63 stay zero)
+// against B columns (s_hi, s_lo, s_hi, s_lo, b_hi, b_lo, b_hi, b_lo): the four products of each hi / lo pair.
+__global__ void __launch_bounds__(256)
+ln_side_kernel(const float2* __restrict__ part, int parts, int M, float inv_k, float eps,
+               __nv_bfloat16* __restrict__ side, float* __restrict__ rstd) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= M) return;
+  const float2* st = part + static_cast<size_t>(row) * parts;
+  float sa = 0.f, sq = 0.f;
+  for (int i = 0; i < parts; ++i) {
+    const float2 v = __ldg(st + i);
+    sa += v.x;
+    sq += v.y;
+  }
+  const float mean = sa * inv_k;
+  const float var = fmaxf(sq * inv_k - mean * mean, 0.f);
+  const float r = rsqrtf(var + eps);
+  const float sd = (var + eps) * r;
+  const float m = -mean;
+  const __nv_bfloat16 m_hi = __float2bfloat16_rn(m), d_hi = __float2bfloat16_rn(sd);
+  const __nv_bfloat16 m_lo = __float2bfloat16_rn(m - __bfloat162float(m_hi));
+  const __nv_bfloat16 d_lo = __float2bfloat16_rn(sd - __bfloat162float(d_hi));
+  auto pair = [](__nv_bfloat16 a, __nv_bfloat16 b) {
+    return static_cast<uint32_t>(__bfloat16_as_ushort(a)) | (static_cast<uint32_t>(__bfloat16_as_ushort(b)) << 16);
+  };
+  *reinterpret_cast<uint4*>(side + static_cast<size_t>(row) * 64) =
+      make_uint4(pair(m_hi, m_hi), pair(m_lo, m_lo), pair(d_hi, d_hi), pair(d_lo, d_lo));
+  rstd[row] = r;
+}
+
 }  // namespace
+
+int ln_side_launch(const float* partials, int parts, int M, int K, float eps, void* side, float* rstd,
+                   cudaStream_t stream) {
+  SONIC_REQUIRE(partials && side && rstd && parts > 0 && M > 0 && K > 0, "ln_side: bad argument");
+  ln_side_kernel<<<(M + 255) / 256, 256, 0, stream>>>(reinterpret_cast<const float2*>(partials), parts, M,
+                                                     1.0f / static_cast<float>(K), eps,
+                                                     static_cast<__nv_bfloat16*>(side), rstd);
+  SONIC_CUDA(cudaGetLastError());
+  return 0;
+}
 
 int groupnorm_launch(const GroupNormOp& op, cudaStream_t stream) {
   const int C = op.c0 + (op.x1 ? op.c1 : 0);

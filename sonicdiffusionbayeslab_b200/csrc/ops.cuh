@@ -29,6 +29,11 @@ int groupnorm_launch(const GroupNormOp& op, cudaStream_t stream);
 int layernorm_launch(const void* x, void* y, int rows, int C, float eps, const float* gamma,
                      const float* beta, cudaStream_t stream);
 
+// Folded LayerNorm (see gemm.cuh): per-row partials [M][parts][2] -> rstd[M] and the first 16 bytes of every
+// 128-byte row of the bf16 side tensor [M][64] (the rest of the row must be zero and is never written).
+int ln_side_launch(const float* partials, int parts, int M, int K, float eps, void* side, float* rstd,
+                   cudaStream_t stream);
+
 // Coefficients of the fused CFG-combine + scheduler update (see include/sonic.h).
 struct UpdateCoeffs {
   float guidance;

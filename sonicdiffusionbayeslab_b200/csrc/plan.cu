@@ -17,7 +17,7 @@
 namespace sonic {
 
 struct PlanOp {
-  enum Kind { kGemm, kAttention, kGroupNorm, kLayerNorm, kToNhwc8, kToNchw, kUpsample, kIm2col, kTimeEmb, kGemv, kSoftmaxRows };
+  enum Kind { kGemm, kAttention, kGroupNorm, kLayerNorm, kToNhwc8, kToNchw, kUpsample, kIm2col, kTimeEmb, kGemv, kSoftmaxRows, kLnSide };
   Kind kind;
   GemmPlan gemm;
   AttentionPlan* att = nullptr;
@@ -62,6 +62,9 @@ static int run_ops(const Plan& plan, cudaStream_t s) {
       case PlanOp::kTimeEmb: rc = timestep_embedding_launch(op.f0, op.i0, static_cast<float*>(op.dst), s); break;
       case PlanOp::kGemv: rc = gemv_batched_launch(op.jobs_dev, op.i0, op.i1, op.f0, op.i2, op.i3, s); break;
       case PlanOp::kSoftmaxRows: rc = softmax_rows_launch(op.dst, op.i0, op.i1, op.l0, op.eps, s); break;
+      case PlanOp::kLnSide:
+        rc = ln_side_launch(op.f0, op.i0, op.i1, op.i2, op.eps, op.dst, const_cast<float*>(op.f1), s);
+        break;
     }
     if (rc) return rc;
   }
@@ -97,8 +100,7 @@ int sonic_plan_add_conv_gemm(sonic_plan_t h, const sonic_gemm_args* a) {
   op.residual = a->residual; op.ld_res = a->ld_res;
   op.out = a->out; op.ld_out = a->ld_out;
   op.epilogue = a->epilogue; op.block_n = a->block_n; op.gn_partial = a->gn_partial;
-  op.ln_stats_out = a->ln_stats_out; op.ln_stats_in = a->ln_stats_in; op.ln_colsum = a->ln_colsum;
-  op.ln_parts = a->ln_parts; op.ln_eps = a->ln_eps;
+  op.ln_stats_out = a->ln_stats_out; op.row_scale = a->row_scale;
   op.stride = a->stride == 2 ? 2 : 1; op.upsample = a->upsample;
   PlanOp p;
   p.kind = PlanOp::kGemm;
@@ -235,6 +237,17 @@ int sonic_plan_add_softmax_rows(sonic_plan_t h, void* x, int32_t rows, int32_t c
   return 0;
 }
 
+int sonic_plan_add_ln_side(sonic_plan_t h, const float* partials, int32_t parts, int32_t M, int32_t K, float eps,
+                           void* side, float* rstd) {
+  SONIC_REQUIRE(h && partials && side && rstd, "sonic_plan_add_ln_side: null argument");
+  PlanOp p;
+  p.kind = PlanOp::kLnSide;
+  p.f0 = partials; p.i0 = parts; p.i1 = M; p.i2 = K; p.eps = eps; p.dst = side; p.f1 = rstd;
+  static_cast<Plan*>(h)->launches += 1;
+  static_cast<Plan*>(h)->ops.push_back(p);
+  return 0;
+}
+
 int sonic_plan_add_timestep_embedding(sonic_plan_t h, const float* t_dev, int32_t dim, float* out) {
   SONIC_REQUIRE(h && t_dev && out && dim % 2 == 0, "sonic_plan_add_timestep_embedding: bad argument");
   PlanOp p;
@@ -334,7 +347,7 @@ int sonic_plan_profile(sonic_plan_t h, sonic_stream_t stream, int32_t max_ops, f
       case PlanOp::kGemm: kinds[i] = 0; flops[i] = op.gemm.flops; break;
       case PlanOp::kAttention: kinds[i] = 1; flops[i] = attention_plan_flops(op.att); break;
       case PlanOp::kGroupNorm: kinds[i] = 2; break;
-      case PlanOp::kLayerNorm: kinds[i] = 3; break;
+      case PlanOp::kLayerNorm: case PlanOp::kLnSide: kinds[i] = 3; break;
       case PlanOp::kGemv: case PlanOp::kTimeEmb: kinds[i] = 5; break;
       default: kinds[i] = 4; break;
     }

@@ -73,17 +73,32 @@ def gemm_block_n(N: int, n_img: int, H: int, W: int, epilogue: int = EPI_NONE) -
     return lib().sonic_gemm_block_n(N, n_img, H, W, epilogue)
 
 
+LN_SIDE_COLS = 64            # one K chunk (128 bytes of bf16) appended to the consumer's operands
+
+
+def _hi_lo(x: torch.Tensor):
+    hi = x.to(torch.bfloat16)
+    lo = (x - hi.float()).to(torch.bfloat16)
+    return hi, lo
+
+
 def fold_layernorm(w, b, gamma, beta):
-    """LayerNorm folded into the Linear that follows it: returns (w', s, b') with
-    ``LN(x) w^T + b == rstd * (x w'^T - mean * s) + b'`` -- w' = bf16(gamma .* w), s_n = sum_k w'_nk (summed over the
-    ROUNDED w', so the mean subtraction is exact for the product the tensor cores compute), b' = w beta + b."""
+    """LayerNorm folded into the Linear that follows it.  Returns the consumer's weight ``[N][K + 64]`` (bf16):
+    columns ``0..K-1`` = bf16(gamma .* w); columns ``K..K+7`` = (s_hi, s_lo, s_hi, s_lo, b_hi, b_lo, b_hi, b_lo) with
+    s_n = sum_k of the ROUNDED gamma.w (so the mean subtraction is exact for the product the tensor cores compute)
+    and b' = w beta + b; the rest zero.  With the side tensor of ``ln_side`` as the extra K chunk of A,
+    ``rstd * (A W^T)`` equals ``LN(x) w^T + b``."""
     wf = w.float()
     wp = (wf * gamma.float()[None, :]).to(torch.bfloat16)
     s = wp.float().sum(dim=1)
     bp = wf @ beta.float()
     if b is not None:
         bp = bp + b.float()
-    return wp.contiguous(), s.contiguous(), bp.contiguous()
+    extra = torch.zeros(w.shape[0], LN_SIDE_COLS, dtype=torch.bfloat16, device=w.device)
+    (s_hi, s_lo), (b_hi, b_lo) = _hi_lo(s), _hi_lo(bp)
+    for col, v in enumerate((s_hi, s_lo, s_hi, s_lo, b_hi, b_lo, b_hi, b_lo)):
+        extra[:, col] = v
+    return torch.cat([wp, extra], dim=1).contiguous()
 
 
 def ln_stats_buffer(rows, N, block_n, device):
@@ -92,9 +107,21 @@ def ln_stats_buffer(rows, N, block_n, device):
     return torch.zeros(rows, parts, 2, device=device, dtype=torch.float32), parts
 
 
+def ln_side(partials, K, eps=1e-5, side=None, rstd=None):
+    """Producer partials [M][parts][2] -> (side tensor [M][64] bf16, rstd [M] fp32); ``sonic_ln_side``."""
+    M, parts = partials.shape[0], partials.shape[1]
+    if side is None:
+        side = torch.zeros(M, LN_SIDE_COLS, device=partials.device, dtype=torch.bfloat16)
+    if rstd is None:
+        rstd = torch.empty(M, device=partials.device, dtype=torch.float32)
+    check(lib().sonic_ln_side(ptr(partials), parts, M, K, C.c_float(eps), ptr(side), ptr(rstd), stream_ptr()),
+          "sonic_ln_side")
+    return side, rstd
+
+
 def conv_gemm(a0, w, N, *, taps=1, n_img=1, H=1, W=None, c0=None, a1=None, c1=0, bias=None,
               row_bias=None, residual=None, out=None, epilogue=EPI_NONE, block_n=0, gn_partial=None,
-              ln_stats_out=None, ln_fold=None, stride=1, upsample=False):
+              ln_stats_out=None, row_scale=None, stride=1, upsample=False):
     """out[M, N'] = epilogue(implicit_gemm(A, w)); see ``sonic_conv_gemm`` in include/sonic.h.
 
     ``a0`` / ``a1`` are NHWC bf16 tensors whose last dim is the pixel pitch; a Linear over
@@ -135,10 +162,9 @@ def conv_gemm(a0, w, N, *, taps=1, n_img=1, H=1, W=None, c0=None, a1=None, c1=0,
         assert block_n and ln_stats_out.dtype == torch.float32 and ln_stats_out.is_contiguous() and \
             ln_stats_out.numel() == M * 2 * ((N + block_n - 1) // block_n) * 2
         args.ln_stats_out = ln_stats_out.data_ptr()
-    if ln_fold is not None:                                          # consumer: (stats buffer, parts, colsum, eps)
-        stats, parts, colsum, eps = ln_fold
-        assert stats.dtype == colsum.dtype == torch.float32 and colsum.numel() == N and stats.numel() == M * parts * 2
-        args.ln_stats_in, args.ln_parts, args.ln_colsum, args.ln_eps = stats.data_ptr(), parts, colsum.data_ptr(), eps
+    if row_scale is not None:                                        # folded-LayerNorm consumer: per-row rstd
+        assert row_scale.dtype == torch.float32 and row_scale.numel() == M and bias is None and residual is None
+        args.row_scale = row_scale.data_ptr()
     check(lib().sonic_conv_gemm(C.byref(args), stream_ptr()), "sonic_conv_gemm")
     return out
 

@@ -181,6 +181,7 @@ class UNetEngine:
         self._w = weights.cache
         self._temb_jobs = []
         self._ctx_kv = {}
+        self._ln_bufs = {}
         self.cache_feature = None
         self.plans = {}
         with torch.no_grad():
@@ -215,13 +216,27 @@ class UNetEngine:
         return self._w[key]
 
     def _folded(self, key, weight_names, bias_name, norm_prefix):
-        """(w', s, b') of ``K.fold_layernorm`` for the (row-concatenated) Linear behind LayerNorm ``norm_prefix``."""
+        """``K.fold_layernorm`` weight [N][K + 64] for the (row-concatenated) Linear behind LayerNorm ``norm_prefix``."""
         if key + ("ln",) not in self._w:
             w = torch.cat([self._src(n) for n in weight_names], 0)
             b = self._src(bias_name) if bias_name else None
-            wp, s_, bp = K.fold_layernorm(w, b, self._src(norm_prefix + ".weight"), self._src(norm_prefix + ".bias"))
-            self._w[key + ("ln",)] = (wp.to(self.dev), s_.to(self.dev), bp.to(self.dev))
+            self._w[key + ("ln",)] = K.fold_layernorm(w, b, self._src(norm_prefix + ".weight"),
+                                                      self._src(norm_prefix + ".bias")).to(self.dev)
         return self._w[key + ("ln",)]
+
+    def _ln_fold(self, plan, h, C_ln):
+        """Between producer and consumer: per-row partials of ``h`` -> (side tensor, rstd).  The buffers are shared by
+        every LayerNorm of that row count (plans run in stream order); side columns 8..63 stay zero for ever."""
+        M = h.shape[0]
+        if M not in self._ln_bufs:
+            self._ln_bufs[M] = (torch.zeros(M, K.LN_SIDE_COLS, device=self.dev, dtype=torch.bfloat16),
+                                torch.empty(M, device=self.dev, dtype=torch.float32))
+        side, rstd = self._ln_bufs[M]
+        part = h._ln_part
+        check(lib().sonic_plan_add_ln_side(plan.h, K.ptr(part), part.shape[1], M, C_ln, C.c_float(1e-5), K.ptr(side),
+                                           K.ptr(rstd)), "sonic_plan_add_ln_side")
+        plan.log.append(f"ln_side rows={M} C={C_ln} parts={part.shape[1]}")
+        return side, rstd
 
     def _conv3(self, name):
         key = ("c3", name)
@@ -231,7 +246,7 @@ class UNetEngine:
 
     # ------------------------------------------------------------------ op recording helpers
     def _gemm(self, plan, a0, w, N, *, n_img=1, H=1, W=None, taps=1, c0=None, a1=None, bias=None,
-              residual=None, out=None, epilogue=K.EPI_NONE, block_n=0, gn_stats=False, ln_stats=False, ln_fold=None,
+              residual=None, out=None, epilogue=K.EPI_NONE, block_n=0, gn_stats=False, ln_stats=False, row_scale=None,
               stride=1, upsample=False):
         ld0 = a0.shape[-1]
         M = a0.numel() // ld0
@@ -268,10 +283,9 @@ class UNetEngine:
                 buf = self.arena.alloc((M, parts, 2), torch.float32)
                 out._ln_part = buf
             g.ln_stats_out = buf.data_ptr()
-        if ln_fold is not None:
-            stats, colsum, eps = ln_fold                     # consumer: A's row partials, s[n], epsilon
-            assert stats.shape[0] == M and colsum.numel() == N
-            g.ln_stats_in, g.ln_parts, g.ln_colsum, g.ln_eps = stats.data_ptr(), stats.shape[1], colsum.data_ptr(), eps
+        if row_scale is not None:                            # folded-LayerNorm consumer (a1 = the side tensor)
+            assert row_scale.numel() == M and bias is None and residual is None
+            g.row_scale = row_scale.data_ptr()
         if gn_stats and self.fuse_gn_stats:
             # the epilogue also writes per-32-row (sum, sumsq) of the output: the consumer GroupNorm needs no
             # statistics pass over the tensor
@@ -284,7 +298,7 @@ class UNetEngine:
         kk = g.c0 + (g.c1 if a1 is not None else 0)
         plan.log.append(f"gemm M={M} N={N} K={kk}x{taps}{'s2' if stride == 2 else 'up' if upsample else ''} "
                         f"img={n_img}x{H}x{W} epi={epilogue}"
-                        f"{' +res' if residual is not None else ''}{' +lnfold' if ln_fold is not None else ''}"
+                        f"{' +res' if residual is not None else ''}{' +lnfold' if row_scale is not None else ''}"
                         f"{' +lnstats' if ln_stats else ''}")
         return out
 
@@ -370,8 +384,9 @@ class UNetEngine:
         # epilogue and the consuming projection applies rstd / mean after the product (``K.fold_layernorm``).
         # self-attention: fused QKV projection, heads read in place by the attention kernel
         if fold:
-            wq, sq_, bq = self._folded(("qkv", tb), [tb + f".attn1.to_{n}.weight" for n in "qkv"], None, tb + ".norm1")
-            qkv = self._gemm(plan, h, wq, 3 * Cc, bias=bq, ln_fold=(h._ln_part, sq_, 1e-5))
+            side, rstd = self._ln_fold(plan, h, Cc)
+            wq = self._folded(("qkv", tb), [tb + f".attn1.to_{n}.weight" for n in "qkv"], None, tb + ".norm1")
+            qkv = self._gemm(plan, h, wq, 3 * Cc, a1=side, row_scale=rstd)
         else:
             ln = self._ln(plan, h, tb + ".norm1")
             key = ("qkv", tb)
@@ -387,8 +402,9 @@ class UNetEngine:
         self.arena.release(ao)
         # cross-attention: K/V come from the per-call ctx plan
         if fold:
-            wq, sq_, bq = self._folded(("xq", tb), [tb + ".attn2.to_q.weight"], None, tb + ".norm2")
-            q = self._gemm(plan, h, wq, Cc, bias=bq, ln_fold=(h._ln_part, sq_, 1e-5))
+            side, rstd = self._ln_fold(plan, h, Cc)
+            wq = self._folded(("xq", tb), [tb + ".attn2.to_q.weight"], None, tb + ".norm2")
+            q = self._gemm(plan, h, wq, Cc, a1=side, row_scale=rstd)
         else:
             ln = self._ln(plan, h, tb + ".norm2")
             q = self._gemm(plan, ln, self._lin(tb + ".attn2.to_q.weight"), Cc)
@@ -404,14 +420,12 @@ class UNetEngine:
         if fold:
             key = ("geglu_ln", tb, bn)
             if key not in self._w:
-                wf, sf, bf = K.fold_layernorm(self._src(tb + ".ff.net.0.proj.weight"), self._src(tb + ".ff.net.0.proj.bias"),
-                                              self._src(tb + ".norm3.weight"), self._src(tb + ".norm3.bias"))
-                wp, bp = K.pack_geglu(wf, bf, bn)
-                _, sp = K.pack_geglu(wf, sf, bn)
-                self._w[key] = (wp.to(self.dev), bp.to(self.dev), sp.to(self.dev))
-            wp, bp, sp = self._w[key]
-            ff = self._gemm(plan, h, wp, 8 * Cc, bias=bp, epilogue=K.EPI_GEGLU, block_n=bn,
-                            ln_fold=(h._ln_part, sp, 1e-5))
+                wf = K.fold_layernorm(self._src(tb + ".ff.net.0.proj.weight"), self._src(tb + ".ff.net.0.proj.bias"),
+                                      self._src(tb + ".norm3.weight"), self._src(tb + ".norm3.bias"))
+                wp, _ = K.pack_geglu(wf, torch.zeros(wf.shape[0], device=wf.device), bn)       # rows interleaved per tile; no bias vector
+                self._w[key] = wp.to(self.dev)
+            side, rstd = self._ln_fold(plan, h, Cc)
+            ff = self._gemm(plan, h, self._w[key], 8 * Cc, a1=side, epilogue=K.EPI_GEGLU, block_n=bn, row_scale=rstd)
         else:
             ln = self._ln(plan, h, tb + ".norm3")
             key = ("geglu", tb, bn)

@@ -130,7 +130,8 @@ def test_narrow_and_strided_outputs(cuda):
 def test_layernorm_folded_into_gemm(cuda, M, C, N, geglu):
     """The LayerNorms of the transformer blocks launch no kernel: the PRODUCER GEMM (here a +residual projection
     of width C) leaves per-row (sum, sumsq) partials of its output, the CONSUMER (a plain / GEGLU projection)
-    applies rstd and mean after the product.  Reference: fp32 LayerNorm -> Linear (-> GEGLU) of the same
+    takes (-mean, std) through the tensor core as one extra K chunk (``sonic_ln_side``'s side tensor against the
+    (s, b') columns of ``fold_layernorm``) and multiplies by rstd in its epilogue.  Reference: fp32 LayerNorm -> Linear (-> GEGLU) of the same
     bf16-rounded tensors, as oracle/unet.py BasicTransformerBlock computes them."""
     from sonicdiffusionbayeslab_b200 import kernels as k
 
@@ -148,18 +149,23 @@ def test_layernorm_folded_into_gemm(cuda, M, C, N, geglu):
     beta = 0.3 * torch.randn(C, device=cuda, generator=g)
     w = torch.randn(N, C, device=cuda, generator=g) / C ** 0.5
     b = torch.randn(N, device=cuda, generator=g)
-    wf, s, bf_ = k.fold_layernorm(w, b, gamma, beta)
+    side, rstd = k.ln_side(stats, C)                                                   # partials -> side tensor + rstd
+    want_rstd = (h.float().var(1, unbiased=False) + 1e-5).rsqrt()
+    assert torch.allclose(rstd, want_rstd, rtol=2e-3)
+    assert torch.allclose(-(side[:, 0].float() + side[:, 2].float()), h.float().mean(1), rtol=1e-3, atol=1e-3)
+    assert (side[:, 8:] == 0).all()
+    wf = k.fold_layernorm(w, b, gamma, beta)
+    assert wf.shape == (N, C + k.LN_SIDE_COLS)
     ln = F.layer_norm(h.float(), (C,), gamma, beta, 1e-5)
     ref = ln @ _bf(w).float().t() + b
     if geglu:
         bnc = k.gemm_block_n(N, 1, 1, M, k.EPI_GEGLU)
-        wpk, bpk = k.pack_geglu(wf, bf_, bnc)
-        _, spk = k.pack_geglu(wf, s, bnc)
-        out = k.conv_gemm(h, wpk, N, bias=bpk, epilogue=k.EPI_GEGLU, block_n=bnc, ln_fold=(stats, parts, spk, 1e-5))
+        wpk, _ = k.pack_geglu(wf, torch.zeros(N, device=cuda), bnc)
+        out = k.conv_gemm(h, wpk, N, a1=side, epilogue=k.EPI_GEGLU, block_n=bnc, row_scale=rstd)   # consumer
         v, gate = ref.chunk(2, dim=-1)
         ref = v * F.gelu(gate)
     else:
-        out = k.conv_gemm(h, wf, N, bias=bf_, ln_fold=(stats, parts, s, 1e-5))
+        out = k.conv_gemm(h, wf, N, a1=side, row_scale=rstd)
     # what the unfused path (LayerNorm kernel -> bf16 -> GEMM) loses on the same data
     ln16 = _bf(ln)
     unf = ln16.float() @ _bf(w).float().t() + b

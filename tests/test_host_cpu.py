@@ -347,19 +347,25 @@ def test_pil_resample_tables_are_bit_exact(hw):
 
 
 def test_fold_layernorm_algebra():
-    """``kernels.fold_layernorm``: LN(x) W^T + b == rstd (x W'^T - mean s) + b' (fp32, CPU)."""
+    """``kernels.fold_layernorm`` + the side-tensor layout of ``sonic_ln_side``:
+    rstd * ([x | -mu_hi -mu_hi -mu_lo -mu_lo std_hi std_hi std_lo std_lo] W''^T) == LN(x) W^T + b  (fp32 emulation, CPU)."""
     from sonicdiffusionbayeslab_b200 import kernels as K
 
     g = torch.Generator().manual_seed(0)
     x = (2.0 + 3.0 * torch.randn(64, 320, generator=g)).bfloat16().float()
     w, b = torch.randn(96, 320, generator=g) / 18, torch.randn(96, generator=g)
     gamma, beta = 1 + 0.2 * torch.randn(320, generator=g), 0.3 * torch.randn(320, generator=g)
-    wp, s, bp = K.fold_layernorm(w, b, gamma, beta)
-    mean, var = x.mean(1, keepdim=True), x.var(1, unbiased=False, keepdim=True)
-    rstd = (var + 1e-5).rsqrt()
-    got = rstd * (x @ wp.float().t() - mean * s) + bp
+    w2 = K.fold_layernorm(w, b, gamma, beta)
+    assert w2.dtype == torch.bfloat16 and w2.shape == (96, 320 + K.LN_SIDE_COLS) and (w2[:, 328:] == 0).all()
+    mean, var = x.mean(1), x.var(1, unbiased=False)
+    rstd, std = (var + 1e-5).rsqrt(), (var + 1e-5).sqrt()
+    (m_hi, m_lo), (d_hi, d_lo) = K._hi_lo(-mean), K._hi_lo(std)
+    side = torch.zeros(64, K.LN_SIDE_COLS)
+    for col, v in enumerate((m_hi, m_hi, m_lo, m_lo, d_hi, d_hi, d_lo, d_lo)):
+        side[:, col] = v.float()
+    got = rstd[:, None] * (torch.cat([x, side], 1) @ w2.float().t())
     want = torch.nn.functional.layer_norm(x, (320,), gamma, beta, 1e-5) @ w.t() + b
-    assert wp.dtype == torch.bfloat16
-    assert (got - want).abs().max().item() < 2e-2 * want.abs().max().item()      # only the bf16 rounding of W'
-    exact = torch.nn.functional.layer_norm(x, (320,), torch.ones(320), torch.zeros(320), 1e-5) @ wp.float().t() + bp
-    assert (got - exact).abs().max().item() < 1e-4 * exact.abs().max().item()    # the identity itself
+    assert (got - want).abs().max().item() < 2e-2 * want.abs().max().item()      # only the bf16 rounding of gamma.W
+    exact = torch.nn.functional.layer_norm(x, (320,), torch.ones(320), torch.zeros(320), 1e-5) @ w2[:, :320].float().t() \
+        + (w.float() @ beta + b)
+    assert (got - exact).abs().max().item() < 2e-4 * exact.abs().max().item()    # the identity itself (hi/lo splits)

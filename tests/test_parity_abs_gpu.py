@@ -36,7 +36,8 @@ pytestmark = pytest.mark.gpu
 EPS_TOL = 4.5e-2                     # UNet eps max-abs, engine vs fp32 oracle (measured 3.2-3.5e-2)
 STEP_TOL = {                         # per-step latent max-abs, measured worst case x 1.3 (bf16 and fp32 latent I/O)
     "ddim20": 1.15e-1, "dpmpp25": 1.25e-1, "pndm20": 3.1e-1, "deepcache_ddim12_i3": 1.9e-1, "two_20_k10": 2.6e-1}
-VS_LIBRARY = 1.05                    # engine error <= VS_LIBRARY x stock-PyTorch-bf16 error (+ 5e-3)
+VS_LIBRARY = 1.05                    # engine MEDIAN step error (and eps error) <= 1.05 x stock-PyTorch-bf16's (+ 5e-3)
+VS_LIBRARY_WORST = 1.2               # the worst step of 12-25 is a noisier statistic: <= 1.2 x stock PyTorch bf16's worst
 
 
 @pytest.fixture(scope="module")
@@ -92,7 +93,7 @@ def test_step_absolute_error_teacher_forced(unit, name, io):
     assert max(r["xmax"]) < 8.0                               # SD-like magnitudes: the absolute figure means something
     assert max(e) <= STEP_TOL[name], e
     if f:
-        assert max(e) <= VS_LIBRARY * max(f) + 5e-3 and med <= VS_LIBRARY * sorted(f)[len(f) // 2] + 5e-3, (e, f)
+        assert max(e) <= VS_LIBRARY_WORST * max(f) + 5e-3 and med <= VS_LIBRARY * sorted(f)[len(f) // 2] + 5e-3, (e, f)
 
 
 def test_batch32_three_dpm_steps_vs_fp32_oracle(unit):
