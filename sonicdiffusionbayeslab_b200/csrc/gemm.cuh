@@ -47,6 +47,7 @@ struct GemmParams {
   // columns holding (s, b') the same way, so the epilogue only multiplies by rstd_row.
   float* ln_stats_out;           // producer: optional [M][2 * n_tiles][2] per-row (sum, sumsq) partials of the OUTPUT
   const float* row_scale;        // consumer: optional [M] per-row factor applied to the accumulator (no bias added)
+  int gelu_tanh;                 // GEGLU with row_scale: 1 = one-MUFU tanh form of the GELU
 };
 
 struct GemmOp {                  // host-side description; pointers are borrowed
