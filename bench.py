@@ -406,7 +406,7 @@ def run_loop_workload(args, model, kw, wl, B, rank, world, local, dev, dist):
     log = eng.plans["full"].log
     names = {0: "conv_gemm_kernel", 1: "attention kernels", 2: "groupnorm (finalize+apply)", 3: "layernorm_kernel",
              4: "layout kernels", 5: "timestep gemv"}
-    agg, hbm = {}, {2: [0.0, 0.0], 3: [0.0, 0.0]}
+    agg, hbm, ln_side = {}, {2: [0.0, 0.0, 0], 3: [0.0, 0.0, 0]}, [0.0, 0.0, 0]
     for (kind, ms, fl), text in zip(prof, log):
         a = agg.setdefault(kind, [0, 0.0, 0.0])
         a[0] += 1
@@ -414,8 +414,14 @@ def run_loop_workload(args, model, kw, wl, B, rank, world, local, dev, dist):
         a[2] += fl
         if kind in hbm:                                     # "groupnorm rows=R C=C ..." / "layernorm rows=R C=C"
             f = dict(p.split("=") for p in text.split()[1:] if "=" in p)
+            if text.startswith("ln_side"):                  # folded LayerNorm: partials in, 16 B of side row + rstd out
+                ln_side[0] += int(f["rows"]) * (int(f["parts"]) * 8 + 20)
+                ln_side[1] += ms
+                ln_side[2] += 1
+                continue
             hbm[kind][0] += 2.0 * int(f["rows"]) * int(f["C"]) * 2       # read once + write once, bf16
             hbm[kind][1] += ms
+            hbm[kind][2] += 1
     tot_ms = sum(a[1] for a in agg.values())
     burst, sustained, hbm_peak, how = _peaks()
     n_unet = len(model.last_step_kinds) or W["steps"]
@@ -436,14 +442,21 @@ def run_loop_workload(args, model, kw, wl, B, rank, world, local, dev, dist):
     upd = time_latent_update(dev, B, cfg_on)
     roof_hbm = {}
     for kind, label in ((2, "groupnorm"), (3, "layernorm")):
-        by, ms = hbm[kind]
+        by, ms, n_ops = hbm[kind]
         ms *= scale
         if ms > 0:
             roof_hbm[label] = {"bound": "hbm", "achieved": round(by / ms / 1e6, 1), "peak": hbm_peak, "unit": "GB/s",
-                               "frac": round(by / ms / 1e6 / hbm_peak, 4), "ops": agg[kind][0],
+                               "frac": round(by / ms / 1e6 / hbm_peak, 4), "ops": n_ops,
                                "bytes_per_step": int(by), "ms_per_step": round(ms, 3)}
         else:
-            roof_hbm[label] = {"ops": 0, "note": "no such kernel in the plan (folded into the consumer GEMM)"}
+            roof_hbm[label] = {"ops": 0, "note": "no such kernel in the plan"}
+    if ln_side[2]:
+        roof_hbm["layernorm"] = {
+            "ops": 0, "folded_into_gemms": ln_side[2],
+            "note": "the LayerNorms make no pass over the activations: row statistics come from the producer GEMM's "
+                    "epilogue, ln_side_kernel turns them into a 16-byte side row + rstd, the consumer GEMM applies them",
+            "ln_side_kernel": {"launches": ln_side[2], "ms_per_step": round(ln_side[1] * scale, 3),
+                               "bytes_per_step": int(ln_side[0]), "bound": "latency (a few MB per launch)"}}
     roof_hbm["latent_update_kernel"] = upd | {"peak": hbm_peak, "frac": round(upd["achieved"] / hbm_peak, 4)}
     n_cached = n_unet - n_full
     launches_per_image_loop = (n_unet - n_cached) * (n_launch + 1) + n_cached * (

@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsonic.so")
+LIB_PATH = os.environ.get("SONIC_LIB") or os.path.join(_HERE, "libsonic.so")      # SONIC_LIB: A/B kernel experiments
 
 
 class SonicError(RuntimeError):

@@ -28,7 +28,8 @@ constexpr int kGemmThreads = 320;         // TMA warp + MMA warp + 8 epilogue wa
 constexpr int kTileM = 128;
 constexpr int kTileK = 64;                 // bf16 elements = one 128B swizzle row
 constexpr int kABytes = kTileM * kTileK * 2;
-constexpr int kAccStride = 256;            // TMEM columns per accumulator buffer
+constexpr int kMaxAcc = 4;                 // TMEM accumulator buffers: 512 columns / block_n rounded to 32 (2 .. 4); more
+                                           // buffers let the MMA warp run further ahead of a bursty epilogue
 constexpr int kMaxGranules = 8;            // 16-column granules per epilogue warp (block_n 256 / 2 / 16)
 constexpr int kEpiWarps = 8;
 constexpr int kChunkCols = 32;             // output columns per staged chunk (64 B of bf16: one swizzle-64B row)
@@ -85,8 +86,8 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(stg_base + kStgBytes);
   uint64_t* empty_bar = full_bar + p.stages;
   uint64_t* tmem_full = empty_bar + p.stages;
-  uint64_t* tmem_empty = tmem_full + 2;
-  uint64_t* res_full = tmem_empty + 2;                               // [kEpiWarps][kStgBufs]
+  uint64_t* tmem_empty = tmem_full + kMaxAcc;
+  uint64_t* res_full = tmem_empty + kMaxAcc;                         // [kEpiWarps][kStgBufs]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(res_full + kEpiWarps * kStgBufs);
 
   const int warp = threadIdx.x >> 5;
@@ -100,7 +101,7 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
-    for (int a = 0; a < 2; ++a) {
+    for (int a = 0; a < kMaxAcc; ++a) {
       mbar_init(&tmem_full[a], 1);
       mbar_init(&tmem_empty[a], kEpiWarps);
     }
@@ -182,7 +183,7 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
       mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
       if (lane == 0) GEMM_TRACE(1, ti, 1);
       tc_fence_after();
-      const uint32_t d_tmem = tmem_base + acc * kAccStride;
+      const uint32_t d_tmem = tmem_base + acc * p.acc_stride;
       for (int kit = 0; kit < k_iters; ++kit) {
         mbar_wait<64>(&full_bar[stage], phase);
         if (kit == 0 && lane == 0) GEMM_TRACE(1, ti, 2);
@@ -201,14 +202,13 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
       if (leader) umma_commit(&tmem_full[acc]);
       __syncwarp();
       if (lane == 0) GEMM_TRACE(1, ti, 3);
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1;
+      if (++acc == p.n_acc) { acc = 0; acc_phase ^= 1; }
     }
   } else if (p.tma_epilogue) {
     // ------------------------------------------------------------------ epilogue, staged through smem
     const int ew = warp - 2;
     const int quarter = warp & 3;                // TMEM lane quarter this warp may read
-    const int col_half = ew >> 2;                // even / odd 32-column chunks
+    const int col_half0 = ew >> 2;               // even / odd 32-column chunks (swapped every other tile, below)
     const bool geglu = p.epilogue == kEpiGeglu;
     const bool has_res = p.residual != nullptr;
     const int out_cols = geglu ? p.block_n / 2 : p.block_n;
@@ -244,6 +244,11 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
       const int row0 = m_tile * kTileM + quarter * 32;       // tiles are 128 consecutive rows of [M][N]
       const int ncol0 = n_tile * p.block_n;                  // B-row / bias index base
       const int ocol0 = n_tile * out_cols;                   // output column base
+      // With an odd chunk count (block_n = 160: 5 chunks) one warp of each quarter gets 3 chunks and the other 2.
+      // The two swap roles on every tile, so over two tiles both do 5 -- the double-buffered accumulators let the
+      // lighter warp run ahead into the next tile instead of idling at tmem_full (ncu: 26 % of epilogue time).
+      const int col_half = (n_chunks & 1) ? (col_half0 ^ (ti & 1)) : col_half0;
+      const int col_half_next = (n_chunks & 1) ? (col_half ^ 1) : col_half0;
       int my_n = 0;                                          // chunks col_half, col_half + 2, ... inside the matrix
       for (int c = col_half; c < n_chunks && ocol0 + c * kChunkCols < p.n_out_total; c += 2) ++my_n;
       const float rs = rs_next;
@@ -258,7 +263,7 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
         const int tile2 = tile + gridDim.x;
         if (tile2 < total_tiles) {
           const int o2 = (tile2 % p.n_tiles) * out_cols, r2 = (tile2 / p.n_tiles) * kTileM + quarter * 32;
-          for (int c = col_half; c < n_chunks && o2 + c * kChunkCols < p.n_out_total; c += 2)
+          for (int c = col_half_next; c < n_chunks && o2 + c * kChunkCols < p.n_out_total; c += 2)
             tma_prefetch_l2_2d(&p.tm_res, o2 + c * kChunkCols, r2);
         }
         if (my_n > 0) {
@@ -272,7 +277,7 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
       mbar_wait<64>(&tmem_full[acc], acc_phase);
       if (threadIdx.x == 64) GEMM_TRACE(2, ti, 2);
       tc_fence_after();
-      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * kAccStride;
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * p.acc_stride;
       if (my_n == 0) {
         __syncwarp();
         if (lane == 0) mbar_arrive(&tmem_empty[acc]);
@@ -428,8 +433,7 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
         reinterpret_cast<float2*>(p.ln_stats_out)[(static_cast<size_t>(row0 + lane) * p.n_tiles + n_tile) * 2 + col_half] =
             make_float2(rs_sum, rs_sq);
       if (threadIdx.x == 64) GEMM_TRACE(2, ti, 3);
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1;
+      if (++acc == p.n_acc) { acc = 0; acc_phase ^= 1; }
     }
     if (lane == 0) bulk_wait_all<0>();
   } else {
@@ -457,7 +461,7 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
       const int g_count = col_half == 0 ? (granules + 1) / 2 : granules - (granules + 1) / 2;
       mbar_wait(&tmem_full[acc], acc_phase);
       tc_fence_after();
-      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * kAccStride;
+      const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * p.acc_stride;
       for (int g = 0; g < g_count; ++g) {
         const int c = (g_begin + g) * 16;
         uint32_t v[16];
@@ -508,8 +512,7 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tmem_empty[acc]);
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1;
+      if (++acc == p.n_acc) { acc = 0; acc_phase ^= 1; }
     }
   }
 
@@ -652,6 +655,9 @@ int gemm_plan(const GemmOp& op, GemmPlan* plan) {
   const int stage_bytes = kABytes + p.block_n * kTileK * 2;
   p.stages = std::max(2, std::min(8, (225 * 1024 - kStgBytes) / stage_bytes));
   p.idesc = make_idesc_bf16(kTileM, p.block_n, false);
+  p.acc_stride = (p.block_n + 31) / 32 * 32;
+  p.n_acc = std::max(2, std::min(kMaxAcc, 512 / p.acc_stride));
+  if (p.n_acc == 2) p.acc_stride = 256;
   if (!op.bias) {
     SONIC_REQUIRE(op.N <= kZeroBiasLen, "gemm: N=%d exceeds the zero-bias vector", op.N);
     if (!g_zero_bias) {

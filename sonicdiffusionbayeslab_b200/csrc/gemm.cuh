@@ -30,6 +30,7 @@ struct GemmParams {
   int tile_w, tile_h, tile_n;    // tile_w*tile_h*tile_n == 128 rows of one M tile
   int tiles_w, tiles_h, tiles_img;
   int m_tiles, n_tiles, block_n, stages;
+  int n_acc, acc_stride;         // TMEM accumulator ring: buffers and columns per buffer
   int m_tiles_src;               // mode 2: M tiles of ONE phase (m_tiles = 4 * m_tiles_src)
   uint32_t idesc;
   const float* bias;             // [N] or null
