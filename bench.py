@@ -276,8 +276,9 @@ def run_own(args):
     if world > 1:
         import torch.distributed as dist_mod
 
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"          # NCCL prints its version banner on stdout otherwise
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", "WARN"):
+            os.environ.pop("NCCL_DEBUG")               # these two levels print a version banner on STDOUT, where only
+                                                       # the JSON line belongs; INFO (what a harness may set) is left alone
         dist = dist_mod
         dist.init_process_group("nccl", device_id=dev)
 
