@@ -29,6 +29,7 @@
 //                             them, and "S(t) complete" implies "PV(t-1) complete".
 #include "ops.cuh"
 
+#include <cstdlib>
 #include <type_traits>
 
 namespace sonic {
@@ -40,6 +41,7 @@ struct AttentionPlan {
   int atoms = 0;       // 64-column smem atoms per row (1, 2, 3)
   int qt = 1;          // 128-query tiles per CTA: 2 = the ping-pong kernel (head dim <= 64)
   bool resident = false;   // two-tile kernel with K / V resident in shared memory, one CTA per (batch, head)
+  int tiles_per_cta = 1;   // one-tile kernel in loop mode (K / V resident, <= 2 key sub-tiles): query tiles per CTA
   size_t smem = 0;
   dim3 grid;
 };
@@ -66,6 +68,7 @@ struct AttParams {
   uint32_t idesc_s, idesc_pv;
   int tail_w;              // keys of the last sub-tile rounded up to 16 / 32 / 64: its S, softmax and PV only span these
   uint32_t idesc_s_tail;   // S product of the last sub-tile (N = tail_w)
+  int tiles_per_cta;       // attention_kernel, K / V resident (<= 2 key sub-tiles): query tiles one CTA walks over
 };
 
 #ifdef SONIC_ATT_TRACE
@@ -104,16 +107,26 @@ attention_kernel(const __grid_constant__ AttParams p) {
   uint64_t* v_empty = bars + 7;       // [2]
   uint64_t* s_full = bars + 9;        // S(t) complete in TMEM (and every earlier MMA, incl. PV(t-1))
   uint64_t* p_full = bars + 10;       // P(t) written over S(t), O rescaled if it had to be
-  uint64_t* o_done = bars + 11;       // last PV complete
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  uint64_t* o_done = bars + 11;       // last PV of the current query tile complete
+  uint64_t* q_empty = bars + 12;      // every S product of the current query tile complete: Q may be overwritten
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int q0 = blockIdx.x * kBlockQ;
   const int head = blockIdx.y;
   const int batch = blockIdx.z;
   const int n_sub = (p.seq_k + kSub - 1) / kSub;
   const int k_steps_s = (p.head_dim + 15) / 16;
+  // Loop mode (short key sequences, i.e. the cross-attention layers): K and V of this (batch, head) stay in the two
+  // ring stages for the whole CTA, which walks over `tiles_per_cta` query tiles -- the per-CTA costs (TMEM
+  // allocation, barrier set-up, first K / V loads) are paid once, and with four CTAs per SM sixteen softmax warps
+  // hide each other's S -> softmax -> PV round trips.  tiles_per_cta == 1 is the plain one-tile kernel.
+  const bool resident = p.tiles_per_cta > 1;
+  const int tile0 = blockIdx.x * p.tiles_per_cta;
+  const int total_tiles = (p.seq_q + kBlockQ - 1) / kBlockQ;
+  const int n_tiles = min(p.tiles_per_cta, total_tiles - tile0);
+  // a ragged last sub-tile (77 keys: 64 + 13) only spans 32 score columns in the softmax and the PV product
+  const int w_last = p.tail_w < kSub ? 32 : kSub;
 
   if (threadIdx.x == 0) {
     mbar_init(q_full, 1);
@@ -121,7 +134,7 @@ attention_kernel(const __grid_constant__ AttParams p) {
       mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1);
       mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1);
     }
-    mbar_init(s_full, 1); mbar_init(p_full, 4); mbar_init(o_done, 1);
+    mbar_init(s_full, 1); mbar_init(p_full, 4); mbar_init(o_done, 1); mbar_init(q_empty, 1);
     fence_barrier_init();
   }
   if (warp == kWarpMma) tmem_alloc<kTmemCols>(tmem_slot);
@@ -134,20 +147,24 @@ attention_kernel(const __grid_constant__ AttParams p) {
   if (warp == kWarpTma) {
     if (lane == 0) {
       tma_prefetch_desc(&p.tm_q); tma_prefetch_desc(&p.tm_k); tma_prefetch_desc(&p.tm_v);
-      mbar_expect_tx(q_full, q_bytes);
-      for (int a = 0; a < p.atoms; ++a)
-        tma_load_4d(sm_q + a * kQAtomBytes, &p.tm_q, q_full, a * 64, head, q0, batch);
-      for (int t = 0; t < n_sub; ++t) {
-        const int st = t & 1;
-        const uint32_t ph = ((t >> 1) & 1) ^ 1;
-        mbar_wait<512>(&k_empty[st], ph);
-        mbar_expect_tx(&k_full[st], kv_bytes);
+      for (int i = 0; i < n_tiles; ++i) {
+        if (i > 0) mbar_wait<256>(q_empty, (i - 1) & 1);
+        mbar_expect_tx(q_full, q_bytes);
         for (int a = 0; a < p.atoms; ++a)
-          tma_load_4d(sm_k + st * kv_bytes + a * kKvAtomBytes, &p.tm_k, &k_full[st], a * 64, head, t * kSub, batch);
-        mbar_wait<512>(&v_empty[st], ph);
-        mbar_expect_tx(&v_full[st], kv_bytes);
-        for (int a = 0; a < p.atoms; ++a)
-          tma_load_4d(sm_v + st * kv_bytes + a * kKvAtomBytes, &p.tm_v, &v_full[st], a * 64, head, t * kSub, batch);
+          tma_load_4d(sm_q + a * kQAtomBytes, &p.tm_q, q_full, a * 64, head, (tile0 + i) * kBlockQ, batch);
+        if (i > 0) continue;                     // K / V: once (resident) -- or the streaming ring of the one-tile form
+        for (int t = 0; t < n_sub; ++t) {
+          const int st = t & 1;
+          const uint32_t ph = ((t >> 1) & 1) ^ 1;
+          if (!resident) mbar_wait<512>(&k_empty[st], ph);
+          mbar_expect_tx(&k_full[st], kv_bytes);
+          for (int a = 0; a < p.atoms; ++a)
+            tma_load_4d(sm_k + st * kv_bytes + a * kKvAtomBytes, &p.tm_k, &k_full[st], a * 64, head, t * kSub, batch);
+          if (!resident) mbar_wait<512>(&v_empty[st], ph);
+          mbar_expect_tx(&v_full[st], kv_bytes);
+          for (int a = 0; a < p.atoms; ++a)
+            tma_load_4d(sm_v + st * kv_bytes + a * kKvAtomBytes, &p.tm_v, &v_full[st], a * 64, head, t * kSub, batch);
+        }
       }
     }
   } else if (warp == kWarpMma) {
@@ -161,46 +178,52 @@ attention_kernel(const __grid_constant__ AttParams p) {
     constexpr int kMaxKS = (kDPV + 15) / 16;
     auto issue_s = [&](int t) {                  // S(t) = Q K_t^T
       const int st = t & 1;
-      mbar_wait(&k_full[st], (t >> 1) & 1);
+      mbar_wait(&k_full[st], resident ? 0 : (t >> 1) & 1);
       tc_fence_after();
       const uint64_t kd = k_desc0 + static_cast<uint64_t>((st * kv_bytes) >> 4);
+      const uint32_t idesc = resident && t + 1 == n_sub ? p.idesc_s_tail : p.idesc_s;
       if (leader) {
 #pragma unroll
         for (int ks = 0; ks < kMaxKS; ++ks) {
           if (ks < k_steps_s) {
             const uint32_t qo = ((ks >> 2) * kQAtomBytes + (ks & 3) * 32) >> 4;
             const uint32_t ko = ((ks >> 2) * kKvAtomBytes + (ks & 3) * 32) >> 4;
-            umma_bf16_ss(tmem_s, q_desc + qo, kd + ko, p.idesc_s, ks != 0);
+            umma_bf16_ss(tmem_s, q_desc + qo, kd + ko, idesc, ks != 0);
           }
         }
         umma_commit(s_full);
-        umma_commit(&k_empty[st]);
+        if (!resident) umma_commit(&k_empty[st]);
+        if (t + 1 == n_sub) umma_commit(q_empty);            // the tile's last S product: Q may be reloaded
       }
       __syncwarp();
     };
-    mbar_wait(q_full, 0);
-    issue_s(0);
-    for (int t = 0; t < n_sub; ++t) {
-      const int st = t & 1;
-      ATT_TRACE(kWarpMma, t, 0);
-      mbar_wait<64>(p_full, t & 1);
-      ATT_TRACE(kWarpMma, t, 1);
-      mbar_wait(&v_full[st], (t >> 1) & 1);
-      tc_fence_after();
-      // A = P from TMEM: 16 keys = 8 columns of bf16 pairs.  B = V: MN-major (rows = keys), 64-column
-      // atoms at LBO = kKvAtomBytes; one K=16 step = 16 key rows = 2048 B.
-      const uint64_t vd = v_desc0 + static_cast<uint64_t>((st * kv_bytes) >> 4);
-      if (leader) {
+    uint32_t n_item = 0;                           // (tile, sub-tile) items so far: the phase of s_full / p_full
+    for (int i = 0; i < n_tiles; ++i) {
+      mbar_wait(q_full, i & 1);
+      issue_s(0);
+      for (int t = 0; t < n_sub; ++t, ++n_item) {
+        const int st = t & 1;
+        ATT_TRACE(kWarpMma, t, 0);
+        mbar_wait<64>(p_full, n_item & 1);
+        ATT_TRACE(kWarpMma, t, 1);
+        mbar_wait(&v_full[st], resident ? 0 : (t >> 1) & 1);
+        tc_fence_after();
+        // A = P from TMEM: 16 keys = 8 columns of bf16 pairs.  B = V: MN-major (rows = keys), 64-column
+        // atoms at LBO = kKvAtomBytes; one K=16 step = 16 key rows = 2048 B.
+        const uint64_t vd = v_desc0 + static_cast<uint64_t>((st * kv_bytes) >> 4);
+        const int pv_steps = (resident && t + 1 == n_sub ? w_last : kSub) / 16;
+        if (leader) {
 #pragma unroll
-        for (int ks = 0; ks < kSub / 16; ++ks)
-          umma_bf16_ts(tmem_o, tmem_s + ks * 8, vd + ks * (2048 >> 4), p.idesc_pv, (t | ks) != 0);
-        umma_commit(&v_empty[st]);
-        if (t + 1 == n_sub) umma_commit(o_done);
+          for (int ks = 0; ks < kSub / 16; ++ks)
+            if (ks < pv_steps) umma_bf16_ts(tmem_o, tmem_s + ks * 8, vd + ks * (2048 >> 4), p.idesc_pv, (t | ks) != 0);
+          if (!resident) umma_commit(&v_empty[st]);
+          if (t + 1 == n_sub) umma_commit(o_done);
+        }
+        __syncwarp();
+        ATT_TRACE(kWarpMma, t, 2);
+        if (t + 1 < n_sub) issue_s(t + 1);
+        ATT_TRACE(kWarpMma, t, 3);
       }
-      __syncwarp();
-      ATT_TRACE(kWarpMma, t, 2);
-      if (t + 1 < n_sub) issue_s(t + 1);
-      ATT_TRACE(kWarpMma, t, 3);
     }
   } else {
     const int row = warp * 32 + lane;
@@ -210,13 +233,14 @@ attention_kernel(const __grid_constant__ AttParams p) {
     float m_run = -INFINITY, l_run = 0.f;
     const float lazy_raw = kLazyLog2 / p.scale_log2;
 
-    auto softmax_sub = [&](int t, auto mask_tag, int valid) {
+    auto softmax_sub = [&](int t, auto mask_tag, int valid, int w) {      // w: score columns of this sub-tile (64 / 32)
       constexpr bool kMask = decltype(mask_tag)::value;
       // pass 1: row max (two 32-column TMEM loads through the same registers: the CTA must stay under
       // 80 registers per thread for four CTAs per SM)
       float tm[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
       for (int c = 0; c < kSub; c += 32) {
+        if (c >= w) break;
         uint32_t v[32];
         tmem_ld32(t_s + c, v);
         tmem_ld_wait();
@@ -250,6 +274,7 @@ attention_kernel(const __grid_constant__ AttParams p) {
       float ps[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
       for (int c = 0; c < kSub; c += 32) {
+        if (c >= w) break;
         uint32_t v[32];
         tmem_ld32(t_s + c, v);
         tmem_ld_wait();
@@ -268,45 +293,55 @@ attention_kernel(const __grid_constant__ AttParams p) {
       l_run += (ps[0] + ps[1]) + (ps[2] + ps[3]);
     };
 
-    for (int t = 0; t < n_sub; ++t) {
-      int valid = p.seq_k - t * kSub;
-      if (p.causal) valid = min(valid, q0 + row - t * kSub + 1);   // per row: keys 0 .. query index
-      ATT_TRACE(warp, t, 0);
-      mbar_wait<64>(s_full, t & 1);
-      ATT_TRACE(warp, t, 1);
+    uint32_t n_item = 0;
+    for (int i = 0; i < n_tiles; ++i) {
+      const int q0 = (tile0 + i) * kBlockQ;
+      m_run = -INFINITY;
+      l_run = 0.f;
+      for (int t = 0; t < n_sub; ++t, ++n_item) {
+        int valid = p.seq_k - t * kSub;
+        if (p.causal) valid = min(valid, q0 + row - t * kSub + 1);   // per row: keys 0 .. query index
+        ATT_TRACE(warp, t, 0);
+        mbar_wait<64>(s_full, n_item & 1);
+        ATT_TRACE(warp, t, 1);
+        tc_fence_after();
+        const int w = resident && t + 1 == n_sub ? w_last : kSub;
+        if (__all_sync(0xffffffffu, valid >= kSub)) softmax_sub(t, std::false_type{}, kSub, w);
+        else softmax_sub(t, std::true_type{}, valid, w);
+        ATT_TRACE(warp, t, 2);
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(p_full);
+        ATT_TRACE(warp, t, 3);
+      }
+      // O of this tile: its last PV is complete; the next tile's first PV waits for p_full, which these warps only
+      // arrive on after the reads below, so the accumulator is not overwritten early.
+      mbar_wait<64>(o_done, i & 1);
       tc_fence_after();
-      if (__all_sync(0xffffffffu, valid >= kSub)) softmax_sub(t, std::false_type{}, kSub);
-      else softmax_sub(t, std::true_type{}, valid);
-      ATT_TRACE(warp, t, 2);
-      tmem_st_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(p_full);
-      ATT_TRACE(warp, t, 3);
-    }
-    mbar_wait<64>(o_done, 0);
-    tc_fence_after();
 
-    const int s_idx = q0 + row;
-    const float inv = 1.0f / l_run;
-    __nv_bfloat16* orow = p.o + (static_cast<size_t>(batch) * p.seq_q + s_idx) * p.ld_o + head * p.head_dim;
+      const int s_idx = q0 + row;
+      const float inv = 1.0f / l_run;
+      __nv_bfloat16* orow = p.o + (static_cast<size_t>(batch) * p.seq_q + s_idx) * p.ld_o + head * p.head_dim;
 #pragma unroll
-    for (int c = 0; c < kDPV; c += 16) {
-      uint32_t v[16];
-      tmem_ld16(t_o + c, v);
-      tmem_ld_wait();
-      if (s_idx < p.seq_q) {
+      for (int c = 0; c < kDPV; c += 16) {
+        uint32_t v[16];
+        tmem_ld16(t_o + c, v);
+        tmem_ld_wait();
+        if (s_idx < p.seq_q) {
 #pragma unroll
-        for (int h = 0; h < 16; h += 8) {
-          if (c + h < p.head_dim) {
-            uint4 u = make_uint4(pack_bf16(__uint_as_float(v[h]) * inv, __uint_as_float(v[h + 1]) * inv),
-                                 pack_bf16(__uint_as_float(v[h + 2]) * inv, __uint_as_float(v[h + 3]) * inv),
-                                 pack_bf16(__uint_as_float(v[h + 4]) * inv, __uint_as_float(v[h + 5]) * inv),
-                                 pack_bf16(__uint_as_float(v[h + 6]) * inv, __uint_as_float(v[h + 7]) * inv));
-            *reinterpret_cast<uint4*>(orow + c + h) = u;
+          for (int h = 0; h < 16; h += 8) {
+            if (c + h < p.head_dim) {
+              uint4 u = make_uint4(pack_bf16(__uint_as_float(v[h]) * inv, __uint_as_float(v[h + 1]) * inv),
+                                   pack_bf16(__uint_as_float(v[h + 2]) * inv, __uint_as_float(v[h + 3]) * inv),
+                                   pack_bf16(__uint_as_float(v[h + 4]) * inv, __uint_as_float(v[h + 5]) * inv),
+                                   pack_bf16(__uint_as_float(v[h + 6]) * inv, __uint_as_float(v[h + 7]) * inv));
+              *reinterpret_cast<uint4*>(orow + c + h) = u;
+            }
           }
         }
       }
+      tc_fence_before();                           // the reads above precede this thread's next p_full arrive
     }
   }
 
@@ -677,6 +712,19 @@ int attention_plan(const AttentionOp& op, AttentionPlan** out) {
   if (!rc) rc = make_qkv_map(&pl->tm_v, op.v, op.ld_v, op.seq_k, op.batch, op.heads, op.head_dim, kSub);
   if (rc) { delete pl; return rc; }
   pl->qt = (pl->dpv <= 64 && op.seq_q > kBlockQ) ? 2 : 1;
+  // Short key sequences (the cross-attention layers: 77 keys): the one-tile kernel in loop mode -- K / V resident, a
+  // CTA walks over several query tiles, four (d <= 64) or two CTAs per SM -- sized so that ONE wave covers the grid.
+  const int n_qt = (op.seq_q + kBlockQ - 1) / kBlockQ;
+  const char* loop_env = getenv("SONIC_ATT_LOOP");
+  if (op.seq_k <= 2 * kSub && n_qt > 1 && !(loop_env && loop_env[0] == '0')) {
+    int sms = 148;
+    int dev = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int slots = (pl->dpv <= 64 ? 4 : 2) * sms;
+    const int per_bh = std::max(1, std::min(n_qt, slots / std::max(1, op.heads * op.batch)));
+    pl->tiles_per_cta = (n_qt + per_bh - 1) / per_bh;
+    pl->qt = 1;
+  }
   if (pl->qt == 2)
     pl->smem = 2 * kQAtomBytes + 2 * kStages2 * kKvAtomBytes + 1024 + 256;
   else
@@ -684,6 +732,7 @@ int attention_plan(const AttentionOp& op, AttentionPlan** out) {
   // <= 128 keys and at least four query-tile pairs per head: one CTA per (batch, head) keeps K / V resident
   pl->resident = pl->qt == 2 && op.seq_k <= 2 * kSub && op.seq_q >= 8 * kBlockQ;
   pl->grid = dim3(pl->resident ? 1 : (op.seq_q + kBlockQ * pl->qt - 1) / (kBlockQ * pl->qt), op.heads, op.batch);
+  if (pl->qt == 1) pl->grid.x = (n_qt + pl->tiles_per_cta - 1) / pl->tiles_per_cta;
   *out = pl;
   return 0;
 }
@@ -706,6 +755,7 @@ int attention_launch(const AttentionPlan* pl, cudaStream_t stream) {
   prm.tail_w = tail <= 16 ? 16 : tail <= 32 ? 32 : kSub;
   prm.idesc_s_tail = make_idesc_bf16(kBlockQ, prm.tail_w, false);
   prm.idesc_pv = make_idesc_bf16(kBlockQ, pl->dpv, true);
+  prm.tiles_per_cta = pl->tiles_per_cta;
   if (pl->qt == 2) return pl->dpv == 48 ? dispatch_att2<48>(pl, prm, stream) : dispatch_att2<64>(pl, prm, stream);
   switch (pl->dpv) {
     case 48: return launch_att<48>(pl, prm, stream);

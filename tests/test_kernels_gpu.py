@@ -26,7 +26,13 @@ def _rel(got, ref):
                                           # full key sub-tiles, ragged keys
                                           (1, 2, 1152, 100, 64), (1, 1, 1024, 64, 40), (2, 3, 2048, 128, 48),
                                           # ragged last key sub-tile narrowed to 16 / 32 columns
-                                          (1, 1, 256, 80, 40), (1, 2, 256, 96, 64), (1, 1, 1024, 90, 40)])
+                                          (1, 1, 256, 80, 40), (1, 2, 256, 96, 64), (1, 1, 1024, 90, 40),
+                                          # one-tile kernel in LOOP mode (<= 128 keys, enough (batch, head) pairs that a
+                                          # CTA walks over several query tiles): the UNet's cross-attention shapes at
+                                          # UNet batch 32 / 16, a ragged last query tile, one / two full key sub-tiles
+                                          (32, 8, 4096, 77, 40), (32, 8, 1024, 77, 80), (32, 8, 256, 77, 160),
+                                          (16, 8, 4096, 77, 40), (40, 8, 1100, 64, 40), (80, 4, 700, 128, 64),
+                                          (64, 8, 384, 100, 80)])
 def test_attention(cuda, B, H, Sq, Sk, d):
     from sonicdiffusionbayeslab_b200 import kernels as k
 
