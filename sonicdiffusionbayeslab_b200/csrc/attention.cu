@@ -69,6 +69,7 @@ struct AttParams {
   int tail_w;              // keys of the last sub-tile rounded up to 16 / 32 / 64: its S, softmax and PV only span these
   uint32_t idesc_s_tail;   // S product of the last sub-tile (N = tail_w)
   int tiles_per_cta;       // attention_kernel, K / V resident (<= 2 key sub-tiles): query tiles one CTA walks over
+  int speculate;           // exponentiate full sub-tiles after the first without the row-maximum pass (see softmax_sub)
 };
 
 #ifdef SONIC_ATT_TRACE
@@ -235,6 +236,32 @@ attention_kernel(const __grid_constant__ AttParams p) {
 
     auto softmax_sub = [&](int t, auto mask_tag, int valid, int w) {      // w: score columns of this sub-tile (64 / 32)
       constexpr bool kMask = decltype(mask_tag)::value;
+      if constexpr (!kMask && kDPV > 64) {
+        // Speculative pass, as in attention2_kernel's softmax_sub (two CTAs per SM here: registers for all 64 columns):
+        // no row-maximum pass on full sub-tiles after the first; a row sum <= 2^8 proves the reference was still valid
+        // and the result is bit-identical to the checked path below.  P is only stored once the check has passed --
+        // it overwrites the scores the fallback needs.
+        if (t > 0 && w == kSub && p.speculate) {
+          const float ms = m_run * p.scale_log2;
+          float ps[4] = {0.f, 0.f, 0.f, 0.f};
+          uint32_t v[kSub], pk[kSub / 2];
+          tmem_ld64(t_s, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < kSub; i += 2) {
+            const float e0 = fast_exp2(fmaf(__uint_as_float(v[i]), p.scale_log2, -ms));
+            const float e1 = fast_exp2(fmaf(__uint_as_float(v[i + 1]), p.scale_log2, -ms));
+            ps[(i >> 1) & 3] += e0 + e1;
+            pk[i >> 1] = pack_bf16(e0, e1);
+          }
+          const float tot = (ps[0] + ps[1]) + (ps[2] + ps[3]);
+          if (!__any_sync(0xffffffffu, !(tot <= 256.0f))) {
+            tmem_st32(t_s, pk);
+            l_run += tot;
+            return;
+          }
+        }
+      }
       // pass 1: row max (two 32-column TMEM loads through the same registers: the CTA must stay under
       // 80 registers per thread for four CTAs per SM)
       float tm[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
@@ -527,6 +554,30 @@ attention2_kernel(const __grid_constant__ AttParams p) {
       else if constexpr (kW == 32) tmem_ld32(t_s, v);
       else tmem_ld16(t_s, v);
       tmem_ld_wait();
+      if constexpr (!kMask && kW == 64) {
+        // Speculative pass (full sub-tiles after the first): exponentiate against the CURRENT reference without
+        // computing the row maximum.  Any P > 2^8 (the lazy bound) forces the row sum above 2^8, so a sum <= 2^8 proves
+        // the reference was still valid and the result is bit-identical to the checked path below; otherwise (rare:
+        // the scores of this sub-tile exceed the running maximum) fall through and redo the row the careful way.
+        if (t > 0 && p.speculate) {
+          const float ms = m_r * p.scale_log2;
+          float ps[4] = {0.f, 0.f, 0.f, 0.f};
+          uint32_t pk[kW / 2];
+#pragma unroll
+          for (int i = 0; i < kW; i += 2) {
+            const float e0 = fast_exp2(fmaf(__uint_as_float(v[i]), p.scale_log2, -ms));
+            const float e1 = fast_exp2(fmaf(__uint_as_float(v[i + 1]), p.scale_log2, -ms));
+            ps[(i >> 1) & 3] += e0 + e1;
+            pk[i >> 1] = pack_bf16(e0, e1);
+          }
+          const float tot = (ps[0] + ps[1]) + (ps[2] + ps[3]);
+          if (!__any_sync(0xffffffffu, !(tot <= 256.0f))) {
+            tmem_st32(t_s, pk);
+            l_r += tot;
+            return;
+          }
+        }
+      }
       float tm[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
       for (int i = 0; i < kW; ++i)
@@ -756,6 +807,10 @@ int attention_launch(const AttentionPlan* pl, cudaStream_t stream) {
   prm.idesc_s_tail = make_idesc_bf16(kBlockQ, prm.tail_w, false);
   prm.idesc_pv = make_idesc_bf16(kBlockQ, pl->dpv, true);
   prm.tiles_per_cta = pl->tiles_per_cta;
+  {
+    const char* e = getenv("SONIC_ATT_SPEC");                         // "0": always take the checked path (A/B, tests)
+    prm.speculate = (e && e[0] == '0') ? 0 : 1;
+  }
   if (pl->qt == 2) return pl->dpv == 48 ? dispatch_att2<48>(pl, prm, stream) : dispatch_att2<64>(pl, prm, stream);
   switch (pl->dpv) {
     case 48: return launch_att<48>(pl, prm, stream);

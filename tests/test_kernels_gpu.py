@@ -97,6 +97,32 @@ def test_attention_rising_scores(cuda, d, Sq):
     assert _rel(out, ref) < 2e-2
 
 
+@pytest.mark.parametrize("d", [40, 80])
+@pytest.mark.parametrize("rising", [False, True])
+def test_attention_speculative_pass_is_bit_identical(cuda, rising, d, monkeypatch):
+    """Both kernels (two-tile: d = 40; one-tile: d = 80) exponentiate full sub-tiles against the current reference WITHOUT the row-maximum pass and
+    falls back to the checked path when a row sum exceeds 2^8 (attention.cu softmax_sub).  By construction the result
+    is bit-identical to the checked path; SONIC_ATT_SPEC=0 selects the latter."""
+    from sonicdiffusionbayeslab_b200 import kernels as k
+
+    B, H, S = 2, 8, 1024
+    C = H * d
+    g = torch.Generator(device="cuda").manual_seed(5)
+    q = torch.randn(B * S, C, device=cuda, generator=g)
+    kk = torch.randn(B * S, C, device=cuda, generator=g)
+    if rising:                                         # every later sub-tile beats the running maximum: all fallbacks
+        q[:, ::d] = 4.0
+        kk[:, ::d] = (torch.linspace(0, 40, S, device=cuda).repeat(B) * (d ** 0.5) / 4.0)[:, None]
+    q, kk = _bf(q), _bf(kk)
+    v = _bf(torch.randn(B * S, C, device=cuda, generator=g))
+    outs = []
+    for flag in ("1", "0"):
+        monkeypatch.setenv("SONIC_ATT_SPEC", flag)
+        outs.append(k.attention(q, kk, v, batch=B, heads=H, seq_q=S, seq_k=S, head_dim=d).clone())
+    torch.cuda.synchronize()
+    assert torch.equal(outs[0], outs[1])
+
+
 @pytest.mark.parametrize("B,hw,C0,C1,silu,eps", [(2, 4096, 320, 0, True, 1e-5), (2, 1024, 640, 320, True, 1e-5),
                                                   (3, 64, 1280, 1280, True, 1e-5), (2, 256, 1280, 0, False, 1e-6),
                                                   (2, 4096, 320, 320, True, 1e-5)])
