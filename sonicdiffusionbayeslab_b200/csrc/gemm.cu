@@ -76,12 +76,22 @@ __device__ long long g_gemm_trace[4][64][4];
 #define GEMM_TRACE(role, i, k) do { } while (0)
 #endif
 
+// kPair: the CTA-pair form (cta_group::2, launched as clusters of two CTAs = the two SMs of a TPC).  A work item is two
+// adjacent M tiles x one N tile; CTA r of the pair loads the A tile of M tile 2j + r and HALF of the B tile (rows
+// [r, r + 1) * block_n / 2), the leader's MMA warp issues M = 256 instructions for both, every accumulator lands in
+// the TMEM of the SM that owns its rows, and each CTA runs its own epilogue.  Operand traffic into an SM drops from
+// 16 KB + block_n * 128 B to 16 KB + block_n * 64 B per K chunk (the one-CTA form needs ~70 B/clk/SM at block_n = 160
+// or 256, which is what the L2 -> SM path delivers with all SMs pulling).  Barriers: TMA bytes of both CTAs are counted
+// on the LEADER's full barrier; tcgen05.commit multicasts to the empty / tmem_full barriers of both CTAs; the
+// epilogue warps of both CTAs arrive on the leader's tmem_empty barrier.
+template <bool kPair>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 conv_gemm_kernel(const __grid_constant__ GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
-  const int stage_bytes = kABytes + p.block_n * kTileK * 2;          // multiple of 1024
+  const int b_rows = kPair ? p.block_n / 2 : p.block_n;              // B rows this CTA fetches
+  const int stage_bytes = kABytes + b_rows * kTileK * 2;             // multiple of 1024
   uint8_t* stg_base = smem + p.stages * stage_bytes;                 // epilogue staging, 32 KB
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(stg_base + kStgBytes);
   uint64_t* empty_bar = full_bar + p.stages;
@@ -92,7 +102,11 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int total_tiles = p.m_tiles * p.n_tiles;
+  const int total_tiles = p.total_work;
+  const int rank = kPair ? static_cast<int>(blockIdx.x & 1) : 0;     // cluster rank: 0 = leader
+  const int worker = kPair ? static_cast<int>(blockIdx.x >> 1) : static_cast<int>(blockIdx.x);
+  const int n_workers = kPair ? static_cast<int>(gridDim.x >> 1) : static_cast<int>(gridDim.x);
+  auto m_tile_of = [&](int tile) { return kPair ? 2 * (tile / p.n_tiles) + rank : tile / p.n_tiles; };
   const int k_chunks = p.k_chunks0 + p.k_chunks1;
   const int k_iters = p.taps * k_chunks;
 
@@ -103,14 +117,18 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
     }
     for (int a = 0; a < kMaxAcc; ++a) {
       mbar_init(&tmem_full[a], 1);
-      mbar_init(&tmem_empty[a], kEpiWarps);
+      mbar_init(&tmem_empty[a], kPair ? 2 * kEpiWarps : kEpiWarps);
     }
     for (int i = 0; i < kEpiWarps * kStgBufs; ++i) mbar_init(&res_full[i], 1);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  if (warp == 1) {
+    if (kPair) tmem_alloc_pair<512>(tmem_slot);
+    else tmem_alloc<512>(tmem_slot);
+  }
   tc_fence_before();
-  __syncthreads();
+  if (kPair) cluster_sync_all();                 // the peer's barriers are initialised before anything signals them
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -125,10 +143,10 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
       int stage = 0;
       uint32_t phase = 0;
       int ti = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
+      for (int tile = worker; tile < total_tiles; tile += n_workers, ++ti) {
         GEMM_TRACE(0, ti, 0);
         const int n_tile = tile % p.n_tiles;
-        int m_tile = tile / p.n_tiles;
+        int m_tile = m_tile_of(tile);
         int phase_a = 0, phase_b = 0, b_tap0 = 0;
         if (p.mode == kModeUpsample) {                       // tiles are phase-major: (phase, source-pixel tile)
           const int ph = m_tile / p.m_tiles_src;
@@ -138,7 +156,7 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
         const int w0 = (m_tile % p.tiles_w) * p.tile_w;
         const int h0 = ((m_tile / p.tiles_w) % p.tiles_h) * p.tile_h;
         const int i0 = (m_tile / (p.tiles_w * p.tiles_h)) * p.tile_n;
-        const int ncol0 = n_tile * p.block_n;
+        const int ncol0 = n_tile * p.block_n + rank * b_rows;
         for (int tap = 0; tap < p.taps; ++tap) {
           int dy = 0, dx = 0;
           const CUtensorMap* ma = &p.tm_a0;
@@ -156,14 +174,18 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
           }
           for (int ch = 0; ch < k_chunks; ++ch) {
             mbar_wait<512>(&empty_bar[stage], phase ^ 1);
-            mbar_expect_tx(&full_bar[stage], stage_bytes);
             uint8_t* sa = smem + stage * stage_bytes;
-            if (ch < p.k_chunks0)
-              tma_load_4d(sa, ma, &full_bar[stage], ch * kTileK, w0 + dx, h0 + dy, i0);
-            else
-              tma_load_4d(sa, &p.tm_a1, &full_bar[stage], (ch - p.k_chunks0) * kTileK, w0 + dx,
-                          h0 + dy, i0);
-            tma_load_3d(sa + kABytes, &p.tm_b, &full_bar[stage], ch * kTileK, ncol0, b_tap0 + tap);
+            const CUtensorMap* mk = ch < p.k_chunks0 ? ma : &p.tm_a1;
+            const int kc = (ch < p.k_chunks0 ? ch : ch - p.k_chunks0) * kTileK;
+            if (kPair) {
+              if (rank == 0) mbar_expect_tx(&full_bar[stage], 2 * stage_bytes);     // both CTAs' bytes
+              tma_load_4d_pair(sa, mk, &full_bar[stage], kc, w0 + dx, h0 + dy, i0);
+              tma_load_3d_pair(sa + kABytes, &p.tm_b, &full_bar[stage], ch * kTileK, ncol0, b_tap0 + tap);
+            } else {
+              mbar_expect_tx(&full_bar[stage], stage_bytes);
+              tma_load_4d(sa, mk, &full_bar[stage], kc, w0 + dx, h0 + dy, i0);
+              tma_load_3d(sa + kABytes, &p.tm_b, &full_bar[stage], ch * kTileK, ncol0, b_tap0 + tap);
+            }
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
           }
         }
@@ -172,13 +194,14 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
-    // Warp-uniform loop (descriptors stay in uniform registers), one elected lane issues.
-    const bool leader = elect_one();
+    // Warp-uniform loop (descriptors stay in uniform registers), one elected lane issues.  In a CTA pair only the
+    // leader CTA's warp runs it (the instructions drive both tensor cores).
+    const bool leader = elect_one() && rank == 0;
     const uint64_t desc0 = make_sw128_desc(smem_u32(smem), 16, 1024);
     int stage = 0, acc = 0;
     uint32_t phase = 0, acc_phase = 0;
     int ti = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
+    for (int tile = worker; tile < total_tiles && rank == 0; tile += n_workers, ++ti) {
       if (lane == 0) GEMM_TRACE(1, ti, 0);
       mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
       if (lane == 0) GEMM_TRACE(1, ti, 1);
@@ -192,14 +215,20 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
         const uint64_t db = da + (kABytes >> 4);
         if (leader) {
 #pragma unroll
-          for (int k = 0; k < kTileK / 16; ++k)  // +32 B per K=16 step inside the 128B atom
-            umma_bf16_ss(d_tmem, da + 2 * k, db + 2 * k, p.idesc, (kit | k) != 0);
-          umma_commit(&empty_bar[stage]);
+          for (int k = 0; k < kTileK / 16; ++k) {  // +32 B per K=16 step inside the 128B atom
+            if (kPair) umma_bf16_ss_pair(d_tmem, da + 2 * k, db + 2 * k, p.idesc, (kit | k) != 0);
+            else umma_bf16_ss(d_tmem, da + 2 * k, db + 2 * k, p.idesc, (kit | k) != 0);
+          }
+          if (kPair) umma_commit_pair(&empty_bar[stage]);
+          else umma_commit(&empty_bar[stage]);
         }
         __syncwarp();
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
-      if (leader) umma_commit(&tmem_full[acc]);
+      if (leader) {
+        if (kPair) umma_commit_pair(&tmem_full[acc]);
+        else umma_commit(&tmem_full[acc]);
+      }
       __syncwarp();
       if (lane == 0) GEMM_TRACE(1, ti, 3);
       if (++acc == p.n_acc) { acc = 0; acc_phase ^= 1; }
@@ -230,12 +259,12 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
     // gemm.cuh), so all that is left here is one multiply by this lane's row scale (rstd).  The scale of the NEXT tile
     // is requested a tile ahead: its L2 latency hides behind the current tile.
     float rs_next = 1.f;
-    if (p.row_scale && static_cast<int>(blockIdx.x) < total_tiles)
-      rs_next = __ldcg(p.row_scale + min((static_cast<int>(blockIdx.x) / p.n_tiles) * kTileM + quarter * 32 + lane, p.M - 1));
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++ti) {
+    if (p.row_scale && worker < total_tiles)
+      rs_next = __ldcg(p.row_scale + min(m_tile_of(worker) * kTileM + quarter * 32 + lane, p.M - 1));
+    for (int tile = worker; tile < total_tiles; tile += n_workers, ++ti) {
       if (threadIdx.x == 64) GEMM_TRACE(2, ti, 0);
       const int n_tile = tile % p.n_tiles;
-      int m_tile = tile / p.n_tiles;
+      int m_tile = m_tile_of(tile);
       int up_phase = 0;
       if (p.mode == kModeUpsample) {                         // phase-major tiles over the SOURCE pixels
         up_phase = m_tile / p.m_tiles_src;
@@ -253,16 +282,16 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
       for (int c = col_half; c < n_chunks && ocol0 + c * kChunkCols < p.n_out_total; c += 2) ++my_n;
       const float rs = rs_next;
       if (p.row_scale) {
-        const int tile2 = tile + gridDim.x;
+        const int tile2 = tile + n_workers;
         if (tile2 < total_tiles)
-          rs_next = __ldcg(p.row_scale + min((tile2 / p.n_tiles) * kTileM + quarter * 32 + lane, p.M - 1));
+          rs_next = __ldcg(p.row_scale + min(m_tile_of(tile2) * kTileM + quarter * 32 + lane, p.M - 1));
       }
       float rs_sum = 0.f, rs_sq = 0.f;                       // producer side: statistics of this lane's output row
       if (has_res && lane == 0) {
         // residual of the NEXT tile into L2 now; this tile's first chunk into the staging buffer
-        const int tile2 = tile + gridDim.x;
+        const int tile2 = tile + n_workers;
         if (tile2 < total_tiles) {
-          const int o2 = (tile2 % p.n_tiles) * out_cols, r2 = (tile2 / p.n_tiles) * kTileM + quarter * 32;
+          const int o2 = (tile2 % p.n_tiles) * out_cols, r2 = m_tile_of(tile2) * kTileM + quarter * 32;
           for (int c = col_half_next; c < n_chunks && o2 + c * kChunkCols < p.n_out_total; c += 2)
             tma_prefetch_l2_2d(&p.tm_res, o2 + c * kChunkCols, r2);
         }
@@ -280,7 +309,7 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * p.acc_stride;
       if (my_n == 0) {
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        if (lane == 0) { if (kPair) mbar_arrive_leader(&tmem_empty[acc]); else mbar_arrive(&tmem_empty[acc]); }
       }
       for (int i = 0; i < my_n; ++i) {
         const int c = col_half + 2 * i;
@@ -343,7 +372,7 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
         if (i == my_n - 1) {                                 // every TMEM read of this tile is done
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+          if (lane == 0) { if (kPair) mbar_arrive_leader(&tmem_empty[acc]); else mbar_arrive(&tmem_empty[acc]); }
         }
         if (p.row_bias) {
           const int img = min((row0 + lane) / (p.H * p.W), p.n_img - 1);
@@ -446,9 +475,9 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
     const int out_cols = geglu ? p.block_n / 2 : p.block_n;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int tile = worker; tile < total_tiles; tile += n_workers) {
       const int n_tile = tile % p.n_tiles;
-      const int m_tile = tile / p.n_tiles;
+      const int m_tile = m_tile_of(tile);
       const int w = (m_tile % p.tiles_w) * p.tile_w + r % p.tile_w;
       const int h = ((m_tile / p.tiles_w) % p.tiles_h) * p.tile_h + (r / p.tile_w) % p.tile_h;
       const int img = (m_tile / (p.tiles_w * p.tiles_h)) * p.tile_n + r / (p.tile_w * p.tile_h);
@@ -511,16 +540,18 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (lane == 0) { if (kPair) mbar_arrive_leader(&tmem_empty[acc]); else mbar_arrive(&tmem_empty[acc]); }
       if (++acc == p.n_acc) { acc = 0; acc_phase ^= 1; }
     }
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (kPair) cluster_sync_all();                 // neither CTA leaves (or frees TMEM) while the peer still uses it
+  else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc<512>(tmem_base);
+    if (kPair) tmem_dealloc_pair<512>(tmem_base);
+    else tmem_dealloc<512>(tmem_base);
   }
 }
 
@@ -652,9 +683,23 @@ int gemm_plan(const GemmOp& op, GemmPlan* plan) {
   SONIC_REQUIRE(op.gn_partial == nullptr || p.tma_epilogue,
                 "gemm: gn_partial needs the staged epilogue (block_n %% 32 == 0, contiguous 128-row tiles)");
   p.n_tiles = (op.N + p.block_n - 1) / p.block_n;
-  const int stage_bytes = kABytes + p.block_n * kTileK * 2;
+  // CTA pairs: two adjacent M tiles share one B tile.  Needs an even SM count, a B half of whole 8-row swizzle atoms,
+  // phase-aligned tile pairs in the upsample form, and enough work that halving the worker count costs no wave.
+  static const int pair_env = [] { const char* e = getenv("SONIC_GEMM_PAIR"); return e ? atoi(e) : 1; }();
+  static const int pair_min = [] { const char* e = getenv("SONIC_GEMM_PAIR_MIN"); return e ? atoi(e) : 0; }();
+  const bool pair_ok = p.block_n % 32 == 0 && g_num_sms % 2 == 0 && p.m_tiles >= 2 &&
+                       (mode != kModeUpsample || p.m_tiles_src % 2 == 0);
+  if (op.pair >= 0) {
+    SONIC_REQUIRE(!op.pair || pair_ok, "gemm: the CTA-pair kernel cannot run this shape");
+    p.pair = op.pair;
+  } else {
+    p.pair = pair_env && pair_ok && static_cast<long>(p.m_tiles) * p.n_tiles >= static_cast<long>(pair_min) * g_num_sms;
+  }
+  p.total_work = p.pair ? ((p.m_tiles + 1) / 2) * p.n_tiles : p.m_tiles * p.n_tiles;
+  const int b_rows = p.pair ? p.block_n / 2 : p.block_n;
+  const int stage_bytes = kABytes + b_rows * kTileK * 2;
   p.stages = std::max(2, std::min(8, (225 * 1024 - kStgBytes) / stage_bytes));
-  p.idesc = make_idesc_bf16(kTileM, p.block_n, false);
+  p.idesc = make_idesc_bf16(p.pair ? 2 * kTileM : kTileM, p.block_n, false);
   p.acc_stride = (p.block_n + 31) / 32 * 32;
   p.n_acc = std::max(2, std::min(kMaxAcc, 512 / p.acc_stride));
   if (p.n_acc == 2) p.acc_stride = 256;
@@ -709,7 +754,7 @@ int gemm_plan(const GemmOp& op, GemmPlan* plan) {
     uint64_t dims[3] = {static_cast<uint64_t>(K), static_cast<uint64_t>(op.N),
                         static_cast<uint64_t>(mode == kModeUpsample ? 16 : op.taps)};
     uint64_t str[2] = {static_cast<uint64_t>(K) * 2, static_cast<uint64_t>(op.N) * K * 2};
-    uint32_t box[3] = {kTileK, static_cast<uint32_t>(p.block_n), 1};
+    uint32_t box[3] = {kTileK, static_cast<uint32_t>(b_rows), 1};
     if (int rc = encode_tensor_map(&p.tm_b, op.w, 3, dims, str, box, 128)) return rc;
   }
   p.tm_out = p.tm_b;
@@ -740,7 +785,7 @@ int gemm_plan(const GemmOp& op, GemmPlan* plan) {
       if (int rc = encode_tensor_map(&p.tm_res, op.residual, 2, dims, str, box, 64)) return rc;
     }
   }
-  plan->grid = std::min(p.m_tiles * p.n_tiles, g_num_sms);
+  plan->grid = p.pair ? 2 * std::min(p.total_work, g_num_sms / 2) : std::min(p.total_work, g_num_sms);
   plan->smem = static_cast<size_t>(p.stages) * stage_bytes + kStgBytes + 1024 /*align*/ + 512 /*barriers*/;
   // algorithmic work of the operator (a 9-tap convolution of every OUTPUT pixel), whatever the kernel executes: the
   // phase form of the upsample convolution runs 4/9 of it
@@ -752,11 +797,27 @@ int gemm_plan(const GemmOp& op, GemmPlan* plan) {
 
 int gemm_launch(const GemmPlan& plan, cudaStream_t stream) {
   if (!g_attr_set) {
-    SONIC_CUDA(cudaFuncSetAttribute(conv_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    227 * 1024));
+    SONIC_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    SONIC_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     g_attr_set = true;
   }
-  conv_gemm_kernel<<<plan.grid, kGemmThreads, plan.smem, stream>>>(plan.p);
+  if (plan.p.pair) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(plan.grid);
+    cfg.blockDim = dim3(kGemmThreads);
+    cfg.dynamicSmemBytes = plan.smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    SONIC_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<true>, plan.p));
+  } else {
+    conv_gemm_kernel<false><<<plan.grid, kGemmThreads, plan.smem, stream>>>(plan.p);
+  }
   SONIC_CUDA(cudaGetLastError());
   return 0;
 }

@@ -49,6 +49,9 @@ struct GemmParams {
   float* ln_stats_out;           // producer: optional [M][2 * n_tiles][2] per-row (sum, sumsq) partials of the OUTPUT
   const float* row_scale;        // consumer: optional [M] per-row factor applied to the accumulator (no bias added)
   int gelu_tanh;                 // GEGLU with row_scale: 1 = one-MUFU tanh form of the GELU
+  int pair;                      // 1: CTA-pair kernel (cta_group::2): work item = two adjacent M tiles x one N tile,
+                                 //    CTA r of the pair owns M tile 2j + r and fetches B rows [r, r + 1) * block_n / 2
+  int total_work;                // work items of the launch: m_tiles * n_tiles, or ceil(m_tiles / 2) * n_tiles
 };
 
 struct GemmOp {                  // host-side description; pointers are borrowed
@@ -68,6 +71,7 @@ struct GemmOp {                  // host-side description; pointers are borrowed
   float* gn_partial = nullptr;
   float* ln_stats_out = nullptr;           // see GemmParams
   const float* row_scale = nullptr;
+  int pair = -1;                 // -1 = choose, 0 / 1 = force the one-CTA / CTA-pair kernel
 };
 
 struct GemmPlan {

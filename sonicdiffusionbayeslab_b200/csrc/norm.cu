@@ -5,6 +5,9 @@
 // bit-reproducible without atomics on the data path.
 #include "ops.cuh"
 
+#include <algorithm>
+#include <cstdlib>
+
 namespace sonic {
 
 namespace {
@@ -232,6 +235,146 @@ gn_apply_kernel(GnSrc s, int hw, int groups, float* __restrict__ stats, const fl
   }
 }
 
+// ---- one-launch form for statistics that come from GEMM epilogue partials ------------------------------------
+// grid (R, n_img) launched as thread-block clusters of R CTAs (one cluster per image, R <= 16): the finalize step
+// of the two-kernel form (a 1024-CTA latency-bound launch plus a launch gap in front of every apply pass) becomes
+// the prologue of the apply kernel.  CTA r of a cluster folds the row blocks [r nb / R, (r + 1) nb / R) of the
+// partials into per-channel and then per-group sums in its own shared memory, the cluster barrier publishes them,
+// every CTA adds the R group partials in rank order through distributed shared memory (fixed assignment, fixed
+// order: bit-reproducible, no atomics, no global scratch) and then normalises its pixel chunk as gn_apply_kernel
+// does.  The hardware co-schedules a cluster, so the barrier cannot deadlock whatever else is resident.
+__device__ __forceinline__ void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+__device__ __forceinline__ float ld_dsmem(const float* local, uint32_t rank) {
+  uint32_t a = static_cast<uint32_t>(__cvta_generic_to_shared(local)), r;
+  float v;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(rank));
+  asm volatile("ld.shared::cluster.f32 %0, [%1];" : "=f"(v) : "r"(r) : "memory");
+  return v;
+}
+
+__global__ void __launch_bounds__(kGnThreads, 2)
+gn_cluster_kernel(GnSrc s, const float* __restrict__ part0, const float* __restrict__ part1, int hw, int groups,
+                  float eps, const float* __restrict__ gamma, const float* __restrict__ beta, int silu,
+                  __nv_bfloat16* __restrict__ y) {
+  extern __shared__ float sm_ch[];               // [2][C] per-channel (sum, sumsq) of this CTA's row blocks
+  __shared__ float s_grp[64];                    // [groups][2] this CTA's group partials (read by the whole cluster)
+  __shared__ float s_fin[64];                    // [groups][2] mean, rstd
+  const int C = s.c0 + s.c1;
+  const int cpg = C / groups;
+  const int img = blockIdx.y;
+  const int R = gridDim.x, rank = blockIdx.x;    // the cluster spans the x dimension
+  const int nb = hw >> 5;                        // 32-row blocks per image
+  const int b0 = static_cast<int>(static_cast<long long>(rank) * nb / R);
+  const int b1 = static_cast<int>(static_cast<long long>(rank + 1) * nb / R);
+  for (int c = threadIdx.x; c < C; c += kGnThreads) {
+    const float2* src = c < s.c0
+        ? reinterpret_cast<const float2*>(part0) + static_cast<size_t>(img) * nb * s.c0 + c
+        : reinterpret_cast<const float2*>(part1) + static_cast<size_t>(img) * nb * s.c1 + (c - s.c0);
+    const int pitch = c < s.c0 ? s.c0 : s.c1;
+    float a = 0.f, q = 0.f;
+    int b = b0;
+    for (; b + 8 <= b1; b += 8) {                // eight loads in flight; summed in block order
+      float2 v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = __ldcg(src + static_cast<size_t>(b + j) * pitch);
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { a += v[j].x; q += v[j].y; }
+    }
+    for (; b < b1; ++b) {
+      const float2 v = __ldcg(src + static_cast<size_t>(b) * pitch);
+      a += v.x;
+      q += v.y;
+    }
+    sm_ch[c] = a;
+    sm_ch[C + c] = q;
+  }
+  __syncthreads();
+  {
+    const int o = threadIdx.x >> 3, sub = threadIdx.x & 7;       // o = g * 2 + (0: sum, 1: sum of squares)
+    float acc = 0.f;
+    if (o < 2 * groups) {
+      const float* src = sm_ch + (o & 1) * C + (o >> 1) * cpg;
+      for (int k = sub; k < cpg; k += 8) acc += src[k];
+    }
+    acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+    acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+    if (o < 2 * groups && sub == 0) s_grp[o] = acc;
+  }
+  cluster_arrive();
+  // while the peers finish: the first batch of this thread's pixels is already on its way from HBM
+  const int vpp = C / 8;
+  const int ppp = kGnThreads / vpp;
+  const int v = threadIdx.x % vpp;
+  const int pl = threadIdx.x / vpp;
+  const int chunk = (hw + R - 1) / R;
+  const int p_begin = rank * chunk;
+  const int p_end = min(hw, p_begin + chunk);
+  const size_t base = static_cast<size_t>(img) * hw;
+  uint4 u[8];
+  if (pl < ppp) {
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      u[k] = p_begin + pl + k * ppp < p_end ? gn_load(s, base + p_begin + pl + k * ppp, v * 8) : make_uint4(0, 0, 0, 0);
+  }
+  cluster_wait();
+  if (threadIdx.x < 2 * groups) {
+    float tot = 0.f;
+    for (int r = 0; r < R; ++r) tot += ld_dsmem(&s_grp[threadIdx.x], static_cast<uint32_t>(r));
+    s_fin[threadIdx.x] = tot;
+  }
+  cluster_arrive();                              // my remote reads are done (matched by the wait before exit)
+  __syncthreads();
+  float mean = 0.f, rstd = 0.f;
+  if (threadIdx.x < groups) {
+    const float inv_n = 1.0f / (static_cast<float>(hw) * cpg);
+    mean = s_fin[2 * threadIdx.x] * inv_n;
+    rstd = rsqrtf(fmaxf(s_fin[2 * threadIdx.x + 1] * inv_n - mean * mean, 0.f) + eps);
+  }
+  __syncthreads();
+  if (threadIdx.x < groups) {
+    s_fin[2 * threadIdx.x] = mean;
+    s_fin[2 * threadIdx.x + 1] = rstd;
+  }
+  __syncthreads();
+  if (pl < ppp) {
+    float sc[8], sh[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int c = v * 8 + j;
+      const int g = c / cpg;
+      sc[j] = s_fin[g * 2 + 1] * __ldg(gamma + c);
+      sh[j] = __ldg(beta + c) - s_fin[g * 2] * sc[j];
+    }
+    auto norm_store = [&](const uint4& u, size_t pix) {
+      uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float lo = fmaf(bf16_lo(w[j]), sc[2 * j], sh[2 * j]);
+        float hi = fmaf(bf16_hi(w[j]), sc[2 * j + 1], sh[2 * j + 1]);
+        if (silu) {
+          lo = silu_tanh(lo);
+          hi = silu_tanh(hi);
+        }
+        w[j] = pack_bf16(lo, hi);
+      }
+      *reinterpret_cast<uint4*>(y + pix * C + v * 8) = make_uint4(w[0], w[1], w[2], w[3]);
+    };
+    for (int p = p_begin + pl; p < p_end; p += 8 * ppp) {
+      if (p != p_begin + pl) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          u[k] = p + k * ppp < p_end ? gn_load(s, base + p + k * ppp, v * 8) : make_uint4(0, 0, 0, 0);
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (p + k * ppp < p_end) norm_store(u[k], base + p + k * ppp);
+    }
+  }
+  cluster_wait();                                // no CTA leaves while a peer may still read its s_grp
+}
+
 // One warp per kRows rows (all loads of the warp's rows are issued before the first reduction, so enough
 // bytes are in flight per SM to cover HBM latency); rows live in registers between the two passes.
 template <int kVecPerLane, int kRows>
@@ -434,7 +577,8 @@ int groupnorm_launch(const GroupNormOp& op, cudaStream_t stream) {
   const int ppp = kGnThreads / (C / 8);
   // >= 4 pixels per pixel-lane per CTA; ONE wave of 3 resident CTAs per SM: fat CTAs amortise the
   // per-CTA reduction / ticket tail (37 thin chunks per image ran the statistics pass at 27% of HBM peak)
-  int chunks = std::max(1, std::min(op.hw / (4 * ppp), (3 * 148) / std::max(1, op.n_img)));
+  static const int slots = [] { const char* e = getenv("SONIC_GN_SLOTS"); return e ? atoi(e) : 3 * 148; }();
+  int chunks = std::max(1, std::min(op.hw / (4 * ppp), slots / std::max(1, op.n_img)));
   chunks = std::min(chunks, kGroupNormMaxChunks);
   dim3 grid(chunks, op.n_img);
   const size_t smem = static_cast<size_t>(ppp) * 2 * C * sizeof(float);
@@ -442,6 +586,31 @@ int groupnorm_launch(const GroupNormOp& op, cudaStream_t stream) {
   if (op.part0) {
     SONIC_REQUIRE(op.hw % 32 == 0, "groupnorm: fused statistics need hw %% 32 == 0 (got %d)", op.hw);
     SONIC_REQUIRE(s.ld0 == s.c0 && (!op.x1 || s.ld1 == s.c1), "groupnorm: fused statistics need dense rows");
+    // One launch: a cluster of R <= 8 CTAs per image (gn_cluster_kernel).  R: one wave of two CTAs per SM and at least
+    // four pixels per pixel lane and CTA.  Measured at UNet batch 32: 2.05 -> 1.73 ms per step over the 61 GroupNorms
+    // (64x64x320 + SiLU: 48.7 -> 40.1 us); clusters of 9 CTAs place badly (54.8 us), and 16 x 16 CTAs on the VAE
+    // decoder's 1 GB tensors lose to the 432 CTAs of the two-kernel form (42.2 vs 40.7 ms per decode), so large
+    // tensors of small batches keep the finalize + apply pair.  SONIC_GN_CLUSTER=0 disables this path (A/B).
+    static const int fused_mode = [] { const char* e = getenv("SONIC_GN_CLUSTER"); return e ? atoi(e) : 1; }();
+    const int R = std::min(std::min(8, (2 * 148) / std::max(1, op.n_img)), std::max(1, op.hw / (4 * ppp)));
+    const bool small = static_cast<size_t>(op.n_img) * op.hw * C * 2 < (8u << 20);      // latency-bound either way
+    if (fused_mode && op.groups <= 32 && (R * op.n_img >= 200 || small)) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(R, op.n_img);
+      cfg.blockDim = dim3(kGnThreads);
+      cfg.dynamicSmemBytes = static_cast<size_t>(2 * C) * sizeof(float);
+      cfg.stream = stream;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = R;
+      attr[0].val.clusterDim.y = 1;
+      attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr;
+      cfg.numAttrs = 1;
+      SONIC_CUDA(cudaLaunchKernelEx(&cfg, gn_cluster_kernel, s, op.part0, op.part1, op.hw, op.groups, op.eps, op.gamma,
+                                    op.beta, op.silu, static_cast<__nv_bfloat16*>(op.y)));
+      return 0;
+    }
     gn_finalize_kernel<<<dim3(op.groups, op.n_img), 128, 0, stream>>>(op.part0, s.c0, op.part1, s.c1, op.hw, op.groups,
                                                                       op.eps, op.stats);
   } else {

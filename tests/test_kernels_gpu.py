@@ -202,7 +202,9 @@ def test_layout_helpers(cuda):
     assert torch.equal(back, a[..., :4].float().permute(0, 3, 1, 2))
 
 
-@pytest.mark.parametrize("B,hw,C0,C1,N0", [(2, 4096, 320, 0, 320), (3, 1024, 640, 320, 640), (2, 64, 1280, 1280, 1280)])
+@pytest.mark.parametrize("B,hw,C0,C1,N0", [(2, 4096, 320, 0, 320), (3, 1024, 640, 320, 640), (2, 64, 1280, 1280, 1280),
+                                          (32, 4096, 320, 0, 320), (16, 1024, 640, 640, 640), (32, 64, 1280, 1280, 1280),
+                                          (5, 256, 1280, 640, 1280)])
 def test_groupnorm_with_gemm_epilogue_statistics(cuda, B, hw, C0, C1, N0):
     """The GEMM epilogue pre-reduces (sum, sumsq) of its OUTPUT per 32-row block; sonic_groupnorm_fused must give
     the same result as the two-pass kernel and as torch.group_norm on the same tensors (single and concat)."""
