@@ -34,8 +34,16 @@ constexpr int kMaxGranules = 8;            // 16-column granules per epilogue wa
 constexpr int kEpiWarps = 8;
 constexpr int kChunkCols = 32;             // output columns per staged chunk (64 B of bf16: one swizzle-64B row)
 constexpr int kStgBufBytes = 32 * kChunkCols * 2;       // 32 rows x 64 B
-constexpr int kStgBufs = 2;                // staging buffers per epilogue warp
-constexpr int kStgBytes = kEpiWarps * kStgBufs * kStgBufBytes;   // 32 KB
+#ifndef SONIC_STG_BUFS
+#define SONIC_STG_BUFS 4
+#endif
+#ifndef SONIC_STG_PENDING
+#define SONIC_STG_PENDING 2
+#endif
+constexpr int kStgBufs = SONIC_STG_BUFS;   // staging buffers per epilogue warp: a ring -- residual chunks are requested
+constexpr int kStgPending = SONIC_STG_PENDING;   // kStgBufs - kStgPending chunks ahead (across tile boundaries) while up to
+                                           // kStgPending tile stores drain behind
+constexpr int kStgBytes = kEpiWarps * kStgBufs * kStgBufBytes;   // 64 KB (6 buffers / 96 KB cost two pipeline stages: slower)
 
 // GELU (erf form, what diffusers' GEGLU computes) as x * sigmoid(2u), u = x (a + b x^2 + c x^4): the
 // tanh-form GELU with its inner polynomial re-fitted (minimax, tools/fit_gelu.py) against the ERF form:
@@ -245,7 +253,7 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
     uint8_t* stg = stg_base + ew * (kStgBufs * kStgBufBytes);
     uint64_t* r_full = res_full + ew * kStgBufs;
     const uint32_t sw = (lane >> 1) & 3;         // swizzle-64B: 16-byte piece j of row r sits at j ^ ((r >> 1) & 3)
-    uint32_t slot = 0;                           // chunks staged so far: buffer = slot & 1, phase = (slot >> 1) & 1
+    uint32_t slot = 0;                           // chunks staged so far: buffer = slot % kStgBufs, phase = (slot / kStgBufs) & 1
     int acc = 0;
     uint32_t acc_phase = 0;
     int ti = 0;
@@ -261,6 +269,34 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
     float rs_next = 1.f;
     if (p.row_scale && worker < total_tiles)
       rs_next = __ldcg(p.row_scale + min(m_tile_of(worker) * kTileM + quarter * 32 + lane, p.M - 1));
+    // Residual ring (lane 0 only): a load cursor runs kStgBufs - 1 chunks ahead of the chunk being processed, across
+    // tile boundaries.  A clock64 trace of the K = 320 +residual projection showed the epilogue as the bottleneck
+    // (5000 cycles per tile against 1850 of MMA): each chunk waited ~1000 cycles for its residual box and each tile
+    // start ~1000 cycles for a store to release its buffer, because the small epilogue TMA operations queue behind
+    // the operand boxes of the producer warp.  With three residual boxes in flight those waits overlap.
+    int l_tile = worker, l_ti = 0, l_i = 0;
+    uint32_t l_slot = 0;
+    auto issue_next_residual = [&]() {           // lane 0
+      while (l_tile < total_tiles) {
+        const int half = (n_chunks & 1) ? (col_half0 ^ (l_ti & 1)) : col_half0;
+        const int oc0 = (l_tile % p.n_tiles) * out_cols;
+        const int c = half + 2 * l_i;
+        if (c < n_chunks && oc0 + c * kChunkCols < p.n_out_total) {
+          const uint32_t b = l_slot % kStgBufs;
+          mbar_expect_tx(&r_full[b], kStgBufBytes);
+          tma_load_2d(stg + b * kStgBufBytes, &p.tm_res, &r_full[b], oc0 + c * kChunkCols,
+                      m_tile_of(l_tile) * kTileM + quarter * 32);
+          ++l_i;
+          ++l_slot;
+          return;
+        }
+        l_tile += n_workers;
+        ++l_ti;
+        l_i = 0;
+      }
+    };
+    if (has_res && lane == 0)
+      for (int k = 0; k < kStgBufs - kStgPending; ++k) issue_next_residual();
     for (int tile = worker; tile < total_tiles; tile += n_workers, ++ti) {
       if (threadIdx.x == 64) GEMM_TRACE(2, ti, 0);
       const int n_tile = tile % p.n_tiles;
@@ -277,7 +313,6 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
       // The two swap roles on every tile, so over two tiles both do 5 -- the double-buffered accumulators let the
       // lighter warp run ahead into the next tile instead of idling at tmem_full (ncu: 26 % of epilogue time).
       const int col_half = (n_chunks & 1) ? (col_half0 ^ (ti & 1)) : col_half0;
-      const int col_half_next = (n_chunks & 1) ? (col_half ^ 1) : col_half0;
       int my_n = 0;                                          // chunks col_half, col_half + 2, ... inside the matrix
       for (int c = col_half; c < n_chunks && ocol0 + c * kChunkCols < p.n_out_total; c += 2) ++my_n;
       const float rs = rs_next;
@@ -287,21 +322,6 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
           rs_next = __ldcg(p.row_scale + min(m_tile_of(tile2) * kTileM + quarter * 32 + lane, p.M - 1));
       }
       float rs_sum = 0.f, rs_sq = 0.f;                       // producer side: statistics of this lane's output row
-      if (has_res && lane == 0) {
-        // residual of the NEXT tile into L2 now; this tile's first chunk into the staging buffer
-        const int tile2 = tile + n_workers;
-        if (tile2 < total_tiles) {
-          const int o2 = (tile2 % p.n_tiles) * out_cols, r2 = m_tile_of(tile2) * kTileM + quarter * 32;
-          for (int c = col_half_next; c < n_chunks && o2 + c * kChunkCols < p.n_out_total; c += 2)
-            tma_prefetch_l2_2d(&p.tm_res, o2 + c * kChunkCols, r2);
-        }
-        if (my_n > 0) {
-          const uint32_t b = slot & 1;
-          bulk_wait_read<1>();                               // the store that last used this buffer has read it
-          mbar_expect_tx(&r_full[b], kStgBufBytes);
-          tma_load_2d(stg + b * kStgBufBytes, &p.tm_res, &r_full[b], ocol0 + col_half * kChunkCols, row0);
-        }
-      }
       if (threadIdx.x == 64) GEMM_TRACE(2, ti, 1);
       mbar_wait<64>(&tmem_full[acc], acc_phase);
       if (threadIdx.x == 64) GEMM_TRACE(2, ti, 2);
@@ -313,7 +333,7 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
       }
       for (int i = 0; i < my_n; ++i) {
         const int c = col_half + 2 * i;
-        const uint32_t b = slot & 1;
+        const uint32_t b = slot % kStgBufs;
         uint8_t* buf = stg + b * kStgBufBytes;
         uint32_t v[32];
         float f[32];
@@ -382,7 +402,7 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
         }
         uint8_t* my_row = buf + lane * 64;
         if (has_res) {
-          mbar_wait<64>(&r_full[b], (slot >> 1) & 1);
+          mbar_wait<64>(&r_full[b], (slot / kStgBufs) & 1);
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const uint4 rr = *reinterpret_cast<const uint4*>(my_row + ((q ^ sw) << 4));
@@ -392,7 +412,7 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
             f[8 * q + 6] += bf16_lo(rr.w); f[8 * q + 7] += bf16_hi(rr.w);
           }
         } else {
-          if (lane == 0) bulk_wait_read<1>();                // the store that last used this buffer has read it
+          if (lane == 0) bulk_wait_read<kStgBufs - 1>();     // the store that last used this buffer has read it
           __syncwarp();
         }
         uint32_t pk[16];
@@ -448,11 +468,9 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
             tma_store_2d(&p.tm_out, buf, ocol0 + c * kChunkCols, row0);
           }
           bulk_commit();
-          if (has_res && i + 1 < my_n) {                     // next chunk's residual into the other buffer
-            const uint32_t nb = b ^ 1;
-            bulk_wait_read<1>();
-            mbar_expect_tx(&r_full[nb], kStgBufBytes);
-            tma_load_2d(stg + nb * kStgBufBytes, &p.tm_res, &r_full[nb], ocol0 + (c + 2) * kChunkCols, row0);
+          if (has_res) {                                     // the ring's next box goes into the buffer chunk P - kStgPending
+            bulk_wait_read<kStgPending>();                   // used, once its store has read it
+            issue_next_residual();
           }
         }
         if (i == 0 && threadIdx.x == 64) GEMM_TRACE(3, ti, 3);
@@ -673,7 +691,7 @@ int gemm_plan(const GemmOp& op, GemmPlan* plan) {
   p.row_scale = op.row_scale;
   {
     const char* e = getenv("SONIC_GELU_TANH");               // experiment switch: one-MUFU GELU in the folded GEGLU epilogue
-    p.gelu_tanh = (e && e[0] == '1') ? 1 : 0;
+    p.gelu_tanh = (e && e[0] == '0') ? 0 : 1;
   }
   SONIC_REQUIRE((op.ln_stats_out == nullptr && op.row_scale == nullptr) || p.tma_epilogue,
                 "gemm: folded LayerNorm needs the staged epilogue (block_n %% 32 == 0, contiguous 128-row tiles)");
@@ -698,7 +716,7 @@ int gemm_plan(const GemmOp& op, GemmPlan* plan) {
   p.total_work = p.pair ? ((p.m_tiles + 1) / 2) * p.n_tiles : p.m_tiles * p.n_tiles;
   const int b_rows = p.pair ? p.block_n / 2 : p.block_n;
   const int stage_bytes = kABytes + b_rows * kTileK * 2;
-  p.stages = std::max(2, std::min(8, (225 * 1024 - kStgBytes) / stage_bytes));
+  p.stages = std::max(2, std::min(8, (224 * 1024 - kStgBytes) / stage_bytes));
   p.idesc = make_idesc_bf16(p.pair ? 2 * kTileM : kTileM, p.block_n, false);
   p.acc_stride = (p.block_n + 31) / 32 * 32;
   p.n_acc = std::max(2, std::min(kMaxAcc, 512 / p.acc_stride));
@@ -786,7 +804,7 @@ int gemm_plan(const GemmOp& op, GemmPlan* plan) {
     }
   }
   plan->grid = p.pair ? 2 * std::min(p.total_work, g_num_sms / 2) : std::min(p.total_work, g_num_sms);
-  plan->smem = static_cast<size_t>(p.stages) * stage_bytes + kStgBytes + 1024 /*align*/ + 512 /*barriers*/;
+  plan->smem = static_cast<size_t>(p.stages) * stage_bytes + kStgBytes + 1024 /*align*/ + 1024 /*barriers*/;
   // algorithmic work of the operator (a 9-tap convolution of every OUTPUT pixel), whatever the kernel executes: the
   // phase form of the upsample convolution runs 4/9 of it
   // (likewise the side-tensor K chunk of a folded LayerNorm is not algorithmic work)
