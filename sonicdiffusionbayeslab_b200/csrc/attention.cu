@@ -87,36 +87,94 @@ __device__ __forceinline__ float fast_exp2(float x) {
   return y;
 }
 
-// exp2 on the FMA / integer pipes: the MUFU unit (16 ex2 per clock and SM) is what bounds the d <= 64 kernels, while
-// two thirds of the issue slots are idle, so kPolyOf8 of every eight exponentials of a row go this way instead.
-// Round-to-nearest split x = j + r (magic-number add), degree-3 minimax polynomial of 2^r on [-1/2, 1/2] (relative
-// error 7.5e-5, a 26th of the bf16 rounding P gets anyway), j added to the exponent field.  The clamp keeps the
-// exponent arithmetic in range: the low side flushes to 2^-125, the high side stays far above the speculative
-// pass's 2^8 bound, so an out-of-range score still forces the checked path.
+// ---- the exponentials of a score row, two at a time ----------------------------------------------------------
+// The d <= 64 kernels are bound by the MUFU unit (16 ex2 per clock and SM) AND short of issue slots (stall sampling:
+// 17 % selected, 29 % fixed-latency waits with two softmax warps per sub-partition), so the arithmetic around the
+// exponentials is done on register PAIRS with Blackwell's packed fp32 instructions (fma.rn.f32x2 / add.rn.f32x2 ->
+// SASS FFMA2 / FADD2): one instruction scales two scores, one adds two exponentials to the row sum -- 5 issue slots
+// per pair instead of 7 -- and kPolyOf8 of every eight pairs take their exponentials from the FMA pipe instead of
+// the MUFU unit: round-to-nearest split x = j + r (magic-number add), degree-3 minimax polynomial of 2^r on
+// [-1/2, 1/2] (relative error 7.5e-5, a 26th of the bf16 rounding P gets anyway), j added to the exponent field.
+// The clamp keeps the exponent arithmetic in range: the low side flushes to 2^-125, the high side stays far above
+// the speculative pass's 2^8 bound, so an out-of-range score still forces the checked path.  The speculative and
+// the checked pass share this code, so they stay bit-identical.
 #ifndef SONIC_ATT_POLY
 #define SONIC_ATT_POLY 1
 #endif
 constexpr int kPolyOf8 = SONIC_ATT_POLY;
-__device__ __forceinline__ float poly_exp2(float x) {
-  x = fminf(fmaxf(x, -125.0f), 125.0f);
-  const float t = x + 12582912.0f;                     // 1.5 * 2^23: the integer part lands in the low mantissa bits
-  const float r = x - (t - 12582912.0f);
-  float p = fmaf(0x1.c3f6a6p-5f, r, 0x1.f0ddccp-3f);
-  p = fmaf(p, r, 0x1.62f31ap-1f);
-  p = fmaf(p, r, 0x1.fff694p-1f);
-  return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
 }
-// Element i of a row (compile-time after unrolling): which unit computes its exponential.  The same map is used by
-// the speculative and the checked pass, so both stay bit-identical.
-__device__ __forceinline__ constexpr bool poly_slot(int i) {
+__device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ constexpr bool poly_pair(int j) {          // pair j of a row (compile-time after unrolling)
   return kPolyOf8 >= 8 ? true
-       : kPolyOf8 == 4 ? (i & 1) == 1
-       : kPolyOf8 == 3 ? ((i & 7) == 2 || (i & 7) == 5 || (i & 7) == 7)
-       : kPolyOf8 == 2 ? (i & 3) == 3
-       : kPolyOf8 == 1 ? (i & 7) == 7
+       : kPolyOf8 == 4 ? (j & 1) == 1
+       : kPolyOf8 == 3 ? ((j & 7) == 2 || (j & 7) == 5 || (j & 7) == 7)
+       : kPolyOf8 == 2 ? (j & 3) == 3
+       : kPolyOf8 == 1 ? (j & 7) == 7
        : false;
 }
-__device__ __forceinline__ float mix_exp2(int i, float x) { return poly_slot(i) ? poly_exp2(x) : fast_exp2(x); }
+__device__ __forceinline__ void poly_exp2_pair(uint64_t x2, float& e0, float& e1) {
+  float x0, x1;
+  unpack2(x2, x0, x1);
+  x0 = fminf(fmaxf(x0, -125.0f), 125.0f);
+  x1 = fminf(fmaxf(x1, -125.0f), 125.0f);
+  const uint64_t xc = pack2(x0, x1);
+  const uint64_t t2 = fadd2(xc, pack2(12582912.0f, 12582912.0f));    // 1.5 * 2^23: the integer part lands in the low mantissa bits
+  const uint64_t j2 = fadd2(t2, pack2(-12582912.0f, -12582912.0f));
+  const uint64_t r2 = ffma2(j2, pack2(-1.0f, -1.0f), xc);
+  uint64_t p2 = ffma2(pack2(0x1.c3f6a6p-5f, 0x1.c3f6a6p-5f), r2, pack2(0x1.f0ddccp-3f, 0x1.f0ddccp-3f));
+  p2 = ffma2(p2, r2, pack2(0x1.62f31ap-1f, 0x1.62f31ap-1f));
+  p2 = ffma2(p2, r2, pack2(0x1.fff694p-1f, 0x1.fff694p-1f));
+  float p0, p1, t0, t1;
+  unpack2(p2, p0, p1);
+  unpack2(t2, t0, t1);
+  e0 = __int_as_float(__float_as_int(p0) + (__float_as_int(t0) << 23));
+  e1 = __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23));
+}
+// kN scores v[0 .. kN) (row columns col0 ...) -> bf16 pairs pk[0 .. kN / 2), exponentials added to the four pair
+// accumulators.  scale2 = (c, c), nms2 = (-m c, -m c).
+template <int kN, bool kMask>
+__device__ __forceinline__ void exp_row(const uint32_t* v, uint32_t* pk, int col0, int valid, uint64_t scale2, uint64_t nms2,
+                                        uint64_t (&acc)[4]) {
+#pragma unroll
+  for (int i = 0; i < kN; i += 2) {
+    const uint64_t x2 = ffma2(pack2(__uint_as_float(v[i]), __uint_as_float(v[i + 1])), scale2, nms2);
+    float e0, e1;
+    if (poly_pair(i >> 1)) {
+      poly_exp2_pair(x2, e0, e1);
+    } else {
+      float x0, x1;
+      unpack2(x2, x0, x1);
+      e0 = fast_exp2(x0);
+      e1 = fast_exp2(x1);
+    }
+    if (kMask && col0 + i >= valid) e0 = 0.f;
+    if (kMask && col0 + i + 1 >= valid) e1 = 0.f;
+    acc[(i >> 1) & 3] = fadd2(acc[(i >> 1) & 3], pack2(e0, e1));
+    pk[i >> 1] = pack_bf16(e0, e1);
+  }
+}
+__device__ __forceinline__ float sum_acc(const uint64_t (&acc)[4]) {
+  float a[8];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) unpack2(acc[k], a[2 * k], a[2 * k + 1]);
+  return ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
+}
 
 template <int kDPV>
 __global__ void __launch_bounds__(kAttThreads, (kDPV <= 64 ? 4 : 2))
@@ -274,18 +332,12 @@ attention_kernel(const __grid_constant__ AttParams p) {
         // it overwrites the scores the fallback needs.
         if (t > 0 && w == kSub && p.speculate) {
           const float ms = m_run * p.scale_log2;
-          float ps[4] = {0.f, 0.f, 0.f, 0.f};
+          uint64_t acc[4] = {0ull, 0ull, 0ull, 0ull};
           uint32_t v[kSub], pk[kSub / 2];
           tmem_ld64(t_s, v);
           tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < kSub; i += 2) {
-            const float e0 = mix_exp2(i, fmaf(__uint_as_float(v[i]), p.scale_log2, -ms));
-            const float e1 = mix_exp2(i + 1, fmaf(__uint_as_float(v[i + 1]), p.scale_log2, -ms));
-            ps[(i >> 1) & 3] += e0 + e1;
-            pk[i >> 1] = pack_bf16(e0, e1);
-          }
-          const float tot = (ps[0] + ps[1]) + (ps[2] + ps[3]);
+          exp_row<kSub, false>(v, pk, 0, kSub, pack2(p.scale_log2, p.scale_log2), pack2(-ms, -ms), acc);
+          const float tot = sum_acc(acc);
           if (!__any_sync(0xffffffffu, !(tot <= 256.0f))) {
             tmem_st32(t_s, pk);
             l_run += tot;
@@ -329,7 +381,8 @@ attention_kernel(const __grid_constant__ AttParams p) {
       // pass 2: P = exp2(S*c - m*c) as bf16 pairs, written over S columns [0, 32): chunk c of S (columns
       // c..c+31) becomes P columns c/2..c/2+15, which only covers S columns this thread has already read.
       const float m_scaled = m_run * p.scale_log2;
-      float ps[4] = {0.f, 0.f, 0.f, 0.f};
+      const uint64_t scale2 = pack2(p.scale_log2, p.scale_log2), nms2 = pack2(-m_scaled, -m_scaled);
+      uint64_t acc[4] = {0ull, 0ull, 0ull, 0ull};
 #pragma unroll
       for (int c = 0; c < kSub; c += 32) {
         if (c >= w) break;
@@ -337,18 +390,10 @@ attention_kernel(const __grid_constant__ AttParams p) {
         tmem_ld32(t_s + c, v);
         tmem_ld_wait();
         uint32_t pk[16];
-#pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          float e0 = mix_exp2(i, fmaf(__uint_as_float(v[i]), p.scale_log2, -m_scaled));
-          float e1 = mix_exp2(i + 1, fmaf(__uint_as_float(v[i + 1]), p.scale_log2, -m_scaled));
-          if (kMask && c + i >= valid) e0 = 0.f;
-          if (kMask && c + i + 1 >= valid) e1 = 0.f;
-          ps[(i >> 1) & 3] += e0 + e1;
-          pk[i >> 1] = pack_bf16(e0, e1);
-        }
+        exp_row<32, kMask>(v, pk, c, valid, scale2, nms2, acc);
         tmem_st16(t_s + (c >> 1), pk);
       }
-      l_run += (ps[0] + ps[1]) + (ps[2] + ps[3]);
+      l_run += sum_acc(acc);
     };
 
     uint32_t n_item = 0;
@@ -592,16 +637,10 @@ attention2_kernel(const __grid_constant__ AttParams p) {
         // the scores of this sub-tile exceed the running maximum) fall through and redo the row the careful way.
         if (t > 0 && p.speculate) {
           const float ms = m_r * p.scale_log2;
-          float ps[4] = {0.f, 0.f, 0.f, 0.f};
+          uint64_t acc[4] = {0ull, 0ull, 0ull, 0ull};
           uint32_t pk[kW / 2];
-#pragma unroll
-          for (int i = 0; i < kW; i += 2) {
-            const float e0 = mix_exp2(i, fmaf(__uint_as_float(v[i]), p.scale_log2, -ms));
-            const float e1 = mix_exp2(i + 1, fmaf(__uint_as_float(v[i + 1]), p.scale_log2, -ms));
-            ps[(i >> 1) & 3] += e0 + e1;
-            pk[i >> 1] = pack_bf16(e0, e1);
-          }
-          const float tot = (ps[0] + ps[1]) + (ps[2] + ps[3]);
+          exp_row<kW, false>(v, pk, 0, kW, pack2(p.scale_log2, p.scale_log2), pack2(-ms, -ms), acc);
+          const float tot = sum_acc(acc);
           if (!__any_sync(0xffffffffu, !(tot <= 256.0f))) {
             tmem_st32(t_s, pk);
             l_r += tot;
@@ -634,21 +673,13 @@ attention2_kernel(const __grid_constant__ AttParams p) {
         m_r = m_new;
       }
       const float m_scaled = m_r * p.scale_log2;
-      float ps[4] = {0.f, 0.f, 0.f, 0.f};
+      uint64_t acc[4] = {0ull, 0ull, 0ull, 0ull};
       uint32_t pk[kW / 2];
-#pragma unroll
-      for (int i = 0; i < kW; i += 2) {
-        float e0 = mix_exp2(i, fmaf(__uint_as_float(v[i]), p.scale_log2, -m_scaled));
-        float e1 = mix_exp2(i + 1, fmaf(__uint_as_float(v[i + 1]), p.scale_log2, -m_scaled));
-        if (kMask && i >= valid) e0 = 0.f;
-        if (kMask && i + 1 >= valid) e1 = 0.f;
-        ps[(i >> 1) & 3] += e0 + e1;
-        pk[i >> 1] = pack_bf16(e0, e1);
-      }
+      exp_row<kW, kMask>(v, pk, 0, valid, pack2(p.scale_log2, p.scale_log2), pack2(-m_scaled, -m_scaled), acc);
       if constexpr (kW == 64) tmem_st32(t_s, pk);
       else if constexpr (kW == 32) tmem_st16(t_s, pk);
       else tmem_st8(t_s, pk);
-      l_r += (ps[0] + ps[1]) + (ps[2] + ps[3]);
+      l_r += sum_acc(acc);
     };
 
     uint32_t n_item = 0;
