@@ -26,10 +26,15 @@ for r in rd:
 
 
 def short(name):
-    m = re.search(r"(\w+)(<[^(]*>)?\(", name)
+    m = re.search(r"(\w*kernel\w*)\s*[<(]", name)
     base = m.group(1) if m else name[:32]
     t = re.search(base + r"<\(int\)(\d+)", name)
-    return f"{base}<{t.group(1)}>" if t else base
+    if t:
+        return f"{base}<{t.group(1)}>"
+    t = re.search(base + r"<\(bool\)(\d)>", name)
+    if t and base == "conv_gemm_kernel":
+        return f"{base}<{'pair' if t.group(1) == '1' else 'single'}>"
+    return base
 
 
 agg = OrderedDict()
@@ -47,7 +52,8 @@ for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1]):
 os.makedirs(os.path.join(root, "profiles"), exist_ok=True)
 open(os.path.join(root, "profiles", f"{tag}_launch_list_summary.md"), "w").write("\n".join(out) + "\n")
 shutil.copy(src, os.path.join(root, "profiles", f"{tag}_launches.csv"))
-g = agg.get("conv_gemm_kernel")
+gs = [a for k, a in agg.items() if k.startswith("conv_gemm_kernel")]
+g = [sum(a[i] for a in gs) for i in range(4)] if gs else None
 if g:
     json.dump({"conv_gemm_kernel": {"launches": g[0], "dram_read_bytes": g[2], "dram_write_bytes": g[3],
                                     "source": f"profiles/{tag}_launches.csv (ncu, one UNet step at UNet batch 32, cold cache per launch)"}},
