@@ -477,19 +477,27 @@ constexpr int kStages2 = 4;
 // current one is processed.
 // kNarrow: the last key sub-tile is ragged and spans only 16 or 32 columns (77 keys: 64 + 16).  A template flag because
 // the extra selects cost the full-width instantiation 4.7 % (1.433 -> 1.500 ms on the 4096-token self-attention).
+// Head dims above 64 can run the same kernel with two / three 64-column shared-memory atoms per Q / K / V tile and 256
+// TMEM columns per query tile: ONE CTA per SM (512 columns) whose four softmax warps ping-pong between two tiles.
+// That wins where the one-tile kernel only fits one CTA per SM (d = 136 ... 160: the UNet's 16x16 level, 39.6 -> 28.8 us)
+// and loses 5 % at d = 80, which keeps the one-tile kernel (attention_plan).
 template <int kDPV, bool kResident, bool kNarrow>
-__global__ void __launch_bounds__(kAttThreads, 2)
+__global__ void __launch_bounds__(kAttThreads, (kDPV <= 64 ? 2 : 1))
 attention2_kernel(const __grid_constant__ AttParams p) {
-  static_assert(kSub + kDPV <= 128, "S/P + O of one query tile must fit 128 TMEM columns");
+  constexpr int kTileCols = kSub + kDPV <= 128 ? 128 : 256;     // TMEM columns of one query tile: S / P, then O
+  static_assert(kSub + kDPV <= 256, "S/P + O of one query tile must fit 256 TMEM columns");
+  static_assert(kDPV <= 64 || (!kResident && !kNarrow), "head dims > 64: streaming form with full sub-tiles only");
+  constexpr int kAtoms = (kDPV + 63) / 64;        // 64-column smem atoms per Q / K / V row (== p.atoms)
+  constexpr int kQTile = kAtoms * kQAtomBytes, kKvTile = kAtoms * kKvAtomBytes;
   constexpr int kQStages = kResident ? 2 : 1;     // pairs of Q tiles in flight
-  constexpr int kKvStages = kResident ? 2 : kStages2;
+  constexpr int kKvStages = kResident ? 2 : (kAtoms == 3 ? 2 : kStages2);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
-  uint8_t* sm_q = smem;                                   // kQStages x 2 tiles x 16 KB (head dim <= 64: one atom)
-  uint8_t* sm_k = sm_q + kQStages * 2 * kQAtomBytes;      // kKvStages x 8 KB
-  uint8_t* sm_v = sm_k + kKvStages * kKvAtomBytes;        // kKvStages x 8 KB
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sm_v + kKvStages * kKvAtomBytes);
+  uint8_t* sm_q = smem;                                   // kQStages x 2 tiles x kAtoms x 16 KB
+  uint8_t* sm_k = sm_q + kQStages * 2 * kQTile;           // kKvStages x kAtoms x 8 KB
+  uint8_t* sm_v = sm_k + kKvStages * kKvTile;             // kKvStages x kAtoms x 8 KB
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sm_v + kKvStages * kKvTile);
   uint64_t* q_full = bars;                        // [2]
   uint64_t* q_empty = bars + 2;                   // [2] every S product of the pair in this Q stage is complete
   uint64_t* k_full = bars + 4;                    // [kStages2]
@@ -522,7 +530,7 @@ attention2_kernel(const __grid_constant__ AttParams p) {
     mbar_init(o_done, 1);
     fence_barrier_init();
   }
-  if (warp == kWarpMma) tmem_alloc<256>(tmem_slot);
+  if (warp == kWarpMma) tmem_alloc<2 * kTileCols>(tmem_slot);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -535,20 +543,26 @@ attention2_kernel(const __grid_constant__ AttParams p) {
         const int qs = i % kQStages;
         const int nq = tiles_of(pair0 + i);
         if (kResident) mbar_wait<256>(&q_empty[qs], ((i / kQStages) & 1) ^ 1);
-        mbar_expect_tx(&q_full[qs], nq * kQAtomBytes);
+        mbar_expect_tx(&q_full[qs], nq * kQTile);
         for (int q = 0; q < nq; ++q)
-          tma_load_4d(sm_q + (qs * 2 + q) * kQAtomBytes, &p.tm_q, &q_full[qs], 0, head,
-                      (pair0 + i) * 2 * kBlockQ + q * kBlockQ, batch);
+#pragma unroll
+          for (int a = 0; a < kAtoms; ++a)
+            tma_load_4d(sm_q + (qs * 2 + q) * kQTile + a * kQAtomBytes, &p.tm_q, &q_full[qs], a * 64, head,
+                        (pair0 + i) * 2 * kBlockQ + q * kBlockQ, batch);
       };
       load_q(0);
       for (int t = 0; t < n_sub; ++t) {
         const int st = t % kKvStages;
         if (!kResident) mbar_wait<512>(&k_empty[st], ((t / kKvStages) & 1) ^ 1);
-        mbar_expect_tx(&k_full[st], kKvAtomBytes);
-        tma_load_4d(sm_k + st * kKvAtomBytes, &p.tm_k, &k_full[st], 0, head, t * kSub, batch);
+        mbar_expect_tx(&k_full[st], kKvTile);
+#pragma unroll
+        for (int a = 0; a < kAtoms; ++a)
+          tma_load_4d(sm_k + st * kKvTile + a * kKvAtomBytes, &p.tm_k, &k_full[st], a * 64, head, t * kSub, batch);
         if (!kResident) mbar_wait<512>(&v_empty[st], ((t / kKvStages) & 1) ^ 1);
-        mbar_expect_tx(&v_full[st], kKvAtomBytes);
-        tma_load_4d(sm_v + st * kKvAtomBytes, &p.tm_v, &v_full[st], 0, head, t * kSub, batch);
+        mbar_expect_tx(&v_full[st], kKvTile);
+#pragma unroll
+        for (int a = 0; a < kAtoms; ++a)
+          tma_load_4d(sm_v + st * kKvTile + a * kKvAtomBytes, &p.tm_v, &v_full[st], a * 64, head, t * kSub, batch);
       }
       for (int i = 1; i < n_pairs; ++i) load_q(i);
     }
@@ -560,13 +574,15 @@ attention2_kernel(const __grid_constant__ AttParams p) {
     const uint64_t v_desc0 = make_sw128_desc(smem_u32(sm_v), kKvAtomBytes, 1024);
     constexpr int kMaxKS = (kDPV + 15) / 16;
     auto issue_s = [&](int qs, int q, int st, bool last) {   // S_q = Q_q K^T of the K tile in stage st
-      const uint64_t qd = q_desc0 + static_cast<uint64_t>(((qs * 2 + q) * kQAtomBytes) >> 4);
-      const uint64_t kd = k_desc0 + static_cast<uint64_t>((st * kKvAtomBytes) >> 4);
+      const uint64_t qd = q_desc0 + static_cast<uint64_t>(((qs * 2 + q) * kQTile) >> 4);
+      const uint64_t kd = k_desc0 + static_cast<uint64_t>((st * kKvTile) >> 4);
       const uint32_t idesc = kNarrow && last ? p.idesc_s_tail : p.idesc_s;   // a ragged last sub-tile only spans tail_w keys
       if (leader) {
 #pragma unroll
         for (int ks = 0; ks < kMaxKS; ++ks)
-          if (ks < k_steps_s) umma_bf16_ss(tmem_base + q * 128, qd + ((ks * 32) >> 4), kd + ((ks * 32) >> 4), idesc, ks != 0);
+          if (ks < k_steps_s)                      // K step ks: atom ks / 4, 32-byte slice ks % 4 of its 128-byte rows
+            umma_bf16_ss(tmem_base + q * kTileCols, qd + (((ks >> 2) * kQAtomBytes + (ks & 3) * 32) >> 4),
+                         kd + (((ks >> 2) * kKvAtomBytes + (ks & 3) * 32) >> 4), idesc, ks != 0);
         umma_commit(&s_full[q]);
       }
       __syncwarp();
@@ -592,8 +608,8 @@ attention2_kernel(const __grid_constant__ AttParams p) {
           mbar_wait<64>(&p_full[q], n_item & 1);
           if (q == 0) mbar_wait(&v_full[st], kResident ? 0 : (t / kKvStages) & 1);
           tc_fence_after();
-          const uint32_t ts = tmem_base + q * 128;
-          const uint64_t vd = v_desc0 + static_cast<uint64_t>((st * kKvAtomBytes) >> 4);
+          const uint32_t ts = tmem_base + q * kTileCols;
+          const uint64_t vd = v_desc0 + static_cast<uint64_t>((st * kKvTile) >> 4);
           const int pv_steps = !kNarrow || more ? kSub / 16 : p.tail_w / 16;
           if (leader) {
 #pragma unroll
@@ -693,7 +709,7 @@ attention2_kernel(const __grid_constant__ AttParams p) {
           if (q < nq) {
             int valid = p.seq_k - t * kSub;
             if (p.causal) valid = min(valid, q0 + q * kBlockQ + row - t * kSub + 1);
-            const uint32_t t_s = tmem_base + q * 128 + lane_addr;
+            const uint32_t t_s = tmem_base + q * kTileCols + lane_addr;
             mbar_wait<64>(&s_full[q], n_item & 1);
             tc_fence_after();
             using W64 = std::integral_constant<int, 64>;
@@ -719,7 +735,7 @@ attention2_kernel(const __grid_constant__ AttParams p) {
           const int s_idx = q0 + q * kBlockQ + row;
           const float inv = 1.0f / l_run[q];
           __nv_bfloat16* orow = p.o + (static_cast<size_t>(batch) * p.seq_q + s_idx) * p.ld_o + head * p.head_dim;
-          const uint32_t t_o = tmem_base + q * 128 + kSub + lane_addr;
+          const uint32_t t_o = tmem_base + q * kTileCols + kSub + lane_addr;
 #pragma unroll
           for (int c = 0; c < kDPV; c += 16) {
             uint32_t v[16];
@@ -748,7 +764,7 @@ attention2_kernel(const __grid_constant__ AttParams p) {
   __syncthreads();
   if (warp == kWarpMma) {
     tc_fence_after();
-    tmem_dealloc<256>(tmem_base);
+    tmem_dealloc<2 * kTileCols>(tmem_base);
   }
 }
 
@@ -768,8 +784,12 @@ int launch_att2(const AttentionPlan* pl, const AttParams& prm, cudaStream_t stre
 template <int kDPV>
 int dispatch_att2(const AttentionPlan* pl, const AttParams& prm, cudaStream_t stream) {
   const bool narrow = prm.tail_w < kSub;
-  if (pl->resident) return narrow ? launch_att2<kDPV, true, true>(pl, prm, stream) : launch_att2<kDPV, true, false>(pl, prm, stream);
-  return narrow ? launch_att2<kDPV, false, true>(pl, prm, stream) : launch_att2<kDPV, false, false>(pl, prm, stream);
+  if constexpr (kDPV > 64) {
+    return launch_att2<kDPV, false, false>(pl, prm, stream);      // attention_plan only sends full-sub-tile streaming shapes here
+  } else {
+    if (pl->resident) return narrow ? launch_att2<kDPV, true, true>(pl, prm, stream) : launch_att2<kDPV, true, false>(pl, prm, stream);
+    return narrow ? launch_att2<kDPV, false, true>(pl, prm, stream) : launch_att2<kDPV, false, false>(pl, prm, stream);
+  }
 }
 
 template <int kDPV>
@@ -825,6 +845,16 @@ int attention_plan(const AttentionOp& op, AttentionPlan** out) {
   if (!rc) rc = make_qkv_map(&pl->tm_v, op.v, op.ld_v, op.seq_k, op.batch, op.heads, op.head_dim, kSub);
   if (rc) { delete pl; return rc; }
   pl->qt = (pl->dpv <= 64 && op.seq_q > kBlockQ) ? 2 : 1;
+  {
+    // Head dims above 64 with whole 64-key sub-tiles: the two-tile kernel with one CTA per SM.  Measured at 32 x 8 heads,
+    // 1024 tokens (tools/att_dsweep.py): d = 136 / 160 (three smem atoms: the one-tile kernel fits ONE CTA per SM)
+    // 323-326 -> 202 us, d = 96 / 128 188 -> 182 us, but d = 72 / 80 162-166 -> 171-175 us (two one-tile CTAs per SM keep
+    // two softmax warps per sub-partition busy, the two-tile CTA only one) -- so d <= 80 stays on the one-tile kernel.
+    // SONIC_ATT2_WIDE=0 / 2: never / for every head dim above 64.
+    const char* e = getenv("SONIC_ATT2_WIDE");
+    const int wide_min = (e && e[0] == '0') ? 1 << 30 : (e && e[0] == '2') ? 65 : 128;
+    if (pl->dpv >= wide_min && op.seq_q > kBlockQ && op.seq_k % kSub == 0 && op.seq_k > 2 * kSub && !op.causal) pl->qt = 2;
+  }
   // Short key sequences (the cross-attention layers: 77 keys): the one-tile kernel in loop mode -- K / V resident, a
   // CTA walks over several query tiles, four (d <= 64) or two CTAs per SM -- sized so that ONE wave covers the grid.
   const int n_qt = (op.seq_q + kBlockQ - 1) / kBlockQ;
@@ -839,7 +869,7 @@ int attention_plan(const AttentionOp& op, AttentionPlan** out) {
     pl->qt = 1;
   }
   if (pl->qt == 2)
-    pl->smem = 2 * kQAtomBytes + 2 * kStages2 * kKvAtomBytes + 1024 + 256;
+    pl->smem = static_cast<size_t>(pl->atoms) * (2 * kQAtomBytes + 2 * (pl->atoms == 3 ? 2 : kStages2) * kKvAtomBytes) + 1024 + 256;
   else
     pl->smem = static_cast<size_t>(pl->atoms) * (kQAtomBytes + 4 * kKvAtomBytes) + 1024 + 256;
   // <= 128 keys and at least four query-tile pairs per head: one CTA per (batch, head) keeps K / V resident
@@ -873,7 +903,15 @@ int attention_launch(const AttentionPlan* pl, cudaStream_t stream) {
     const char* e = getenv("SONIC_ATT_SPEC");                         // "0": always take the checked path (A/B, tests)
     prm.speculate = (e && e[0] == '0') ? 0 : 1;
   }
-  if (pl->qt == 2) return pl->dpv == 48 ? dispatch_att2<48>(pl, prm, stream) : dispatch_att2<64>(pl, prm, stream);
+  if (pl->qt == 2) {
+    switch (pl->dpv) {
+      case 48: return dispatch_att2<48>(pl, prm, stream);
+      case 64: return dispatch_att2<64>(pl, prm, stream);
+      case 80: return dispatch_att2<80>(pl, prm, stream);
+      case 128: return dispatch_att2<128>(pl, prm, stream);
+      default: return dispatch_att2<160>(pl, prm, stream);
+    }
+  }
   switch (pl->dpv) {
     case 48: return launch_att<48>(pl, prm, stream);
     case 64: return launch_att<64>(pl, prm, stream);

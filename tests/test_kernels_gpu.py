@@ -32,7 +32,13 @@ def _rel(got, ref):
                                           # UNet batch 32 / 16, a ragged last query tile, one / two full key sub-tiles
                                           (32, 8, 4096, 77, 40), (32, 8, 1024, 77, 80), (32, 8, 256, 77, 160),
                                           (16, 8, 4096, 77, 40), (40, 8, 1100, 64, 40), (80, 4, 700, 128, 64),
-                                          (64, 8, 384, 100, 80)])
+                                          (64, 8, 384, 100, 80),
+                                          # two-tile kernel at head dims > 64 (two / three smem atoms, 256 TMEM columns
+                                          # per tile, one CTA per SM): odd tile count, ragged last query tile, head dims
+                                          # 72 / 96 / 128 / 136, the bench shapes of the 32x32 and 16x16 levels
+                                          (2, 2, 384, 512, 80), (1, 3, 300, 256, 160), (1, 2, 512, 320, 128),
+                                          (1, 2, 256, 192, 96), (1, 2, 640, 448, 72), (1, 1, 256, 256, 136),
+                                          (32, 8, 1024, 1024, 80), (32, 8, 256, 256, 160)])
 def test_attention(cuda, B, H, Sq, Sk, d):
     from sonicdiffusionbayeslab_b200 import kernels as k
 
@@ -70,7 +76,26 @@ def test_attention_causal(cuda, B, H, S, d):
     assert _rel(out, ref) < 2e-2
 
 
-@pytest.mark.parametrize("d,Sq", [(40, 512), (40, 128), (80, 256)])
+@pytest.mark.parametrize("d", [80, 160])
+def test_attention_wide_two_tile_kernel_matches_one_tile_kernel(cuda, d, monkeypatch):
+    """Head dims above 64 can run the two-tile kernel (one CTA per SM; default for d >= 96, SONIC_ATT2_WIDE=2 forces it for
+    every d > 64, =0 selects the one-tile kernel).  Same sub-tile order and the same softmax code: bit-identical."""
+    from sonicdiffusionbayeslab_b200 import kernels as k
+
+    B, H, S = 2, 4, 768
+    C = H * d
+    g = torch.Generator(device="cuda").manual_seed(d)
+    qkv = _bf(torch.randn(B * S, 3 * C, device=cuda, generator=g))
+    outs = []
+    for flag in ("2", "0"):
+        monkeypatch.setenv("SONIC_ATT2_WIDE", flag)
+        outs.append(k.attention(qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:], batch=B, heads=H, seq_q=S, seq_k=S,
+                                head_dim=d).clone())
+    torch.cuda.synchronize()
+    assert torch.equal(outs[0], outs[1])
+
+
+@pytest.mark.parametrize("d,Sq", [(40, 512), (40, 128), (80, 256), (160, 384)])
 def test_attention_rising_scores(cuda, d, Sq):
     """Scores that keep growing along the key axis (up to e^60 between the first and the last sub-tile): the lazy
     running reference must be raised, and the O accumulator rescaled in tensor memory, many times per row."""
