@@ -468,6 +468,14 @@ attention_kernel(const __grid_constant__ AttParams p) {
 // 4-stage rings.
 //   TMEM columns of tile q:  q*128 + [0, 64) S / P,  q*128 + 64 + [0, kDPV) O.
 constexpr int kStages2 = 4;
+#ifndef SONIC_ATT_HINT_P
+#define SONIC_ATT_HINT_P 64
+#endif
+#ifndef SONIC_ATT_HINT_S
+#define SONIC_ATT_HINT_S 64
+#endif
+constexpr uint32_t kHintP = SONIC_ATT_HINT_P;   // suspend hints (ns) of the two waits on the S -> softmax -> PV chain of the two-tile kernel
+constexpr uint32_t kHintS = SONIC_ATT_HINT_S;
 
 // kResident (cross-attention: at most two key sub-tiles, i.e. <= 128 keys): ONE CTA per (batch, head) keeps K and V
 // in shared memory and walks over ALL query-tile pairs of that head, Q double-buffered.  The streaming form launched
@@ -605,7 +613,9 @@ attention2_kernel(const __grid_constant__ AttParams p) {
         const int st1 = (t + 1) % kKvStages;
         const bool more = t + 1 < n_sub;
         for (int q = 0; q < nq; ++q) {
-          mbar_wait<64>(&p_full[q], n_item & 1);
+          ATT_TRACE(kWarpMma, 2 * t + q, 0);
+          mbar_wait<kHintP>(&p_full[q], n_item & 1);
+          ATT_TRACE(kWarpMma, 2 * t + q, 1);
           if (q == 0) mbar_wait(&v_full[st], kResident ? 0 : (t / kKvStages) & 1);
           tc_fence_after();
           const uint32_t ts = tmem_base + q * kTileCols;
@@ -619,9 +629,11 @@ attention2_kernel(const __grid_constant__ AttParams p) {
             if (!more && q == nq - 1) umma_commit(o_done);
           }
           __syncwarp();
+          ATT_TRACE(kWarpMma, 2 * t + q, 2);
           if (more) {
             if (q == 0) { mbar_wait(&k_full[st1], kResident ? 0 : ((t + 1) / kKvStages) & 1); tc_fence_after(); }
             issue_s(qs, q, st1, t + 2 == n_sub);
+            ATT_TRACE(kWarpMma, 2 * t + q, 3);
             if (q == nq - 1) {
               if (leader) {
                 if (!kResident) umma_commit(&k_empty[st1]);
@@ -710,7 +722,9 @@ attention2_kernel(const __grid_constant__ AttParams p) {
             int valid = p.seq_k - t * kSub;
             if (p.causal) valid = min(valid, q0 + q * kBlockQ + row - t * kSub + 1);
             const uint32_t t_s = tmem_base + q * kTileCols + lane_addr;
-            mbar_wait<64>(&s_full[q], n_item & 1);
+            ATT_TRACE(warp, 2 * t + q, 0);
+            mbar_wait<kHintS>(&s_full[q], n_item & 1);
+            ATT_TRACE(warp, 2 * t + q, 1);
             tc_fence_after();
             using W64 = std::integral_constant<int, 64>;
             const int w = kNarrow && t + 1 == n_sub ? p.tail_w : kSub;
@@ -718,10 +732,12 @@ attention2_kernel(const __grid_constant__ AttParams p) {
             else if (kNarrow && w == 32) softmax_sub(m_run[q], l_run[q], t_s, t, std::true_type{}, std::integral_constant<int, 32>{}, valid);
             else if (__all_sync(0xffffffffu, valid >= kSub)) softmax_sub(m_run[q], l_run[q], t_s, t, std::false_type{}, W64{}, kSub);
             else softmax_sub(m_run[q], l_run[q], t_s, t, std::true_type{}, W64{}, valid);
+            ATT_TRACE(warp, 2 * t + q, 2);
             tmem_st_wait();
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&p_full[q]);
+            ATT_TRACE(warp, 2 * t + q, 3);
           }
         }
       }
