@@ -588,9 +588,15 @@ constexpr int kZeroBiasLen = 16384;                // >= the widest layer (GEGLU
 __device__ float g_zero_bias_dev[kZeroBiasLen];    // zero-initialised: the "bias" of bias-free layers
 const float* g_zero_bias = nullptr;
 
-int pick_block_n(int N, int m_tiles, bool geglu, int num_sms) {
+int pair_enabled() {
+  static const int on = [] { const char* e = getenv("SONIC_GEMM_PAIR"); return e ? atoi(e) : 1; }();
+  return on;
+}
+
+int pick_block_n(int N, int m_tiles, bool geglu, int num_sms, bool pair) {
   // Prefer wide tiles (A re-use, fewer smem bytes per MMA cycle) but avoid tail waves.
   static const int cands[] = {256, 224, 192, 160, 128, 96, 64, 32, 16};   // multiples of 32: staged epilogue chunks
+  static const int model = [] { const char* e = getenv("SONIC_BN_MODEL"); return e ? atoi(e) : 1; }();
   int best = 0;
   double best_cost = 1e30;
   for (int bn : cands) {
@@ -598,11 +604,22 @@ int pick_block_n(int N, int m_tiles, bool geglu, int num_sms) {
     if (bn == 16 && N >= 32) continue;            // 16 only for the padded 4 -> 16 conv_out (direct-store epilogue)
     if (geglu && (bn % 64 != 0 || N % bn != 0)) continue;
     const int n_tiles = (N + bn - 1) / bn;
-    const long tiles = static_cast<long>(m_tiles) * n_tiles;
-    const long waves = (tiles + num_sms - 1) / num_sms;
-    // per-tile time ~ max(MMA cycles ~ bn, smem-feed cycles ~ (128+bn)/2) + fixed overhead
-    const double per_tile = std::max<double>(bn, (128.0 + bn) * 0.5 * 1.1) + 12.0;
-    const double cost = waves * per_tile;
+    double cost;
+    if (pair && model) {
+      // CTA pairs: work items of two M tiles on num_sms / 2 clusters; an MMA of width bn costs bn / 2 + ~48 cycles
+      // (round-1 microbenchmark), so wide tiles are worth a partly filled last wave more often than "bn + 12" says
+      const long items = static_cast<long>((m_tiles + 1) / 2) * n_tiles;
+      const long workers = std::max(1, num_sms / 2);
+      const long waves = (items + workers - 1) / workers;
+      static const double ovh = [] { const char* e = getenv("SONIC_BN_OVH"); return e ? atof(e) : 51.0; }();
+      cost = waves * (bn * 0.5 + ovh);
+    } else {
+      const long tiles = static_cast<long>(m_tiles) * n_tiles;
+      const long waves = (tiles + num_sms - 1) / num_sms;
+      // per-tile time ~ max(MMA cycles ~ bn, smem-feed cycles ~ (128+bn)/2) + fixed overhead
+      const double per_tile = std::max<double>(bn, (128.0 + bn) * 0.5 * 1.1) + 12.0;
+      cost = waves * per_tile;
+    }
     if (cost < best_cost - 1e-9) { best_cost = cost; best = bn; }
   }
   return best ? best : 16;
@@ -625,7 +642,7 @@ int gemm_choose_block_n(int N, int n_img, int H, int W, int epilogue) {
     const int tn = kTileM / (W * th);
     m_tiles = (H / th) * ((n_img + tn - 1) / tn);
   }
-  return pick_block_n(N, m_tiles, epilogue == kEpiGeglu, g_num_sms);
+  return pick_block_n(N, m_tiles, epilogue == kEpiGeglu, g_num_sms, pair_enabled() && m_tiles >= 2 && g_num_sms % 2 == 0);
 }
 
 int gemm_plan(const GemmOp& op, GemmPlan* plan) {
@@ -676,7 +693,9 @@ int gemm_plan(const GemmOp& op, GemmPlan* plan) {
   p.m_tiles_src = p.tiles_w * p.tiles_h * p.tiles_img;
   p.m_tiles = p.m_tiles_src * (mode == kModeUpsample ? 4 : 1);
   const bool geglu = op.epilogue == kEpiGeglu;
-  p.block_n = op.block_n ? op.block_n : pick_block_n(op.N, p.m_tiles, geglu, g_num_sms);
+  const bool pair_shape = g_num_sms % 2 == 0 && p.m_tiles >= 2 && (mode != kModeUpsample || p.m_tiles_src % 2 == 0);
+  p.block_n = op.block_n ? op.block_n
+                         : pick_block_n(op.N, p.m_tiles, geglu, g_num_sms, pair_shape && op.pair != 0 && (op.pair > 0 || pair_enabled()));
   SONIC_REQUIRE(p.block_n % 16 == 0 && p.block_n >= 16 && p.block_n <= 256, "gemm: bad block_n %d",
                 p.block_n);
   SONIC_REQUIRE(!geglu || (p.block_n % 32 == 0 && op.N % p.block_n == 0),
@@ -703,7 +722,7 @@ int gemm_plan(const GemmOp& op, GemmPlan* plan) {
   p.n_tiles = (op.N + p.block_n - 1) / p.block_n;
   // CTA pairs: two adjacent M tiles share one B tile.  Needs an even SM count, a B half of whole 8-row swizzle atoms,
   // phase-aligned tile pairs in the upsample form, and enough work that halving the worker count costs no wave.
-  static const int pair_env = [] { const char* e = getenv("SONIC_GEMM_PAIR"); return e ? atoi(e) : 1; }();
+  const int pair_env = pair_enabled();
   static const int pair_min = [] { const char* e = getenv("SONIC_GEMM_PAIR_MIN"); return e ? atoi(e) : 0; }();
   const bool pair_ok = p.block_n % 32 == 0 && g_num_sms % 2 == 0 && p.m_tiles >= 2 &&
                        (mode != kModeUpsample || p.m_tiles_src % 2 == 0);
