@@ -405,7 +405,7 @@ def run_loop_workload(args, model, kw, wl, B, rank, world, local, dev, dist):
         prof = eng.plans["full"].profile(ctypes.c_void_p(side.cuda_stream))
     torch.cuda.synchronize()
     log = eng.plans["full"].log
-    names = {0: "conv_gemm_kernel", 1: "attention kernels", 2: "groupnorm (finalize+apply)", 3: "layernorm_kernel",
+    names = {0: "conv_gemm_kernel", 1: "attention kernels", 2: "groupnorm (gn_cluster_kernel)", 3: "layernorm_kernel",
              4: "layout kernels", 5: "timestep gemv"}
     agg, hbm, ln_side = {}, {2: [0.0, 0.0, 0], 3: [0.0, 0.0, 0]}, [0.0, 0.0, 0]
     for (kind, ms, fl), text in zip(prof, log):

@@ -116,8 +116,10 @@ int sonic_groupnorm_silu(const void* x0, int32_t c0, const void* x1, int32_t c1,
                          const float* beta, int32_t silu, float* stats, void* y,
                          sonic_stream_t stream);
 /* GroupNorm whose statistics come from the producing GEMMs' `gn_partial` buffers (hw must be a multiple of 32):
- * a small finalize kernel folds the per-32-row partials of each image in a fixed order (bit-reproducible), then
- * the same apply kernel as above runs.  part0 / part1 have row pitch c0 / c1 channels. */
+ * ONE launch -- a thread-block cluster of up to 8 CTAs per image folds the per-32-row partials in a fixed order
+ * (cluster barrier + distributed shared memory: bit-reproducible, no atomics, no global scratch) and normalises its
+ * pixel chunks; large tensors of small batches use a finalize kernel followed by the apply kernel above instead.
+ * part0 / part1 have row pitch c0 / c1 channels; `stats` is only touched by the two-kernel form. */
 int sonic_groupnorm_fused(const void* x0, int32_t c0, const float* part0, const void* x1, int32_t c1,
                           const float* part1, int32_t n_img, int32_t hw, int32_t groups, float eps,
                           const float* gamma, const float* beta, int32_t silu, float* stats, void* y,

@@ -5,9 +5,9 @@
 // 160) are zero-filled by the TMA unit, never padded in HBM.
 //
 // Two kernels share the scheme below.  attention_kernel: one CTA = one 128-row query tile of one (batch, head)
-// (head dims 80 / 160, or at most 128 queries).  attention2_kernel (head dims <= 64, further down): one CTA owns TWO
-// query tiles and ping-pongs between them, optionally with K / V resident in shared memory for short key sequences;
-// it is the one the 64x64 UNet level and the CLIP towers run on.
+// (head dim 80, at most 128 queries, and -- in loop mode -- the cross-attention layers).  attention2_kernel (further
+// down): one CTA owns TWO query tiles and ping-pongs between them; two CTAs per SM for head dims <= 64 (the 64x64 UNet
+// level and the CLIP towers), one CTA per SM with 256 TMEM columns per tile for head dims >= 96 (the 16x16 level).
 // Keys are consumed in sub-tiles of 64 and everything between the two GEMMs lives in tensor memory:
 //   TMEM columns  [0, 64)        S = Q K^T scores of a sub-tile, fp32; once a thread has read its row it
 //                                overwrites columns [0, 32) with P = exp2(...) as bf16 pairs -- the A operand

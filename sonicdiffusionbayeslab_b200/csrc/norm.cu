@@ -1,8 +1,11 @@
 // HBM-bound normalisation kernels over channels-last bf16 activations:
 //   GroupNorm(32 groups) [+ SiLU] over the channel-concat of up to two tensors, and LayerNorm.
 // Both read each element once per pass with 128-bit accesses; GroupNorm statistics are reduced in
-// a fixed order (per-CTA partials, finalised by the last CTA of each image), so results are
-// bit-reproducible without atomics on the data path.
+// a fixed order, so results are bit-reproducible without atomics on the data path.  Three forms:
+//   gn_cluster_kernel                  statistics from the producing GEMMs' epilogue partials, ONE launch (a cluster of
+//                                      up to 8 CTAs per image): every GroupNorm of the UNet at the bench batch
+//   gn_finalize_kernel + gn_apply      the same partials, two launches (large tensors of small batches: the VAE)
+//   gn_stats_kernel + gn_apply         a statistics pass over the tensor (no producer partials)
 #include "ops.cuh"
 
 #include <algorithm>
