@@ -348,9 +348,25 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
           tmem_ld32(t_row + out_cols + c * kChunkCols, gt);
           tmem_ld_wait();
           if (p.row_scale && p.gelu_tanh) {                    // bias already inside the accumulator
+            // two outputs per instruction (packed fp32 pairs): this epilogue, not the MMA, bounds the 64x64 FFN projection
+            const uint64_t rs2 = pack2(rs, rs);
 #pragma unroll
-            for (int j = 0; j < 32; ++j)
-              f[j] = (rs * __uint_as_float(v[j])) * gelu_erf_tanh(rs * __uint_as_float(gt[j]));
+            for (int j = 0; j < 32; j += 2) {
+              const uint64_t x = fmul2(rs2, pack2(__uint_as_float(gt[j]), __uint_as_float(gt[j + 1])));
+              float q0, q1;
+              unpack2(fmul2(x, x), q0, q1);
+              const uint64_t x2 = pack2(fminf(q0, 64.0f), fminf(q1, 64.0f));
+              uint64_t u = ffma2(pack2(-0.000351517477f, -0.000351517477f), x2, pack2(0.0370056506f, 0.0370056506f));
+              u = ffma2(u, x2, pack2(0.797507879f, 0.797507879f));
+              float a0, a1, t0, t1;
+              unpack2(fmul2(u, x), a0, a1);
+              asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(a0));
+              asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(a1));
+              const uint64_t h = fmul2(x, pack2(0.5f, 0.5f));
+              const uint64_t gl = ffma2(h, pack2(t0, t1), h);
+              const uint64_t val = fmul2(rs2, pack2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])));
+              unpack2(fmul2(val, gl), f[j], f[j + 1]);
+            }
           } else if (p.row_scale) {
 #pragma unroll
             for (int j = 0; j < 32; ++j)
