@@ -383,17 +383,17 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
           }
         } else if (p.row_scale) {
           tmem_ld_wait();
+          const uint64_t rs2 = pack2(rs, rs);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) f[j] = rs * __uint_as_float(v[j]);
+          for (int j = 0; j < 32; j += 2)
+            unpack2(fmul2(rs2, pack2(__uint_as_float(v[j]), __uint_as_float(v[j + 1]))), f[j], f[j + 1]);
         } else {
           tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 32; j += 4) {
+          for (int j = 0; j < 32; j += 4) {                    // two bias adds per instruction (packed fp32 pairs)
             const float4 bv = __ldg(bias_v + (j >> 2));
-            f[j] = __uint_as_float(v[j]) + bv.x;
-            f[j + 1] = __uint_as_float(v[j + 1]) + bv.y;
-            f[j + 2] = __uint_as_float(v[j + 2]) + bv.z;
-            f[j + 3] = __uint_as_float(v[j + 3]) + bv.w;
+            unpack2(fadd2(pack2(__uint_as_float(v[j]), __uint_as_float(v[j + 1])), pack2(bv.x, bv.y)), f[j], f[j + 1]);
+            unpack2(fadd2(pack2(__uint_as_float(v[j + 2]), __uint_as_float(v[j + 3])), pack2(bv.z, bv.w)), f[j + 2], f[j + 3]);
           }
         }
         if (i == 0 && threadIdx.x == 64) GEMM_TRACE(3, ti, 1);
@@ -422,10 +422,11 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const uint4 rr = *reinterpret_cast<const uint4*>(my_row + ((q ^ sw) << 4));
-            f[8 * q] += bf16_lo(rr.x);     f[8 * q + 1] += bf16_hi(rr.x);
-            f[8 * q + 2] += bf16_lo(rr.y); f[8 * q + 3] += bf16_hi(rr.y);
-            f[8 * q + 4] += bf16_lo(rr.z); f[8 * q + 5] += bf16_hi(rr.z);
-            f[8 * q + 6] += bf16_lo(rr.w); f[8 * q + 7] += bf16_hi(rr.w);
+            const uint32_t rw[4] = {rr.x, rr.y, rr.z, rr.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              unpack2(fadd2(pack2(f[8 * q + 2 * e], f[8 * q + 2 * e + 1]), pack2(bf16_lo(rw[e]), bf16_hi(rw[e]))),
+                      f[8 * q + 2 * e], f[8 * q + 2 * e + 1]);
           }
         } else {
           if (lane == 0) bulk_wait_read<kStgBufs - 1>();     // the store that last used this buffer has read it
@@ -438,13 +439,16 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
         for (int q = 0; q < 4; ++q)
           *reinterpret_cast<uint4*>(my_row + ((q ^ sw) << 4)) = make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
         if (p.ln_stats_out) {                                // of the bf16-ROUNDED values: what the consumer multiplies
-          float a0 = 0.f, a1 = 0.f, q0 = 0.f, q1 = 0.f;
+          uint64_t a2 = pack2(0.f, 0.f), q2 = pack2(0.f, 0.f);   // (even, odd) column accumulators, as before: a0 / a1, q0 / q1
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            const float lo = bf16_lo(pk[j]), hi = bf16_hi(pk[j]);
-            a0 += lo; a1 += hi;
-            q0 = fmaf(lo, lo, q0); q1 = fmaf(hi, hi, q1);
+            const uint64_t x = pack2(bf16_lo(pk[j]), bf16_hi(pk[j]));
+            a2 = fadd2(a2, x);
+            q2 = ffma2(x, x, q2);
           }
+          float a0, a1, q0, q1;
+          unpack2(a2, a0, a1);
+          unpack2(q2, q0, q1);
           rs_sum += a0 + a1;
           rs_sq += q0 + q1;
         }
