@@ -369,3 +369,24 @@ def test_fold_layernorm_algebra():
     exact = torch.nn.functional.layer_norm(x, (320,), torch.ones(320), torch.zeros(320), 1e-5) @ w2[:, :320].float().t() \
         + (w.float() @ beta + b)
     assert (got - exact).abs().max().item() < 2e-4 * exact.abs().max().item()    # the identity itself (hi/lo splits)
+
+
+def test_gemm_tile_width_choices_for_the_cta_pair_kernel():
+    """`sonic_gemm_choose_block_n` (csrc/gemm.cu pick_block_n) without a GPU assumes 148 SMs = 74 CTA pairs: the tile
+    widths of the UNet's layer shapes at UNet batch 32 follow waves x (bn / 2 + ~48 cycles per K step) -- wide tiles
+    where the last wave stays full enough, narrow ones for tiny problems; GEGLU tiles hold a value and a gate half."""
+    from sonicdiffusionbayeslab_b200 import kernels as k
+
+    cases = {
+        (320, 32, 64, 64, k.EPI_NONE): 160,       # the only even split of 320 below 256
+        (640, 32, 32, 32, k.EPI_NONE): 160,       # 512 items on 74 clusters: 7 waves of 160 beat 6 of 256
+        (1920, 1, 1, 32768, k.EPI_NONE): 256,     # QKV of the 32x32 level
+        (3840, 1, 1, 8192, k.EPI_NONE): 256,      # QKV of the 16x16 level
+        (2560, 1, 1, 131072, k.EPI_GEGLU): 256,   # 128 value + 128 gate columns per tile
+        (16, 32, 64, 64, k.EPI_NONE): 16,         # the padded 4 -> 16 conv_out
+    }
+    for (N, n_img, H, W, epi), want in cases.items():
+        assert k.gemm_block_n(N, n_img, H, W, epi) == want, (N, n_img, H, W, epi)
+    for N in (320, 640, 960, 1280, 1920, 2560, 3840):
+        bn = k.gemm_block_n(N, 32, 16, 16)
+        assert bn % 32 == 0 and 32 <= bn <= 256          # staged epilogue chunks, pairable halves of whole swizzle atoms
