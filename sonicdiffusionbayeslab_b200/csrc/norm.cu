@@ -569,6 +569,19 @@ int ln_side_launch(const float* partials, int parts, int M, int K, float eps, vo
   return 0;
 }
 
+// CTAs per cluster of the one-launch form for this operator, or 0 if it runs as finalize (or statistics) + apply.
+static int gn_cluster_size(const GroupNormOp& op) {
+  if (!op.part0) return 0;
+  const int C = op.c0 + (op.x1 ? op.c1 : 0);
+  const int ppp = kGnThreads / (C / 8);
+  static const int fused_mode = [] { const char* e = getenv("SONIC_GN_CLUSTER"); return e ? atoi(e) : 1; }();
+  const int R = std::min(std::min(8, (2 * 148) / std::max(1, op.n_img)), std::max(1, op.hw / (4 * ppp)));
+  const bool small = static_cast<size_t>(op.n_img) * op.hw * C * 2 < (8u << 20);      // latency-bound either way
+  return (fused_mode && op.groups <= 32 && (R * op.n_img >= 200 || small)) ? R : 0;
+}
+
+int groupnorm_launch_count(const GroupNormOp& op) { return gn_cluster_size(op) > 0 ? 1 : 2; }
+
 int groupnorm_launch(const GroupNormOp& op, cudaStream_t stream) {
   const int C = op.c0 + (op.x1 ? op.c1 : 0);
   SONIC_REQUIRE(op.x0 && op.y && op.stats && op.gamma && op.beta, "groupnorm: null operand");
@@ -594,10 +607,8 @@ int groupnorm_launch(const GroupNormOp& op, cudaStream_t stream) {
     // (64x64x320 + SiLU: 48.7 -> 40.1 us); clusters of 9 CTAs place badly (54.8 us), and 16 x 16 CTAs on the VAE
     // decoder's 1 GB tensors lose to the 432 CTAs of the two-kernel form (42.2 vs 40.7 ms per decode), so large
     // tensors of small batches keep the finalize + apply pair.  SONIC_GN_CLUSTER=0 disables this path (A/B).
-    static const int fused_mode = [] { const char* e = getenv("SONIC_GN_CLUSTER"); return e ? atoi(e) : 1; }();
-    const int R = std::min(std::min(8, (2 * 148) / std::max(1, op.n_img)), std::max(1, op.hw / (4 * ppp)));
-    const bool small = static_cast<size_t>(op.n_img) * op.hw * C * 2 < (8u << 20);      // latency-bound either way
-    if (fused_mode && op.groups <= 32 && (R * op.n_img >= 200 || small)) {
+    const int R = gn_cluster_size(op);
+    if (R > 0) {
       cudaLaunchConfig_t cfg = {};
       cfg.gridDim = dim3(R, op.n_img);
       cfg.blockDim = dim3(kGnThreads);

@@ -25,6 +25,7 @@ struct GroupNormOp {
   void* y = nullptr;                                // [n_img*hw][c0+c1] bf16
 };
 int groupnorm_launch(const GroupNormOp& op, cudaStream_t stream);
+int groupnorm_launch_count(const GroupNormOp& op);   // kernels the call above launches for this operator: 1 (cluster form) or 2
 
 int layernorm_launch(const void* x, void* y, int rows, int C, float eps, const float* gamma,
                      const float* beta, cudaStream_t stream);

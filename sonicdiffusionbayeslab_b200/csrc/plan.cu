@@ -138,7 +138,7 @@ int sonic_plan_add_groupnorm(sonic_plan_t h, const void* x0, int32_t c0, const v
   p.gn.x0 = x0; p.gn.c0 = c0; p.gn.x1 = x1; p.gn.c1 = c1;
   p.gn.n_img = n_img; p.gn.hw = hw; p.gn.groups = groups; p.gn.eps = eps;
   p.gn.gamma = gamma; p.gn.beta = beta; p.gn.silu = silu; p.gn.stats = stats; p.gn.y = y;
-  plan->launches += 2;
+  plan->launches += groupnorm_launch_count(p.gn);
   plan->ops.push_back(p);
   return 0;
 }
@@ -155,7 +155,7 @@ int sonic_plan_add_groupnorm_fused(sonic_plan_t h, const void* x0, int32_t c0, c
   p.gn.x0 = x0; p.gn.c0 = c0; p.gn.x1 = x1; p.gn.c1 = c1; p.gn.part0 = part0; p.gn.part1 = part1;
   p.gn.n_img = n_img; p.gn.hw = hw; p.gn.groups = groups; p.gn.eps = eps;
   p.gn.gamma = gamma; p.gn.beta = beta; p.gn.silu = silu; p.gn.stats = stats; p.gn.y = y;
-  plan->launches += 2;
+  plan->launches += groupnorm_launch_count(p.gn);
   plan->ops.push_back(p);
   return 0;
 }
