@@ -43,6 +43,10 @@ def test_library_is_blackwell_native():
         pytest.skip("cuobjdump unavailable")
     for mnemonic in ("UTCHMMA", "LDTM", "UTMALDG"):
         assert mnemonic in sass, mnemonic
+    # the CTA-pair GEMM (cta_group::2 MMA, multicast commit, pair TMA loads), cluster barriers (pair GEMM, GroupNorm)
+    # and the packed fp32 pair arithmetic of the softmax / GEMM epilogues
+    for mnemonic in ("UTCHMMA.2CTA", "UTCBAR.2CTA.MULTICAST", "UTMALDG.4D.2CTA", "UCGABAR_WAIT", "FFMA2", "FADD2", "FMUL2"):
+        assert mnemonic in sass, mnemonic
     assert "HMMA.16816" not in sass            # no legacy mma.sync tensor path
 
 
