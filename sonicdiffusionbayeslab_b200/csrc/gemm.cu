@@ -40,6 +40,17 @@ constexpr int kStgBufBytes = 32 * kChunkCols * 2;       // 32 rows x 64 B
 #ifndef SONIC_STG_PENDING
 #define SONIC_STG_PENDING 2
 #endif
+#ifndef SONIC_HINT_ACC
+#define SONIC_HINT_ACC 128
+#endif
+#ifndef SONIC_HINT_FULL
+#define SONIC_HINT_FULL 64
+#endif
+#ifndef SONIC_HINT_TF
+#define SONIC_HINT_TF 64
+#endif
+constexpr uint32_t kHintAcc = SONIC_HINT_ACC, kHintFull = SONIC_HINT_FULL, kHintTf = SONIC_HINT_TF;   // suspend hints (ns): MMA warp's
+                                           // waits for a free accumulator / a full stage, epilogue's wait for a full accumulator
 constexpr int kStgBufs = SONIC_STG_BUFS;   // staging buffers per epilogue warp: a ring -- residual chunks are requested
 constexpr int kStgPending = SONIC_STG_PENDING;   // kStgBufs - kStgPending chunks ahead (across tile boundaries) while up to
                                            // kStgPending tile stores drain behind
@@ -211,12 +222,12 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
     int ti = 0;
     for (int tile = worker; tile < total_tiles && rank == 0; tile += n_workers, ++ti) {
       if (lane == 0) GEMM_TRACE(1, ti, 0);
-      mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+      mbar_wait<kHintAcc>(&tmem_empty[acc], acc_phase ^ 1);
       if (lane == 0) GEMM_TRACE(1, ti, 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * p.acc_stride;
       for (int kit = 0; kit < k_iters; ++kit) {
-        mbar_wait<64>(&full_bar[stage], phase);
+        mbar_wait<kHintFull>(&full_bar[stage], phase);
         if (kit == 0 && lane == 0) GEMM_TRACE(1, ti, 2);
         tc_fence_after();
         const uint64_t da = desc0 + static_cast<uint64_t>((stage * stage_bytes) >> 4);
@@ -323,7 +334,7 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
       }
       float rs_sum = 0.f, rs_sq = 0.f;                       // producer side: statistics of this lane's output row
       if (threadIdx.x == 64) GEMM_TRACE(2, ti, 1);
-      mbar_wait<64>(&tmem_full[acc], acc_phase);
+      mbar_wait<kHintTf>(&tmem_full[acc], acc_phase);
       if (threadIdx.x == 64) GEMM_TRACE(2, ti, 2);
       tc_fence_after();
       const uint32_t t_row = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + acc * p.acc_stride;
