@@ -155,9 +155,18 @@ class DDIMScheduler(_SchedulerBase):
         a = self.alphas_cumprod[t]
         ap = self.alphas_cumprod[prev_t] if prev_t >= 0 else self.final_alpha_cumprod
         beta = 1 - a
-        assert self.config.prediction_type == "epsilon"
-        pred_x0 = (sample - beta ** 0.5 * model_output) / a ** 0.5
-        pred_eps = model_output
+        pt = self.config.prediction_type                  # diffusers 0.32.1 scheduling_ddim.py ``step`` item 3
+        if pt == "epsilon":
+            pred_x0 = (sample - beta ** 0.5 * model_output) / a ** 0.5
+            pred_eps = model_output
+        elif pt == "sample":
+            pred_x0 = model_output
+            pred_eps = (sample - a ** 0.5 * pred_x0) / beta ** 0.5
+        elif pt == "v_prediction":
+            pred_x0 = (a ** 0.5) * sample - (beta ** 0.5) * model_output
+            pred_eps = (a ** 0.5) * model_output + (beta ** 0.5) * sample
+        else:
+            raise ValueError(f"prediction_type given as {pt} must be one of `epsilon`, `sample`, or `v_prediction`")
         if self.config.clip_sample:
             pred_x0 = pred_x0.clamp(-1.0, 1.0)
         var = self._get_variance(t, prev_t)
@@ -186,7 +195,7 @@ class DPMSolverScheduler(_SchedulerBase):
     _defaults = dict(
         num_train_timesteps=1000, beta_start=0.0001, beta_end=0.02, beta_schedule="linear",
         trained_betas=None, solver_order=2, prediction_type="epsilon", thresholding=False,
-        algorithm_type="dpmsolver++", solver_type="midpoint", lower_order_final=True,
+        dynamic_thresholding_ratio=0.995, sample_max_value=1.0, algorithm_type="dpmsolver++", solver_type="midpoint", lower_order_final=True,
         euler_at_final=False, use_karras_sigmas=False, lambda_min_clipped=-float("inf"),
         variance_type=None, timestep_spacing="linspace", steps_offset=0, final_sigmas_type="zero",
     )
@@ -251,15 +260,55 @@ class DPMSolverScheduler(_SchedulerBase):
         alpha_t = 1 / ((sigma ** 2 + 1) ** 0.5)
         return alpha_t, sigma * alpha_t
 
+    def _threshold_sample(self, sample):
+        """diffusers 0.32.1 ``_threshold_sample`` ("dynamic thresholding", Imagen): per sample the
+        ``dynamic_thresholding_ratio`` quantile s of |x0|, clamped to [1, sample_max_value]; x0 <- clamp(x0, -s, s) / s.
+        Third-party restatement; reached from /root/reference/src/schedulers.py:58-59,85-90 (off in every shipped
+        config)."""
+        dtype = sample.dtype
+        b = sample.shape[0]
+        flat = sample.float().reshape(b, -1)
+        s = torch.quantile(flat.abs(), self.config.get("dynamic_thresholding_ratio", 0.995), dim=1)
+        s = torch.clamp(s, min=1, max=self.config.get("sample_max_value", 1.0)).unsqueeze(1)
+        flat = torch.clamp(flat, -s, s) / s
+        return flat.reshape(sample.shape).to(dtype)
+
     def convert_model_output(self, model_output, sample):
-        """/root/reference/src/schedulers.py:14-96 (epsilon prediction, no thresholding)."""
-        assert self.config.prediction_type == "epsilon" and not self.config.thresholding
+        """/root/reference/src/schedulers.py:14-96: every ``prediction_type`` branch (:36-56 for the ``++`` algorithms,
+        :65-83 for the others) and the thresholding branches (:58-59, :85-90)."""
+        pt = self.config.prediction_type
         sigma = self.sigmas[self.step_index]
         alpha_t, sigma_t = self._sigma_to_alpha_sigma_t(sigma)
-        x0_pred = (sample - sigma_t * model_output) / alpha_t          # :40-42 / :92-94
         if self.config.algorithm_type in ("dpmsolver++", "sde-dpmsolver++"):
+            if pt == "epsilon":
+                x0_pred = (sample - sigma_t * model_output) / alpha_t  # :40-42
+            elif pt == "sample":
+                x0_pred = model_output                                 # :43-44
+            elif pt == "v_prediction":
+                x0_pred = alpha_t * sample - sigma_t * model_output    # :45-48
+            elif pt == "flow_prediction":
+                x0_pred = sample - sigma * model_output                # :49-51 (sigma itself, not sigma_t)
+            else:
+                raise ValueError(f"prediction_type given as {pt} must be one of `epsilon`, `sample`, "
+                                 "`v_prediction`, or `flow_prediction` for the DPMSolverMultistepScheduler.")
+            if self.config.thresholding:
+                x0_pred = self._threshold_sample(x0_pred)              # :58-59
             return x0_pred, x0_pred                                    # intended semantics of :61 (C-1)
-        return model_output, x0_pred                                   # :96
+        if pt == "epsilon":
+            epsilon = model_output                                     # :66-71
+        elif pt == "sample":
+            epsilon = (sample - alpha_t * model_output) / sigma_t      # :72-75
+        elif pt == "v_prediction":
+            epsilon = alpha_t * model_output + sigma_t * sample        # :76-79
+        else:
+            raise ValueError(f"prediction_type given as {pt} must be one of `epsilon`, `sample`, or"
+                             " `v_prediction` for the DPMSolverMultistepScheduler.")
+        if self.config.thresholding:                                   # :85-90
+            x0_pred = (sample - sigma_t * epsilon) / alpha_t
+            x0_pred = self._threshold_sample(x0_pred)
+            epsilon = (sample - alpha_t * x0_pred) / sigma_t
+        x0_pred = (sample - sigma_t * epsilon) / alpha_t               # :92-94
+        return epsilon, x0_pred                                        # :96
 
     def _lambdas(self, *sig):
         out = []

@@ -211,9 +211,12 @@ class DDIMSchedulerMy(FusedScheduler):
 
     def __init__(self, **kw):
         super().__init__(**kw)
-        if self.config.prediction_type != "epsilon" or self.config.thresholding or self.config.clip_sample:
-            raise NotImplementedError("fused DDIM step supports epsilon prediction without clipping "
-                                      "(the SD-v1.5 configuration of the reference)")
+        if self.config.prediction_type not in ("epsilon", "sample", "v_prediction"):
+            raise ValueError(f"prediction_type given as {self.config.prediction_type} must be one of `epsilon`, "
+                             "`sample`, or `v_prediction`")
+        if self.config.thresholding or self.config.clip_sample:
+            raise NotImplementedError("fused DDIM step: no clipping / thresholding of x0 "
+                                      "(off in the SD-v1.5 configuration of the reference)")
         self.final_alpha_cumprod = torch.tensor(1.0) if self.config.set_alpha_to_one else self.alphas_cumprod[0]
         self._set_grid(np.arange(0, self.config.num_train_timesteps)[::-1].copy(), None)
         self.num_inference_steps = None
@@ -246,10 +249,17 @@ class DDIMSchedulerMy(FusedScheduler):
         beta = 1 - a
         var = ((1 - ap) / beta) * (1 - a / ap)
         std = eta * var ** 0.5
-        inv_sqrt_a = 1.0 / _f(a ** 0.5)
-        c = dict(guidance=guidance, m_x=inv_sqrt_a, m_e=-_f(beta ** 0.5) * inv_sqrt_a,
-                 c_m0=_f(ap ** 0.5), c_e=_f((1 - ap - std ** 2) ** 0.5))
-        c["x0_x"], c["x0_e"] = c["m_x"], c["m_e"]
+        sa, sb, direction = _f(a ** 0.5), _f(beta ** 0.5), _f((1 - ap - std ** 2) ** 0.5)
+        # prev = sqrt(ap) x0 + direction * pred_eps, with x0 = m (rounded to the model dtype like the reference's
+        # pred_original_sample tensor) and pred_eps linear in (model output e, x) for every prediction type
+        pt = self.config.prediction_type
+        if pt == "epsilon":
+            c = dict(m_x=1.0 / sa, m_e=-sb / sa, c_e=direction)
+        elif pt == "sample":
+            c = dict(m_x=0.0, m_e=1.0, c_x=direction / sb, c_e=-direction * sa / sb)
+        else:                                             # v_prediction
+            c = dict(m_x=sa, m_e=-sb, c_x=direction * sb, c_e=direction * sa)
+        c.update(guidance=guidance, c_m0=_f(ap ** 0.5), x0_x=c["m_x"], x0_e=c["m_e"])
         noise = None
         if eta > 0:
             noise = self._draw(sample, generator, sample.dtype)
@@ -269,8 +279,9 @@ class DPMSolverScheduler(FusedScheduler):
 
     _defaults = dict(
         num_train_timesteps=1000, beta_start=0.0001, beta_end=0.02, beta_schedule="linear", trained_betas=None,
-        solver_order=2, prediction_type="epsilon", thresholding=False, algorithm_type="dpmsolver++",
-        solver_type="midpoint", lower_order_final=True, euler_at_final=False, use_karras_sigmas=False,
+        solver_order=2, prediction_type="epsilon", thresholding=False, dynamic_thresholding_ratio=0.995,
+        sample_max_value=1.0, algorithm_type="dpmsolver++", solver_type="midpoint", lower_order_final=True,
+        euler_at_final=False, use_karras_sigmas=False,
         lambda_min_clipped=-float("inf"), variance_type=None, timestep_spacing="linspace", steps_offset=0,
         final_sigmas_type="zero",
     )
@@ -291,9 +302,15 @@ class DPMSolverScheduler(FusedScheduler):
         if cfg.algorithm_type not in ("dpmsolver++", "sde-dpmsolver++") and cfg.final_sigmas_type == "zero":
             raise ValueError(f"`final_sigmas_type` {cfg.final_sigmas_type} is not supported for "
                              f"`algorithm_type` {cfg.algorithm_type}. Please choose `sigma_min` instead.")
-        if cfg.prediction_type != "epsilon" or cfg.thresholding or cfg.use_karras_sigmas:
-            raise NotImplementedError("fused DPM-Solver step supports epsilon prediction, no thresholding, "
-                                      "no Karras sigmas (the SD-v1.5 configuration of the reference)")
+        pp = cfg.algorithm_type in ("dpmsolver++", "sde-dpmsolver++")
+        allowed = ("epsilon", "sample", "v_prediction") + (("flow_prediction",) if pp else ())
+        if cfg.prediction_type not in allowed:                   # src/schedulers.py:52-56 / :80-83
+            raise ValueError(f"prediction_type given as {cfg.prediction_type} must be one of `epsilon`, `sample`, "
+                             + ("`v_prediction`, or `flow_prediction`" if pp else "or `v_prediction`")
+                             + " for the DPMSolverMultistepScheduler.")
+        if cfg.thresholding or cfg.use_karras_sigmas:
+            raise NotImplementedError("fused DPM-Solver step: no dynamic thresholding (a per-image quantile, "
+                                      "src/schedulers.py:58-59,85-90; off in every shipped config) and no Karras sigmas")
         if not 1 <= cfg.solver_order <= 3:
             raise NotImplementedError("solver_order must be 1, 2 or 3")
         self.alpha_t = torch.sqrt(self.alphas_cumprod)
@@ -347,11 +364,32 @@ class DPMSolverScheduler(FusedScheduler):
         return a, s, torch.log(a) - torch.log(s)
 
     def _convert_coeffs(self):
-        a_s, s_s = self._sigma_to_alpha_sigma_t(self.sigmas[self.step_index])
-        x0_x, x0_e = 1.0 / _f(a_s), -_f(s_s) / _f(a_s)
+        """``convert_model_output`` (src/schedulers.py:14-96) as the fused kernel's two linear forms of (x, model
+        output e): the converted output kept as multistep history, ``m = m_x x + m_e e``, and the returned x0
+        prediction ``x0 = x0_x x + x0_e e`` -- every ``prediction_type`` branch is linear, so none needs a kernel of
+        its own.  Scalars are float32 exactly as the reference computes them (sigma -> alpha_t, sigma_t), combined in
+        Python floats; the non-``++`` x0 is ``(x - sigma_t eps) / alpha_t`` (:92-94) with eps substituted."""
+        sigma = self.sigmas[self.step_index]
+        a_s, s_s = self._sigma_to_alpha_sigma_t(sigma)
+        a, s = _f(a_s), _f(s_s)
+        pt = self.config.prediction_type
         if self.config.algorithm_type in ("dpmsolver++", "sde-dpmsolver++"):
+            if pt == "epsilon":
+                x0_x, x0_e = 1.0 / a, -s / a                     # :40-42
+            elif pt == "sample":
+                x0_x, x0_e = 0.0, 1.0                            # :43-44
+            elif pt == "v_prediction":
+                x0_x, x0_e = a, -s                               # :45-48
+            else:                                                # flow_prediction, :49-51: sigma itself
+                x0_x, x0_e = 1.0, -_f(sigma)
             return dict(m_x=x0_x, m_e=x0_e, x0_x=x0_x, x0_e=x0_e)
-        return dict(m_x=0.0, m_e=1.0, x0_x=x0_x, x0_e=x0_e)
+        if pt == "epsilon":
+            m_x, m_e = 0.0, 1.0                                  # :66-71
+        elif pt == "sample":
+            m_x, m_e = 1.0 / s, -a / s                           # :72-75
+        else:                                                    # v_prediction, :76-79
+            m_x, m_e = s, a
+        return dict(m_x=m_x, m_e=m_e, x0_x=(1.0 - s * m_x) / a, x0_e=-s * m_e / a)
 
     def convert_model_output(self, model_output, *args, sample=None, **kwargs):
         """src/schedulers.py:14-96 -> (converted model output, x0_pred); one fused launch."""

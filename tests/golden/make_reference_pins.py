@@ -11,7 +11,9 @@ What each fixture pins
   sched/<case>/{prev,x0}   /root/reference/src/schedulers.py:14-187 ``convert_model_output`` + ``step`` (order
                            selection, lower-order-final, history shift, fp32 upcast, return tuple) over the
                            synthetic epsilon sequence; the ``++`` cases run with the one-line C-1 source patch
-                           (oracle/refexec.py ``C1_PATCH``), the others unmodified
+                           (oracle/refexec.py ``C1_PATCH``), the others unmodified; every ``prediction_type``
+                           branch (:36-56, :65-83) and -- for the oracle only -- the thresholding branches
+                           (:58-59, :85-90) over the oracle's restatement of diffusers' ``_threshold_sample``
   pipe/<case>/per_step     /root/reference/src/models.py ``call`` of the four pipeline classes (loop body,
                            CFG combine, RNG order, two-scheduler switch, interleave partition, skip mask)
                            over a tiny oracle UNet
@@ -48,7 +50,7 @@ def main():
     arrays, meta = {}, {"scheduler_timesteps": {}, "pipeline_timesteps": {}, "pipeline_info": {}, "switch": [],
                         "raises": {}, "registry": {}}
 
-    for name, (kind, over, n, patch, seed) in RC.SCHEDULER_CASES.items():
+    for name, (kind, over, n, patch, seed) in {**RC.SCHEDULER_CASES, **RC.THRESHOLD_CASES}.items():
         ns = ref_c1 if patch else ref
         prevs, x0s, ts = RC.run_scheduler_case(RC.make_scheduler(kind, over, ref=ns), n, seed)
         arrays[f"sched/{name}/prev"] = torch.stack(prevs).numpy()

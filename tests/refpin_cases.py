@@ -31,6 +31,31 @@ SCHEDULER_CASES = {
     "dpmpp_o3_n20": ("dpm", dict(solver_order=3, algorithm_type="dpmsolver++", final_sigmas_type="zero"), 20, True, None),
     "dpmpp_o2_n8_heun": ("dpm", dict(solver_order=2, algorithm_type="dpmsolver++", solver_type="heun"), 8, True, None),
     "sde_dpmpp_o2_n10": ("dpm", dict(solver_order=2, algorithm_type="sde-dpmsolver++"), 10, True, 11),
+    # the other ``prediction_type`` branches of convert_model_output (schedulers.py:43-51, :72-79): the synthetic
+    # sequence then plays the network's x0 / v / flow output
+    "dpm_o2_n10_sample": ("dpm", dict(solver_order=2, algorithm_type="dpmsolver", final_sigmas_type="sigma_min",
+                                       prediction_type="sample"), 10, False, None),
+    "dpm_o2_n10_vpred": ("dpm", dict(solver_order=2, algorithm_type="dpmsolver", final_sigmas_type="sigma_min",
+                                      prediction_type="v_prediction"), 10, False, None),
+    "sde_dpm_o2_n8_vpred": ("dpm", dict(solver_order=2, algorithm_type="sde-dpmsolver", final_sigmas_type="sigma_min",
+                                         prediction_type="v_prediction"), 8, False, 11),
+    "dpmpp_o2_n10_sample": ("dpm", dict(solver_order=2, algorithm_type="dpmsolver++", prediction_type="sample"), 10,
+                            True, None),
+    "dpmpp_o2_n10_vpred": ("dpm", dict(solver_order=2, algorithm_type="dpmsolver++", prediction_type="v_prediction"),
+                           10, True, None),
+    "dpmpp_o3_n12_vpred": ("dpm", dict(solver_order=3, algorithm_type="dpmsolver++", prediction_type="v_prediction"),
+                           12, True, None),
+    "dpmpp_o2_n10_flow": ("dpm", dict(solver_order=2, algorithm_type="dpmsolver++", prediction_type="flow_prediction"),
+                          10, True, None),
+}
+
+# convert_model_output's thresholding branches (schedulers.py:58-59, :85-90) over the oracle's restatement of
+# diffusers' ``_threshold_sample``: pinned for the oracle only -- the product raises NotImplementedError for them
+THRESHOLD_CASES = {
+    "dpm_o2_n10_thr": ("dpm", dict(solver_order=2, algorithm_type="dpmsolver", final_sigmas_type="sigma_min",
+                                    thresholding=True, sample_max_value=2.0), 10, False, None),
+    "dpmpp_o2_n10_thr": ("dpm", dict(solver_order=2, algorithm_type="dpmsolver++", thresholding=True,
+                                      sample_max_value=2.0), 10, True, None),
 }
 
 # name -> dict(pipe=..., ...) ; "patch": needs the C-1 source patch

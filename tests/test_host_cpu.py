@@ -115,10 +115,17 @@ def _pairs():
          dict(solver_order=2, algorithm_type="sde-dpmsolver", final_sigmas_type="sigma_min"), 8, {}),
         (S.LCMScheduler, O.LCMScheduler, {}, 4, {}),
         (S.PNDMScheduler, O.PNDMScheduler, {}, 12, {}),
+        (S.DDIMSchedulerMy, O.DDIMScheduler, dict(prediction_type="v_prediction"), 10, {}),
+        (S.DDIMSchedulerMy, O.DDIMScheduler, dict(prediction_type="sample"), 10, {"eta": 0.3}),
+        (S.DPMSolverScheduler, O.DPMSolverScheduler, dict(solver_order=2, algorithm_type="dpmsolver++",
+                                                          prediction_type="v_prediction"), 12, {}),
+        (S.DPMSolverScheduler, O.DPMSolverScheduler,
+         dict(solver_order=3, algorithm_type="dpmsolver", final_sigmas_type="sigma_min", prediction_type="sample"), 12, {}),
     ]
 
 
-def _emulated_launch(self, coeffs, eps, eps_text, sample, hist=(), noise=None, want_m0=False, want_x0=True, out=None):
+def _emulated_launch(self, coeffs, eps, eps_text, sample, hist=(), noise=None, want_m0=False, want_x0=True, out=None,
+                     ring=True):
     """float64 model of sonic_latent_update (include/sonic.h) for fp32 tensors on the CPU."""
     c = {k: float(coeffs.get(k, 0.0)) for k in ("guidance", "m_x", "m_e", "x0_x", "x0_e", "c_x", "c_e", "c_m0",
                                                 "c_h1", "c_h2", "c_h3", "c_z")}
@@ -134,7 +141,7 @@ def _emulated_launch(self, coeffs, eps, eps_text, sample, hist=(), noise=None, w
     return xn.to(f), (m0.to(f) if want_m0 else None), (x0.to(f) if want_x0 else None)
 
 
-@pytest.mark.parametrize("idx", range(13))
+@pytest.mark.parametrize("idx", range(17))
 def test_scheduler_coefficients_reproduce_oracle_updates(idx, monkeypatch):
     """Every scheduler's reduction to linear-combination coefficients, step by step, against the
     oracle's literal formulas (fp32, CPU, no GPU needed)."""
