@@ -215,6 +215,7 @@ attention_kernel(const __grid_constant__ AttParams p) {
   tc_fence_after();
   const uint32_t tmem_s = *tmem_slot;
   const uint32_t tmem_o = tmem_s + kSub;
+  pdl_wait();                                    // the set-up above may overlap the previous kernel's tail (SONIC_PDL)
 
   if (warp == kWarpTma) {
     if (lane == 0) {
@@ -238,6 +239,7 @@ attention_kernel(const __grid_constant__ AttParams p) {
             tma_load_4d(sm_v + st * kv_bytes + a * kKvAtomBytes, &p.tm_v, &v_full[st], a * 64, head, t * kSub, batch);
         }
       }
+      pdl_launch_dependents();                   // every load of this CTA has been issued
     }
   } else if (warp == kWarpMma) {
     // The WHOLE warp runs this loop with warp-uniform control flow (so descriptors and TMEM addresses
@@ -525,6 +527,7 @@ attention2_kernel(const __grid_constant__ AttParams p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                                    // the set-up above may overlap the previous kernel's tail (SONIC_PDL)
 
   if (warp == kWarpTma) {
     if (lane == 0) {
@@ -555,6 +558,7 @@ attention2_kernel(const __grid_constant__ AttParams p) {
           tma_load_4d(sm_v + st * kKvTile + a * kKvAtomBytes, &p.tm_v, &v_full[st], a * 64, head, t * kSub, batch);
       }
       for (int i = 1; i < n_pairs; ++i) load_q(i);
+      pdl_launch_dependents();                   // every load of this CTA has been issued
     }
   } else if (warp == kWarpMma) {
     // Warp-uniform control flow, one elected lane issues (see attention_kernel).
@@ -774,7 +778,11 @@ int launch_att2(const AttentionPlan* pl, const AttParams& prm, cudaStream_t stre
                                     cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  attention2_kernel<kDPV, kResident, kNarrow><<<pl->grid, kAttThreads, pl->smem, stream>>>(prm);
+  if (pdl_enabled())
+    SONIC_CUDA(launch_kernel_ex(attention2_kernel<kDPV, kResident, kNarrow>, pl->grid, dim3(kAttThreads), pl->smem, stream,
+                                1, prm));
+  else
+    attention2_kernel<kDPV, kResident, kNarrow><<<pl->grid, kAttThreads, pl->smem, stream>>>(prm);
   SONIC_CUDA(cudaGetLastError());
   return 0;
 }
@@ -797,7 +805,10 @@ int launch_att(const AttentionPlan* pl, const AttParams& prm, cudaStream_t strea
     SONIC_CUDA(cudaFuncSetAttribute(attention_kernel<kDPV>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  attention_kernel<kDPV><<<pl->grid, kAttThreads, pl->smem, stream>>>(prm);
+  if (pdl_enabled())
+    SONIC_CUDA(launch_kernel_ex(attention_kernel<kDPV>, pl->grid, dim3(kAttThreads), pl->smem, stream, 1, prm));
+  else
+    attention_kernel<kDPV><<<pl->grid, kAttThreads, pl->smem, stream>>>(prm);
   SONIC_CUDA(cudaGetLastError());
   return 0;
 }

@@ -24,6 +24,41 @@ int check_cuda(cudaError_t e, const char* what, const char* file, int line);
     if (!(cond)) { ::sonic::set_error(__VA_ARGS__); return -2; }                 \
   } while (0)
 
+// Programmatic dependent launch (SONIC_PDL=1; default off): the plan's hot kernels are launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization, so the NEXT kernel's CTAs become resident and run their
+// prologue (barrier set-up, TMEM allocation, descriptor prefetch) while the previous kernel's last CTAs drain; they
+// then block in pdl_wait() until the previous grid has completed and its writes are visible.  Every kernel that can be
+// launched this way executes pdl_wait() on ALL threads before its first global access and before any exit path, so
+// completion stays transitive along the stream; without the launch attribute both instructions are no-ops.
+bool pdl_enabled();
+// Launch with optional cluster width and, if pdl_enabled(), the programmatic-serialization attribute.
+template <typename... P, typename... A>
+inline cudaError_t launch_kernel_ex(void (*kernel)(P...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                                    unsigned cluster_x, A&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  unsigned n = 0;
+  if (cluster_x > 1) {
+    attr[n].id = cudaLaunchAttributeClusterDimension;
+    attr[n].val.clusterDim.x = cluster_x;
+    attr[n].val.clusterDim.y = 1;
+    attr[n].val.clusterDim.z = 1;
+    ++n;
+  }
+  if (pdl_enabled()) {
+    attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[n].val.programmaticStreamSerializationAllowed = 1;
+    ++n;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = n;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<P>(args)...);
+}
+
 // cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda link dependency).
 // dims/strides are innermost-first; strides[i] is the byte stride of dim i+1.
 // swizzle_bytes: 0 (none), 64 or 128.
@@ -308,6 +343,10 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32
       ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
       : "memory");
 }
+
+// ------------------------------------------------------------------ programmatic dependent launch
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 // ------------------------------------------------------------------ CTA pairs (cta_group::2)
 // Two CTAs of a cluster on the two SMs of a TPC run ONE tcgen05.mma of M = 256: the leader (cluster rank 0) issues it,

@@ -2,6 +2,7 @@
 #include "common.cuh"
 
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 namespace sonic {
@@ -23,6 +24,11 @@ void set_error(const char* fmt, ...) {
 }
 
 const char* last_error() { return g_err; }
+
+bool pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("SONIC_PDL"); return e && atoi(e) != 0; }();
+  return on;
+}
 
 int check_cuda(cudaError_t e, const char* what, const char* file, int line) {
   if (e == cudaSuccess) return 0;

@@ -150,6 +150,7 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
   else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();                                    // everything above may overlap the previous kernel's tail (SONIC_PDL)
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -210,6 +211,7 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
         }
         GEMM_TRACE(0, ti, 1);
       }
+      pdl_launch_dependents();                   // this CTA's last operand loads are in flight: the next kernel may set up
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
@@ -569,7 +571,7 @@ conv_gemm_kernel(const __grid_constant__ GemmParams p) {
           }
           if (p.residual) {
             const uint4* rp = reinterpret_cast<const uint4*>(p.residual + grow * p.ld_res + oc);
-            const uint4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
+            const uint4 r0 = __ldcg(rp), r1 = __ldcg(rp + 1);   // activations: coherent path (the kernel can overlap its producer's tail)
             const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
@@ -870,19 +872,9 @@ int gemm_launch(const GemmPlan& plan, cudaStream_t stream) {
     g_attr_set = true;
   }
   if (plan.p.pair) {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(plan.grid);
-    cfg.blockDim = dim3(kGemmThreads);
-    cfg.dynamicSmemBytes = plan.smem;
-    cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = 2;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    SONIC_CUDA(cudaLaunchKernelEx(&cfg, conv_gemm_kernel<true>, plan.p));
+    SONIC_CUDA(launch_kernel_ex(conv_gemm_kernel<true>, dim3(plan.grid), dim3(kGemmThreads), plan.smem, stream, 2, plan.p));
+  } else if (pdl_enabled()) {
+    SONIC_CUDA(launch_kernel_ex(conv_gemm_kernel<false>, dim3(plan.grid), dim3(kGemmThreads), plan.smem, stream, 1, plan.p));
   } else {
     conv_gemm_kernel<false><<<plan.grid, kGemmThreads, plan.smem, stream>>>(plan.p);
   }

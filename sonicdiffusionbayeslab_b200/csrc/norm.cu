@@ -34,6 +34,12 @@ __device__ __forceinline__ uint4 gn_load(const GnSrc& s, size_t pix, int ch) {
   const __nv_bfloat16* p = ch < s.c0 ? s.x0 + pix * s.ld0 + ch : s.x1 + pix * s.ld1 + (ch - s.c0);
   return __ldg(reinterpret_cast<const uint4*>(p));
 }
+// The cluster kernel can be launched while the kernel that wrote x is still draining (SONIC_PDL): the non-coherent
+// path (ld.global.nc) is only defined for data nobody writes during the reader's lifetime, so it reads through L2.
+__device__ __forceinline__ uint4 gn_load_cg(const GnSrc& s, size_t pix, int ch) {
+  const __nv_bfloat16* p = ch < s.c0 ? s.x0 + pix * s.ld0 + ch : s.x1 + pix * s.ld1 + (ch - s.c0);
+  return __ldcg(reinterpret_cast<const uint4*>(p));
+}
 
 // Scratch layout (floats): partial[n_img][kGroupNormMaxChunks][groups][2] | final[n_img][groups][2]
 //                          | ticket[n_img] (int, zero between launches)
@@ -270,6 +276,8 @@ gn_cluster_kernel(GnSrc s, const float* __restrict__ part0, const float* __restr
   const int nb = hw >> 5;                        // 32-row blocks per image
   const int b0 = static_cast<int>(static_cast<long long>(rank) * nb / R);
   const int b1 = static_cast<int>(static_cast<long long>(rank + 1) * nb / R);
+  pdl_wait();                                    // SONIC_PDL: launched while the producing GEMM drains
+  pdl_launch_dependents();
   for (int c = threadIdx.x; c < C; c += kGnThreads) {
     const float2* src = c < s.c0
         ? reinterpret_cast<const float2*>(part0) + static_cast<size_t>(img) * nb * s.c0 + c
@@ -319,7 +327,7 @@ gn_cluster_kernel(GnSrc s, const float* __restrict__ part0, const float* __restr
   if (pl < ppp) {
 #pragma unroll
     for (int k = 0; k < 8; ++k)
-      u[k] = p_begin + pl + k * ppp < p_end ? gn_load(s, base + p_begin + pl + k * ppp, v * 8) : make_uint4(0, 0, 0, 0);
+      u[k] = p_begin + pl + k * ppp < p_end ? gn_load_cg(s, base + p_begin + pl + k * ppp, v * 8) : make_uint4(0, 0, 0, 0);
   }
   cluster_wait();
   if (threadIdx.x < 2 * groups) {
@@ -368,7 +376,7 @@ gn_cluster_kernel(GnSrc s, const float* __restrict__ part0, const float* __restr
       if (p != p_begin + pl) {
 #pragma unroll
         for (int k = 0; k < 8; ++k)
-          u[k] = p + k * ppp < p_end ? gn_load(s, base + p + k * ppp, v * 8) : make_uint4(0, 0, 0, 0);
+          u[k] = p + k * ppp < p_end ? gn_load_cg(s, base + p + k * ppp, v * 8) : make_uint4(0, 0, 0, 0);
       }
 #pragma unroll
       for (int k = 0; k < 8; ++k)
@@ -533,11 +541,13 @@ __global__ void __launch_bounds__(256)
 ln_side_kernel(const float2* __restrict__ part, int parts, int M, float inv_k, float eps,
                __nv_bfloat16* __restrict__ side, float* __restrict__ rstd) {
   const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  pdl_wait();                                    // SONIC_PDL: before the first global access and before any exit
+  pdl_launch_dependents();
   if (row >= M) return;
   const float2* st = part + static_cast<size_t>(row) * parts;
   float sa = 0.f, sq = 0.f;
   for (int i = 0; i < parts; ++i) {
-    const float2 v = __ldg(st + i);
+    const float2 v = __ldcg(st + i);             // written by the GEMM this kernel may overlap (SONIC_PDL): through L2
     sa += v.x;
     sq += v.y;
   }
@@ -562,9 +572,14 @@ ln_side_kernel(const float2* __restrict__ part, int parts, int M, float inv_k, f
 int ln_side_launch(const float* partials, int parts, int M, int K, float eps, void* side, float* rstd,
                    cudaStream_t stream) {
   SONIC_REQUIRE(partials && side && rstd && parts > 0 && M > 0 && K > 0, "ln_side: bad argument");
-  ln_side_kernel<<<(M + 255) / 256, 256, 0, stream>>>(reinterpret_cast<const float2*>(partials), parts, M,
-                                                     1.0f / static_cast<float>(K), eps,
-                                                     static_cast<__nv_bfloat16*>(side), rstd);
+  if (pdl_enabled())
+    SONIC_CUDA(launch_kernel_ex(ln_side_kernel, dim3((M + 255) / 256), dim3(256), 0, stream, 1,
+                                reinterpret_cast<const float2*>(partials), parts, M, 1.0f / static_cast<float>(K), eps,
+                                static_cast<__nv_bfloat16*>(side), rstd));
+  else
+    ln_side_kernel<<<(M + 255) / 256, 256, 0, stream>>>(reinterpret_cast<const float2*>(partials), parts, M,
+                                                       1.0f / static_cast<float>(K), eps,
+                                                       static_cast<__nv_bfloat16*>(side), rstd);
   SONIC_CUDA(cudaGetLastError());
   return 0;
 }
@@ -609,18 +624,24 @@ int groupnorm_launch(const GroupNormOp& op, cudaStream_t stream) {
     // tensors of small batches keep the finalize + apply pair.  SONIC_GN_CLUSTER=0 disables this path (A/B).
     const int R = gn_cluster_size(op);
     if (R > 0) {
+      // R == 1 still goes through the cluster attribute (a cluster of one), as before
       cudaLaunchConfig_t cfg = {};
       cfg.gridDim = dim3(R, op.n_img);
       cfg.blockDim = dim3(kGnThreads);
       cfg.dynamicSmemBytes = static_cast<size_t>(2 * C) * sizeof(float);
       cfg.stream = stream;
-      cudaLaunchAttribute attr[1];
+      cudaLaunchAttribute attr[2];
       attr[0].id = cudaLaunchAttributeClusterDimension;
       attr[0].val.clusterDim.x = R;
       attr[0].val.clusterDim.y = 1;
       attr[0].val.clusterDim.z = 1;
-      cfg.attrs = attr;
       cfg.numAttrs = 1;
+      if (pdl_enabled()) {
+        attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[1].val.programmaticStreamSerializationAllowed = 1;
+        cfg.numAttrs = 2;
+      }
+      cfg.attrs = attr;
       SONIC_CUDA(cudaLaunchKernelEx(&cfg, gn_cluster_kernel, s, op.part0, op.part1, op.hw, op.groups, op.eps, op.gamma,
                                     op.beta, op.silu, static_cast<__nv_bfloat16*>(op.y)));
       return 0;

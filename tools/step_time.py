@@ -5,6 +5,7 @@ import os
 import statistics
 import sys
 import time
+import zlib
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
@@ -15,6 +16,7 @@ from sonicdiffusionbayeslab_b200.unet_spec import random_unet_state_dict
 tag = sys.argv[1] if len(sys.argv) > 1 else ""
 n_lat = int(sys.argv[2]) if len(sys.argv) > 2 else 16
 dev = torch.device("cuda:0")
+torch.manual_seed(0)                      # same inputs in every process: the digest below is comparable across A/B runs
 eng = UNetEngine(random_unet_state_dict(29), n_latents=n_lat, cfg_dup=True, device=dev)
 eng.x_in.normal_()
 eng.set_context(torch.randn(2 * n_lat, 77, 768, device=dev).bfloat16())
@@ -37,5 +39,6 @@ for _ in range(9):
     time.sleep(0.3)
     bursts.append(run(3))
 sustained = run(40)
+digest = zlib.crc32(eng.forward(500.0).float().cpu().numpy().tobytes())
 print(f"{tag} UNet step (graph replay, UNet batch {2 * n_lat}): burst min {min(bursts):.3f} median "
-      f"{statistics.median(bursts):.3f} ms; sustained x40 {sustained:.3f} ms")
+      f"{statistics.median(bursts):.3f} ms; sustained x40 {sustained:.3f} ms; eps crc32 {digest:08x}")
