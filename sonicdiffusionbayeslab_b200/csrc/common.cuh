@@ -346,7 +346,18 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32
 
 // ------------------------------------------------------------------ programmatic dependent launch
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+// -DSONIC_PDL_TRIGGER: 1 = every PDL kernel signals early (the persistent / tensor-core kernels once a CTA's last
+// loads are issued, the small ones right after their wait); 2 = only the small kernels (cluster GroupNorm, ln_side);
+// 0 = nobody (the dependent grid is released when the last CTA exits: only the launch latency overlaps).
+#ifndef SONIC_PDL_TRIGGER
+#define SONIC_PDL_TRIGGER 1
+#endif
+__device__ __forceinline__ void pdl_launch_dependents() {            // tensor-core kernels
+  if (SONIC_PDL_TRIGGER == 1) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+__device__ __forceinline__ void pdl_launch_dependents_small() {      // cluster GroupNorm, ln_side
+  if (SONIC_PDL_TRIGGER >= 1) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
 
 // ------------------------------------------------------------------ CTA pairs (cta_group::2)
 // Two CTAs of a cluster on the two SMs of a TPC run ONE tcgen05.mma of M = 256: the leader (cluster rank 0) issues it,

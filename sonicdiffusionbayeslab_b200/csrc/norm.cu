@@ -277,7 +277,7 @@ gn_cluster_kernel(GnSrc s, const float* __restrict__ part0, const float* __restr
   const int b0 = static_cast<int>(static_cast<long long>(rank) * nb / R);
   const int b1 = static_cast<int>(static_cast<long long>(rank + 1) * nb / R);
   pdl_wait();                                    // SONIC_PDL: launched while the producing GEMM drains
-  pdl_launch_dependents();
+  pdl_launch_dependents_small();
   for (int c = threadIdx.x; c < C; c += kGnThreads) {
     const float2* src = c < s.c0
         ? reinterpret_cast<const float2*>(part0) + static_cast<size_t>(img) * nb * s.c0 + c
@@ -542,7 +542,7 @@ ln_side_kernel(const float2* __restrict__ part, int parts, int M, float inv_k, f
                __nv_bfloat16* __restrict__ side, float* __restrict__ rstd) {
   const int row = blockIdx.x * blockDim.x + threadIdx.x;
   pdl_wait();                                    // SONIC_PDL: before the first global access and before any exit
-  pdl_launch_dependents();
+  pdl_launch_dependents_small();
   if (row >= M) return;
   const float2* st = part + static_cast<size_t>(row) * parts;
   float sa = 0.f, sq = 0.f;
