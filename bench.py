@@ -27,8 +27,9 @@ Own arm: ONE JSON line with
              the same GPU at the same UNet batch -- the "existing Blackwell kernels" bar (rank 0, N=1 only)
   cpu_baseline  the oracle (CPU restatement of the reference path) on this box's host cores, bounded sample
 Reference arm (--impl reference): the oracle's CPU path (there is no runnable reference: its arithmetic lives in
-diffusers, absent here) on all host threads; each step is a bounded sample (ONE CFG denoising step at batch 1,
-fp32) extrapolated to the workload -- the line's ``config`` says so.
+diffusers, absent here) on all host threads; each step is a bounded sample -- the first n of one image's 25 CFG
+denoising steps at batch 1, fp32, n sized from a calibration step (25 = the whole image on a fast host), extrapolated
+x25/n otherwise -- and the line's ``config`` says exactly which.
 """
 from __future__ import annotations
 
@@ -504,7 +505,7 @@ def run_loop_workload(args, model, kw, wl, B, rank, world, local, dev, dist):
         except Exception as e:                              # noqa: BLE001  (an OOM here must not lose the bench line)
             line["gpu_library_baseline"] = {"error": f"{type(e).__name__}: {e}"[:300]}
     if world == 1 and not args.no_cpu_baseline:
-        line["cpu_baseline"] = cpu_baseline(sample_steps=1)
+        line["cpu_baseline"] = cpu_baseline()
     return line
 
 
@@ -674,17 +675,21 @@ def run_two_schedulers(args, model, kw, n_prompts, rank, world, local, dev, dist
 
 
 # ----------------------------------------------------------------------------------------- CPU oracle arms
-def _oracle_cfg_step_seconds(n_steps, threads):
-    """Times the oracle (reference restatement) on CPU: batch 1, CFG 7.5, DPM-Solver++ steps."""
+_ORACLE = {}
+
+
+def _oracle_run(n_steps, threads):
+    """Seconds the oracle (reference restatement) takes on the CPU for the first ``n_steps`` steps of the 25-step
+    DPM-Solver++ trajectory at batch 1 with CFG 7.5 (2 UNet sample-forwards per step), fp32, ``threads`` threads."""
     from oracle.pipeline import denoise
     from oracle.schedulers import SD15_SCHEDULER_CONFIG, DPMSolverScheduler
     from oracle.unet import make_unet
 
     torch.set_num_threads(threads)
-    net = make_unet(29)
-    g = torch.Generator().manual_seed(29)
-    pe, ne = torch.randn(1, 77, 768, generator=g), torch.randn(1, 77, 768, generator=g)
-    lat = torch.randn(1, 4, 64, 64, generator=g)
+    if "net" not in _ORACLE:
+        g = torch.Generator().manual_seed(29)
+        _ORACLE.update(net=make_unet(29), pe=torch.randn(1, 77, 768, generator=g),
+                       ne=torch.randn(1, 77, 768, generator=g), lat=torch.randn(1, 4, 64, 64, generator=g))
 
     class Trunc(DPMSolverScheduler):            # run only the first n_steps of the 25-step schedule
         def set_timesteps(self, *a, **k):
@@ -694,21 +699,43 @@ def _oracle_cfg_step_seconds(n_steps, threads):
     sched = Trunc.from_config(SD15_SCHEDULER_CONFIG, solver_order=2, algorithm_type="dpmsolver++",
                               final_sigmas_type="zero")
     t0 = time.perf_counter()
-    denoise(net, sched, pe, ne, lat, 25, guidance_scale=GUIDANCE)
-    return (time.perf_counter() - t0) / n_steps
+    denoise(_ORACLE["net"], sched, _ORACLE["pe"], _ORACLE["ne"], _ORACLE["lat"], STEPS_PER_IMAGE,
+            guidance_scale=GUIDANCE)
+    return time.perf_counter() - t0
 
 
-def cpu_baseline(sample_steps=1):
+STEPS_PER_IMAGE = 25
+
+
+def _sample_size(step_seconds, budget_s):
+    """Denoising steps per timed CPU sample: as many of the image's 25 as fit ``budget_s`` (25 = a whole image, no
+    extrapolation), at least one."""
+    return max(1, min(STEPS_PER_IMAGE, int(budget_s / max(step_seconds, 1e-3))))
+
+
+def _sample_text(n, s):
+    whole = n == STEPS_PER_IMAGE
+    return (f"{'the whole 25-step image' if whole else f'the first {n} of the 25 denoising steps of one image'} at "
+            f"batch 1, CFG 7.5 (2 UNet sample-forwards per step), fp32, {s:.2f} s/step"
+            + ("" if whole else f", extrapolated x{STEPS_PER_IMAGE}/{n}"))
+
+
+def cpu_baseline(budget_s=15.0):
+    """The oracle on the host cores next to the GPU number: one warm-up step (which also sizes the sample), then ONE
+    timed sample of as many denoising steps as fit ~``budget_s`` seconds."""
     threads = len(os.sched_getaffinity(0))
-    _oracle_cfg_step_seconds(1, threads)                       # warm-up (allocations, thread pool)
-    s = _oracle_cfg_step_seconds(sample_steps, threads)
-    return {"value": round(1.0 / (s * 25), 6), "unit": "images/s", "cores": threads, "kind": "port",
-            "sample": f"{sample_steps} CFG denoising step(s) at batch 1 (2 UNet sample-forwards each, fp32) of the "
-                      f"25-step DPM-Solver++ schedule, {s:.2f} s/step, extrapolated x25",
+    _oracle_run(1, threads)                                    # allocations, thread pool
+    n = _sample_size(_oracle_run(1, threads), budget_s)
+    s = _oracle_run(n, threads) / n
+    return {"value": round(1.0 / (s * STEPS_PER_IMAGE), 6), "unit": "images/s", "cores": threads, "kind": "port",
+            "sample": _sample_text(n, s), "sampled_steps": n, "extrapolated": n != STEPS_PER_IMAGE,
             "gflops": round(2 * FLOP_PER_SAMPLE_FWD / s / 1e9, 1)}
 
 
 def run_reference(args):
+    """``--impl reference``: the reference's CPU path (its oracle restatement -- diffusers is not installable here) on
+    all host threads.  A "step" is one bounded sample of the workload: the first n denoising steps of one image, n
+    sized from a calibration step so that one sample takes at most ~27 s (n = 25, a whole image, at <= 1.08 s/step)."""
     rank = int(os.environ.get("RANK", 0))
     if rank != 0:
         return
@@ -717,28 +744,26 @@ def run_reference(args):
                                                                "workload (dpm_solver) only"}), flush=True)
         return
     threads = len(os.sched_getaffinity(0))
-    for _ in range(min(args.warmup, 1)):
-        _oracle_cfg_step_seconds(1, threads)
-    times = [_oracle_cfg_step_seconds(1, threads) for _ in range(max(1, min(args.steps, 3)))]
+    _oracle_run(1, threads)                                    # warm-up (untimed) ...
+    n = _sample_size(_oracle_run(1, threads), 27.0)            # ... and calibration
+    times = [_oracle_run(n, threads) / n for _ in range(max(1, min(args.steps, 3)))]
     s = statistics.mean(times)
-    value = 1.0 / (s * 25)
+    value = 1.0 / (s * STEPS_PER_IMAGE)
     W = WORKLOADS["dpm_solver"]
     line = {
         "impl": "reference", "metric": W["metric"],
         "value": round(value, 6), "unit": "images/s", "n_gpus": int(os.environ.get("WORLD_SIZE", 1)),
-        "steps": len(times), "warmup": min(args.warmup, 1), "ms_per_step": round(s * 1e3 * 25, 1),
+        "steps": len(times), "warmup": 2, "ms_per_step": round(s * 1e3 * STEPS_PER_IMAGE, 1),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         # what THIS arm really ran -- not the GPU arm's batch-16 bf16 workload
         "config": {"workload": "bounded CPU sample of configs/dpm_solver_config.yaml: the oracle restatement of the "
-                               "reference loop, ONE classifier-free-guidance denoising step (2 UNet sample-forwards) of "
-                               "the 25-step DPM-Solver++ schedule at batch 1, fp32, all host threads; images/s = "
+                               f"reference loop, {_sample_text(n, s)}, all host threads; images/s = "
                                "1 / (25 x seconds per step)",
-                   "per_gpu_batch": 1, "dtype": "f32", "extrapolated": True, "sampled_steps": len(times),
-                   "steps_per_image": 25, "gpu_arm_workload": W["text"]},
+                   "per_gpu_batch": 1, "dtype": "f32", "extrapolated": n != STEPS_PER_IMAGE, "sampled_steps": n,
+                   "samples": len(times), "steps_per_image": STEPS_PER_IMAGE, "gpu_arm_workload": W["text"]},
         "cpu_baseline": {"value": round(value, 6), "unit": "images/s", "cores": threads, "kind": "port",
-                         "sample": f"oracle restatement of the reference path (diffusers is not installable here), fp32, "
-                                   f"all host threads: {len(times)} x 1 CFG denoising step at batch 1 (2 UNet "
-                                   f"sample-forwards), mean {s:.2f} s/step, extrapolated x25 steps per image"},
+                         "sample": "oracle restatement of the reference path (diffusers is not installable here), all "
+                                   f"host threads: {len(times)} sample(s) of {_sample_text(n, s)}"},
         "e2e": {"value": round(value, 6), "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
