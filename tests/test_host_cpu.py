@@ -401,3 +401,19 @@ def test_gemm_tile_width_choices_for_the_cta_pair_kernel():
     for N in (320, 640, 960, 1280, 1920, 2560, 3840):
         bn = k.gemm_block_n(N, 32, 16, 16)
         assert bn % 32 == 0 and 32 <= bn <= 256          # staged epilogue chunks, pairable halves of whole swizzle atoms
+
+
+def test_bench_cpu_sample_sizing():
+    """bench.py sizes the CPU arm's timed sample from a calibration step: a whole 25-step image when it fits the
+    budget (no extrapolation), else the first n steps; the line's text says which."""
+    import importlib.util
+    import os
+
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(os.path.dirname(os.path.dirname(
+        os.path.abspath(__file__))), "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    assert bench._sample_size(1.01, 27.0) == 25 and bench._sample_size(1.2, 27.0) == 22
+    assert bench._sample_size(3.9, 15.0) == 3 and bench._sample_size(100.0, 15.0) == 1
+    assert "whole 25-step image" in bench._sample_text(25, 1.0) and "extrapolated" not in bench._sample_text(25, 1.0)
+    assert "first 4 of the 25" in bench._sample_text(4, 3.9) and "extrapolated x25/4" in bench._sample_text(4, 3.9)
