@@ -161,6 +161,34 @@ int sonic_latent_update_x0n(const sonic_update_coeffs* k, const void* eps_uncond
                             const void* noise, void* out_sample, void* out_m0, void* out_x0, int64_t n,
                             int64_t n_x0, int32_t dtype, sonic_stream_t stream);
 
+/* The same fused update with a NON-LINEAR post-processing of the x0 prediction -- the branches of
+ * /root/reference/src/schedulers.py:58-59 and :85-90 (`thresholding`, diffusers `_threshold_sample`) and diffusers'
+ * `clip_sample` (DDIM step, item 4); off in every shipped config, so this is a separate kernel and the linear one above
+ * stays the hot path:
+ *   x0  = round_dtype(x0_x*x + x0_e*e)
+ *   mode 1:  x0' = clamp(x0, -clip, clip)
+ *   mode 2:  x0' = clamp(x0, -s, s) / s,  s = thr[image]  (sonic_x0_threshold below; n_per_image elements per image)
+ *   m0  = p_x*x + p_0*x0'   (the converted model output re-derived from the processed x0: p = (0, 1) for the `++`
+ *                            algorithms and DDIM, (1/sigma_t, -alpha_t/sigma_t) for `dpmsolver` / `sde-dpmsolver`)
+ *   x'  as in sonic_latent_update; out_x0 receives x0'. */
+typedef struct sonic_x0_post {
+  int32_t mode;
+  float clip;
+  float p_x, p_0;
+  const float* thr;
+  int64_t n_per_image;
+} sonic_x0_post;
+int sonic_latent_update_post(const sonic_update_coeffs* k, const sonic_x0_post* post, const void* eps_uncond,
+                             const void* eps_text, const void* sample, const void* h1, const void* h2, const void* h3,
+                             const void* noise, void* out_sample, void* out_m0, void* out_x0, int64_t n, int64_t n_x0,
+                             int32_t dtype, sonic_stream_t stream);
+/* Dynamic-thresholding scale per image: thr[i] = clamp(quantile(|x0_i|, ratio), 1, max_value) with x0 as above and the
+ * quantile of torch.quantile (exact order statistics, linear interpolation at ratio*(n-1) in float32).  One CTA per
+ * image; n_per_image*4 bytes of shared memory (<= 200 KiB). */
+int sonic_x0_threshold(const sonic_update_coeffs* k, const void* eps_uncond, const void* eps_text, const void* sample,
+                       int32_t n_img, int64_t n_per_image, float ratio, float max_value, float* thr, int32_t dtype,
+                       sonic_stream_t stream);
+
 /* Layout helpers used around the UNet (exposed for tests). */
 int sonic_nchw_to_nhwc8(const void* x, int32_t dtype, int32_t n_img, int32_t C, int32_t hw,
                         int32_t dup, void* y, sonic_stream_t stream);

@@ -100,6 +100,19 @@ class _SchedulerBase:
     def scale_model_input(self, sample, timestep=None):
         return sample
 
+    def _threshold_sample(self, sample):
+        """diffusers 0.32.1 ``_threshold_sample`` ("dynamic thresholding", Imagen): per sample the
+        ``dynamic_thresholding_ratio`` quantile s of |x0|, clamped to [1, sample_max_value]; x0 <- clamp(x0, -s, s) / s.
+        Third-party restatement; reached from /root/reference/src/schedulers.py:58-59,85-90 (off in every shipped
+        config)."""
+        dtype = sample.dtype
+        b = sample.shape[0]
+        flat = sample.float().reshape(b, -1)
+        s = torch.quantile(flat.abs(), self.config.get("dynamic_thresholding_ratio", 0.995), dim=1)
+        s = torch.clamp(s, min=1, max=self.config.get("sample_max_value", 1.0)).unsqueeze(1)
+        flat = torch.clamp(flat, -s, s) / s
+        return flat.reshape(sample.shape).to(dtype)
+
     def index_for_timestep(self, timestep):
         cand = (self.timesteps == timestep).nonzero()
         if len(cand) == 0:
@@ -121,7 +134,8 @@ class DDIMScheduler(_SchedulerBase):
     _defaults = dict(
         num_train_timesteps=1000, beta_start=0.0001, beta_end=0.02, beta_schedule="linear",
         trained_betas=None, clip_sample=True, set_alpha_to_one=True, steps_offset=0,
-        prediction_type="epsilon", thresholding=False, timestep_spacing="leading",
+        prediction_type="epsilon", thresholding=False, dynamic_thresholding_ratio=0.995, clip_sample_range=1.0,
+        sample_max_value=1.0, timestep_spacing="leading",
     )
 
     def __init__(self, **kw):
@@ -167,8 +181,10 @@ class DDIMScheduler(_SchedulerBase):
             pred_eps = (a ** 0.5) * model_output + (beta ** 0.5) * sample
         else:
             raise ValueError(f"prediction_type given as {pt} must be one of `epsilon`, `sample`, or `v_prediction`")
-        if self.config.clip_sample:
-            pred_x0 = pred_x0.clamp(-1.0, 1.0)
+        if self.config.thresholding:                       # step item 4: thresholding wins over clipping
+            pred_x0 = self._threshold_sample(pred_x0)
+        elif self.config.clip_sample:
+            pred_x0 = pred_x0.clamp(-self.config.clip_sample_range, self.config.clip_sample_range)
         var = self._get_variance(t, prev_t)
         std = eta * var ** 0.5
         direction = (1 - ap - std ** 2) ** 0.5 * pred_eps
@@ -259,19 +275,6 @@ class DPMSolverScheduler(_SchedulerBase):
     def _sigma_to_alpha_sigma_t(sigma):
         alpha_t = 1 / ((sigma ** 2 + 1) ** 0.5)
         return alpha_t, sigma * alpha_t
-
-    def _threshold_sample(self, sample):
-        """diffusers 0.32.1 ``_threshold_sample`` ("dynamic thresholding", Imagen): per sample the
-        ``dynamic_thresholding_ratio`` quantile s of |x0|, clamped to [1, sample_max_value]; x0 <- clamp(x0, -s, s) / s.
-        Third-party restatement; reached from /root/reference/src/schedulers.py:58-59,85-90 (off in every shipped
-        config)."""
-        dtype = sample.dtype
-        b = sample.shape[0]
-        flat = sample.float().reshape(b, -1)
-        s = torch.quantile(flat.abs(), self.config.get("dynamic_thresholding_ratio", 0.995), dim=1)
-        s = torch.clamp(s, min=1, max=self.config.get("sample_max_value", 1.0)).unsqueeze(1)
-        flat = torch.clamp(flat, -s, s) / s
-        return flat.reshape(sample.shape).to(dtype)
 
     def convert_model_output(self, model_output, sample):
         """/root/reference/src/schedulers.py:14-96: every ``prediction_type`` branch (:36-56 for the ``++`` algorithms,

@@ -103,6 +103,29 @@ int sonic_latent_update_x0n(const sonic_update_coeffs* k, const void* eps_uncond
                               static_cast<cudaStream_t>(stream));
 }
 
+int sonic_latent_update_post(const sonic_update_coeffs* k, const sonic_x0_post* post, const void* eps_uncond,
+                             const void* eps_text, const void* sample, const void* h1, const void* h2, const void* h3,
+                             const void* noise, void* out_sample, void* out_m0, void* out_x0, int64_t n, int64_t n_x0,
+                             int32_t dtype, sonic_stream_t stream) {
+  SONIC_REQUIRE(k != nullptr && post != nullptr, "sonic_latent_update_post: null coefficients");
+  UpdateCoeffs c{k->guidance, k->m_x, k->m_e, k->x0_x, k->x0_e, k->c_x, k->c_e, k->c_m0, k->c_h1, k->c_h2,
+                 k->c_h3, k->c_z};
+  X0Post q{post->mode, post->clip, post->p_x, post->p_0, post->thr, static_cast<long>(post->n_per_image)};
+  return latent_update_post_launch(c, q, eps_uncond, eps_text, sample, h1, h2, h3, noise, out_sample, out_m0, out_x0,
+                                   static_cast<long>(n), static_cast<long>(n_x0), dtype,
+                                   static_cast<cudaStream_t>(stream));
+}
+
+int sonic_x0_threshold(const sonic_update_coeffs* k, const void* eps_uncond, const void* eps_text, const void* sample,
+                       int32_t n_img, int64_t n_per_image, float ratio, float max_value, float* thr, int32_t dtype,
+                       sonic_stream_t stream) {
+  SONIC_REQUIRE(k != nullptr, "sonic_x0_threshold: null coefficients");
+  UpdateCoeffs c{k->guidance, k->m_x, k->m_e, k->x0_x, k->x0_e, k->c_x, k->c_e, k->c_m0, k->c_h1, k->c_h2,
+                 k->c_h3, k->c_z};
+  return x0_threshold_launch(c, eps_uncond, eps_text, sample, n_img, static_cast<long>(n_per_image), ratio, max_value,
+                             thr, dtype, static_cast<cudaStream_t>(stream));
+}
+
 int sonic_nchw_to_nhwc8(const void* x, int32_t dtype, int32_t n_img, int32_t C, int32_t hw, int32_t dup, void* y,
                         sonic_stream_t stream) {
   return nchw_to_nhwc8_launch(x, dtype, n_img, C, hw, dup, y, static_cast<cudaStream_t>(stream));

@@ -129,6 +129,99 @@ int launch_update(const UpdateCoeffs& k, const void* eu, const void* et, const v
   return 0;
 }
 
+// ------------------------------------------------------------------------------ x0 clipping / dynamic thresholding
+// The guided model output and the x0 prediction exactly as update_math forms them, with x0 rounded to the model dtype
+// like the reference's x0_pred tensor before it is clipped / thresholded.
+template <typename T>
+__device__ __forceinline__ float guided_x0(const UpdateCoeffs& k, const T* eu, const T* et, const T* x, long i, float& e,
+                                           float& xv) {
+  const float u = Vec8<T>::ld1(eu + i);
+  e = et ? u + k.guidance * (Vec8<T>::ld1(et + i) - u) : u;
+  e = Vec8<T>::round(e);
+  xv = Vec8<T>::ld1(x + i);
+  return Vec8<T>::round(k.x0_x * xv + k.x0_e * e);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+latent_update_post_kernel(const UpdateCoeffs k, const UpdatePtrs<T> p, const X0Post q, long n, long n_x0) {
+  for (long i = blockIdx.x * static_cast<long>(blockDim.x) + threadIdx.x; i < n;
+       i += static_cast<long>(gridDim.x) * blockDim.x) {
+    float e, x;
+    float x0 = guided_x0<T>(k, p.eu, p.et, p.x, i, e, x);
+    if (q.mode == 2) {
+      const float s = q.thr[i / q.n_per_image];
+      x0 = fminf(fmaxf(x0, -s), s) / s;
+    } else {
+      x0 = fminf(fmaxf(x0, -q.clip), q.clip);
+    }
+    const float om = Vec8<T>::round(q.p_x * x + q.p_0 * x0);
+    const float ox = k.c_x * x + k.c_e * e + k.c_m0 * om + (p.h1 ? k.c_h1 * Vec8<T>::ld1(p.h1 + i) : 0.f) +
+                     (p.h2 ? k.c_h2 * Vec8<T>::ld1(p.h2 + i) : 0.f) + (p.h3 ? k.c_h3 * Vec8<T>::ld1(p.h3 + i) : 0.f) +
+                     (p.z ? k.c_z * Vec8<T>::ld1(p.z + i) : 0.f);
+    // every load of element i precedes its stores, so out_sample may alias sample / history
+    if (p.ox) Vec8<T>::st1(p.ox + i, ox);
+    if (p.om) Vec8<T>::st1(p.om + i, om);
+    if (p.o0 && i < n_x0) Vec8<T>::st1(p.o0 + i, x0);
+  }
+}
+
+// k-th smallest (0-based) of n non-negative floats held as their bit patterns: most-significant-digit-first radix
+// select, 8 bits per pass over a 256-bin shared histogram.  Called by the whole CTA.
+__device__ float radix_select(const uint32_t* keys, int n, unsigned rank, unsigned* hist, unsigned* sh) {
+  uint32_t prefix = 0, mask = 0;
+  for (int shift = 24; shift >= 0; shift -= 8) {
+    for (int b = threadIdx.x; b < 256; b += blockDim.x) hist[b] = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const uint32_t kk = keys[i];
+      if ((kk & mask) == prefix) atomicAdd(&hist[(kk >> shift) & 255u], 1u);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      unsigned cum = 0;
+      int b = 0;
+      for (; b < 255; ++b) {
+        if (rank < cum + hist[b]) break;
+        cum += hist[b];
+      }
+      sh[0] = static_cast<unsigned>(b);
+      sh[1] = rank - cum;
+    }
+    __syncthreads();
+    prefix |= sh[0] << shift;
+    mask |= 255u << shift;
+    rank = sh[1];
+    __syncthreads();
+  }
+  return __uint_as_float(prefix);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(1024)
+x0_threshold_kernel(const UpdateCoeffs k, const T* eu, const T* et, const T* x, int n_per_image, float ratio,
+                    float max_value, float* __restrict__ thr) {
+  extern __shared__ uint32_t keys[];             // |x0| of this image
+  __shared__ unsigned hist[256];
+  __shared__ unsigned sh[2];
+  const long base = static_cast<long>(blockIdx.x) * n_per_image;
+  for (int i = threadIdx.x; i < n_per_image; i += blockDim.x) {
+    float e, xv;
+    keys[i] = __float_as_uint(fabsf(guided_x0<T>(k, eu, et, x, base + i, e, xv)));
+  }
+  __syncthreads();
+  // torch.quantile(|x0|, ratio, dim=1), interpolation "linear": position ratio * (n - 1) in float32
+  const float pos = ratio * static_cast<float>(n_per_image - 1);
+  const float lo = floorf(pos);
+  const float w = pos - lo;
+  const float a = radix_select(keys, n_per_image, static_cast<unsigned>(lo), hist, sh);
+  const float b = radix_select(keys, n_per_image, static_cast<unsigned>(ceilf(pos)), hist, sh);
+  if (threadIdx.x == 0) {
+    const float v = w < 0.5f ? a + w * (b - a) : b - (b - a) * (1.0f - w);      // at::lerp
+    thr[blockIdx.x] = fminf(fmaxf(v, 1.0f), max_value);
+  }
+}
+
 // ------------------------------------------------------------------------------ layout helpers
 template <typename T>
 __global__ void nchw_to_nhwc8_kernel(const T* __restrict__ x, int n_img, int C, int hw, int dup,
@@ -250,6 +343,75 @@ int latent_update_launch(const UpdateCoeffs& k, const void* eps_uncond, const vo
     return launch_update<__nv_bfloat16>(k, eps_uncond, eps_text, sample, h1, h2, h3, noise, out_sample, out_m0,
                                         out_x0, n, n_x0, stream);
   SONIC_REQUIRE(false, "latent_update: unknown dtype %d", dtype);
+}
+
+namespace {
+template <typename T>
+int launch_update_post(const UpdateCoeffs& k, const X0Post& q, const void* eu, const void* et, const void* x,
+                       const void* h1, const void* h2, const void* h3, const void* z, void* ox, void* om, void* o0, long n,
+                       long n_x0, cudaStream_t stream) {
+  UpdatePtrs<T> p{static_cast<const T*>(eu), static_cast<const T*>(et), static_cast<const T*>(x),
+                  static_cast<const T*>(h1), static_cast<const T*>(h2), static_cast<const T*>(h3),
+                  static_cast<const T*>(z),  static_cast<T*>(ox),       static_cast<T*>(om),
+                  static_cast<T*>(o0)};
+  const int blocks = static_cast<int>(std::min<long>((n + 255) / 256, 148L * 8));
+  latent_update_post_kernel<T><<<std::max(blocks, 1), 256, 0, stream>>>(k, p, q, n, n_x0);
+  SONIC_CUDA(cudaGetLastError());
+  return 0;
+}
+
+template <typename T>
+int launch_threshold(const UpdateCoeffs& k, const void* eu, const void* et, const void* x, int n_img, int n_per_image,
+                     float ratio, float max_value, float* thr, cudaStream_t stream) {
+  const size_t smem = static_cast<size_t>(n_per_image) * sizeof(uint32_t);
+  SONIC_CUDA(cudaFuncSetAttribute(x0_threshold_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(smem)));
+  x0_threshold_kernel<T><<<n_img, 1024, smem, stream>>>(k, static_cast<const T*>(eu), static_cast<const T*>(et),
+                                                       static_cast<const T*>(x), n_per_image, ratio, max_value, thr);
+  SONIC_CUDA(cudaGetLastError());
+  return 0;
+}
+}  // namespace
+
+int latent_update_post_launch(const UpdateCoeffs& k, const X0Post& post, const void* eps_uncond, const void* eps_text,
+                              const void* sample, const void* h1, const void* h2, const void* h3, const void* noise,
+                              void* out_sample, void* out_m0, void* out_x0, long n, long n_x0, int dtype,
+                              cudaStream_t stream) {
+  SONIC_REQUIRE(eps_uncond && sample, "latent_update_post: eps and sample are required");
+  SONIC_REQUIRE(n > 0, "latent_update_post: n=%ld", n);
+  SONIC_REQUIRE(post.mode == 1 || post.mode == 2, "latent_update_post: mode %d (1 = clip, 2 = dynamic threshold)",
+                post.mode);
+  if (post.mode == 1) SONIC_REQUIRE(post.clip > 0.f, "latent_update_post: clip range %g must be positive", post.clip);
+  if (post.mode == 2)
+    SONIC_REQUIRE(post.thr && post.n_per_image > 0 && n % post.n_per_image == 0,
+                  "latent_update_post: dynamic thresholding needs thr and n_per_image dividing n (n=%ld, per image %ld)",
+                  n, post.n_per_image);
+  if (n_x0 < 0 || n_x0 > n) n_x0 = n;
+  if (dtype == kF32)
+    return launch_update_post<float>(k, post, eps_uncond, eps_text, sample, h1, h2, h3, noise, out_sample, out_m0,
+                                     out_x0, n, n_x0, stream);
+  if (dtype == kBF16)
+    return launch_update_post<__nv_bfloat16>(k, post, eps_uncond, eps_text, sample, h1, h2, h3, noise, out_sample,
+                                             out_m0, out_x0, n, n_x0, stream);
+  SONIC_REQUIRE(false, "latent_update_post: unknown dtype %d", dtype);
+}
+
+int x0_threshold_launch(const UpdateCoeffs& k, const void* eps_uncond, const void* eps_text, const void* sample,
+                        int n_img, long n_per_image, float ratio, float max_value, float* thr, int dtype,
+                        cudaStream_t stream) {
+  SONIC_REQUIRE(eps_uncond && sample && thr, "x0_threshold: eps, sample and thr are required");
+  SONIC_REQUIRE(n_img > 0 && n_per_image > 1, "x0_threshold: n_img=%d n_per_image=%ld", n_img, n_per_image);
+  SONIC_REQUIRE(n_per_image * 4 <= 200 * 1024, "x0_threshold: %ld elements per image do not fit shared memory",
+                n_per_image);
+  SONIC_REQUIRE(ratio >= 0.f && ratio <= 1.f && max_value >= 1.f, "x0_threshold: ratio %g / max_value %g", ratio,
+                max_value);
+  if (dtype == kF32)
+    return launch_threshold<float>(k, eps_uncond, eps_text, sample, n_img, static_cast<int>(n_per_image), ratio,
+                                   max_value, thr, stream);
+  if (dtype == kBF16)
+    return launch_threshold<__nv_bfloat16>(k, eps_uncond, eps_text, sample, n_img, static_cast<int>(n_per_image), ratio,
+                                           max_value, thr, stream);
+  SONIC_REQUIRE(false, "x0_threshold: unknown dtype %d", dtype);
 }
 
 int nchw_to_nhwc8_launch(const void* x, int dtype, int n_img, int C, int hw, int dup, void* y,

@@ -42,6 +42,27 @@ struct UpdateCoeffs {
   float x0_x, x0_e;
   float c_x, c_e, c_m0, c_h1, c_h2, c_h3, c_z;
 };
+// Non-linear post-processing of the x0 prediction inside the fused update (off in every shipped config; the linear
+// kernel above stays the hot path): mode 1 clamps x0 to +-clip (diffusers ``clip_sample``), mode 2 is dynamic
+// thresholding (src/schedulers.py:58-59,85-90 -> diffusers ``_threshold_sample``): x0 <- clamp(x0, -s, s) / s with the
+// per-image s = thr[img] computed by x0_threshold_launch.  The converted model output is then re-derived from the
+// processed x0:  m0 = p_x * x + p_0 * x0'.
+struct X0Post {
+  int mode;
+  float clip;
+  float p_x, p_0;
+  const float* thr;
+  long n_per_image;
+};
+int latent_update_post_launch(const UpdateCoeffs& k, const X0Post& post, const void* eps_uncond, const void* eps_text,
+                              const void* sample, const void* h1, const void* h2, const void* h3, const void* noise,
+                              void* out_sample, void* out_m0, void* out_x0, long n, long n_x0, int dtype,
+                              cudaStream_t stream);
+// thr[img] = clamp(quantile_ratio(|x0| over the image's n_per_image elements), 1, max_value); the quantile is exact
+// (radix select of the two neighbouring order statistics, linear interpolation like torch.quantile).
+int x0_threshold_launch(const UpdateCoeffs& k, const void* eps_uncond, const void* eps_text, const void* sample,
+                        int n_img, long n_per_image, float ratio, float max_value, float* thr, int dtype,
+                        cudaStream_t stream);
 int latent_update_launch(const UpdateCoeffs& k, const void* eps_uncond, const void* eps_text,
                          const void* sample, const void* h1, const void* h2, const void* h3,
                          const void* noise, void* out_sample, void* out_m0, void* out_x0, long n,

@@ -181,6 +181,11 @@ class UpdateCoeffs(C.Structure):
                                          "c_h1", "c_h2", "c_h3", "c_z")]
 
 
+class X0Post(C.Structure):            # include/sonic.h: sonic_x0_post
+    _fields_ = [("mode", C.c_int32), ("clip", C.c_float), ("p_x", C.c_float), ("p_0", C.c_float),
+                ("thr", C.c_void_p), ("n_per_image", C.c_int64)]
+
+
 def _dtype_code(t: torch.Tensor) -> int:
     if t.dtype == torch.float32:
         return 0
@@ -260,15 +265,43 @@ def make_coeffs(coeffs: dict) -> UpdateCoeffs:
     return k
 
 
+def x0_threshold(coeffs: dict, eps, sample, *, eps_text=None, ratio=0.995, max_value=1.0):
+    """Per-image dynamic-thresholding scale ``clamp(quantile(|x0|, ratio), 1, max_value)`` of the x0 prediction the
+    fused update forms from (eps, sample): ``sonic_x0_threshold`` (diffusers ``_threshold_sample``, reached from
+    /root/reference/src/schedulers.py:58-59,85-90).  Returns a float32 tensor [batch]."""
+    k = make_coeffs(coeffs)
+    for t in (eps, eps_text):
+        assert t is None or (t.dtype == sample.dtype and t.is_cuda and t.is_contiguous())
+    assert sample.is_cuda and sample.is_contiguous()
+    n_img = sample.shape[0]
+    thr = torch.empty(n_img, device=sample.device, dtype=torch.float32)
+    check(lib().sonic_x0_threshold(C.byref(k), ptr(eps), ptr(eps_text), ptr(sample), n_img,
+                                   C.c_int64(sample.numel() // n_img), C.c_float(ratio), C.c_float(max_value), ptr(thr),
+                                   _dtype_code(sample), stream_ptr()), "sonic_x0_threshold")
+    return thr
+
+
 def latent_update(coeffs: dict, eps, sample, *, eps_text=None, h1=None, h2=None, h3=None, noise=None,
-                  out_sample=None, out_m0=None, out_x0=None):
-    """Fused CFG + scheduler update; see ``sonic_latent_update`` in include/sonic.h."""
+                  out_sample=None, out_m0=None, out_x0=None, post=None):
+    """Fused CFG + scheduler update; see ``sonic_latent_update`` in include/sonic.h.  ``post``: the non-linear x0
+    post-processing of ``sonic_latent_update_post`` -- ``dict(mode=1, clip=r, p_x=, p_0=)`` (clip_sample) or
+    ``dict(mode=2, thr=<x0_threshold(...)>, p_x=, p_0=)`` (dynamic thresholding)."""
     k = make_coeffs(coeffs)
     code = _dtype_code(sample)
     for t in (eps, eps_text, h1, h2, h3, noise, out_sample, out_m0, out_x0):
         assert t is None or (t.dtype == sample.dtype and t.is_cuda and t.is_contiguous())
     n = sample.numel()
     n_x0 = n if out_x0 is None else min(n, out_x0.numel())      # a shorter out_x0 receives the leading images only
+    if post is not None:
+        thr = post.get("thr")
+        assert thr is None or (thr.is_cuda and thr.dtype == torch.float32 and thr.numel() == sample.shape[0])
+        q = X0Post(int(post["mode"]), float(post.get("clip", 0.0)), float(post["p_x"]), float(post["p_0"]),
+                   None if thr is None else thr.data_ptr(), n // sample.shape[0])
+        check(lib().sonic_latent_update_post(C.byref(k), C.byref(q), ptr(eps), ptr(eps_text), ptr(sample), ptr(h1),
+                                             ptr(h2), ptr(h3), ptr(noise), ptr(out_sample), ptr(out_m0), ptr(out_x0),
+                                             C.c_int64(n), C.c_int64(n_x0), code, stream_ptr()),
+              "sonic_latent_update_post")
+        return out_sample, out_m0, out_x0
     check(lib().sonic_latent_update_x0n(C.byref(k), ptr(eps), ptr(eps_text), ptr(sample), ptr(h1), ptr(h2), ptr(h3),
                                         ptr(noise), ptr(out_sample), ptr(out_m0), ptr(out_x0), C.c_int64(n),
                                         C.c_int64(n_x0), code, stream_ptr()), "sonic_latent_update_x0n")

@@ -162,7 +162,10 @@ class FusedScheduler:
 
     # -- the device step
     def _launch(self, coeffs, eps, eps_text, sample, hist=(), noise=None, want_m0=False, want_x0=True, out=None,
-                ring=True):
+                ring=True, post=None):
+        """One fused launch.  ``post``: non-linear x0 post-processing (``dict(mode=1, clip=)`` for ``clip_sample``,
+        ``dict(mode=2, ratio=, max_value=)`` for dynamic thresholding, plus ``p_x`` / ``p_0``) -- the thresholding
+        scale is one extra launch (a per-image quantile) in front of the update."""
         if self._replay_device is not None:
             return sample, (sample if want_m0 else None), (sample if want_x0 else None)
         if not sample.is_cuda:
@@ -175,9 +178,24 @@ class FusedScheduler:
             rows = sample.shape[0] if self.x0_rows is None else min(self.x0_rows, sample.shape[0])
             out_x0 = torch.empty((rows,) + tuple(sample.shape[1:]), dtype=sample.dtype, device=sample.device)
         h = list(hist) + [None] * (3 - len(hist))
-        K.latent_update(coeffs, eps.contiguous(), sample, eps_text=eps_text, h1=h[0], h2=h[1], h3=h[2], noise=noise,
-                        out_sample=out_sample, out_m0=out_m0, out_x0=out_x0)
+        eps = eps.contiguous()
+        if post is not None and post["mode"] == 2:
+            post = dict(post, thr=K.x0_threshold(coeffs, eps, sample, eps_text=eps_text, ratio=post["ratio"],
+                                                 max_value=post["max_value"]))
+        K.latent_update(coeffs, eps, sample, eps_text=eps_text, h1=h[0], h2=h[1], h3=h[2], noise=noise,
+                        out_sample=out_sample, out_m0=out_m0, out_x0=out_x0, post=post)
         return out_sample, out_m0, out_x0
+
+    def _x0_post(self, p_x=0.0, p_0=1.0):
+        """The config's x0 post-processing as the ``post`` argument of ``_launch`` (None: the linear hot path).
+        Thresholding wins over clipping, as in diffusers (``if thresholding ... elif clip_sample``)."""
+        cfg = self.config
+        if cfg.get("thresholding"):
+            return dict(mode=2, ratio=cfg.get("dynamic_thresholding_ratio", 0.995),
+                        max_value=cfg.get("sample_max_value", 1.0), p_x=p_x, p_0=p_0)
+        if cfg.get("clip_sample"):
+            return dict(mode=1, clip=cfg.get("clip_sample_range", 1.0), p_x=p_x, p_0=p_0)
+        return None
 
     _RING = 6            # > the longest history any scheduler keeps alive (PNDM: 4 ets + the one being written)
 
@@ -206,7 +224,7 @@ class DDIMSchedulerMy(FusedScheduler):
     _defaults = dict(
         num_train_timesteps=1000, beta_start=0.0001, beta_end=0.02, beta_schedule="linear", trained_betas=None,
         clip_sample=True, set_alpha_to_one=True, steps_offset=0, prediction_type="epsilon", thresholding=False,
-        timestep_spacing="leading",
+        dynamic_thresholding_ratio=0.995, clip_sample_range=1.0, sample_max_value=1.0, timestep_spacing="leading",
     )
 
     def __init__(self, **kw):
@@ -214,9 +232,6 @@ class DDIMSchedulerMy(FusedScheduler):
         if self.config.prediction_type not in ("epsilon", "sample", "v_prediction"):
             raise ValueError(f"prediction_type given as {self.config.prediction_type} must be one of `epsilon`, "
                              "`sample`, or `v_prediction`")
-        if self.config.thresholding or self.config.clip_sample:
-            raise NotImplementedError("fused DDIM step: no clipping / thresholding of x0 "
-                                      "(off in the SD-v1.5 configuration of the reference)")
         self.final_alpha_cumprod = torch.tensor(1.0) if self.config.set_alpha_to_one else self.alphas_cumprod[0]
         self._set_grid(np.arange(0, self.config.num_train_timesteps)[::-1].copy(), None)
         self.num_inference_steps = None
@@ -264,7 +279,8 @@ class DDIMSchedulerMy(FusedScheduler):
         if eta > 0:
             noise = self._draw(sample, generator, sample.dtype)
             c["c_z"] = _f(std)
-        prev, _, x0 = self._launch(c, eps, eps_text, sample, noise=noise, out=out)
+        # clip_sample / thresholding act on pred_original_sample only (use_clipped_model_output is False): m0 = x0'
+        prev, _, x0 = self._launch(c, eps, eps_text, sample, noise=noise, out=out, post=self._x0_post())
         return (prev, x0)
 
 
@@ -308,9 +324,8 @@ class DPMSolverScheduler(FusedScheduler):
             raise ValueError(f"prediction_type given as {cfg.prediction_type} must be one of `epsilon`, `sample`, "
                              + ("`v_prediction`, or `flow_prediction`" if pp else "or `v_prediction`")
                              + " for the DPMSolverMultistepScheduler.")
-        if cfg.thresholding or cfg.use_karras_sigmas:
-            raise NotImplementedError("fused DPM-Solver step: no dynamic thresholding (a per-image quantile, "
-                                      "src/schedulers.py:58-59,85-90; off in every shipped config) and no Karras sigmas")
+        if cfg.use_karras_sigmas:
+            raise NotImplementedError("fused DPM-Solver step: no Karras sigmas (not used by any reference config)")
         if not 1 <= cfg.solver_order <= 3:
             raise NotImplementedError("solver_order must be 1, 2 or 3")
         self.alpha_t = torch.sqrt(self.alphas_cumprod)
@@ -391,6 +406,16 @@ class DPMSolverScheduler(FusedScheduler):
             m_x, m_e = s, a
         return dict(m_x=m_x, m_e=m_e, x0_x=(1.0 - s * m_x) / a, x0_e=-s * m_e / a)
 
+    def _threshold_post(self):
+        """``thresholding`` (src/schedulers.py:58-59 / :85-90): x0 is dynamically thresholded and the converted model
+        output re-derived from it -- x0' itself for the ``++`` algorithms, ``(x - alpha_t x0') / sigma_t`` otherwise."""
+        if not self.config.thresholding:
+            return None
+        if self.config.algorithm_type in ("dpmsolver++", "sde-dpmsolver++"):
+            return self._x0_post(0.0, 1.0)
+        a_s, s_s = self._sigma_to_alpha_sigma_t(self.sigmas[self.step_index])
+        return self._x0_post(1.0 / _f(s_s), -_f(a_s) / _f(s_s))
+
     def convert_model_output(self, model_output, *args, sample=None, **kwargs):
         """src/schedulers.py:14-96 -> (converted model output, x0_pred); one fused launch."""
         if sample is None:
@@ -402,7 +427,8 @@ class DPMSolverScheduler(FusedScheduler):
             raise ValueError("convert_model_output needs an initialised step index (call step first)")
         c = self._convert_coeffs()
         c["c_x"] = 1.0                                            # out_sample is a scratch copy of x
-        _, m0, x0 = self._launch(c, model_output, None, sample, want_m0=True, ring=False)   # caller owns the result
+        _, m0, x0 = self._launch(c, model_output, None, sample, want_m0=True, ring=False,   # caller owns the result
+                                 post=self._threshold_post())
         return m0, x0
 
     def feed_history(self, eps, eps_text, guidance, sample):
@@ -414,7 +440,7 @@ class DPMSolverScheduler(FusedScheduler):
                              "sigmas[None] in the reference: the main scheduler has to take a step first)")
         c = dict(guidance=guidance, **self._convert_coeffs())
         c["c_x"] = 1.0
-        _, m0, _ = self._launch(c, eps, eps_text, sample, want_m0=True, want_x0=False)
+        _, m0, _ = self._launch(c, eps, eps_text, sample, want_m0=True, want_x0=False, post=self._threshold_post())
         for i in range(self.config.solver_order - 1):
             self.model_outputs[i] = self.model_outputs[i + 1]
         self.model_outputs[-1] = m0
@@ -519,7 +545,8 @@ class DPMSolverScheduler(FusedScheduler):
         hist = [m for m in (self.model_outputs[-1], self.model_outputs[-2] if cfg.solver_order > 1 else None)
                 if m is not None][: order - 1]
         # history as seen by this step: model_outputs[-1] is m1 (previous), [-2] is m2
-        prev, m0, x0 = self._launch(c, eps, eps_text, sample, hist=hist, noise=noise, want_m0=True, out=out)
+        prev, m0, x0 = self._launch(c, eps, eps_text, sample, hist=hist, noise=noise, want_m0=True, out=out,
+                                    post=self._threshold_post())
         for i in range(cfg.solver_order - 1):
             self.model_outputs[i] = self.model_outputs[i + 1]
         self.model_outputs[-1] = m0

@@ -121,11 +121,31 @@ def _pairs():
                                                           prediction_type="v_prediction"), 12, {}),
         (S.DPMSolverScheduler, O.DPMSolverScheduler,
          dict(solver_order=3, algorithm_type="dpmsolver", final_sigmas_type="sigma_min", prediction_type="sample"), 12, {}),
+        (S.DDIMSchedulerMy, O.DDIMScheduler, dict(clip_sample=True, clip_sample_range=1.5), 10, {}),
+        (S.DDIMSchedulerMy, O.DDIMScheduler, dict(thresholding=True, sample_max_value=2.5, prediction_type="v_prediction"),
+         10, {"eta": 0.2}),
+        (S.DPMSolverScheduler, O.DPMSolverScheduler, dict(solver_order=2, algorithm_type="dpmsolver++", thresholding=True,
+                                                          sample_max_value=3.0), 10, {}),
+        (S.DPMSolverScheduler, O.DPMSolverScheduler,
+         dict(solver_order=2, algorithm_type="sde-dpmsolver", final_sigmas_type="sigma_min", thresholding=True,
+              dynamic_thresholding_ratio=0.9, sample_max_value=2.0), 8, {}),
     ]
 
 
+def _emulated_post(x0, x, post):
+    """sonic_latent_update_post (include/sonic.h): clip or dynamic thresholding of x0, then m0 = p_x x + p_0 x0'."""
+    if post["mode"] == 2:
+        b = x0.shape[0]
+        s_ = torch.quantile(x0.reshape(b, -1).abs().float(), post["ratio"], dim=1).clamp(min=1, max=post["max_value"])
+        s_ = s_.to(x0.dtype).reshape((b,) + (1,) * (x0.dim() - 1))
+        x0 = torch.maximum(torch.minimum(x0, s_), -s_) / s_
+    else:
+        x0 = x0.clamp(-post["clip"], post["clip"])
+    return x0, post["p_x"] * x + post["p_0"] * x0
+
+
 def _emulated_launch(self, coeffs, eps, eps_text, sample, hist=(), noise=None, want_m0=False, want_x0=True, out=None,
-                     ring=True):
+                     ring=True, post=None):
     """float64 model of sonic_latent_update (include/sonic.h) for fp32 tensors on the CPU."""
     c = {k: float(coeffs.get(k, 0.0)) for k in ("guidance", "m_x", "m_e", "x0_x", "x0_e", "c_x", "c_e", "c_m0",
                                                 "c_h1", "c_h2", "c_h3", "c_z")}
@@ -134,6 +154,8 @@ def _emulated_launch(self, coeffs, eps, eps_text, sample, hist=(), noise=None, w
     x = sample.to(d)
     m0 = c["m_x"] * x + c["m_e"] * e
     x0 = c["x0_x"] * x + c["x0_e"] * e
+    if post is not None:
+        x0, m0 = _emulated_post(x0, x, post)
     h = [t.to(d) for t in hist] + [torch.zeros_like(x)] * (3 - len(hist))
     z = torch.zeros_like(x) if noise is None else noise.to(d)
     xn = c["c_x"] * x + c["c_e"] * e + c["c_m0"] * m0 + c["c_h1"] * h[0] + c["c_h2"] * h[1] + c["c_h3"] * h[2] + c["c_z"] * z
@@ -141,7 +163,7 @@ def _emulated_launch(self, coeffs, eps, eps_text, sample, hist=(), noise=None, w
     return xn.to(f), (m0.to(f) if want_m0 else None), (x0.to(f) if want_x0 else None)
 
 
-@pytest.mark.parametrize("idx", range(17))
+@pytest.mark.parametrize("idx", range(21))
 def test_scheduler_coefficients_reproduce_oracle_updates(idx, monkeypatch):
     """Every scheduler's reduction to linear-combination coefficients, step by step, against the
     oracle's literal formulas (fp32, CPU, no GPU needed)."""

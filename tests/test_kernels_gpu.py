@@ -206,6 +206,81 @@ def test_latent_update_generic(cuda, dtype, tol):
         assert (got.float() - ref).abs().max().item() <= tol * max(1.0, ref.abs().max().item())
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("shape", [(3, 4, 8, 8), (16, 4, 64, 64), (2, 4, 96, 96)])
+@pytest.mark.parametrize("ratio", [0.995, 0.5])
+def test_x0_threshold_equals_torch_quantile(cuda, dtype, shape, ratio):
+    """sonic_x0_threshold: per-image clamp(quantile(|x0|, ratio), 1, max) of the x0 prediction the fused update
+    forms -- exact order statistics (radix select), so it equals torch.quantile on the same x0 to float32 rounding."""
+    from sonicdiffusionbayeslab_b200 import kernels as k
+
+    g = torch.Generator(device="cuda").manual_seed(7)
+    B = shape[0]
+    x = (2.0 * torch.randn(shape, device=cuda, generator=g)).to(dtype)
+    eps2 = torch.randn((2 * B,) + shape[1:], device=cuda, generator=g).to(dtype)
+    c = dict(guidance=7.5, x0_x=1.3, x0_e=-0.6)
+    thr = k.x0_threshold(c, eps2[:B], x, eps_text=eps2[B:], ratio=ratio, max_value=6.0)
+    e = (eps2[:B].float() + 7.5 * (eps2[B:].float() - eps2[:B].float())).to(dtype).float()
+    x0 = (1.3 * x.float() - 0.6 * e).to(dtype).float()
+    ref = torch.quantile(x0.reshape(B, -1).abs(), ratio, dim=1).clamp(min=1, max=6.0)
+    assert thr.shape == (B,) and (thr - ref).abs().max().item() <= 1e-5 * ref.abs().max().item(), (thr, ref)
+    assert (ref > 1).any() and (ref < 6).any()            # the clamp is not what is being compared
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-5), (torch.bfloat16, 2e-2)])
+@pytest.mark.parametrize("mode", [1, 2])
+def test_latent_update_post(cuda, dtype, tol, mode):
+    """sonic_latent_update_post: x0 clipped (mode 1) or dynamically thresholded (mode 2), the converted model output
+    re-derived from it, in place over the sample, x0 written for the first image only."""
+    from sonicdiffusionbayeslab_b200 import kernels as k
+
+    g = torch.Generator(device="cuda").manual_seed(5)
+    B = 3
+    mk = lambda: torch.randn(B, 4, 64, 64, device=cuda, generator=g).to(dtype)
+    eps2 = torch.randn(2 * B, 4, 64, 64, device=cuda, generator=g).to(dtype)
+    x, h1, z = mk(), mk(), mk()
+    c = dict(guidance=7.5, x0_x=1.1, x0_e=-0.7, c_x=0.5, c_e=0.2, c_m0=-0.4, c_h1=0.3, c_z=0.05)
+    f = lambda t: t.float()
+    e = (f(eps2[:B]) + 7.5 * (f(eps2[B:]) - f(eps2[:B]))).to(dtype).float()
+    x0 = (1.1 * f(x) - 0.7 * e).to(dtype).float()
+    if mode == 2:
+        s_ = torch.quantile(x0.reshape(B, -1).abs(), 0.9, dim=1).clamp(min=1, max=4.0).reshape(B, 1, 1, 1)
+        post = dict(mode=2, p_x=0.25, p_0=-0.8,
+                    thr=k.x0_threshold(c, eps2[:B], x, eps_text=eps2[B:], ratio=0.9, max_value=4.0))
+        x0p = torch.maximum(torch.minimum(x0, s_), -s_) / s_
+    else:
+        post = dict(mode=1, clip=1.5, p_x=0.25, p_0=-0.8)
+        x0p = x0.clamp(-1.5, 1.5)
+    m0 = (0.25 * f(x) - 0.8 * x0p).to(dtype).float()
+    xn = 0.5 * f(x) + 0.2 * e - 0.4 * m0 + 0.3 * f(h1) + 0.05 * f(z)
+    xs = x.clone()
+    om, o0 = torch.empty_like(x), torch.empty_like(x[:1])
+    k.latent_update(c, eps2[:B], xs, eps_text=eps2[B:], h1=h1, noise=z, out_sample=xs, out_m0=om, out_x0=o0, post=post)
+    for got, ref in ((xs, xn), (om, m0), (o0, x0p[:1])):
+        assert (got.float() - ref).abs().max().item() <= tol * max(1.0, ref.abs().max().item())
+
+
+def test_ddim_clip_sample_matches_oracle(cuda):
+    """diffusers' DDIM default ``clip_sample=True`` through the product scheduler (post-processing update) vs the oracle."""
+    from oracle import schedulers as O
+    from oracle.schedulers import SD15_SCHEDULER_CONFIG
+    from sonicdiffusionbayeslab_b200 import schedulers as S
+
+    kw = dict(clip_sample=True, clip_sample_range=1.25)
+    ps, os_ = S.DDIMSchedulerMy.from_config(SD15_SCHEDULER_CONFIG, **kw), O.DDIMScheduler.from_config(SD15_SCHEDULER_CONFIG, **kw)
+    ps.set_timesteps(8, device=cuda)
+    os_.set_timesteps(8, device=cuda)
+    g = torch.Generator(device="cuda").manual_seed(3)
+    x = torch.randn(2, 4, 64, 64, device=cuda, generator=g)
+    for t in os_.timesteps:
+        eps = 0.7 * torch.randn(2, 4, 64, 64, device=cuda, generator=g) + 0.2 * x
+        rp, ro = ps.step(eps, t, x), os_.step(eps, t, x)
+        for a, b in zip(rp, ro):
+            assert (a - b).abs().max().item() <= 1e-4 * max(1.0, b.abs().max().item())
+        assert ro[1].abs().max().item() <= 1.25 + 1e-6
+        x = ro[0]
+
+
 def test_layout_helpers(cuda):
     from sonicdiffusionbayeslab_b200 import kernels as k
 

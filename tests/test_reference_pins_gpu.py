@@ -2,8 +2,9 @@
 the fixtures that executing the REFERENCE'S OWN ``DPMSolverScheduler.step`` / ``convert_model_output`` produced
 (/root/reference/src/schedulers.py:14-187 via oracle/refexec.py; tests/golden/make_reference_pins.py).
 
-Tolerance (BASELINE.json north_star): fp32 I/O max-abs <= 1e-4; bf16 I/O max-abs <= 2e-2 relative to
-max(1, |x|max) of the tensor (the synthetic trajectory reaches |x0| ~ 20, where one bf16 ulp is 0.125).
+Tolerance (BASELINE.json north_star; refpin_cases.step_tolerance): fp32 I/O max-abs <= 1e-4; bf16 I/O max-abs <= 2e-2
+relative to max(1, |x|max) of the tensor (the synthetic trajectory reaches |x0| ~ 20, where one bf16 ulp is 0.125);
+the two dynamic-thresholding cases (quantile kernel + post-processing update) 4e-2 in bf16, see there.
 Teacher-forced from the fixture after every step, so kernel error does not compound through the recursion.
 """
 import json
@@ -25,12 +26,13 @@ PINS = np.load(os.path.join(HERE, "golden", "reference_pins.npz"))
 META = json.load(open(os.path.join(HERE, "golden", "reference_pins.json")))
 
 
-@pytest.mark.parametrize("name", list(RC.SCHEDULER_CASES))
-@pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-4), (torch.bfloat16, 2e-2)])
-def test_fused_step_matches_reference_source(cuda, name, dtype, tol):
+@pytest.mark.parametrize("name", list(RC.ALL_SCHEDULER_CASES))
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_fused_step_matches_reference_source(cuda, name, dtype):
     from sonicdiffusionbayeslab_b200 import schedulers as S
 
-    kind, over, n, patch, seed = RC.SCHEDULER_CASES[name]
+    tol = RC.step_tolerance(name, dtype)
+    kind, over, n, patch, seed = RC.ALL_SCHEDULER_CASES[name]
     want_prev = torch.from_numpy(PINS[f"sched/{name}/prev"])
     want_x0 = torch.from_numpy(PINS[f"sched/{name}/x0"])
     sched = RC.make_scheduler(kind, over, module=S)
