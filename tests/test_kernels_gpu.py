@@ -219,12 +219,14 @@ def test_x0_threshold_equals_torch_quantile(cuda, dtype, shape, ratio):
     x = (2.0 * torch.randn(shape, device=cuda, generator=g)).to(dtype)
     eps2 = torch.randn((2 * B,) + shape[1:], device=cuda, generator=g).to(dtype)
     c = dict(guidance=7.5, x0_x=1.3, x0_e=-0.6)
-    thr = k.x0_threshold(c, eps2[:B], x, eps_text=eps2[B:], ratio=ratio, max_value=6.0)
+    thr = k.x0_threshold(c, eps2[:B], x, eps_text=eps2[B:], ratio=ratio, max_value=1000.0)
     e = (eps2[:B].float() + 7.5 * (eps2[B:].float() - eps2[:B].float())).to(dtype).float()
     x0 = (1.3 * x.float() - 0.6 * e).to(dtype).float()
-    ref = torch.quantile(x0.reshape(B, -1).abs(), ratio, dim=1).clamp(min=1, max=6.0)
+    ref = torch.quantile(x0.reshape(B, -1).abs(), ratio, dim=1).clamp(min=1, max=1000.0)
     assert thr.shape == (B,) and (thr - ref).abs().max().item() <= 1e-5 * ref.abs().max().item(), (thr, ref)
-    assert (ref > 1).any() and (ref < 6).any()            # the clamp is not what is being compared
+    assert (ref > 1).all() and (ref < 1000).all()         # the clamp is not what is being compared
+    lo = k.x0_threshold(c, eps2[:B], x, eps_text=eps2[B:], ratio=ratio, max_value=1.5)
+    assert torch.equal(lo, torch.full_like(lo, 1.5))      # ... and it clamps
 
 
 @pytest.mark.parametrize("dtype,tol", [(torch.float32, 1e-5), (torch.bfloat16, 2e-2)])
