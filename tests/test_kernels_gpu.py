@@ -223,7 +223,10 @@ def test_x0_threshold_equals_torch_quantile(cuda, dtype, shape, ratio):
     e = (eps2[:B].float() + 7.5 * (eps2[B:].float() - eps2[:B].float())).to(dtype).float()
     x0 = (1.3 * x.float() - 0.6 * e).to(dtype).float()
     ref = torch.quantile(x0.reshape(B, -1).abs(), ratio, dim=1).clamp(min=1, max=1000.0)
-    assert thr.shape == (B,) and (thr - ref).abs().max().item() <= 1e-5 * ref.abs().max().item(), (thr, ref)
+    # bf16: |x0| sits on the bf16 grid, and the kernel's fused multiply-adds round a few elements one grid step away
+    # from this two-rounding torch formula -- an order statistic can move by one bf16 step (2^-7 relative)
+    tol = 1e-5 if dtype == torch.float32 else 2.0 ** -7
+    assert thr.shape == (B,) and ((thr - ref).abs() <= tol * ref).all(), (thr, ref)
     assert (ref > 1).all() and (ref < 1000).all()         # the clamp is not what is being compared
     lo = k.x0_threshold(c, eps2[:B], x, eps_text=eps2[B:], ratio=ratio, max_value=1.5)
     assert torch.equal(lo, torch.full_like(lo, 1.5))      # ... and it clamps
