@@ -476,7 +476,15 @@ class LCMScheduler(_SchedulerBase):
         beta, beta_prev = 1 - a, 1 - ap
         c_skip, c_out = self.get_scalings_for_boundary_condition_discrete(
             torch.as_tensor(timestep).to("cpu"))
-        x0 = (sample - beta.sqrt() * model_output) / a.sqrt()
+        pt = self.config.prediction_type                   # diffusers 0.32.1 scheduling_lcm.py ``step`` item 3
+        if pt == "epsilon":
+            x0 = (sample - beta.sqrt() * model_output) / a.sqrt()
+        elif pt == "sample":
+            x0 = model_output
+        elif pt == "v_prediction":
+            x0 = a.sqrt() * sample - beta.sqrt() * model_output
+        else:
+            raise ValueError(f"prediction_type given as {pt} must be one of `epsilon`, `sample` or `v_prediction`")
         if self.config.clip_sample:
             x0 = x0.clamp(-1.0, 1.0)
         denoised = c_out * x0 + c_skip * sample
@@ -547,6 +555,11 @@ class PNDMScheduler(_SchedulerBase):
         a = self.alphas_cumprod[t]
         ap = self.alphas_cumprod[prev_t] if prev_t >= 0 else self.final_alpha_cumprod
         beta, beta_prev = 1 - a, 1 - ap
+        if self.config.prediction_type == "v_prediction":  # the (combined) v outputs become a noise prediction here
+            model_output = (a ** 0.5) * model_output + (beta ** 0.5) * sample
+        elif self.config.prediction_type != "epsilon":
+            raise ValueError(f"prediction_type given as {self.config.prediction_type} must be one of `epsilon` or "
+                             "`v_prediction`")
         sample_coeff = (ap / a) ** 0.5
         denom = a * beta_prev ** 0.5 + (a * beta * ap) ** 0.5
         return sample_coeff * sample - (ap - a) * model_output / denom

@@ -569,8 +569,12 @@ class LCMScheduler(FusedScheduler):
 
     def __init__(self, **kw):
         super().__init__(**kw)
-        if self.config.prediction_type != "epsilon" or self.config.thresholding or self.config.clip_sample:
-            raise NotImplementedError("fused LCM step supports epsilon prediction without clipping")
+        if self.config.prediction_type not in ("epsilon", "sample", "v_prediction"):
+            raise ValueError(f"prediction_type given as {self.config.prediction_type} must be one of `epsilon`, "
+                             "`sample` or `v_prediction`")
+        if self.config.thresholding or self.config.clip_sample:
+            raise NotImplementedError("fused LCM step: no clipping / thresholding of x0 (off in the LCM configuration "
+                                      "of the reference)")
         self.final_alpha_cumprod = torch.tensor(1.0) if self.config.set_alpha_to_one else self.alphas_cumprod[0]
         self.sigma_data = 0.5
 
@@ -605,8 +609,9 @@ class LCMScheduler(FusedScheduler):
         a = self.alphas_cumprod[t]
         ap = self.alphas_cumprod[prev_t] if prev_t >= 0 else self.final_alpha_cumprod
         c_skip, c_out = self.get_scalings_for_boundary_condition_discrete(torch.tensor(t))
-        inv = 1.0 / _f(a.sqrt())
-        m_x, m_e = inv, -_f((1 - a).sqrt()) * inv                    # predicted_original_sample
+        sa, sb = _f(a.sqrt()), _f((1 - a).sqrt())
+        pt = self.config.prediction_type                             # predicted_original_sample = m_x x + m_e e
+        m_x, m_e = (1.0 / sa, -sb / sa) if pt == "epsilon" else (0.0, 1.0) if pt == "sample" else (sa, -sb)
         c = dict(guidance=guidance, m_x=m_x, m_e=m_e,
                  x0_x=_f(c_out) * m_x + _f(c_skip), x0_e=_f(c_out) * m_e)   # denoised
         last = self.step_index == self.num_inference_steps - 1
@@ -635,8 +640,11 @@ class PNDMScheduler(FusedScheduler):
 
     def __init__(self, **kw):
         super().__init__(**kw)
-        if not self.config.skip_prk_steps or self.config.prediction_type != "epsilon":
-            raise NotImplementedError("only the PLMS path (skip_prk_steps=True, epsilon) of SD-v1.5 is fused")
+        if self.config.prediction_type not in ("epsilon", "v_prediction"):
+            raise ValueError(f"prediction_type given as {self.config.prediction_type} must be one of `epsilon` or "
+                             "`v_prediction`")
+        if not self.config.skip_prk_steps:
+            raise NotImplementedError("only the PLMS path (skip_prk_steps=True) of SD-v1.5 is fused")
         self.final_alpha_cumprod = torch.tensor(1.0) if self.config.set_alpha_to_one else self.alphas_cumprod[0]
         self.ets, self.counter, self.cur_sample = [], 0, None
 
@@ -686,6 +694,13 @@ class PNDMScheduler(FusedScheduler):
             c["c_m0"], c["c_h1"], c["c_h2"], c["c_h3"] = (-55 / 24 * kappa, 59 / 24 * kappa, -37 / 24 * kappa,
                                                           9 / 24 * kappa)
             hist = [self.ets[-1], self.ets[-2], self.ets[-3]]
+        if self.config.prediction_type == "v_prediction":
+            # _get_prev_sample turns the combined v outputs into a noise prediction with the CURRENT sample:
+            # eps = sqrt(a) v + sqrt(beta) x  ->  every history weight scales by sqrt(a), x gains -kappa sqrt(beta)
+            for key in ("c_m0", "c_h1", "c_h2", "c_h3"):
+                if key in c:
+                    c[key] *= _f(a ** 0.5)
+            c["c_x"] -= kappa * _f(beta ** 0.5)
         src = sample
         if not append:
             src = self.cur_sample

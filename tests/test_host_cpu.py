@@ -121,6 +121,9 @@ def _pairs():
                                                           prediction_type="v_prediction"), 12, {}),
         (S.DPMSolverScheduler, O.DPMSolverScheduler,
          dict(solver_order=3, algorithm_type="dpmsolver", final_sigmas_type="sigma_min", prediction_type="sample"), 12, {}),
+        (S.LCMScheduler, O.LCMScheduler, dict(prediction_type="v_prediction"), 4, {}),
+        (S.LCMScheduler, O.LCMScheduler, dict(prediction_type="sample"), 3, {}),
+        (S.PNDMScheduler, O.PNDMScheduler, dict(prediction_type="v_prediction"), 10, {}),
         (S.DDIMSchedulerMy, O.DDIMScheduler, dict(clip_sample=True, clip_sample_range=1.5), 10, {}),
         (S.DDIMSchedulerMy, O.DDIMScheduler, dict(thresholding=True, sample_max_value=2.5, prediction_type="v_prediction"),
          10, {"eta": 0.2}),
@@ -163,7 +166,7 @@ def _emulated_launch(self, coeffs, eps, eps_text, sample, hist=(), noise=None, w
     return xn.to(f), (m0.to(f) if want_m0 else None), (x0.to(f) if want_x0 else None)
 
 
-@pytest.mark.parametrize("idx", range(21))
+@pytest.mark.parametrize("idx", range(24))
 def test_scheduler_coefficients_reproduce_oracle_updates(idx, monkeypatch):
     """Every scheduler's reduction to linear-combination coefficients, step by step, against the
     oracle's literal formulas (fp32, CPU, no GPU needed)."""
