@@ -269,7 +269,7 @@ class DDIMSchedulerMy(FusedScheduler):
         # pred_original_sample tensor) and pred_eps linear in (model output e, x) for every prediction type
         pt = self.config.prediction_type
         if pt == "epsilon":
-            c = dict(m_x=1.0 / sa, m_e=-sb / sa, c_e=direction)
+            c = dict(m_x=1.0 / sa, m_e=-sb * (1.0 / sa), c_e=direction)
         elif pt == "sample":
             c = dict(m_x=0.0, m_e=1.0, c_x=direction / sb, c_e=-direction * sa / sb)
         else:                                             # v_prediction
@@ -611,7 +611,7 @@ class LCMScheduler(FusedScheduler):
         c_skip, c_out = self.get_scalings_for_boundary_condition_discrete(torch.tensor(t))
         sa, sb = _f(a.sqrt()), _f((1 - a).sqrt())
         pt = self.config.prediction_type                             # predicted_original_sample = m_x x + m_e e
-        m_x, m_e = (1.0 / sa, -sb / sa) if pt == "epsilon" else (0.0, 1.0) if pt == "sample" else (sa, -sb)
+        m_x, m_e = (1.0 / sa, -sb * (1.0 / sa)) if pt == "epsilon" else (0.0, 1.0) if pt == "sample" else (sa, -sb)
         c = dict(guidance=guidance, m_x=m_x, m_e=m_e,
                  x0_x=_f(c_out) * m_x + _f(c_skip), x0_e=_f(c_out) * m_e)   # denoised
         last = self.step_index == self.num_inference_steps - 1
