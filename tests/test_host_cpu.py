@@ -442,3 +442,27 @@ def test_bench_cpu_sample_sizing():
     assert bench._sample_size(3.9, 15.0) == 3 and bench._sample_size(100.0, 15.0) == 1
     assert "whole 25-step image" in bench._sample_text(25, 1.0) and "extrapolated" not in bench._sample_text(25, 1.0)
     assert "first 4 of the 25" in bench._sample_text(4, 3.9) and "extrapolated x25/4" in bench._sample_text(4, 3.9)
+
+
+def test_skip_steps_example_config_resolves():
+    """configs/skip_steps_config.yaml (the reference ships none for skip_steps_exp.py): names resolve through the
+    registries, the zipped lists have one skip list per sweep point, and the driver builds the scheduler with the
+    solver keys of skip_steps_exp.py:21-26."""
+    import os
+
+    from sonicdiffusionbayeslab_b200 import models as M
+    from sonicdiffusionbayeslab_b200 import schedulers as S
+    from sonicdiffusionbayeslab_b200.config import load as load_config
+    from sonicdiffusionbayeslab_b200.registry import methods_registry, models_registry, schedulers_registry
+
+    import sonicdiffusionbayeslab_b200.experiments  # noqa: F401
+
+    cfg = load_config(os.path.join(ROOT, "configs", "skip_steps_config.yaml"))
+    assert models_registry[cfg.model.model_name] is M.StableDiffusionModelSkipTimesteps
+    assert methods_registry[cfg.experiment.method].__name__ == "SkipStepsMethod"
+    assert schedulers_registry[cfg.scheduler.scheduler_name] is S.DPMSolverScheduler
+    p = cfg.experiment_params
+    assert len(p.skip_steps) == len(p.num_inference_steps) == 2
+    assert [list(v) for v in p.skip_steps] == [[3, 7, 11], [2, 4, 6, 8, 10]]
+    assert all(max(s) < n for s, n in zip(p.skip_steps, p.num_inference_steps))
+    assert (p.solver_order, p.algorithm_type, p.final_sigmas_type) == (2, "dpmsolver++", "zero")
