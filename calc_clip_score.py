@@ -9,6 +9,7 @@ Differences from the reference, each forced by a defect or by the deployment:
   * images go to the metric as uint8 (``pil_to_tensor``), the form torchmetrics' CLIPScore expects and the
     in-pipeline path uses (base_experiment.py:198-201); the reference feeds float [0,1] tensors from ``ToTensor``
     (calc_clip_score.py:69-73), which the HF processor rescales a second time (SURVEY appendix C-8);
+    ``--literal_float_rescale`` reproduces that arithmetic for a like-for-like number;
   * preprocessing (bicubic + antialias resize, centre crop, normalise) and both CLIP towers run on the GPU
     (metrics/metrics.py, clip_engine.py) instead of PIL on the host + library modules;
   * under torchrun the image list is sharded in contiguous blocks and the ONLY collective of the whole system runs
@@ -50,12 +51,15 @@ def _to_uint8(images):
 
 
 def calc_clip_score(dataset, model_name_or_path="openai/clip-vit-base-patch16", device=None, batch_size=32,
-                    gather_images=False):
-    """Returns (score, n_images[, gathered uint8 images]).  Sharded over the default process group if one exists."""
+                    gather_images=False, literal_float_rescale=False):
+    """Returns (score, n_images[, gathered uint8 images]).  Sharded over the default process group if one exists.
+    ``literal_float_rescale``: score what the reference script literally scores -- its float [0,1] tensors are
+    rescaled by 1/255 a second time inside the HF processor (SURVEY C-8: near-black images)."""
     rank, world = D.world()
     if device is None:
         device = f"cuda:{int(os.environ.get('LOCAL_RANK', 0)) % max(1, torch.cuda.device_count())}"
     metric = ClipScoreMetric(model_name_or_path=model_name_or_path).to(device)
+    metric.literal_float_rescale = bool(literal_float_rescale)
     n = len(dataset)
     per = (n + world - 1) // world
     lo, hi = min(n, rank * per), min(n, (rank + 1) * per)
@@ -86,6 +90,9 @@ if __name__ == "__main__":
                         help="CLIP model name or path to use for scoring")
     parser.add_argument("--synthetic", type=int, default=0, help="score N seeded synthetic images instead of a folder")
     parser.add_argument("--gather_images", action="store_true", help="also all-gather the uint8 images")
+    parser.add_argument("--literal_float_rescale", action="store_true",
+                        help="reproduce the reference script's literal arithmetic: float [0,1] inputs rescaled by 1/255 "
+                             "a second time by the HF processor (calc_clip_score.py:68-72, SURVEY C-8)")
     args = parser.parse_args()
 
     dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", 0)) % max(1, torch.cuda.device_count()))
@@ -103,7 +110,7 @@ if __name__ == "__main__":
         dataset = ImageDatasetWithPrompts(image_dir=args.folder_path, prompts_file=args.prompts_file,
                                           transform=transforms.Compose([transforms.PILToTensor()]))
     out = calc_clip_score(dataset, model_name_or_path=args.model_name_or_path, device=dev, batch_size=args.batch_size,
-                          gather_images=args.gather_images)
+                          gather_images=args.gather_images, literal_float_rescale=args.literal_float_rescale)
     if rank == 0:
         print(f"CLIP Score: {out[0]}")
     if world > 1:

@@ -113,10 +113,11 @@ class ClipVisionEngine(ClipEncoderEngine):
         return self.features_from_patches()
 
     @torch.no_grad()
-    def image_features_from_images(self, images):
+    def image_features_from_images(self, images, rescale_twice=False):
         """uint8 (or float [0,1]) images (n, 3, H, W) -> embeddings: the fused preprocessing kernel
         (``sonic_clip_preprocess``) writes the patch rows of the embedding GEMM directly."""
-        K.clip_preprocess(images.contiguous(), size=self.grid * self.patch, patches_out=self.patches, patch=self.patch)
+        K.clip_preprocess(images.contiguous(), size=self.grid * self.patch, patches_out=self.patches, patch=self.patch,
+                          rescale_twice=rescale_twice)
         return self.features_from_patches()
 
     @torch.no_grad()

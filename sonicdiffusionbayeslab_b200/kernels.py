@@ -404,7 +404,19 @@ def _resample_tables(H, W, size, device):
     return _resample_cache[key]
 
 
-def clip_preprocess(images: torch.Tensor, size: int = 224, patches_out: torch.Tensor = None, patch: int = 16):
+def clip_norm_constants(rescale_twice: bool = False):
+    """(mean, std) for ``sonic_clip_preprocess``, which computes ``(v / 255 - mean) / std`` on the resized uint8 ``v``.
+    ``rescale_twice`` reproduces the LITERAL behaviour of /root/reference/calc_clip_score.py:68-72 (SURVEY C-8): float
+    [0,1] tensors go to the HF processor, which brings them back to [0,1] after its PIL resize and then applies its 1/255
+    rescale a second time -- ``(v / 255 / 255 - mean) / std == (v / 255 - 255 mean) / (255 std)``, i.e. the same kernel
+    with both constants scaled by 255 (to a grey level on natural images; HF's float path does not round / clamp the
+    resized values to uint8, so bicubic overshoot on noise-like images differs by more)."""
+    f = 255.0 if rescale_twice else 1.0
+    return tuple(f * m for m in CLIP_MEAN), tuple(f * s for s in CLIP_STD)
+
+
+def clip_preprocess(images: torch.Tensor, size: int = 224, patches_out: torch.Tensor = None, patch: int = 16,
+                    rescale_twice: bool = False):
     """uint8 (n,3,H,W) -- or float / bf16 in [0,1], quantised in the kernel like base_experiment.py:198-199 -- ->
     normalised fp32 (n,3,size,size), bit-identical to HF ``CLIPImageProcessor`` on PIL; with ``patches_out`` the
     bf16 patch rows of the ViT patch-embedding GEMM are written instead (one launch, no torch ops)."""
@@ -412,7 +424,8 @@ def clip_preprocess(images: torch.Tensor, size: int = 224, patches_out: torch.Te
     code = {torch.float32: 0, torch.bfloat16: 1, torch.uint8: 2}[images.dtype]
     n, _, H, W = images.shape
     tb = _resample_tables(H, W, size, images.device)
-    mean, std = (C.c_float * 3)(*CLIP_MEAN), (C.c_float * 3)(*CLIP_STD)
+    mean, std = clip_norm_constants(rescale_twice)
+    mean, std = (C.c_float * 3)(*mean), (C.c_float * 3)(*std)
     if patches_out is None:
         out, mode = torch.empty((n, 3, size, size), device=images.device, dtype=torch.float32), 0
     else:

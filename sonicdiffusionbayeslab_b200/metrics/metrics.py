@@ -137,7 +137,8 @@ class ClipScoreMetric(Metric):
                             "float [0,1] inputs are the calc_clip_score.py defect (SURVEY C-8)")
         ids, _ = self.tokenizer(text)
         vis, txt = self._native(len(text))
-        fi = vis.image_features_from_images(images.to(self.device)).float()      # fused preprocess -> patch rows
+        fi = vis.image_features_from_images(images.to(self.device),             # fused preprocess -> patch rows
+                                            rescale_twice=getattr(self, "literal_float_rescale", False)).float()
         ft = txt.text_features(ids.to(self.device)).float()
         fi = fi / fi.norm(p=2, dim=-1, keepdim=True)
         ft = ft / ft.norm(p=2, dim=-1, keepdim=True)

@@ -466,3 +466,33 @@ def test_skip_steps_example_config_resolves():
     assert [list(v) for v in p.skip_steps] == [[3, 7, 11], [2, 4, 6, 8, 10]]
     assert all(max(s) < n for s, n in zip(p.skip_steps, p.num_inference_steps))
     assert (p.solver_order, p.algorithm_type, p.final_sigmas_type) == (2, "dpmsolver++", "zero")
+
+
+def test_literal_float_rescale_constants_match_hf_processor():
+    """``--literal_float_rescale`` of calc_clip_score.py (SURVEY C-8): the reference script hands float [0,1] tensors
+    to torchmetrics' CLIPScore, whose HF processor rescales them by 1/255 a second time.  The product reproduces that
+    with the SAME preprocessing kernel and (255 mean, 255 std); checked here against ``CLIPImageProcessor`` itself
+    on natural-image-like (smooth) inputs to two grey levels / 65025 / std: HF resizes float inputs without the uint8
+    rounding and clamping of the PIL path, so only bicubic overshoot on noise-like images would differ by more."""
+    import warnings
+
+    from sonicdiffusionbayeslab_b200 import kernels as K
+    from transformers import CLIPImageProcessor
+
+    proc = CLIPImageProcessor(do_resize=True, size={"shortest_edge": 224}, resample=3, do_center_crop=True,
+                              crop_size={"height": 224, "width": 224}, do_rescale=True, rescale_factor=1 / 255,
+                              do_normalize=True, image_mean=list(K.CLIP_MEAN), image_std=list(K.CLIP_STD),
+                              do_convert_rgb=True)
+    g = torch.Generator().manual_seed(0)
+    low = torch.rand(2, 3, 12, 15, generator=g)
+    u8 = (torch.nn.functional.interpolate(low, size=(256, 320), mode="bicubic", align_corners=False).clamp(0, 1)
+          * 255).to(torch.uint8)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        std_out = proc(images=[i for i in u8], return_tensors="pt")["pixel_values"]
+        lit_out = proc(images=[i for i in u8.float() / 255], return_tensors="pt")["pixel_values"]
+    m1, s1 = (torch.tensor(v).view(1, 3, 1, 1) for v in K.clip_norm_constants(False))
+    m2, s2 = (torch.tensor(v).view(1, 3, 1, 1) for v in K.clip_norm_constants(True))
+    v_over_255 = std_out * s1 + m1                       # what the kernel holds before normalising
+    assert (lit_out - (v_over_255 - m2) / s2).abs().max().item() < 2.0 / (65025 * min(K.CLIP_STD))
+    assert (lit_out - std_out).abs().max().item() > 1.0  # ... and it is a different image (near black)
