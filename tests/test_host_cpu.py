@@ -48,6 +48,10 @@ def test_library_is_blackwell_native():
     for mnemonic in ("UTCHMMA.2CTA", "UTCBAR.2CTA.MULTICAST", "UTMALDG.4D.2CTA", "UCGABAR_WAIT", "FFMA2", "FADD2", "FMUL2"):
         assert mnemonic in sass, mnemonic
     assert "HMMA.16816" not in sass            # no legacy mma.sync tensor path
+    # programmatic dependent launch (SONIC_PDL): every kernel that can be launched with the attribute -- 2 GEMM,
+    # 16 attention instantiations, cluster GroupNorm, ln_side -- waits (griddepcontrol.wait -> ACQBULK) exactly once,
+    # and with the stock trigger policy signals (launch_dependents -> PREEXIT) exactly once
+    assert sass.count("ACQBULK") == sass.count("PREEXIT") == 20
 
 
 def test_missing_library_fails_loudly(monkeypatch):
