@@ -65,6 +65,22 @@ def retrieve_timesteps(scheduler, num_inference_steps=None, device=None, timeste
     return scheduler.timesteps, num_inference_steps
 
 
+def postprocess_images(image01: torch.Tensor, output_type: str):
+    """diffusers ``VaeImageProcessor.postprocess`` on already-denormalised [0, 1] tensors (models.py:313-315):
+    ``"pt"`` the tensor, ``"np"`` float32 NHWC numpy, ``"pil"`` a list of PIL images (``(x * 255).round()`` uint8)."""
+    if output_type == "pt":
+        return image01
+    arr = image01.cpu().permute(0, 2, 3, 1).float().numpy()
+    if output_type == "np":
+        return arr
+    if output_type == "pil":
+        from PIL import Image
+
+        u8 = (arr * 255).round().astype("uint8")
+        return [Image.fromarray(a.squeeze(-1), mode="L") if a.shape[-1] == 1 else Image.fromarray(a) for a in u8]
+    raise ValueError(f"output_type {output_type!r}: expected one of 'latent', 'pt', 'np', 'pil'")
+
+
 def _load_safetensors(path):
     from safetensors.torch import load_file
 
@@ -215,6 +231,84 @@ class _PipelineBase:
         self._weights = None
         self._engines = {}
 
+    # ---------------------------------------------------------------- argument checks
+    _callback_tensor_inputs = ["latents", "prompt_embeds", "negative_prompt_embeds"]
+
+    def check_inputs(self, prompt, height, width, callback_steps, negative_prompt=None, prompt_embeds=None,
+                     negative_prompt_embeds=None, ip_adapter_image=None, ip_adapter_image_embeds=None,
+                     callback_on_step_end_tensor_inputs=None):
+        """diffusers ``StableDiffusionPipeline.check_inputs`` as called at models.py:103-114: same conditions, same
+        ``ValueError`` texts."""
+        if height % 8 != 0 or width % 8 != 0:
+            raise ValueError(f"`height` and `width` have to be divisible by 8 but are {height} and {width}.")
+        if callback_steps is not None and (not isinstance(callback_steps, int) or callback_steps <= 0):
+            raise ValueError(f"`callback_steps` has to be a positive integer but is {callback_steps} of type"
+                             f" {type(callback_steps)}.")
+        if callback_on_step_end_tensor_inputs is not None and not all(
+                k in self._callback_tensor_inputs for k in callback_on_step_end_tensor_inputs):
+            raise ValueError(
+                f"`callback_on_step_end_tensor_inputs` has to be in {self._callback_tensor_inputs}, but found "
+                f"{[k for k in callback_on_step_end_tensor_inputs if k not in self._callback_tensor_inputs]}")
+        if prompt is not None and prompt_embeds is not None:
+            raise ValueError(f"Cannot forward both `prompt`: {prompt} and `prompt_embeds`: {prompt_embeds}. Please make "
+                             "sure to only forward one of the two.")
+        elif prompt is None and prompt_embeds is None:
+            raise ValueError("Provide either `prompt` or `prompt_embeds`. Cannot leave both `prompt` and `prompt_embeds` "
+                             "undefined.")
+        elif prompt is not None and (not isinstance(prompt, str) and not isinstance(prompt, list)):
+            raise ValueError(f"`prompt` has to be of type `str` or `list` but is {type(prompt)}")
+        if negative_prompt is not None and negative_prompt_embeds is not None:
+            raise ValueError(f"Cannot forward both `negative_prompt`: {negative_prompt} and `negative_prompt_embeds`:"
+                             f" {negative_prompt_embeds}. Please make sure to only forward one of the two.")
+        if prompt_embeds is not None and negative_prompt_embeds is not None:
+            if prompt_embeds.shape != negative_prompt_embeds.shape:
+                raise ValueError("`prompt_embeds` and `negative_prompt_embeds` must have the same shape when passed "
+                                 f"directly, but got: `prompt_embeds` {prompt_embeds.shape} != `negative_prompt_embeds`"
+                                 f" {negative_prompt_embeds.shape}.")
+        if ip_adapter_image is not None and ip_adapter_image_embeds is not None:
+            raise ValueError("Provide either `ip_adapter_image` or `ip_adapter_image_embeds`. Cannot leave both "
+                             "`ip_adapter_image` and `ip_adapter_image_embeds` defined.")
+
+    def _check_call(self, prompt, height, width, negative_prompt, prompt_embeds, negative_prompt_embeds, latents,
+                    timesteps, sigmas, num_images_per_prompt, guidance_rescale, output_type, kwargs):
+        """The head of the reference ``call`` (models.py:64-114) -- default size, ``check_inputs`` -- followed by what
+        this engine does not implement: every such argument raises instead of being ignored."""
+        kwargs.pop("callback", None)                            # deprecated and unused by the reference loop's callers
+        callback_steps = kwargs.pop("callback_steps", None)
+        tensor_inputs = kwargs.pop("callback_on_step_end_tensor_inputs", ["latents"])
+        ip_image, ip_embeds = kwargs.pop("ip_adapter_image", None), kwargs.pop("ip_adapter_image_embeds", None)
+        if not height or not width:                             # models.py:85-100: both default together
+            height = width = self.unet.config.sample_size * self.vae_scale_factor
+        self.check_inputs(prompt, height, width, callback_steps, negative_prompt, prompt_embeds, negative_prompt_embeds,
+                          ip_image, ip_embeds, tensor_inputs)
+        if output_type not in ("latent", "pt", "np", "pil"):
+            raise ValueError(f"output_type {output_type!r}: expected one of 'latent', 'pt', 'np', 'pil'")
+        want = self.latent_size * self.vae_scale_factor
+        if (height, width) != (want, want):
+            raise NotImplementedError(f"height x width = {height} x {width}: this pipeline's engines are recorded for "
+                                      f"{want} x {want} (latent_size={self.latent_size}); build it with another "
+                                      "latent_size for other resolutions")
+        if timesteps is not None and sigmas is not None:
+            raise ValueError("Only one of `timesteps` or `sigmas` can be passed. Please choose one to set custom values")
+        if sigmas is not None:
+            raise ValueError(f"The current scheduler class {self.scheduler.__class__}'s `set_timesteps` does not support "
+                             "custom sigmas schedules. Please check whether you are using the correct scheduler.")
+        unsupported = {"num_images_per_prompt": num_images_per_prompt not in (None, 1),
+                       "guidance_rescale": bool(guidance_rescale), "ip_adapter_image": ip_image is not None,
+                       "ip_adapter_image_embeds": ip_embeds is not None,
+                       "cross_attention_kwargs": kwargs.pop("cross_attention_kwargs", None) is not None,
+                       "clip_skip": kwargs.pop("clip_skip", None) is not None,
+                       "callback_on_step_end_tensor_inputs other than ['latents']": list(tensor_inputs) != ["latents"]}
+        bad = [k for k, v in unsupported.items() if v]
+        if bad:
+            raise NotImplementedError(f"{', '.join(bad)}: not used by any reference driver and not implemented by the "
+                                      "B200 engine")
+        if latents is not None:
+            batch = (1 if isinstance(prompt, str) else len(prompt)) if prompt is not None else prompt_embeds.shape[0]
+            shape = (batch, self.arch.in_channels, self.latent_size, self.latent_size)
+            if tuple(latents.shape) != shape:
+                raise ValueError(f"Unexpected latents shape, got {tuple(latents.shape)}, expected {shape}")
+
     # ---------------------------------------------------------------- engine plumbing
     def engine(self, n_latents, cfg_dup) -> UNetEngine:
         if self.device.type != "cuda":
@@ -357,18 +451,20 @@ class _PipelineBase:
             raise RuntimeError("the VAE decoder runs on the B200 engine: call .to('cuda') first")
         return self.vae_engine(z.shape[0]).decode(z.to(self.dtype)).clone()
 
-    def _finish(self, eng, x0_preds, output_type, exec_time):
+    def _finish(self, eng, x0_preds, output_type, exec_time, return_dict=True):
+        """models.py:287-335: decode, ``image_processor.postprocess`` (denormalise + output type), return arity."""
         latents = eng.x_in.clone()
         images_x0 = []
         if output_type == "latent":
             image = latents
         else:
             sf = self.vae.config.scaling_factor
-            image = self._decode(latents / sf)
-            image = (image / 2 + 0.5).clamp(0, 1)
+            image = postprocess_images((self._decode(latents / sf) / 2 + 0.5).clamp(0, 1), output_type)
             if self.decode_x0_preds:
                 for x0 in x0_preds:
-                    images_x0.append((self._decode(x0 / sf) / 2 + 0.5).clamp(0, 1))
+                    images_x0.append(postprocess_images((self._decode(x0 / sf) / 2 + 0.5).clamp(0, 1), output_type))
+        if not return_dict:
+            return (image, None), exec_time, images_x0
         return PipelineOutput(images=image, nsfw_content_detected=None), exec_time, images_x0
 
     def __call__(self, *args, return_execution_time=True, **kwargs):
@@ -386,11 +482,9 @@ class StableDiffusionModel(_PipelineBase):
              eta: float = 0.0, generator=None, latents=None, prompt_embeds=None, negative_prompt_embeds=None,
              output_type="pil", return_dict=True, guidance_rescale: float = 0.0, skip_timesteps=(),
              callback_on_step_end=None, **kwargs):
-        if guidance_rescale:
-            raise NotImplementedError("guidance_rescale is 0 in every reference config and is not fused")
-        if output_type not in ("pt", "latent"):
-            raise NotImplementedError("output_type must be 'pt' (as the experiments use) or 'latent'")
         rng_only, rng_rows = kwargs.pop("rng_only", False), kwargs.pop("rng_rows", None)
+        self._check_call(prompt, height, width, negative_prompt, prompt_embeds, negative_prompt_embeds, latents,
+                         timesteps, sigmas, num_images_per_prompt, guidance_rescale, output_type, kwargs)
         self._guidance_scale = guidance_scale
         batch = (1 if isinstance(prompt, str) else len(prompt)) if prompt is not None else prompt_embeds.shape[0]
         do_cfg = self.do_classifier_free_guidance
@@ -428,7 +522,7 @@ class StableDiffusionModel(_PipelineBase):
         torch.cuda.synchronize(self.device)
         exec_time = time.perf_counter() - start
         self._x0_reset([self.scheduler])
-        return self._finish(eng, x0_preds, output_type, exec_time)
+        return self._finish(eng, x0_preds, output_type, exec_time, return_dict)
 
 
 @models_registry.add_to_registry("stable_diffusion_model_skip_timesteps")
@@ -452,9 +546,9 @@ class StableDiffusionModelTwoSchedulers(_PipelineBase):
              num_images_per_prompt=1, eta: float = 0.0, generator=None, latents=None, prompt_embeds=None,
              negative_prompt_embeds=None, output_type="pil", return_dict=True, guidance_rescale: float = 0.0,
              callback_on_step_end=None, **kwargs):
-        if output_type not in ("pt", "latent"):
-            raise NotImplementedError("output_type must be 'pt' or 'latent'")
         rng_only, rng_rows = kwargs.pop("rng_only", False), kwargs.pop("rng_rows", None)
+        self._check_call(prompt, height, width, negative_prompt, prompt_embeds, negative_prompt_embeds, latents,
+                         timesteps, sigmas, num_images_per_prompt, guidance_rescale, output_type, kwargs)
         self._guidance_scale = guidance_scale
         batch = (1 if isinstance(prompt, str) else len(prompt)) if prompt is not None else prompt_embeds.shape[0]
         do_cfg = self.do_classifier_free_guidance
@@ -494,7 +588,7 @@ class StableDiffusionModelTwoSchedulers(_PipelineBase):
         torch.cuda.synchronize(self.device)
         exec_time = time.perf_counter() - start
         self._x0_reset([self.scheduler_first, self.scheduler_second])
-        return self._finish(eng, x0_preds, output_type, exec_time)
+        return self._finish(eng, x0_preds, output_type, exec_time, return_dict)
 
     def switch_timestamp(self, timesteps_first, timesteps_second, num_step_switch, type_switch="closest"):
         """models.py:704-730 -> python lists of np.int64 (bit-exact integer schedule)."""
@@ -540,13 +634,13 @@ class StableDiffusionModelInterlivingSchedulers(_PipelineBase):
              num_images_per_prompt=1, eta: float = 0.0, generator=None, latents=None, prompt_embeds=None,
              negative_prompt_embeds=None, output_type="pil", return_dict=True, guidance_rescale: float = 0.0,
              callback_on_step_end=None, **kwargs):
-        if output_type not in ("pt", "latent"):
-            raise NotImplementedError("output_type must be 'pt' or 'latent'")
         main, inter_s = self.scheduler_main, self.scheduler_inter
         if main is None or inter_s is None:
             raise ValueError("scheduler_main / scheduler_inter must be set (interliving_exp.py:40-62)")
         interliving_steps = list(interliving_steps or [])
         rng_only, rng_rows = kwargs.pop("rng_only", False), kwargs.pop("rng_rows", None)
+        self._check_call(prompt, height, width, negative_prompt, prompt_embeds, negative_prompt_embeds, latents,
+                         timesteps, sigmas, num_images_per_prompt, guidance_rescale, output_type, kwargs)
         self._guidance_scale = guidance_scale
         batch = (1 if isinstance(prompt, str) else len(prompt)) if prompt is not None else prompt_embeds.shape[0]
         do_cfg = self.do_classifier_free_guidance
@@ -589,4 +683,4 @@ class StableDiffusionModelInterlivingSchedulers(_PipelineBase):
         torch.cuda.synchronize(self.device)
         exec_time = time.perf_counter() - start
         self._x0_reset([main, inter_s])
-        return self._finish(eng, x0_preds, output_type, exec_time)
+        return self._finish(eng, x0_preds, output_type, exec_time, return_dict)

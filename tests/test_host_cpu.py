@@ -500,3 +500,63 @@ def test_literal_float_rescale_constants_match_hf_processor():
     v_over_255 = std_out * s1 + m1                       # what the kernel holds before normalising
     assert (lit_out - (v_over_255 - m2) / s2).abs().max().item() < 2.0 / (65025 * min(K.CLIP_STD))
     assert (lit_out - std_out).abs().max().item() > 1.0  # ... and it is a different image (near black)
+
+
+def test_pipeline_call_argument_checks():
+    """The head of the reference ``call`` (src/models.py:64-114 -> diffusers ``check_inputs``): same conditions and
+    ``ValueError``s; arguments the engine does not implement raise instead of being ignored; everything is decided
+    before the first CUDA access."""
+    from sonicdiffusionbayeslab_b200 import models as M
+    from sonicdiffusionbayeslab_b200 import schedulers as S
+    from sonicdiffusionbayeslab_b200.text import HashTokenizer
+
+    pipes = [cls({}, vae=None, text_encoder=None, tokenizer=HashTokenizer(),
+                 scheduler=S.DDIMSchedulerMy.from_config(M.SD15_SCHEDULER_CONFIG))
+             for cls in (M.StableDiffusionModel, M.StableDiffusionModelSkipTimesteps, M.StableDiffusionModelTwoSchedulers)]
+    pipes[2].scheduler_first = S.DDIMSchedulerMy.from_config(M.SD15_SCHEDULER_CONFIG)
+    pipes[2].scheduler_second = S.DPMSolverScheduler.from_config(M.SD15_SCHEDULER_CONFIG)
+    pe, ne = torch.zeros(2, 77, 768), torch.zeros(2, 77, 768)
+    lat = torch.zeros(2, 4, 64, 64)
+    for pipe in pipes:
+        ok = dict(prompt_embeds=pe, negative_prompt_embeds=ne, latents=lat, output_type="latent")
+        for bad, exc, frag in [
+            (dict(prompt_embeds=None), ValueError, "Provide either `prompt` or `prompt_embeds`"),
+            (dict(prompt=["a", "b"]), ValueError, "Cannot forward both `prompt`"),
+            (dict(prompt=("a", "b"), prompt_embeds=None), ValueError, "has to be of type `str` or `list`"),
+            (dict(height=510, width=512), ValueError, "divisible by 8"),
+            (dict(height=768, width=768), NotImplementedError, "latent_size"),
+            (dict(negative_prompt="x"), ValueError, "Cannot forward both `negative_prompt`"),
+            (dict(negative_prompt_embeds=ne[:1]), ValueError, "must have the same shape"),
+            (dict(sigmas=[1.0, 0.5]), ValueError, "custom sigmas"),
+            (dict(sigmas=[1.0], timesteps=[5]), ValueError, "Only one of `timesteps` or `sigmas`"),
+            (dict(num_images_per_prompt=2), NotImplementedError, "num_images_per_prompt"),
+            (dict(guidance_rescale=0.7), NotImplementedError, "guidance_rescale"),
+            (dict(clip_skip=1), NotImplementedError, "clip_skip"),
+            (dict(callback_steps=0), ValueError, "callback_steps"),
+            (dict(callback_on_step_end_tensor_inputs=["latents", "nope"]), ValueError, "tensor_inputs"),
+            (dict(callback_on_step_end_tensor_inputs=["prompt_embeds"]), NotImplementedError, "tensor_inputs"),
+            (dict(output_type="jpeg"), ValueError, "output_type"),
+            (dict(latents=lat[:, :, :32]), ValueError, "Unexpected latents shape"),
+        ]:
+            with pytest.raises(exc, match=frag.replace("(", r"\\(")):
+                pipe(**{**ok, **bad})
+        with pytest.raises(RuntimeError, match="CUDA"):         # valid arguments: only now is the device needed
+            pipe(**ok)
+
+
+def test_postprocess_images_follows_diffusers():
+    """``VaeImageProcessor.postprocess`` (src/models.py:313-315) on denormalised tensors: pt / np / pil."""
+    import numpy as np
+
+    from sonicdiffusionbayeslab_b200.models import postprocess_images
+
+    g = torch.Generator().manual_seed(0)
+    x = torch.rand(2, 3, 8, 8, generator=g)
+    assert postprocess_images(x, "pt") is x
+    arr = postprocess_images(x, "np")
+    assert arr.shape == (2, 8, 8, 3) and arr.dtype == np.float32 and np.array_equal(arr, x.permute(0, 2, 3, 1).numpy())
+    pil = postprocess_images(x, "pil")
+    assert len(pil) == 2 and pil[0].size == (8, 8) and pil[0].mode == "RGB"
+    assert np.array_equal(np.asarray(pil[1]), (arr[1] * 255).round().astype("uint8"))
+    with pytest.raises(ValueError):
+        postprocess_images(x, "jpeg")
