@@ -1,0 +1,152 @@
+"""The product's pipeline ``call`` bodies (sonicdiffusionbayeslab_b200/models.py) end to end on the CPU, against the
+per-step latents that EXECUTING THE REFERENCE'S OWN ``call`` bodies produced (tests/golden/reference_pins.npz,
+``pipe/<case>/per_step``; /root/reference/src/models.py:21-335 / 338-730 / 733-1135 / 1138-1467 via oracle/refexec.py).
+
+Only the two native pieces are replaced, by the checker's stand-ins: the UNet launch plan by the tiny oracle UNet the
+fixtures were made with (a fake engine with the real engine's surface: ``x_in`` / ``set_context`` / ``forward`` /
+``n_lat``) and the fused update kernel by its float64 model (tests/test_host_cpu.py ``_emulated_launch``).  Everything
+else -- argument checks, timestep retrieval, classifier-free-guidance batching, scheduler dispatch, two-scheduler
+switch, interleave partition and history feeding, skip mask, in-place latent update through ``out=``, RNG order,
+callback contract, return arity -- is the product code that runs on the GPU.
+"""
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+
+import refpin_cases as RC  # noqa: E402
+from test_host_cpu import _emulated_launch  # noqa: E402
+
+PINS = np.load(os.path.join(HERE, "golden", "reference_pins.npz"))
+META = json.load(open(os.path.join(HERE, "golden", "reference_pins.json")))
+
+
+class FakeEngine:
+    """The surface of ``UNetEngine`` the pipelines use, over the oracle UNet (fp32, CPU)."""
+
+    def __init__(self, net, n_latents, cfg_dup):
+        self.net, self.n_lat, self.cfg_dup = net, n_latents, cfg_dup
+        self.x_in = torch.zeros(n_latents, RC.C, RC.HW, RC.HW)
+        self.ctx = None
+        self.calls = []
+
+    def set_context(self, ctx):
+        self.ctx = ctx.float()
+
+    @torch.no_grad()
+    def forward(self, t, cached=False):
+        assert not cached
+        self.calls.append(int(t))
+        x = torch.cat([self.x_in] * 2) if self.cfg_dup else self.x_in
+        return self.net(x, torch.tensor(int(t)), encoder_hidden_states=self.ctx)[0]
+
+
+def _launch_in_place(self, coeffs, eps, eps_text, sample, hist=(), noise=None, want_m0=False, want_x0=True, out=None,
+                     ring=True, post=None):
+    """The kernel model, honouring ``out=`` like the kernel does (the pipelines update the resident latents in place)."""
+    xn, m0, x0 = _emulated_launch(self, coeffs, eps, eps_text, sample, hist=hist, noise=noise, want_m0=want_m0,
+                                  want_x0=want_x0, post=post)
+    if out is not None:
+        out.copy_(xn)
+        xn = out
+    return xn, m0, x0
+
+
+@pytest.fixture(scope="module")
+def net():
+    n = torch.get_num_threads()
+    torch.set_num_threads(1)
+    yield RC.tiny_unet()
+    torch.set_num_threads(n)
+
+
+@pytest.fixture()
+def harness(monkeypatch, net):
+    from sonicdiffusionbayeslab_b200 import models as M
+    from sonicdiffusionbayeslab_b200 import schedulers as S
+    from sonicdiffusionbayeslab_b200.text import HashTokenizer
+    from sonicdiffusionbayeslab_b200.unet_engine import UNetArch
+
+    monkeypatch.setattr(S.FusedScheduler, "_launch", _launch_in_place)
+    monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
+    engines = []
+
+    def engine(self, n_latents, cfg_dup):
+        engines.append(FakeEngine(net, n_latents, cfg_dup))
+        return engines[-1]
+
+    def encode_prompt(self, prompt, do_cfg, prompt_embeds=None, negative_prompt_embeds=None, negative_prompt=None):
+        return prompt_embeds, negative_prompt_embeds             # fp32 embeddings as the fixtures used (no bf16 cast)
+
+    monkeypatch.setattr(M._PipelineBase, "engine", engine)
+    monkeypatch.setattr(M._PipelineBase, "encode_prompt", encode_prompt)
+
+    def make(cls, scheduler):
+        return cls({}, vae=None, text_encoder=None, tokenizer=HashTokenizer(), scheduler=scheduler, arch=UNetArch(),
+                   torch_dtype=torch.float32, latent_size=RC.HW)
+
+    return M, S, make, engines
+
+
+@pytest.mark.parametrize("name", list(RC.PIPELINE_CASES))
+def test_product_call_bodies_reproduce_reference_source(name, harness):
+    M, S, make, engines = harness
+    case = RC.PIPELINE_CASES[name]
+    pe, ne, lat = RC.pipeline_inputs()
+    default = S.PNDMScheduler.from_config(RC.SD15)
+    seen, per_step = [], []
+
+    def cb(pipe, i, t, kwargs):
+        seen.append(int(t))
+        per_step.append(kwargs["latents"].clone())
+        return {}
+
+    common = dict(prompt_embeds=pe, negative_prompt_embeds=ne, guidance_scale=case["guidance"], output_type="latent",
+                  callback_on_step_end=cb)
+    if case.get("gen_seed") is not None:
+        common["generator"] = torch.Generator().manual_seed(case["gen_seed"])
+    if not case.get("draw_latents"):
+        common["latents"] = lat
+    else:
+        common["height"], common["width"] = 8 * RC.HW, 8 * RC.HW
+    kind = case["pipe"]
+    if kind in ("single", "skip"):
+        cls = M.StableDiffusionModel if kind == "single" else M.StableDiffusionModelSkipTimesteps
+        pipe = make(cls, RC.make_scheduler(*case["sched"], module=S))
+        kw = dict(num_inference_steps=case["steps"])
+        if kind == "skip":
+            kw["skip_timesteps"] = list(case["skip"])
+    elif kind == "two":
+        pipe = make(M.StableDiffusionModelTwoSchedulers, default)
+        pipe.scheduler_first = RC.make_scheduler(*case["first"], module=S)
+        pipe.scheduler_second = RC.make_scheduler(*case["second"], module=S)
+        kw = dict(num_inference_steps_first=case["n1"], num_inference_steps_second=case["n1"],
+                  num_step_switch=case["k"], type_switch=case["type_switch"])
+    else:
+        pipe = make(M.StableDiffusionModelInterlivingSchedulers, default)
+        pipe.scheduler_main = RC.make_scheduler(*case["main"], module=S)
+        pipe.scheduler_inter = RC.make_scheduler(*case["inter"], module=S)
+        kw = dict(num_inference_steps=case["steps"], interliving_steps=list(case["groups"]))
+    out, secs, x0 = pipe(**common, **kw)
+    want = torch.from_numpy(PINS[f"pipe/{name}/per_step"])
+    assert seen == META["pipeline_timesteps"][name]                      # integer schedule: bit-exact
+    assert engines[-1].calls == seen                                     # one UNet evaluation per executed step
+    assert len(per_step) == want.shape[0]
+    scale = max(1.0, want.abs().max().item())
+    worst = max((g - w).abs().max().item() for g, w in zip(per_step, want)) / scale
+    print(f"\n[{name}] product call body vs reference source: worst per-step max-abs / range {worst:.2e}")
+    assert worst <= 5e-6, (name, worst)                                  # fp32 host path, float64 kernel model
+    assert torch.equal(out.images, per_step[-1]) and secs >= 0
+    info = META["pipeline_info"][name]
+    assert pipe.num_timesteps == info["num_timesteps"]
+    assert x0 == []                                                      # output_type="latent": nothing is decoded
+    tup = pipe(**{**common, "callback_on_step_end": None,
+                  **({"generator": torch.Generator().manual_seed(case["gen_seed"])} if case.get("gen_seed") is not None
+                     else {})}, **kw, return_dict=False)
+    assert isinstance(tup[0], tuple) and tup[0][1] is None and torch.equal(tup[0][0], out.images)   # models.py:322-323
