@@ -150,3 +150,67 @@ def test_product_call_bodies_reproduce_reference_source(name, harness):
                   **({"generator": torch.Generator().manual_seed(case["gen_seed"])} if case.get("gen_seed") is not None
                      else {})}, **kw, return_dict=False)
     assert isinstance(tup[0], tuple) and tup[0][1] is None and torch.equal(tup[0][0], out.images)   # models.py:322-323
+
+
+class DeepCacheFakeEngine(FakeEngine):
+    """Fake engine whose cached plan is the oracle's DeepCache wrapper: the PRODUCT decides
+    which steps replay the cached plan; the oracle's own full / skip rule must agree on every call."""
+
+    def __init__(self, net, n_latents, cfg_dup, t_list, interval, branch):
+        from oracle.deepcache import DeepCacheOracle
+
+        super().__init__(net, n_latents, cfg_dup)
+        self.t_list, self.flags = t_list, []
+        self.dc = DeepCacheOracle(net)
+        self.dc.set_params(cache_interval=interval, cache_branch_id=branch)
+
+    @torch.no_grad()
+    def forward(self, t, cached=False):
+        cur = self.t_list.index(int(t))
+        start = cur if self.dc.start is None else self.dc.start
+        assert ((cur - start) % self.dc.interval != 0) == cached, (int(t), cur, cached)
+        self.calls.append(int(t))
+        self.flags.append(bool(cached))
+        x = torch.cat([self.x_in] * 2) if self.cfg_dup else self.x_in
+        return self.dc.forward(x, torch.tensor(int(t)), self.ctx, cur)
+
+
+@pytest.mark.parametrize("sched,steps,interval,branch", [("ddim", 12, 3, 0), ("pndm", 7, 2, 0), ("pndm", 9, 5, 4),
+                                                          ("ddim", 10, 4, 7)])
+def test_product_deepcache_loop_equals_oracle(sched, steps, interval, branch, harness, net, monkeypatch):
+    """``DeepCacheSDHelper`` + the pipeline's full / cached decision (deep_cache.py:24-29,58; appendix A.4 -- with
+    PLMS the repeated timestep maps to its FIRST index) against the oracle's wrapper semantics, through the product's
+    ``call``: same per-step latents, the cached plan replayed on exactly the steps the oracle skips."""
+    from oracle import schedulers as O
+    from oracle.deepcache import DeepCacheOracle
+    from oracle.pipeline import denoise
+    from sonicdiffusionbayeslab_b200.deepcache import DeepCacheSDHelper
+
+    M, S, make, engines = harness
+    pe, ne, lat = RC.pipeline_inputs()
+    pipe = make(M.StableDiffusionModel, RC.make_scheduler(sched, {}, module=S))
+
+    def engine(self, n_latents, cfg_dup):
+        assert self._deepcache["branch"] == branch
+        engines.append(DeepCacheFakeEngine(net, n_latents, cfg_dup, list(self.scheduler._timesteps_host), interval,
+                                           branch))
+        return engines[-1]
+
+    monkeypatch.setattr(M._PipelineBase, "engine", engine)
+    helper = DeepCacheSDHelper(pipe=pipe)
+    helper.set_params(cache_interval=interval, cache_branch_id=branch)
+    helper.enable()
+    per_step = []
+    out, _, _ = pipe(prompt_embeds=pe, negative_prompt_embeds=ne, latents=lat, num_inference_steps=steps,
+                     guidance_scale=7.5, output_type="latent",
+                     callback_on_step_end=lambda p, i, t, kw: per_step.append(kw["latents"].clone()) or {})
+    helper.disable()
+    dc = DeepCacheOracle(net)
+    dc.set_params(cache_interval=interval, cache_branch_id=branch)
+    ref = denoise(net, RC.make_scheduler(sched, {}, module=O), pe, ne, lat, steps, deepcache=dc)
+    eng = engines[-1]
+    assert eng.calls == ref["timesteps"] and pipe.last_step_kinds == ["cached" if f else "full" for f in eng.flags]
+    assert eng.flags[0] is False and any(eng.flags)
+    worst = max((g - w).abs().max().item() for g, w in zip(per_step, ref["per_step"]))
+    assert worst <= 5e-6 * max(1.0, ref["latents"].abs().max().item()), worst
+    assert pipe._deepcache is None
