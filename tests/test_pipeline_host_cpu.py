@@ -214,3 +214,34 @@ def test_product_deepcache_loop_equals_oracle(sched, steps, interval, branch, ha
     worst = max((g - w).abs().max().item() for g, w in zip(per_step, ref["per_step"]))
     assert worst <= 5e-6 * max(1.0, ref["latents"].abs().max().item()), worst
     assert pipe._deepcache is None
+
+
+@pytest.mark.parametrize("sched,over,steps", [
+    ("dpm", dict(solver_order=2, algorithm_type="dpmsolver++", thresholding=True, sample_max_value=2.5), 8),
+    ("dpm", dict(solver_order=2, algorithm_type="dpmsolver", final_sigmas_type="sigma_min", prediction_type="v_prediction",
+                 thresholding=True, sample_max_value=3.0), 8),
+    ("ddim", dict(prediction_type="v_prediction", clip_sample=True, clip_sample_range=1.5), 6),
+    ("lcm", dict(prediction_type="sample"), 4),
+    ("pndm", dict(prediction_type="v_prediction"), 6),
+])
+def test_product_loop_with_prediction_types_and_x0_postprocessing(sched, over, steps, harness, net):
+    """The scheduler options added on top of the SD-v1.5 defaults (every ``prediction_type``, ``thresholding``,
+    ``clip_sample``) through the product's classifier-free-guidance loop -- the fused CFG + update (+ quantile) path --
+    against the oracle loop with the oracle schedulers."""
+    from oracle import schedulers as O
+    from oracle.pipeline import denoise
+
+    M, S, make, engines = harness
+    pe, ne, lat = RC.pipeline_inputs()
+    guidance = 0.0 if sched == "lcm" else 7.5
+    gens = [torch.Generator().manual_seed(5) for _ in range(2)]
+    pipe = make(M.StableDiffusionModel, RC.make_scheduler(sched, over, module=S))
+    per_step = []
+    pipe(prompt_embeds=pe, negative_prompt_embeds=ne, latents=lat, num_inference_steps=steps, guidance_scale=guidance,
+         generator=gens[0], output_type="latent",
+         callback_on_step_end=lambda p, i, t, kw: per_step.append(kw["latents"].clone()) or {})
+    ref = denoise(net, RC.make_scheduler(sched, over, module=O), pe, ne, lat, steps, guidance_scale=guidance,
+                  generator=gens[1])
+    assert engines[-1].calls == ref["timesteps"]
+    worst = max((g - w).abs().max().item() for g, w in zip(per_step, ref["per_step"]))
+    assert worst <= 2e-5 * max(1.0, max(w.abs().max().item() for w in ref["per_step"])), worst
