@@ -22,6 +22,8 @@ tests/golden/make_reference_pins.py, checked by tests/test_reference_pins_{cpu,g
   * skip-timesteps loop       /root/reference/src/models.py:1138-1467
   * DPM-Solver override       /root/reference/src/schedulers.py:14-187 (``convert_model_output`` + ``step``)
   * plugin registry           /root/reference/src/utils/class_registry.py:8-68, src/registry.py:3-6
+  * experiment drivers        /root/reference/src/experiments/*.py (all eight methods, over the recording fake
+                              backend of tests/driver_cases.py; tests/test_reference_drivers_cpu.py)
 
 Restated from call sites only (nothing executable without the absent packages):
 

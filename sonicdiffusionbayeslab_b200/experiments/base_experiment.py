@@ -157,6 +157,7 @@ class BaseMethod(ABC):
             self.clip_score_gen_metric.update(gen_u8.to(self.device), list(prompts))
             self.image_reward_metric.update(real_u8, gen_u8, prompts)
             self.fid_metric.update(gen_u8, real=False)
+            self.fid_metric.update(real_u8, real=True)
             if idx % self.config.logger.get("log_images_step", 1) == 0:
                 k = self.config.experiment.get("number_save_images", 8)
                 self.logger.log_batch_of_images(images=gen_u8[:k], name_images=name_images, captions=list(prompts)[:k])
@@ -188,12 +189,19 @@ class BaseMethod(ABC):
             m.reset()
 
     # ---------------------------------------------------------------- shared sweep skeleton
+    def _new_table(self):
+        """Every driver starts its metric table afresh in ``run_experiment`` (``self.metric_dict = defaultdict(list)``,
+        e.g. ddim.py:29; deep_cache.py:39 once per cache interval)."""
+        self.metric_dict = defaultdict(list)
+
     def _sweep_point(self, batch_size, steps, name_images, guidance_scale=7.5, additional_values=None,
-                     **call_kwargs):
+                     x0_log_name=None, **call_kwargs):
         loader = self._local_dataloader(batch_size)
         self.model.to(self.device)
         gen_images, x0_preds = self.generate(loader, steps, batch_size, guidance_scale=guidance_scale, **call_kwargs)
         self.model.to("cpu")
+        if x0_log_name is not None:                       # default_sd.py:89-92 / skip_steps_exp.py:117-120
+            self.logger.log_batch_of_images(images=x0_preds, name_images=x0_log_name)
         gen_loader = DataLoader(gen_images, batch_size=batch_size, shuffle=False)
         self.validate(loader, gen_loader, name_images=name_images, name_table=f"{self.config.experiment_name}",
                       additional_values=additional_values)

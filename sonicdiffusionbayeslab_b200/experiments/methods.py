@@ -26,6 +26,7 @@ class DDIMMethod(BaseMethod):
 
     def run_experiment(self):
         bs = self.config.inference.get("batch_size", 1)
+        self._new_table()
         for steps in self.num_inference_steps:
             self._sweep_point(bs, steps, f"{self.config.experiment_name}, Inference steps: {steps}")
 
@@ -45,6 +46,7 @@ class DPMSolverMethod(BaseMethod):
                                        final_sigmas_type=self.final_sigmas_type)
 
     def run_experiment(self):
+        self._new_table()
         for steps in self.num_inference_steps:
             self._sweep_point(self.batch_size, steps, f"{self.config.experiment_name}, Solver order: "
                                                       f"{self.solver_order}, Inference steps: {steps}")
@@ -61,6 +63,7 @@ class ConsistencyModelMethod(BaseMethod):
     def run_experiment(self):
         self.model.load_lora_weights(self.config.experiment_params.adapter_id)
         self.model.fuse_lora()
+        self._new_table()
         for steps in self.num_inference_steps:
             self._sweep_point(self.batch_size, steps, f"{self.config.experiment_name}, Inference steps: {steps}",
                               guidance_scale=self.guidance_scale)
@@ -91,6 +94,7 @@ class DeepCacheMethod(_StockScheduler):
             helper = DeepCacheSDHelper(pipe=self.model)
             helper.set_params(cache_interval=interval, cache_branch_id=self.cache_branch_id)
             helper.enable()
+            self._new_table()                              # deep_cache.py:39: one table per cache interval
             for steps in self.num_inference_steps:
                 self._sweep_point(bs, steps, f"{self.config.experiment_name}, Inference steps: {steps}, "
                                              f"Cache interval: {interval}",
@@ -105,8 +109,10 @@ class DefaultStableDiffusion(_StockScheduler):
 
     def run_experiment(self):
         bs = self.config.inference.get("batch_size", 1)
+        self._new_table()
         for steps in self.num_inference_steps:
-            self._sweep_point(bs, steps, f"{self.config.experiment_name}, Inference steps: {steps}")
+            self._sweep_point(bs, steps, f"{self.config.experiment_name}, Inference steps: {steps}",
+                              x0_log_name=f"X0 preds {self.config.experiment_name}, Inference steps: {steps}")
 
 
 @methods_registry.add_to_registry("two_schedulers")
@@ -134,6 +140,7 @@ class TwoSchedulerMethod(BaseMethod):
         self.model.scheduler_second = self._make(self.config.scheduler.scheduler_second, self.second)
 
     def run_experiment(self):
+        self._new_table()
         for n1, n2, k in zip(self.num_inference_steps_first, self.num_inference_steps_second, self.num_step_switch):
             self._sweep_point(self.batch_size, None,
                               f"{self.config.experiment_name}, Step first: {n1}, Step second: {n2}, Switch: {k}",
@@ -166,13 +173,14 @@ class SkipStepsMethod(BaseMethod):
                                        final_sigmas_type=self.final_sigmas_type)
 
     def run_experiment(self):
+        self._new_table()
         for steps, skip in zip(self.num_inference_steps, self.skip_steps):
             skip = [int(v) for v in skip]
             label = " ".join(map(str, skip))
-            self._sweep_point(self.batch_size, steps,
-                              f"{self.config.experiment_name}, Step main: {steps}, Skip steps:{label}",
+            name = f"{self.config.experiment_name}, Step main: {steps}, Skip steps:{label}"
+            self._sweep_point(self.batch_size, steps, name, x0_log_name=f"X0 preds {name}",
                               additional_values={"num_inference_steps": steps, "skip_steps": label},
-                              skip_timesteps=tuple(skip))
+                              skip_timesteps=skip)                  # the list itself, skip_steps_exp.py:55-62
 
 
 @methods_registry.add_to_registry("interliving_schedulers")
@@ -200,6 +208,7 @@ class InterlivingSchedulersMethod(BaseMethod):
         self.model.scheduler_inter = self._make(self.config.scheduler.scheduler_inter, self.inter)
 
     def run_experiment(self):
+        self._new_table()
         for n, inter in zip(self.num_inference_steps_first, self.interliving_steps):
             inter = [int(v) for v in inter]
             self._sweep_point(self.batch_size, n,

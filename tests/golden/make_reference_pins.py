@@ -23,6 +23,8 @@ What each fixture pins
                            the ``self.scheduler.config.solver_order`` read of models.py:638 with the stock PNDM
                            default scheduler
   json: registry           ``ClassRegistry.add_to_registry`` argument dataclasses (class_registry.py:17-68)
+  reference_driver_events.json   the event logs of the reference's OWN experiment drivers (src/experiments/*.py, all
+                           eight methods) over the recording fake backend of tests/driver_cases.py
 """
 from __future__ import annotations
 
@@ -38,6 +40,7 @@ ROOT = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
+import driver_cases as DC  # noqa: E402
 import refpin_cases as RC  # noqa: E402
 from oracle import refexec  # noqa: E402
 from oracle import schedulers as O  # noqa: E402
@@ -116,6 +119,25 @@ def main():
                                          repr(f.default)] for f in dataclasses.fields(reg.args["probe"])]
     meta["registry"]["reference_names"] = {
         "models": sorted(ref.registry.models_registry.classes), "schedulers": sorted(ref.registry.schedulers_registry.classes)}
+
+    # the reference's own experiment drivers (src/experiments/*.py) over the recording fake backend
+    drivers = {"events": {}, "raises": {}}
+    import contextlib
+    import io
+
+    for name, case in DC.DRIVER_CASES.items():
+        with contextlib.redirect_stderr(io.StringIO()), contextlib.redirect_stdout(io.StringIO()):
+            drivers["events"][name] = DC.run_reference_driver(case)
+    for name, case in DC.RAISING_CASES.items():
+        try:
+            with contextlib.redirect_stderr(io.StringIO()), contextlib.redirect_stdout(io.StringIO()):
+                DC.run_reference_driver(case)
+            drivers["raises"][name] = None
+        except Exception as e:                            # noqa: BLE001
+            drivers["raises"][name] = type(e).__name__
+    with open(os.path.join(HERE, "reference_driver_events.json"), "w") as f:
+        json.dump(drivers, f, indent=1, sort_keys=True)
+    print(f"wrote {len(drivers['events'])} driver event logs, driver raises = {drivers['raises']}")
 
     np.savez_compressed(os.path.join(HERE, "reference_pins.npz"), **arrays)
     with open(os.path.join(HERE, "reference_pins.json"), "w") as f:
