@@ -122,13 +122,15 @@ class BaseMethod(ABC):
         return D.shard_batches(batches[-1][1] if batches else 0, batch_size, self.rank, self.world)
 
     # ---------------------------------------------------------------- generation (the hot-path caller)
-    def generate(self, test_dataloader, steps, batch_size=1, guidance_scale=7.5, **call_kwargs):
+    def generate(self, test_dataloader, steps, batch_size=1, guidance_scale=7.5, accumulate_x0=False, **call_kwargs):
         """base_experiment.py:122-163.  ONE generator serves every batch (and every noisy scheduler step) of the
         whole experiment (:51-53,149), so under sharding each rank walks the GLOBAL batch list in order: the
         batches it owns run on the engine, the others are *replayed* (``rng_only=True``: the pipeline draws the
         initial latents and the per-step noise it would have drawn and advances the generator, nothing else).
-        Rank r's images are therefore bit-identical to images [its block] of the single-process run."""
-        gen_images_list, x0_preds = [], []
+        Rank r's images are therefore bit-identical to images [its block] of the single-process run.
+        ``x0_preds``: the LAST batch's list (base_experiment.py:145,163), or with ``accumulate_x0`` every batch's
+        (the ``generate`` overrides of default_sd.py:26,49 and skip_steps_exp.py:37,62)."""
+        gen_images_list, x0_preds, x0_all = [], [], []
         mine = set(self._my_batches(batch_size))
         local = iter(test_dataloader)
         for start, stop in self._global_batches(batch_size):
@@ -142,15 +144,21 @@ class BaseMethod(ABC):
             assert len(prompts) == stop - start
             out, inference_time, x0_preds = self.model(prompts, guidance_scale=guidance_scale,
                                                        generator=self.generator, output_type="pt", **kw, **call_kwargs)
+            x0_all.extend(x0_preds)
             imgs = out.images.float().cpu()
             gen_images_list.extend(imgs[i] for i in range(imgs.shape[0]))
             self.time_metric.update(inference_time, len(prompts))
-        return gen_images_list, x0_preds
+        return gen_images_list, (x0_all if accumulate_x0 else x0_preds)
 
     def validate(self, test_dataloader, gen_dataloader, name_images, name_table, additional_values=None,
                  x0_preds_dataloader=None):
         self.clip_score_gen_metric.to(self.device)
-        for idx, (input_batch, gen_images) in enumerate(zip(test_dataloader, gen_dataloader)):
+        # base_experiment.py:176-190: with an x0 loader the three loaders are zipped -- the SHORTEST one (usually the
+        # x0 grids: one batch per ``batch_size`` denoising steps) bounds the batches that are validated, as there
+        loaders = (test_dataloader, gen_dataloader) + ((x0_preds_dataloader,) if x0_preds_dataloader is not None else ())
+        for idx, batch in enumerate(zip(*loaders)):
+            input_batch, gen_images = batch[0], batch[1]
+            x0_preds = batch[2] if x0_preds_dataloader is not None else None
             image_files, real_images, prompts = input_batch["image_file"], input_batch["image"], input_batch["prompt"]
             real_u8 = (real_images * 255).to(torch.uint8).cpu()
             gen_u8 = (gen_images * 255).to(torch.uint8).cpu()
@@ -161,6 +169,10 @@ class BaseMethod(ABC):
             if idx % self.config.logger.get("log_images_step", 1) == 0:
                 k = self.config.experiment.get("number_save_images", 8)
                 self.logger.log_batch_of_images(images=gen_u8[:k], name_images=name_images, captions=list(prompts)[:k])
+            if x0_preds and idx % self.config.logger.get("log_x0_step", 1) == 0:          # base_experiment.py:216-223
+                k = self.config.experiment.get("number_x0", 1)
+                self.logger.log_batch_of_images(images=x0_preds[:k], name_images=name_images,
+                                                captions=list(prompts)[:k])
             if self.config.logger.save:
                 out_dir = self.config.logger.save_dir.format(experiment=self.config.experiment_name, args=name_images)
                 for f, img in zip(image_files, gen_u8.unbind(0)):
@@ -189,20 +201,30 @@ class BaseMethod(ABC):
             m.reset()
 
     # ---------------------------------------------------------------- shared sweep skeleton
+    def collate_grid(self, batch):
+        """base_experiment.py:274-284: the x0 predictions of ``batch_size`` consecutive denoising steps as one grid."""
+        from torchvision.utils import make_grid
+
+        return [make_grid(torch.stack(list(images)), nrow=8, normalize=True, padding=2) for images in zip(*batch)]
+
     def _new_table(self):
         """Every driver starts its metric table afresh in ``run_experiment`` (``self.metric_dict = defaultdict(list)``,
         e.g. ddim.py:29; deep_cache.py:39 once per cache interval)."""
         self.metric_dict = defaultdict(list)
 
     def _sweep_point(self, batch_size, steps, name_images, guidance_scale=7.5, additional_values=None,
-                     x0_log_name=None, **call_kwargs):
+                     x0_log_name=None, x0_grids=False, **call_kwargs):
         loader = self._local_dataloader(batch_size)
         self.model.to(self.device)
-        gen_images, x0_preds = self.generate(loader, steps, batch_size, guidance_scale=guidance_scale, **call_kwargs)
+        gen_images, x0_preds = self.generate(loader, steps, batch_size, guidance_scale=guidance_scale,
+                                             accumulate_x0=x0_log_name is not None, **call_kwargs)
         self.model.to("cpu")
         if x0_log_name is not None:                       # default_sd.py:89-92 / skip_steps_exp.py:117-120
             self.logger.log_batch_of_images(images=x0_preds, name_images=x0_log_name)
         gen_loader = DataLoader(gen_images, batch_size=batch_size, shuffle=False)
+        x0_loader = None
+        if x0_grids and self.config.experiment_params.get("use_x0", False):              # e.g. ddim.py:41-56
+            x0_loader = DataLoader(x0_preds, batch_size=batch_size, shuffle=False, collate_fn=self.collate_grid)
         self.validate(loader, gen_loader, name_images=name_images, name_table=f"{self.config.experiment_name}",
-                      additional_values=additional_values)
+                      additional_values=additional_values, x0_preds_dataloader=x0_loader)
         return gen_images, x0_preds

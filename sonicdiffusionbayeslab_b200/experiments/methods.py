@@ -28,7 +28,7 @@ class DDIMMethod(BaseMethod):
         bs = self.config.inference.get("batch_size", 1)
         self._new_table()
         for steps in self.num_inference_steps:
-            self._sweep_point(bs, steps, f"{self.config.experiment_name}, Inference steps: {steps}")
+            self._sweep_point(bs, steps, f"{self.config.experiment_name}, Inference steps: {steps}", x0_grids=True)
 
 
 @methods_registry.add_to_registry("dpm_solver")
@@ -49,7 +49,7 @@ class DPMSolverMethod(BaseMethod):
         self._new_table()
         for steps in self.num_inference_steps:
             self._sweep_point(self.batch_size, steps, f"{self.config.experiment_name}, Solver order: "
-                                                      f"{self.solver_order}, Inference steps: {steps}")
+                                                      f"{self.solver_order}, Inference steps: {steps}", x0_grids=True)
 
 
 @methods_registry.add_to_registry("consistency_model")
@@ -146,8 +146,8 @@ class TwoSchedulerMethod(BaseMethod):
                               f"{self.config.experiment_name}, Step first: {n1}, Step second: {n2}, Switch: {k}",
                               additional_values={"num_inference_steps_first": n1, "num_inference_steps_second": n2,
                                                  "switch_step": k},
-                              num_inference_steps_first=n1, num_inference_steps_second=n2, num_step_switch=k,
-                              type_switch=self.type_switch)
+                              x0_grids=True, num_inference_steps_first=n1, num_inference_steps_second=n2,
+                              num_step_switch=k, type_switch=self.type_switch)
 
 
 @methods_registry.add_to_registry("skip_steps")
@@ -215,4 +215,4 @@ class InterlivingSchedulersMethod(BaseMethod):
                               f"{self.config.experiment_name}, Step main: {n}, Inter steps:{' '.join(map(str, inter))}",
                               additional_values={"num_inference_steps_main": n,
                                                  "num_inter_steps": " ".join(map(str, inter))},
-                              interliving_steps=inter)
+                              x0_grids=True, interliving_steps=inter)

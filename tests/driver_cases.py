@@ -48,6 +48,7 @@ DPM = {"solver_order": 2, "algorithm_type": "dpmsolver++", "final_sigmas_type": 
 SD = "stable_diffusion_model"
 DRIVER_CASES = {
     "ddim": _base("ddim", SD, {"scheduler_name": "ddim_scheduler"}, {"num_inference_steps": [4, 6]}),
+    "ddim_use_x0": _base("ddim", SD, {"scheduler_name": "ddim_scheduler"}, {"num_inference_steps": [4], "use_x0": True}),
     "dpm_solver": _base("dpm_solver", SD, {"scheduler_name": "dpm_solver_scheduler"},
                         {"num_inference_steps": [5, 7], **DPM}),
     "dpm_solver_batch_count": _base("dpm_solver", SD, {"scheduler_name": "dpm_solver_scheduler"},
@@ -66,6 +67,12 @@ DRIVER_CASES = {
                              "first_algorithm_type": "dpmsolver++", "first_final_sigmas_type": "zero",
                              "first_order_solver": 3, "second_algorithm_type": "dpmsolver",
                              "second_final_sigmas_type": "sigma_min", "second_order_solver": 1}),
+    "two_schedulers_use_x0": _base("two_schedulers", "stable_diffusion_model_two_schedulers",
+                                   {"scheduler_first": "dpm_solver_scheduler", "scheduler_second": "dpm_solver_scheduler"},
+                                   {"num_inference_steps_first": [10], "num_inference_steps_second": [10],
+                                    "num_step_switch": [4], "type_switch": "left_closest", "use_x0": True,
+                                    "first_algorithm_type": "dpmsolver++", "first_final_sigmas_type": "zero",
+                                    "second_algorithm_type": "dpmsolver++", "second_final_sigmas_type": "zero"}),
     "skip_steps": _base("skip_steps", "stable_diffusion_model_skip_timesteps", {"scheduler_name": "dpm_solver_scheduler"},
                         {"num_inference_steps": [8, 10], "skip_steps": [[2, 5], [1, 2, 7]], **DPM}),
     "interliving_schedulers": _base("interliving_schedulers", "stable_diffusion_model_interliving_schedulers",
@@ -162,8 +169,10 @@ class Backend:
                 object.__setattr__(self, "num_timesteps", int(steps))
                 log.append(["call", n, {k: _plain(v) for k, v in sorted(kw.items())},
                             isinstance(generator, torch.Generator)])
-                imgs = torch.rand(n, 3, 8, 8, generator=torch.Generator().manual_seed(n))
-                return types.SimpleNamespace(images=imgs), 0.25, []
+                g = torch.Generator().manual_seed(n)
+                imgs = torch.rand(n, 3, 8, 8, generator=g)
+                x0 = [torch.rand(1, 3, 8, 8, generator=g) for _ in range(3)]     # x0_pred[0] of three denoising steps
+                return types.SimpleNamespace(images=imgs), 0.25, x0
 
         class FakeMetric:
             def __init__(self, *a, **kw):
