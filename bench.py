@@ -472,7 +472,9 @@ def run_loop_workload(args, model, kw, wl, B, rank, world, local, dev, dist):
                    "l2": "working set larger than L2 (weights 1.7 GB + streamed activations)"},
         "e2e": {"value": round(images / e2e_s, 3), "unit": "images/s",
                 "h2d_bytes_per_step": int(pe_host.numel() * 2 * (2 if cfg_on else 1) + lat_host.numel() * 2),
-                "d2h_bytes_per_step": int(out_host.numel() * 2)},
+                "d2h_bytes_per_step": int(out_host.numel() * 2),
+                # its OWN timed region (host wall clock around K plugin calls incl. the copies, max over ranks)
+                "ms_per_step": round(e2e_s / args.steps * 1e3, 3), "timer": "perf_counter around synchronised calls"},
         "gpu_launches": int(args.steps * 2 * (eng.stats("ctx")[0] + launches_per_image_loop)),
         "unet_step_ms": round(unet_ms, 3),
         "unet_calls_per_image": n_unet, "deepcache_cached_steps": n_cached or None,
