@@ -245,3 +245,23 @@ def test_product_loop_with_prediction_types_and_x0_postprocessing(sched, over, s
     assert engines[-1].calls == ref["timesteps"]
     worst = max((g - w).abs().max().item() for g, w in zip(per_step, ref["per_step"]))
     assert worst <= 2e-5 * max(1.0, max(w.abs().max().item() for w in ref["per_step"])), worst
+
+
+@pytest.mark.parametrize("n,skip", [(20, [2, 3, 9, 15, 16]), (10, [0, 4, 9])])
+def test_skip_steps_gpu_harness_dry_run(n, skip, harness, net):
+    """tests/test_skip_steps_gpu.py's harness (tests/skip_case.py) over the fake engine: the loop-index / executed-step
+    mapping, the forcing and the structural assertions of the GPU test hold on the CPU, where product and oracle differ
+    only by the float64 kernel model (also with the first and the last index skipped)."""
+    import skip_case
+
+    M, S, make, engines = harness
+    pe, ne, lat = RC.pipeline_inputs()
+    noise = torch.randn(lat.shape, generator=torch.Generator().manual_seed(3))
+    model = make(M.StableDiffusionModelSkipTimesteps, S.PNDMScheduler.from_config(RC.SD15))
+    r = skip_case.run(model, net, None, pe, ne, lat, noise, n, skip)
+    executed = [i for i in range(n) if i not in skip]
+    assert [i for i, _ in r["seen"]] == executed
+    assert [t for _, t in r["seen"]] == [r["timesteps"][i] for i in executed] == engines[-1].calls
+    assert model.num_timesteps == n and len(model.last_step_kinds) == len(executed)
+    assert r["x0"] == [] and r["torch_bf16"] is None
+    assert max(r["engine"]) <= 5e-6 * max(1.0, r["xmax"]), r["engine"]
