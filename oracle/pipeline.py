@@ -36,9 +36,30 @@ def _extra(scheduler, generator, eta):
     return kw
 
 
+def rescale_noise_cfg(noise_cfg, noise_pred_text, guidance_rescale=0.0):
+    """diffusers ``rescale_noise_cfg`` as called at /root/reference/src/models.py:244-250 (and :583-589, :1001-1007,
+    :1374-1380): the guided prediction is brought to the per-image standard deviation of the text prediction
+    (``torch.std`` over all non-batch dims, Bessel-corrected) and blended with weight ``guidance_rescale``."""
+    dims = list(range(1, noise_pred_text.ndim))
+    std_text = noise_pred_text.std(dim=dims, keepdim=True)
+    std_cfg = noise_cfg.std(dim=dims, keepdim=True)
+    rescaled = noise_cfg * (std_text / std_cfg)
+    return guidance_rescale * rescaled + (1 - guidance_rescale) * noise_cfg
+
+
+def _guide(noise_pred, guidance_scale, guidance_rescale):
+    """models.py:238-250: ``u + g (c - u)``, then the optional std rescale."""
+    u, c = noise_pred.chunk(2)
+    out = u + guidance_scale * (c - u)
+    if guidance_rescale > 0.0:
+        out = rescale_noise_cfg(out, c, guidance_rescale=guidance_rescale)
+    return out
+
+
 @torch.no_grad()
 def denoise(unet, scheduler, prompt_embeds, negative_prompt_embeds, latents, num_inference_steps,
-            guidance_scale=7.5, generator=None, eta=0.0, deepcache=None, forced_latents=None, skip_timesteps=None):
+            guidance_scale=7.5, generator=None, eta=0.0, deepcache=None, forced_latents=None, skip_timesteps=None,
+            guidance_rescale=0.0):
     """Returns dict(latents=final, per_step=[latents after each EXECUTED step], x0=[x0 preds], timesteps=[...],
     timesteps_run=[timesteps of the executed steps]).
 
@@ -71,8 +92,7 @@ def denoise(unet, scheduler, prompt_embeds, negative_prompt_embeds, latents, num
         else:
             noise_pred = unet(x_in, t, encoder_hidden_states=ctx)[0]
         if do_cfg:
-            u, c = noise_pred.chunk(2)
-            noise_pred = u + guidance_scale * (c - u)
+            noise_pred = _guide(noise_pred, guidance_scale, guidance_rescale)
         step = scheduler.step(noise_pred, t, latents, **extra, return_dict=False)
         latents = step[0]
         if len(step) == 2:
@@ -99,7 +119,7 @@ def switch_timestamp(timesteps_first, timesteps_second, num_step_switch, type_sw
 @torch.no_grad()
 def denoise_two(unet, scheduler_first, scheduler_second, prompt_embeds, negative_prompt_embeds, latents,
                 num_inference_steps_first, num_step_switch, type_switch="closest", guidance_scale=7.5,
-                generator=None, eta=0.0, forced_latents=None):
+                generator=None, eta=0.0, forced_latents=None, guidance_rescale=0.0):
     do_cfg = guidance_scale > 1
     ctx = torch.cat([negative_prompt_embeds, prompt_embeds]) if do_cfg else prompt_embeds
     device = latents.device
@@ -118,8 +138,7 @@ def denoise_two(unet, scheduler_first, scheduler_second, prompt_embeds, negative
         x_in = torch.cat([latents] * 2) if do_cfg else latents
         noise_pred = unet(x_in, torch.as_tensor(t, device=device), encoder_hidden_states=ctx)[0]
         if do_cfg:
-            u, c = noise_pred.chunk(2)
-            noise_pred = u + guidance_scale * (c - u)
+            noise_pred = _guide(noise_pred, guidance_scale, guidance_rescale)
         # the history seeding of models.py:603-611 cannot run (SURVEY C-4) and is a no-op for order <= 2
         latents = sched.step(noise_pred, t, latents, **extra, return_dict=False)[0]
         per_step.append(latents)
@@ -142,7 +161,8 @@ def interleave_partition(timesteps_main, solver_order, interliving_steps):
 
 @torch.no_grad()
 def denoise_interleaved(unet, scheduler_main, scheduler_inter, prompt_embeds, negative_prompt_embeds, latents,
-                        num_inference_steps, interliving_steps, guidance_scale=7.5, generator=None, eta=0.0):
+                        num_inference_steps, interliving_steps, guidance_scale=7.5, generator=None, eta=0.0,
+                        guidance_rescale=0.0):
     """The interleaved loop as written: the main (multistep DPM) scheduler walks its grid with its OWN step counter
     (models.py:1035 passes ``t`` but the step index only ever increments, src/schedulers.py:176), the inter
     scheduler (set up on N // order steps, models.py:888-894) replaces whole groups, and after every step the
@@ -171,8 +191,7 @@ def denoise_interleaved(unet, scheduler_main, scheduler_inter, prompt_embeds, ne
         x_in = torch.cat([latents] * 2) if do_cfg else latents
         noise_pred = unet(x_in, torch.as_tensor(t, device=device), encoder_hidden_states=ctx)[0]
         if do_cfg:
-            u, c = noise_pred.chunk(2)
-            noise_pred = u + guidance_scale * (c - u)
+            noise_pred = _guide(noise_pred, guidance_scale, guidance_rescale)
         if t in inter:
             latents = scheduler_inter.step(noise_pred, t, latents, **e_inter, return_dict=False)[0]
             feed(scheduler_main, noise_pred, latents)

@@ -181,6 +181,10 @@ class _PipelineBase:
         return self._guidance_scale
 
     @property
+    def guidance_rescale(self):
+        return getattr(self, "_guidance_rescale", 0.0)
+
+    @property
     def do_classifier_free_guidance(self):
         return self._guidance_scale > 1 and self.unet.config.time_cond_proj_dim is None
 
@@ -293,8 +297,9 @@ class _PipelineBase:
         if sigmas is not None:
             raise ValueError(f"The current scheduler class {self.scheduler.__class__}'s `set_timesteps` does not support "
                              "custom sigmas schedules. Please check whether you are using the correct scheduler.")
+        self._guidance_rescale = float(guidance_rescale or 0.0)   # models.py:117
         unsupported = {"num_images_per_prompt": num_images_per_prompt not in (None, 1),
-                       "guidance_rescale": bool(guidance_rescale), "ip_adapter_image": ip_image is not None,
+                       "ip_adapter_image": ip_image is not None,
                        "ip_adapter_image_embeds": ip_embeds is not None,
                        "cross_attention_kwargs": kwargs.pop("cross_attention_kwargs", None) is not None,
                        "clip_skip": kwargs.pop("clip_skip", None) is not None,
@@ -406,13 +411,31 @@ class _PipelineBase:
             dc["start"] = cur
         return (cur - dc["start"]) % dc["interval"] != 0
 
+    def _guided(self, eps, B, do_cfg, guidance_scale):
+        """What the fused update is given: ``(eps_uncond, eps_text, g)`` -- the kernel forms ``u + g (c - u)`` itself
+        (models.py:238-242) -- or ``(eps, None, 0)`` without guidance.  ``guidance_rescale`` > 0 (models.py:244-250,
+        diffusers ``rescale_noise_cfg``; 0 in every reference driver) needs two per-image standard deviations between
+        the combine and the update: that branch forms the guided prediction with the same torch expressions as the
+        reference, on the device, and hands the update kernel the finished prediction."""
+        if not do_cfg:
+            return eps, None, 0.0
+        u, c = eps[:B], eps[B:]
+        phi = self.guidance_rescale
+        if phi <= 0.0:
+            return u, c, guidance_scale
+        uf, cf = u.float(), c.float()
+        cfg = uf + guidance_scale * (cf - uf)
+        dims = list(range(1, cfg.ndim))
+        rescaled = cfg * (cf.std(dim=dims, keepdim=True) / cfg.std(dim=dims, keepdim=True))
+        return (phi * rescaled + (1 - phi) * cfg).to(eps.dtype), None, 0.0
+
     def _denoise_step(self, eng, scheduler, t, do_cfg, guidance_scale, cached, extra):
         """models.py:217-261 for one timestep: UNet plan replay + one fused update kernel."""
         eps = eng.forward(float(t), cached=cached)
-        B = eng.n_lat
-        if do_cfg:
-            return scheduler.step_cfg(eps[:B], eps[B:], guidance_scale, t, eng.x_in, out=eng.x_in, **extra)
-        return scheduler._step(eps, None, 0.0, t, eng.x_in, out=eng.x_in, **extra)
+        eps_u, eps_c, g = self._guided(eps, eng.n_lat, do_cfg, guidance_scale)
+        if eps_c is not None:
+            return scheduler.step_cfg(eps_u, eps_c, g, t, eng.x_in, out=eng.x_in, **extra)
+        return scheduler._step(eps_u, None, 0.0, t, eng.x_in, out=eng.x_in, **extra)
 
     def _x0_mode(self, schedulers, output_type):
         """The loop keeps ``x0_pred[0]`` only (models.py:257-261) and ``output_type="latent"`` never decodes it:
@@ -673,7 +696,7 @@ class StableDiffusionModelInterlivingSchedulers(_PipelineBase):
             stepper, extra, other = (inter_s, extra_inter, main) if t in t_inter else (main, extra_main,
                                                                                        inter_s if feed_inter else None)
             eps = eng.forward(float(t))
-            eps_u, eps_c, g = (eps[:B], eps[B:], guidance_scale) if do_cfg else (eps, None, 0.0)
+            eps_u, eps_c, g = self._guided(eps, B, do_cfg, guidance_scale)
             step = stepper._step(eps_u, eps_c, g, t, eng.x_in, out=eng.x_in, **extra)
             if len(step) == 2 and step[1] is not None:
                 x0_preds.append(step[1][0:1])

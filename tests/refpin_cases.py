@@ -103,6 +103,14 @@ PIPELINE_CASES = {
     "skip_dpmpp": dict(pipe="skip", sched=("dpm", dict(solver_order=2, algorithm_type="dpmsolver++",
                                                         final_sigmas_type="zero")), steps=10, skip=[1, 2, 7],
                        guidance=7.5, patch=True),
+    # ``guidance_rescale`` > 0: the ``rescale_noise_cfg`` branch of every loop (models.py:244-250, 583-589, 1001-1007)
+    "loop_ddim6_rescale": dict(pipe="single", sched=("ddim", {}), steps=6, guidance=7.5, rescale=0.7, patch=False),
+    "two_ddim_dpmstock_rescale": dict(pipe="two", first=("ddim", {}),
+                                      second=("dpm_stock", dict(algorithm_type="dpmsolver++")), n1=10, k=3,
+                                      type_switch="closest", guidance=7.5, rescale=0.5, patch=False),
+    "inter_dpmpp_ddim_rescale": dict(pipe="inter", main=("dpm", dict(solver_order=2, algorithm_type="dpmsolver++")),
+                                     inter=("ddim", {}), steps=10, groups=[1, 3], guidance=7.5, rescale=1.0,
+                                     patch=True),
 }
 
 # (n_first, n_second or None = second runs on the first grid like the pipeline, num_step_switch)
@@ -176,6 +184,8 @@ def run_pipeline_reference(case, ns, net):
                   callback_on_step_end=rec)
     if case.get("gen_seed") is not None:
         common["generator"] = torch.Generator().manual_seed(case["gen_seed"])
+    if case.get("rescale"):
+        common["guidance_rescale"] = case["rescale"]
     if not case.get("draw_latents"):
         common["latents"] = lat
     else:
@@ -217,20 +227,23 @@ def run_pipeline_oracle(case, net):
     kind = case["pipe"]
     if case.get("draw_latents"):
         lat = P.prepare_latents((B, C, HW, HW), gen, "cpu", pe.dtype)
+    rs = case.get("rescale", 0.0)
     if kind == "single":
         r = P.denoise(net, make_scheduler(*case["sched"], module=O), pe, ne, lat, case["steps"],
-                      guidance_scale=case["guidance"], generator=gen)
+                      guidance_scale=case["guidance"], generator=gen, guidance_rescale=rs)
         ts = r["timesteps"]
     elif kind == "skip":
         r = P.denoise(net, make_scheduler(*case["sched"], module=O), pe, ne, lat, case["steps"],
-                      guidance_scale=case["guidance"], generator=gen, skip_timesteps=case["skip"])
+                      guidance_scale=case["guidance"], generator=gen, skip_timesteps=case["skip"], guidance_rescale=rs)
         ts = r["timesteps_run"]
     elif kind == "two":
         r = P.denoise_two(net, make_scheduler(*case["first"], module=O), make_scheduler(*case["second"], module=O),
-                          pe, ne, lat, case["n1"], case["k"], case["type_switch"], guidance_scale=case["guidance"])
+                          pe, ne, lat, case["n1"], case["k"], case["type_switch"], guidance_scale=case["guidance"],
+                          guidance_rescale=rs)
         ts = r["timesteps"][0] + r["timesteps"][1]
     else:
         r = P.denoise_interleaved(net, make_scheduler(*case["main"], module=O), make_scheduler(*case["inter"], module=O),
-                                  pe, ne, lat, case["steps"], case["groups"], guidance_scale=case["guidance"])
+                                  pe, ne, lat, case["steps"], case["groups"], guidance_scale=case["guidance"],
+                                  guidance_rescale=rs)
         ts = r["timesteps"][0]
     return dict(per_step=r["per_step"], timesteps=[int(t) for t in ts], final=r["latents"])

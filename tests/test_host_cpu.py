@@ -530,7 +530,6 @@ def test_pipeline_call_argument_checks():
             (dict(sigmas=[1.0, 0.5]), ValueError, "custom sigmas"),
             (dict(sigmas=[1.0], timesteps=[5]), ValueError, "Only one of `timesteps` or `sigmas`"),
             (dict(num_images_per_prompt=2), NotImplementedError, "num_images_per_prompt"),
-            (dict(guidance_rescale=0.7), NotImplementedError, "guidance_rescale"),
             (dict(clip_skip=1), NotImplementedError, "clip_skip"),
             (dict(callback_steps=0), ValueError, "callback_steps"),
             (dict(callback_on_step_end_tensor_inputs=["latents", "nope"]), ValueError, "tensor_inputs"),
@@ -542,6 +541,9 @@ def test_pipeline_call_argument_checks():
                 pipe(**{**ok, **bad})
         with pytest.raises(RuntimeError, match="CUDA"):         # valid arguments: only now is the device needed
             pipe(**ok)
+        with pytest.raises(RuntimeError, match="CUDA"):         # guidance_rescale is implemented (models.py:244-250)
+            pipe(**ok, guidance_rescale=0.7)
+        assert pipe.guidance_rescale == 0.7
 
 
 def test_postprocess_images_follows_diffusers():

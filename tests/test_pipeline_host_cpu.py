@@ -111,6 +111,8 @@ def test_product_call_bodies_reproduce_reference_source(name, harness):
                   callback_on_step_end=cb)
     if case.get("gen_seed") is not None:
         common["generator"] = torch.Generator().manual_seed(case["gen_seed"])
+    if case.get("rescale"):
+        common["guidance_rescale"] = case["rescale"]                     # rescale_noise_cfg branch, models.py:244-250
     if not case.get("draw_latents"):
         common["latents"] = lat
     else:
