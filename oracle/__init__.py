@@ -24,6 +24,9 @@ tests/golden/make_reference_pins.py, checked by tests/test_reference_pins_{cpu,g
   * plugin registry           /root/reference/src/utils/class_registry.py:8-68, src/registry.py:3-6
   * experiment drivers        /root/reference/src/experiments/*.py (all eight methods, over the recording fake
                               backend of tests/driver_cases.py; tests/test_reference_drivers_cpu.py)
+  * metric plugins / dataset  /root/reference/src/metrics/metrics.py:25-41,115-131 (``calc_metric`` batching,
+                              ``TimeMetric``), src/dataset/dataset.py, src/utils/model_utils.py
+                              (``refexec.load_plugins``; tests/test_reference_plugins_cpu.py)
 
 Restated from call sites only (nothing executable without the absent packages):
 

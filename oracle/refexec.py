@@ -267,6 +267,91 @@ def load(root: str = REF_ROOT, patch_c1: bool = False):
     return ns
 
 
+def load_plugins(root: str = REF_ROOT, features=None):
+    """The reference's metric plugins, dataset and driver helpers compiled where they lie:
+    ``src/metrics/metrics.py`` (``TimeMetric`` :115-131, ``ClipScoreMetric.calc_metric`` :25-41),
+    ``src/dataset/dataset.py`` and ``src/utils/model_utils.py``.  Third-party surface, restated: a minimal
+    ``torchmetrics.Metric`` (``add_state`` / ``reset`` to the defaults) and torchmetrics 1.6.1 ``CLIPScore``'s state
+    arithmetic (``score += sum_i 100 cos_i``, ``n_samples += n``, ``compute = max(score / n, 0)``; SURVEY appendix
+    A.5) over an injectable feature function ``features(images, text) -> (f_img, f_txt)`` standing in for the CLIP
+    towers.  ``ImageReward`` and the FID base are inert stubs (out of scope)."""
+    ns = load(root)
+
+    def mod(name, **attrs):
+        m = types.ModuleType(name)
+        m.__dict__.update(attrs)
+        return m
+
+    class Metric(torch.nn.Module):
+        def __init__(self, **kwargs):
+            super().__init__()
+            self._defaults = {}
+
+        def add_state(self, name, default, dist_reduce_fx=None):
+            self._defaults[name] = default.clone()
+            setattr(self, name, default.clone())
+
+        def reset(self):
+            for k, v in self._defaults.items():
+                setattr(self, k, v.clone())
+
+    class CLIPScore(Metric):
+        def __init__(self, model_name_or_path="openai/clip-vit-large-patch14", **kwargs):
+            super().__init__(**kwargs)
+            self.model_name_or_path = model_name_or_path
+            self.add_state("score", torch.tensor(0.0), dist_reduce_fx="sum")
+            self.add_state("n_samples", torch.tensor(0, dtype=torch.long), dist_reduce_fx="sum")
+            self.seen = []
+
+        def update(self, images, text):
+            fi, ft = features(images, text)
+            self.seen.append((images, list(text) if not isinstance(text, str) else [text]))
+            score = 100 * (fi * ft).sum(axis=-1)
+            self.score += score.sum(0)
+            self.n_samples += len(score)
+
+        def compute(self):
+            return torch.max(self.score / self.n_samples, torch.zeros_like(self.score))
+
+    stubs = {
+        "ImageReward": mod("ImageReward", load=lambda **k: None),
+        "torchmetrics": mod("torchmetrics", Metric=Metric),
+        "torchmetrics.image": mod("torchmetrics.image"),
+        "torchmetrics.image.fid": mod("torchmetrics.image.fid", FrechetInceptionDistance=type(
+            "FrechetInceptionDistance", (Metric,), {})),
+        "torchmetrics.multimodal": mod("torchmetrics.multimodal"),
+        "torchmetrics.multimodal.clip_score": mod("torchmetrics.multimodal.clip_score", CLIPScore=CLIPScore),
+    }
+    names = ["src", "src.utils", "src.registry", "src.utils.model_utils", "src.metrics", "src.metrics.metrics",
+             "src.dataset", "src.dataset.dataset"]
+    saved = {k: sys.modules.get(k) for k in list(stubs) + names}
+    try:
+        sys.modules.update(stubs)
+        for n in ("src", "src.utils", "src.metrics", "src.dataset"):
+            pkg = types.ModuleType(n)
+            pkg.__path__ = []
+            sys.modules[n] = pkg
+        sys.modules["src.registry"] = ns.registry
+        loaded = {}
+        for n, rel in (("src.utils.model_utils", "src/utils/model_utils.py"),
+                       ("src.metrics.metrics", "src/metrics/metrics.py"), ("src.dataset.dataset", "src/dataset/dataset.py")):
+            path = os.path.join(root, rel)
+            m = types.ModuleType(n)
+            m.__file__ = path
+            sys.modules[n] = m
+            with open(path) as f:
+                exec(compile(f.read(), path, "exec"), m.__dict__)
+            loaded[n] = m
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    return types.SimpleNamespace(metrics=loaded["src.metrics.metrics"], dataset=loaded["src.dataset.dataset"],
+                                 model_utils=loaded["src.utils.model_utils"], registry=ns.registry)
+
+
 class Recorder:
     """``callback_on_step_end``: records the latents after every step (models.py:263-273) and, optionally,
     teacher-forces the next step from a given list."""
