@@ -270,7 +270,8 @@ def load(root: str = REF_ROOT, patch_c1: bool = False):
 def load_plugins(root: str = REF_ROOT, features=None):
     """The reference's metric plugins, dataset and driver helpers compiled where they lie:
     ``src/metrics/metrics.py`` (``TimeMetric`` :115-131, ``ClipScoreMetric.calc_metric`` :25-41),
-    ``src/dataset/dataset.py`` and ``src/utils/model_utils.py``.  Third-party surface, restated: a minimal
+    ``src/dataset/dataset.py``, ``src/utils/model_utils.py`` and the script function ``calc_clip_score.py:13-37``.
+    Third-party surface, restated: a minimal
     ``torchmetrics.Metric`` (``add_state`` / ``reset`` to the defaults) and torchmetrics 1.6.1 ``CLIPScore``'s state
     arithmetic (``score += sum_i 100 cos_i``, ``n_samples += n``, ``compute = max(score / n, 0)``; SURVEY appendix
     A.5) over an injectable feature function ``features(images, text) -> (f_img, f_txt)`` standing in for the CLIP
@@ -323,7 +324,7 @@ def load_plugins(root: str = REF_ROOT, features=None):
         "torchmetrics.multimodal.clip_score": mod("torchmetrics.multimodal.clip_score", CLIPScore=CLIPScore),
     }
     names = ["src", "src.utils", "src.registry", "src.utils.model_utils", "src.metrics", "src.metrics.metrics",
-             "src.dataset", "src.dataset.dataset"]
+             "src.dataset", "src.dataset.dataset", "reference_calc_clip_score"]
     saved = {k: sys.modules.get(k) for k in list(stubs) + names}
     try:
         sys.modules.update(stubs)
@@ -334,7 +335,8 @@ def load_plugins(root: str = REF_ROOT, features=None):
         sys.modules["src.registry"] = ns.registry
         loaded = {}
         for n, rel in (("src.utils.model_utils", "src/utils/model_utils.py"),
-                       ("src.metrics.metrics", "src/metrics/metrics.py"), ("src.dataset.dataset", "src/dataset/dataset.py")):
+                       ("src.metrics.metrics", "src/metrics/metrics.py"), ("src.dataset.dataset", "src/dataset/dataset.py"),
+                       ("reference_calc_clip_score", "calc_clip_score.py")):
             path = os.path.join(root, rel)
             m = types.ModuleType(n)
             m.__file__ = path
@@ -349,7 +351,8 @@ def load_plugins(root: str = REF_ROOT, features=None):
             else:
                 sys.modules[k] = v
     return types.SimpleNamespace(metrics=loaded["src.metrics.metrics"], dataset=loaded["src.dataset.dataset"],
-                                 model_utils=loaded["src.utils.model_utils"], registry=ns.registry)
+                                 model_utils=loaded["src.utils.model_utils"], registry=ns.registry,
+                                 calc_clip_score=loaded["reference_calc_clip_score"].calc_clip_score)
 
 
 class Recorder:

@@ -168,3 +168,40 @@ def test_driver_helpers_equal_reference_source(ref, tmp_path):
     (tmp_path / "id").mkdir()
     with pytest.raises(FileNotFoundError):
         theirs.save_image(str(tmp_path / "id"), "x.png", img)
+
+
+@pytest.mark.parametrize("n,batch_size", [(7, 3), (4, 32)])
+def test_calc_clip_score_function_equals_reference_source(ref, tmp_path, n, batch_size, monkeypatch):
+    """/root/reference/calc_clip_score.py:13-37 (one CLIPScore fed batch by batch) against the product's root script
+    function (features per batch, one score from all features -- the form that all-gathers under sharding): same
+    images and prompts in, same score out up to the order of the fp32 sum."""
+    import importlib.util
+
+    from PIL import Image
+    from torchvision import transforms
+
+    from sonicdiffusionbayeslab_b200.metrics.metrics import ClipScoreMetric
+
+    g = np.random.default_rng(n)
+    prompts = {}
+    for i in range(n):
+        Image.fromarray(g.integers(0, 256, (20, 20, 3), dtype=np.uint8)).save(tmp_path / f"{i:03d}.png")
+        prompts[f"{i:03d}.png"] = f"a synthetic caption {i}"
+    pj = tmp_path.parent / f"{tmp_path.name}_prompts.json"
+    pj.write_text(json.dumps(prompts))
+    tf = transforms.Compose([transforms.PILToTensor()])                   # uint8, the form CLIPScore expects (C-8)
+    ds = ref.dataset.ImageDatasetWithPrompts(str(tmp_path), str(pj), transform=tf)
+    want = ref.calc_clip_score(torch.utils.data.DataLoader(ds, batch_size=batch_size, shuffle=False),
+                               model_name_or_path="openai/clip-vit-base-patch16", device="cpu", batch_size=batch_size)
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("product_calc_clip_score", os.path.join(root, "calc_clip_score.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    monkeypatch.setattr(ClipScoreMetric, "features", lambda self, imgs, text: fake_features(imgs, text))
+    with pytest.warns(RuntimeWarning, match="RANDOM-INIT CLIP"):
+        got, count = mod.calc_clip_score(mod.ImageDatasetWithPrompts(str(tmp_path), str(pj), transform=tf),
+                                         model_name_or_path="openai/clip-vit-base-patch16", device="cpu",
+                                         batch_size=batch_size)
+    assert count == n
+    assert abs(got - want) <= 1e-4 * max(1.0, abs(want)), (got, want)
