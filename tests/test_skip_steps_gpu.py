@@ -44,6 +44,6 @@ def test_skip_timesteps_pipeline_vs_fp32_oracle(cuda):
     assert [t for _, t in r["seen"]] == [r["timesteps"][i] for i in executed]  # UNet timesteps: grid values
     assert model.num_timesteps == N_STEPS and len(model.last_step_kinds) == len(executed)
     assert r["x0"] == [] and r["secs"] > 0
-    assert r["xmax"] < 8.0
+    assert r["xmax"] < 10.0                                                    # SD-like magnitudes
     assert max(e) <= 1.2 * max(f) + 2e-2, (e, f)
     assert torch.isfinite(r["out"].images.float()).all()
