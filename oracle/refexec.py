@@ -141,7 +141,14 @@ class _StableDiffusionPipeline:
                       negative_prompt_embeds=None, lora_scale=None, clip_skip=None):
         if prompt_embeds is None:
             raise ValueError("the pin harness passes prompt_embeds (models.py:45-47)")
-        return prompt_embeds, negative_prompt_embeds
+
+        def per_image(e):                                  # diffusers encode_prompt: the n images of a prompt adjacent
+            if e is None:
+                return None
+            b, seq, _ = e.shape
+            return e.repeat(1, num_images_per_prompt, 1).view(b * num_images_per_prompt, seq, -1)
+
+        return per_image(prompt_embeds), per_image(negative_prompt_embeds)
 
     def prepare_latents(self, batch_size, num_channels_latents, height, width, dtype, device, generator, latents=None):
         shape = (batch_size, num_channels_latents, int(height) // self.vae_scale_factor,

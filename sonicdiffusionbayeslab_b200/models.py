@@ -298,8 +298,11 @@ class _PipelineBase:
             raise ValueError(f"The current scheduler class {self.scheduler.__class__}'s `set_timesteps` does not support "
                              "custom sigmas schedules. Please check whether you are using the correct scheduler.")
         self._guidance_rescale = float(guidance_rescale or 0.0)   # models.py:117
-        unsupported = {"num_images_per_prompt": num_images_per_prompt not in (None, 1),
-                       "ip_adapter_image": ip_image is not None,
+        n_img = 1 if num_images_per_prompt is None else num_images_per_prompt
+        if not isinstance(n_img, int) or isinstance(n_img, bool) or n_img < 1:
+            raise ValueError(f"`num_images_per_prompt` has to be a positive integer but is {num_images_per_prompt!r}")
+        self._images_per_prompt = n_img
+        unsupported = {"ip_adapter_image": ip_image is not None,
                        "ip_adapter_image_embeds": ip_embeds is not None,
                        "cross_attention_kwargs": kwargs.pop("cross_attention_kwargs", None) is not None,
                        "clip_skip": kwargs.pop("clip_skip", None) is not None,
@@ -309,7 +312,7 @@ class _PipelineBase:
             raise NotImplementedError(f"{', '.join(bad)}: not used by any reference driver and not implemented by the "
                                       "B200 engine")
         if latents is not None:
-            batch = (1 if isinstance(prompt, str) else len(prompt)) if prompt is not None else prompt_embeds.shape[0]
+            batch = self._batch_size(prompt, prompt_embeds)
             shape = (batch, self.arch.in_channels, self.latent_size, self.latent_size)
             if tuple(latents.shape) != shape:
                 raise ValueError(f"Unexpected latents shape, got {tuple(latents.shape)}, expected {shape}")
@@ -347,6 +350,22 @@ class _PipelineBase:
                                                 mlp=c.intermediate_size, device=self.device)
         ids, _ = self.tokenizer(list(prompts))
         return self._engines[key].last_hidden_state(ids).clone()
+
+    def _batch_size(self, prompt, prompt_embeds):
+        """Latents per call: prompts x ``num_images_per_prompt`` (models.py:123-128 and ``batch_size *
+        num_images_per_prompt`` at :173)."""
+        prompts = (1 if isinstance(prompt, str) else len(prompt)) if prompt is not None else prompt_embeds.shape[0]
+        return prompts * getattr(self, "_images_per_prompt", 1)
+
+    def _context(self, pe, ne, do_cfg):
+        """UNet context: ``cat([negative, positive])`` under guidance (models.py:154-155), every prompt's embedding
+        repeated ``num_images_per_prompt`` times in place (diffusers ``encode_prompt``: ``repeat(1, n, 1).view(B * n,
+        seq, -1)``, i.e. the n images of a prompt are adjacent)."""
+        n = getattr(self, "_images_per_prompt", 1)
+        if n > 1:
+            pe = pe.repeat_interleave(n, dim=0)
+            ne = ne.repeat_interleave(n, dim=0) if ne is not None else None
+        return torch.cat([ne, pe]) if do_cfg else pe
 
     def encode_prompt(self, prompt, do_cfg, prompt_embeds=None, negative_prompt_embeds=None, negative_prompt=None):
         if prompt_embeds is None:
@@ -509,7 +528,7 @@ class StableDiffusionModel(_PipelineBase):
         self._check_call(prompt, height, width, negative_prompt, prompt_embeds, negative_prompt_embeds, latents,
                          timesteps, sigmas, num_images_per_prompt, guidance_rescale, output_type, kwargs)
         self._guidance_scale = guidance_scale
-        batch = (1 if isinstance(prompt, str) else len(prompt)) if prompt is not None else prompt_embeds.shape[0]
+        batch = self._batch_size(prompt, prompt_embeds)
         do_cfg = self.do_classifier_free_guidance
         ts, num_inference_steps = retrieve_timesteps(self.scheduler, num_inference_steps, self.device, timesteps)
         t_list = [int(t) for t in ts.tolist()]
@@ -520,7 +539,7 @@ class StableDiffusionModel(_PipelineBase):
             plan = [(self.scheduler, t, extra) for i, t in enumerate(t_list) if i not in skip]
             return self._replay_rng(plan, batch, latents, generator, self.scheduler.init_noise_sigma)
         pe, ne = self.encode_prompt(prompt, do_cfg, prompt_embeds, negative_prompt_embeds, negative_prompt)
-        ctx = torch.cat([ne, pe]) if do_cfg else pe
+        ctx = self._context(pe, ne, do_cfg)
         latents = self.prepare_latents(batch, generator, latents, self.scheduler.init_noise_sigma, rng_rows)
         eng = self.engine(batch, do_cfg)
         eng.set_context(ctx)
@@ -573,7 +592,7 @@ class StableDiffusionModelTwoSchedulers(_PipelineBase):
         self._check_call(prompt, height, width, negative_prompt, prompt_embeds, negative_prompt_embeds, latents,
                          timesteps, sigmas, num_images_per_prompt, guidance_rescale, output_type, kwargs)
         self._guidance_scale = guidance_scale
-        batch = (1 if isinstance(prompt, str) else len(prompt)) if prompt is not None else prompt_embeds.shape[0]
+        batch = self._batch_size(prompt, prompt_embeds)
         do_cfg = self.do_classifier_free_guidance
         # models.py:487-494: the second scheduler runs on the FIRST scheduler's grid (N2 unused)
         ts1, _ = retrieve_timesteps(self.scheduler_first, num_inference_steps_first, self.device, timesteps)
@@ -590,7 +609,7 @@ class StableDiffusionModelTwoSchedulers(_PipelineBase):
                    [(self.scheduler_second, int(t), extra2) for t in second]
             return self._replay_rng(plan, batch, latents, generator, self.scheduler_first.init_noise_sigma)
         pe, ne = self.encode_prompt(prompt, do_cfg, prompt_embeds, negative_prompt_embeds, negative_prompt)
-        ctx = torch.cat([ne, pe]) if do_cfg else pe
+        ctx = self._context(pe, ne, do_cfg)
         latents = self.prepare_latents(batch, generator, latents, self.scheduler_first.init_noise_sigma, rng_rows)
         eng = self.engine(batch, do_cfg)
         eng.set_context(ctx)
@@ -665,7 +684,7 @@ class StableDiffusionModelInterlivingSchedulers(_PipelineBase):
         self._check_call(prompt, height, width, negative_prompt, prompt_embeds, negative_prompt_embeds, latents,
                          timesteps, sigmas, num_images_per_prompt, guidance_rescale, output_type, kwargs)
         self._guidance_scale = guidance_scale
-        batch = (1 if isinstance(prompt, str) else len(prompt)) if prompt is not None else prompt_embeds.shape[0]
+        batch = self._batch_size(prompt, prompt_embeds)
         do_cfg = self.do_classifier_free_guidance
         order = main.config.solver_order
         ts_main, _ = retrieve_timesteps(main, num_inference_steps, self.device, timesteps)        # models.py:880-886
@@ -681,7 +700,7 @@ class StableDiffusionModelInterlivingSchedulers(_PipelineBase):
             plan = [(inter_s, t, extra_inter) if t in t_inter else (main, t, extra_main) for t in kept]
             return self._replay_rng(plan, batch, latents, generator, self.scheduler.init_noise_sigma)
         pe, ne = self.encode_prompt(prompt, do_cfg, prompt_embeds, negative_prompt_embeds, negative_prompt)
-        ctx = torch.cat([ne, pe]) if do_cfg else pe
+        ctx = self._context(pe, ne, do_cfg)
         latents = self.prepare_latents(batch, generator, latents, self.scheduler.init_noise_sigma, rng_rows)
         feed_inter = isinstance(inter_s, S.DPMSolverScheduler)                                    # models.py:1045
         eng = self.engine(batch, do_cfg)

@@ -108,6 +108,13 @@ PIPELINE_CASES = {
     "two_ddim_dpmstock_rescale": dict(pipe="two", first=("ddim", {}),
                                       second=("dpm_stock", dict(algorithm_type="dpmsolver++")), n1=10, k=3,
                                       type_switch="closest", guidance=7.5, rescale=0.5, patch=False),
+    # ``num_images_per_prompt`` > 1: latents for B x n images, each prompt's embeddings repeated n times in place
+    # (models.py:123-128,139-149,173; the repetition itself is diffusers' ``encode_prompt``, restated in the stub)
+    "loop_ddim6_n2": dict(pipe="single", sched=("ddim", {}), steps=6, guidance=7.5, patch=False, n_img=2, gen_seed=31,
+                          draw_latents=True),
+    "inter_dpmpp_ddim_n2": dict(pipe="inter", main=("dpm", dict(solver_order=2, algorithm_type="dpmsolver++")),
+                                inter=("ddim", {}), steps=10, groups=[1, 3], guidance=7.5, patch=True, n_img=2,
+                                gen_seed=37, draw_latents=True),
     "inter_dpmpp_ddim_rescale": dict(pipe="inter", main=("dpm", dict(solver_order=2, algorithm_type="dpmsolver++")),
                                      inter=("ddim", {}), steps=10, groups=[1, 3], guidance=7.5, rescale=1.0,
                                      patch=True),
@@ -186,6 +193,8 @@ def run_pipeline_reference(case, ns, net):
         common["generator"] = torch.Generator().manual_seed(case["gen_seed"])
     if case.get("rescale"):
         common["guidance_rescale"] = case["rescale"]
+    if case.get("n_img"):
+        common["num_images_per_prompt"] = case["n_img"]
     if not case.get("draw_latents"):
         common["latents"] = lat
     else:
@@ -225,8 +234,11 @@ def run_pipeline_oracle(case, net):
     pe, ne, lat = pipeline_inputs()
     gen = torch.Generator().manual_seed(case["gen_seed"]) if case.get("gen_seed") is not None else None
     kind = case["pipe"]
+    n_img = case.get("n_img", 1)
+    if n_img > 1:                                            # the n images of a prompt are adjacent rows
+        pe, ne = pe.repeat_interleave(n_img, dim=0), ne.repeat_interleave(n_img, dim=0)
     if case.get("draw_latents"):
-        lat = P.prepare_latents((B, C, HW, HW), gen, "cpu", pe.dtype)
+        lat = P.prepare_latents((B * n_img, C, HW, HW), gen, "cpu", pe.dtype)
     rs = case.get("rescale", 0.0)
     if kind == "single":
         r = P.denoise(net, make_scheduler(*case["sched"], module=O), pe, ne, lat, case["steps"],

@@ -529,7 +529,8 @@ def test_pipeline_call_argument_checks():
             (dict(negative_prompt_embeds=ne[:1]), ValueError, "must have the same shape"),
             (dict(sigmas=[1.0, 0.5]), ValueError, "custom sigmas"),
             (dict(sigmas=[1.0], timesteps=[5]), ValueError, "Only one of `timesteps` or `sigmas`"),
-            (dict(num_images_per_prompt=2), NotImplementedError, "num_images_per_prompt"),
+            (dict(num_images_per_prompt=0), ValueError, "num_images_per_prompt"),
+            (dict(num_images_per_prompt=2), ValueError, "Unexpected latents shape"),     # 2 prompts x 2 -> 4 latents
             (dict(clip_skip=1), NotImplementedError, "clip_skip"),
             (dict(callback_steps=0), ValueError, "callback_steps"),
             (dict(callback_on_step_end_tensor_inputs=["latents", "nope"]), ValueError, "tensor_inputs"),
@@ -544,6 +545,8 @@ def test_pipeline_call_argument_checks():
         with pytest.raises(RuntimeError, match="CUDA"):         # guidance_rescale is implemented (models.py:244-250)
             pipe(**ok, guidance_rescale=0.7)
         assert pipe.guidance_rescale == 0.7
+        with pytest.raises(RuntimeError, match="CUDA"):         # num_images_per_prompt is implemented (models.py:173)
+            pipe(**{**ok, "latents": torch.zeros(6, 4, 64, 64)}, num_images_per_prompt=3)
 
 
 def test_postprocess_images_follows_diffusers():

@@ -113,6 +113,8 @@ def test_product_call_bodies_reproduce_reference_source(name, harness):
         common["generator"] = torch.Generator().manual_seed(case["gen_seed"])
     if case.get("rescale"):
         common["guidance_rescale"] = case["rescale"]                     # rescale_noise_cfg branch, models.py:244-250
+    if case.get("n_img"):
+        common["num_images_per_prompt"] = case["n_img"]                  # B x n latents, embeddings repeated in place
     if not case.get("draw_latents"):
         common["latents"] = lat
     else:
