@@ -47,6 +47,16 @@ def rescale_noise_cfg(noise_cfg, noise_pred_text, guidance_rescale=0.0):
     return guidance_rescale * rescaled + (1 - guidance_rescale) * noise_cfg
 
 
+def _edited(context_edit, i, ctx):
+    """``callback_on_step_end`` may return new ``prompt_embeds`` (models.py:263-273): they replace the UNet context --
+    under guidance the concatenated ``[negative, positive]`` batch, models.py:154-155 -- of every later step.
+    ``context_edit(i, ctx)`` returns the replacement after loop index ``i``, or None."""
+    if context_edit is None:
+        return ctx
+    new = context_edit(i, ctx)
+    return ctx if new is None else new
+
+
 def _guide(noise_pred, guidance_scale, guidance_rescale):
     """models.py:238-250: ``u + g (c - u)``, then the optional std rescale."""
     u, c = noise_pred.chunk(2)
@@ -59,7 +69,7 @@ def _guide(noise_pred, guidance_scale, guidance_rescale):
 @torch.no_grad()
 def denoise(unet, scheduler, prompt_embeds, negative_prompt_embeds, latents, num_inference_steps,
             guidance_scale=7.5, generator=None, eta=0.0, deepcache=None, forced_latents=None, skip_timesteps=None,
-            guidance_rescale=0.0):
+            guidance_rescale=0.0, context_edit=None):
     """Returns dict(latents=final, per_step=[latents after each EXECUTED step], x0=[x0 preds], timesteps=[...],
     timesteps_run=[timesteps of the executed steps]).
 
@@ -98,6 +108,7 @@ def denoise(unet, scheduler, prompt_embeds, negative_prompt_embeds, latents, num
         if len(step) == 2:
             x0s.append(step[1][0].unsqueeze(0))
         per_step.append(latents)
+        ctx = _edited(context_edit, i, ctx)
     return dict(latents=latents, per_step=per_step, x0=x0s, timesteps=t_list, timesteps_run=ran)
 
 
@@ -119,7 +130,7 @@ def switch_timestamp(timesteps_first, timesteps_second, num_step_switch, type_sw
 @torch.no_grad()
 def denoise_two(unet, scheduler_first, scheduler_second, prompt_embeds, negative_prompt_embeds, latents,
                 num_inference_steps_first, num_step_switch, type_switch="closest", guidance_scale=7.5,
-                generator=None, eta=0.0, forced_latents=None, guidance_rescale=0.0):
+                generator=None, eta=0.0, forced_latents=None, guidance_rescale=0.0, context_edit=None):
     do_cfg = guidance_scale > 1
     ctx = torch.cat([negative_prompt_embeds, prompt_embeds]) if do_cfg else prompt_embeds
     device = latents.device
@@ -142,6 +153,7 @@ def denoise_two(unet, scheduler_first, scheduler_second, prompt_embeds, negative
         # the history seeding of models.py:603-611 cannot run (SURVEY C-4) and is a no-op for order <= 2
         latents = sched.step(noise_pred, t, latents, **extra, return_dict=False)[0]
         per_step.append(latents)
+        ctx = _edited(context_edit, i, ctx)
     return dict(latents=latents, per_step=per_step, timesteps=([int(t) for t in first], [int(t) for t in second]))
 
 

@@ -277,9 +277,12 @@ class _PipelineBase:
                     timesteps, sigmas, num_images_per_prompt, guidance_rescale, output_type, kwargs):
         """The head of the reference ``call`` (models.py:64-114) -- default size, ``check_inputs`` -- followed by what
         this engine does not implement: every such argument raises instead of being ignored."""
-        kwargs.pop("callback", None)                            # deprecated and unused by the reference loop's callers
+        # the deprecated pair (models.py:65-80): called by the single-scheduler loops only (:275-282, :1407-1414; the
+        # two-scheduler and interleaved bodies accept and never call it, :641-650 / :1074-1083)
+        self._legacy_callback = (kwargs.pop("callback", None), kwargs.get("callback_steps"))
         callback_steps = kwargs.pop("callback_steps", None)
         tensor_inputs = kwargs.pop("callback_on_step_end_tensor_inputs", ["latents"])
+        self._callback_inputs = list(tensor_inputs)
         ip_image, ip_embeds = kwargs.pop("ip_adapter_image", None), kwargs.pop("ip_adapter_image_embeds", None)
         if not height or not width:                             # models.py:85-100: both default together
             height = width = self.unet.config.sample_size * self.vae_scale_factor
@@ -305,8 +308,7 @@ class _PipelineBase:
         unsupported = {"ip_adapter_image": ip_image is not None,
                        "ip_adapter_image_embeds": ip_embeds is not None,
                        "cross_attention_kwargs": kwargs.pop("cross_attention_kwargs", None) is not None,
-                       "clip_skip": kwargs.pop("clip_skip", None) is not None,
-                       "callback_on_step_end_tensor_inputs other than ['latents']": list(tensor_inputs) != ["latents"]}
+                       "clip_skip": kwargs.pop("clip_skip", None) is not None}
         bad = [k for k, v in unsupported.items() if v]
         if bad:
             raise NotImplementedError(f"{', '.join(bad)}: not used by any reference driver and not implemented by the "
@@ -365,7 +367,9 @@ class _PipelineBase:
         if n > 1:
             pe = pe.repeat_interleave(n, dim=0)
             ne = ne.repeat_interleave(n, dim=0) if ne is not None else None
-        return torch.cat([ne, pe]) if do_cfg else pe
+        # what ``callback_on_step_end`` may ask for by name (models.py:263-267): the loop's locals of those names
+        self._callback_tensors = {"prompt_embeds": torch.cat([ne, pe]) if do_cfg else pe, "negative_prompt_embeds": ne}
+        return self._callback_tensors["prompt_embeds"]
 
     def encode_prompt(self, prompt, do_cfg, prompt_embeds=None, negative_prompt_embeds=None, negative_prompt=None):
         if prompt_embeds is None:
@@ -468,14 +472,37 @@ class _PipelineBase:
             s_.x0_rows, s_.skip_x0, s_.rng_rows = None, False, None
 
     def _run_callback(self, callback, eng, i, t):
-        """``callback_on_step_end(pipe, i, t, {"latents": ...})`` as at models.py:263-273; a returned
-        ``{"latents": tensor}`` replaces the resident latents (used for teacher-forced parity runs)."""
+        """``callback_on_step_end(pipe, i, t, {name: tensor for name in callback_on_step_end_tensor_inputs})`` as at
+        models.py:263-273.  A returned ``latents`` replaces the resident latents (teacher-forced parity runs use it), a
+        returned ``prompt_embeds`` -- the UNet context, ``[negative, positive]`` under guidance -- replaces the
+        context of every later step; a returned ``negative_prompt_embeds`` is kept for later callbacks and, as in the
+        reference, feeds nothing else."""
         if callback is None:
             return
-        out = callback(self, i, t, {"latents": eng.x_in}) or {}
+        held = self._callback_tensors
+        names = getattr(self, "_callback_inputs", ["latents"])
+        out = callback(self, i, t, {k: eng.x_in if k == "latents" else held[k] for k in names}) or {}
         new = out.get("latents")
         if new is not None and new.data_ptr() != eng.x_in.data_ptr():
             eng.x_in.copy_(new)
+        ctx = out.get("prompt_embeds")
+        if ctx is not None and ctx is not held["prompt_embeds"]:
+            held["prompt_embeds"] = ctx.to(device=held["prompt_embeds"].device, dtype=held["prompt_embeds"].dtype)
+            eng.set_context(held["prompt_embeds"])
+        if out.get("negative_prompt_embeds") is not None:
+            held["negative_prompt_embeds"] = out["negative_prompt_embeds"]
+
+    def _run_legacy_callback(self, i, t, eng, n_timesteps, num_inference_steps):
+        """The deprecated ``callback(step_idx, t, latents)`` every ``callback_steps`` indices, under the progress-bar
+        condition of models.py:275-282 (``num_warmup_steps`` of :205: PLMS' grid has one timestep more than steps)."""
+        callback, callback_steps = getattr(self, "_legacy_callback", (None, None))
+        if callback is None:
+            return
+        order = getattr(self.scheduler, "order", 1)
+        num_warmup_steps = n_timesteps - num_inference_steps * order
+        if i == n_timesteps - 1 or ((i + 1) > num_warmup_steps and (i + 1) % order == 0):
+            if i % callback_steps == 0:
+                callback(i // order, t, eng.x_in)
 
     def vae_engine(self, n_img):
         """Native decoder plan for ``n_img`` latents (vae_engine.VaeEngine), built on first use."""
@@ -561,6 +588,7 @@ class StableDiffusionModel(_PipelineBase):
             if len(step) == 2 and step[1] is not None:
                 x0_preds.append(step[1][0:1])
             self._run_callback(callback_on_step_end, eng, i, t)
+            self._run_legacy_callback(i, t, eng, len(t_list), num_inference_steps)
         torch.cuda.synchronize(self.device)
         exec_time = time.perf_counter() - start
         self._x0_reset([self.scheduler])

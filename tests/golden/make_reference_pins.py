@@ -51,7 +51,7 @@ def main():
     ref = refexec.load(patch_c1=False)
     ref_c1 = refexec.load(patch_c1=True)
     arrays, meta = {}, {"scheduler_timesteps": {}, "pipeline_timesteps": {}, "pipeline_info": {}, "switch": [],
-                        "raises": {}, "registry": {}}
+                        "raises": {}, "registry": {}, "callback_shapes": {}, "legacy_callback": {}}
 
     for name, (kind, over, n, patch, seed) in {**RC.SCHEDULER_CASES, **RC.THRESHOLD_CASES}.items():
         ns = ref_c1 if patch else ref
@@ -68,6 +68,10 @@ def main():
         meta["pipeline_timesteps"][name] = r["timesteps"]
         meta["pipeline_info"][name] = {"n_x0": r["n_x0"], "num_timesteps": r["num_timesteps"]}
         assert torch.equal(r["final"], r["per_step"][-1])
+        if r["cb_shapes"] is not None:                 # what ``callback_on_step_end`` is handed (models.py:263-267)
+            meta["callback_shapes"][name] = [{k: list(v) for k, v in d.items()} for d in r["cb_shapes"]]
+        if r["legacy_calls"] is not None:              # the deprecated ``callback`` (models.py:275-282)
+            meta["legacy_callback"][name] = r["legacy_calls"]
 
     # switch_timestamp, called unbound from the compiled reference class (it does not touch ``self``)
     switch = ref.StableDiffusionModelTwoSchedulers.switch_timestamp

@@ -108,6 +108,18 @@ PIPELINE_CASES = {
     "two_ddim_dpmstock_rescale": dict(pipe="two", first=("ddim", {}),
                                       second=("dpm_stock", dict(algorithm_type="dpmsolver++")), n1=10, k=3,
                                       type_switch="closest", guidance=7.5, rescale=0.5, patch=False),
+    # ``callback_on_step_end_tensor_inputs`` beyond latents (models.py:263-273): the callback is handed the UNet context
+    # (``prompt_embeds`` = cat([negative, positive]) under guidance, models.py:154-155) and the negative embeddings,
+    # and the ``prompt_embeds`` it returns after loop index ``at`` replace the context of every later step
+    "loop_ddim6_ctxedit": dict(pipe="single", sched=("ddim", {}), steps=6, guidance=7.5, patch=False,
+                               ctx_edit=dict(at=2, scale=0.5)),
+    "two_ddim_dpmstock_ctxedit": dict(pipe="two", first=("ddim", {}),
+                                      second=("dpm_stock", dict(algorithm_type="dpmsolver++")), n1=10, k=3,
+                                      type_switch="closest", guidance=7.5, patch=False, ctx_edit=dict(at=4, scale=-1.0)),
+    # the deprecated ``callback`` / ``callback_steps`` pair of the single-scheduler loops (models.py:275-282): PLMS has
+    # N + 1 timesteps, so one warm-up index is passed over (models.py:205)
+    "loop_pndm6_legacy_cb": dict(pipe="single", sched=("pndm", {}), steps=6, guidance=7.5, patch=False,
+                                 legacy_cb=dict(callback_steps=2)),
     # ``num_images_per_prompt`` > 1: latents for B x n images, each prompt's embeddings repeated n times in place
     # (models.py:123-128,139-149,173; the repetition itself is diffusers' ``encode_prompt``, restated in the stub)
     "loop_ddim6_n2": dict(pipe="single", sched=("ddim", {}), steps=6, guidance=7.5, patch=False, n_img=2, gen_seed=31,
@@ -176,6 +188,47 @@ def run_scheduler_case(sched, n_steps, noise_seed, device="cpu", dtype=torch.flo
     return prevs, x0s, [int(t) for t in sched.timesteps.tolist()]
 
 
+CB_INPUTS = ["latents", "prompt_embeds", "negative_prompt_embeds"]
+
+
+def context_edit(case):
+    """The deterministic edit of the ``ctx_edit`` cases: after loop index ``at`` the context rows are reversed (under
+    guidance that swaps the negative and the positive halves) and scaled."""
+    e = case.get("ctx_edit")
+    if not e:
+        return None
+
+    def edit(i, ctx):
+        return ctx.flip(0) * e["scale"] if i == e["at"] else None
+
+    return edit
+
+
+class EditingRecorder:
+    """``callback_on_step_end`` for the ``ctx_edit`` cases: records like ``refexec.Recorder`` plus the shapes of the
+    tensors it is handed, and returns the edited ``prompt_embeds``."""
+
+    def __init__(self, edit):
+        self.per_step, self.timesteps, self.shapes, self.edit = [], [], [], edit
+
+    def __call__(self, pipe, i, t, kwargs):
+        self.per_step.append(kwargs["latents"].clone())
+        self.timesteps.append(int(t))
+        self.shapes.append({k: tuple(v.shape) for k, v in kwargs.items()})
+        new = self.edit(i, kwargs["prompt_embeds"])
+        return {} if new is None else {"prompt_embeds": new}
+
+
+class LegacyCallback:
+    """The deprecated ``callback(step_idx, t, latents)``: records (step_idx, t) and a checksum of the latents."""
+
+    def __init__(self):
+        self.calls = []
+
+    def __call__(self, step_idx, t, latents):
+        self.calls.append([int(step_idx), int(t), round(float(latents.double().abs().sum()), 6)])
+
+
 def run_pipeline_reference(case, ns, net):
     """One pipeline case through the reference's own ``call`` (models.py) compiled by oracle/refexec.py.
     Returns dict(per_step=[latents after each executed step], timesteps=[...], final=latents, n_x0=int,
@@ -184,11 +237,17 @@ def run_pipeline_reference(case, ns, net):
     from oracle import schedulers as O
 
     pe, ne, lat = pipeline_inputs()
-    rec = refexec.Recorder()
+    rec = EditingRecorder(context_edit(case)) if case.get("ctx_edit") else refexec.Recorder()
     default = O.PNDMScheduler.from_config(SD15)            # what from_pretrained leaves in pipe.scheduler
     kind = case["pipe"]
     common = dict(prompt_embeds=pe, negative_prompt_embeds=ne, guidance_scale=case["guidance"], output_type="pt",
                   callback_on_step_end=rec)
+    if case.get("ctx_edit"):
+        common["callback_on_step_end_tensor_inputs"] = list(CB_INPUTS)
+    legacy = None
+    if case.get("legacy_cb"):
+        legacy = LegacyCallback()
+        common.update(callback=legacy, callback_steps=case["legacy_cb"]["callback_steps"])
     if case.get("gen_seed") is not None:
         common["generator"] = torch.Generator().manual_seed(case["gen_seed"])
     if case.get("rescale"):
@@ -223,7 +282,8 @@ def run_pipeline_reference(case, ns, net):
         pipe.scheduler_inter = make_scheduler(*case["inter"], ref=ns)
         out, _, x0 = pipe(**common, num_inference_steps=case["steps"], interliving_steps=list(case["groups"]))
     return dict(per_step=rec.per_step, timesteps=rec.timesteps, final=out.images, n_x0=len(x0),
-                num_timesteps=pipe.num_timesteps)
+                num_timesteps=pipe.num_timesteps, cb_shapes=getattr(rec, "shapes", None),
+                legacy_calls=legacy.calls if legacy else None)
 
 
 def run_pipeline_oracle(case, net):
@@ -242,7 +302,8 @@ def run_pipeline_oracle(case, net):
     rs = case.get("rescale", 0.0)
     if kind == "single":
         r = P.denoise(net, make_scheduler(*case["sched"], module=O), pe, ne, lat, case["steps"],
-                      guidance_scale=case["guidance"], generator=gen, guidance_rescale=rs)
+                      guidance_scale=case["guidance"], generator=gen, guidance_rescale=rs,
+                      context_edit=context_edit(case))
         ts = r["timesteps"]
     elif kind == "skip":
         r = P.denoise(net, make_scheduler(*case["sched"], module=O), pe, ne, lat, case["steps"],
@@ -251,7 +312,7 @@ def run_pipeline_oracle(case, net):
     elif kind == "two":
         r = P.denoise_two(net, make_scheduler(*case["first"], module=O), make_scheduler(*case["second"], module=O),
                           pe, ne, lat, case["n1"], case["k"], case["type_switch"], guidance_scale=case["guidance"],
-                          guidance_rescale=rs)
+                          guidance_rescale=rs, context_edit=context_edit(case))
         ts = r["timesteps"][0] + r["timesteps"][1]
     else:
         r = P.denoise_interleaved(net, make_scheduler(*case["main"], module=O), make_scheduler(*case["inter"], module=O),

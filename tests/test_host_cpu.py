@@ -534,7 +534,6 @@ def test_pipeline_call_argument_checks():
             (dict(clip_skip=1), NotImplementedError, "clip_skip"),
             (dict(callback_steps=0), ValueError, "callback_steps"),
             (dict(callback_on_step_end_tensor_inputs=["latents", "nope"]), ValueError, "tensor_inputs"),
-            (dict(callback_on_step_end_tensor_inputs=["prompt_embeds"]), NotImplementedError, "tensor_inputs"),
             (dict(output_type="jpeg"), ValueError, "output_type"),
             (dict(latents=lat[:, :, :32]), ValueError, "Unexpected latents shape"),
         ]:
@@ -545,6 +544,8 @@ def test_pipeline_call_argument_checks():
         with pytest.raises(RuntimeError, match="CUDA"):         # guidance_rescale is implemented (models.py:244-250)
             pipe(**ok, guidance_rescale=0.7)
         assert pipe.guidance_rescale == 0.7
+        with pytest.raises(RuntimeError, match="CUDA"):         # any subset of the three names (models.py:263-267)
+            pipe(**ok, callback_on_step_end_tensor_inputs=["prompt_embeds", "negative_prompt_embeds"])
         with pytest.raises(RuntimeError, match="CUDA"):         # num_images_per_prompt is implemented (models.py:173)
             pipe(**{**ok, "latents": torch.zeros(6, 4, 64, 64)}, num_images_per_prompt=3)
 

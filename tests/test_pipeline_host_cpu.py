@@ -102,13 +102,22 @@ def test_product_call_bodies_reproduce_reference_source(name, harness):
     default = S.PNDMScheduler.from_config(RC.SD15)
     seen, per_step = [], []
 
+    edit, shapes = RC.context_edit(case), []
+
     def cb(pipe, i, t, kwargs):
         seen.append(int(t))
         per_step.append(kwargs["latents"].clone())
-        return {}
+        shapes.append({k: list(v.shape) for k, v in kwargs.items()})
+        new = edit(i, kwargs["prompt_embeds"]) if edit else None        # ctx_edit cases: replace the UNet context
+        return {} if new is None else {"prompt_embeds": new}
 
     common = dict(prompt_embeds=pe, negative_prompt_embeds=ne, guidance_scale=case["guidance"], output_type="latent",
                   callback_on_step_end=cb)
+    if edit:
+        common["callback_on_step_end_tensor_inputs"] = list(RC.CB_INPUTS)
+    legacy = RC.LegacyCallback() if case.get("legacy_cb") else None
+    if legacy:
+        common.update(callback=legacy, callback_steps=case["legacy_cb"]["callback_steps"])
     if case.get("gen_seed") is not None:
         common["generator"] = torch.Generator().manual_seed(case["gen_seed"])
     if case.get("rescale"):
@@ -147,10 +156,19 @@ def test_product_call_bodies_reproduce_reference_source(name, harness):
     print(f"\n[{name}] product call body vs reference source: worst per-step max-abs / range {worst:.2e}")
     assert worst <= 5e-6, (name, worst)                                  # fp32 host path, float64 kernel model
     assert torch.equal(out.images, per_step[-1]) and secs >= 0
+    if edit:                                                             # what the callback is handed, models.py:263-267
+        assert shapes == META["callback_shapes"][name]
+    else:
+        assert all(list(d) == ["latents"] for d in shapes)
+    if legacy:                                                           # deprecated callback, models.py:275-282
+        want_calls = META["legacy_callback"][name]
+        assert [c[:2] for c in legacy.calls] == [c[:2] for c in want_calls]
+        assert all(abs(a[2] - b[2]) <= 1e-5 * abs(b[2]) for a, b in zip(legacy.calls, want_calls))
     info = META["pipeline_info"][name]
     assert pipe.num_timesteps == info["num_timesteps"]
     assert x0 == []                                                      # output_type="latent": nothing is decoded
-    tup = pipe(**{**common, "callback_on_step_end": None,
+    common.pop("callback", None)
+    tup = pipe(**{**common, "callback_on_step_end": cb if edit else None,     # the edit is part of the computation
                   **({"generator": torch.Generator().manual_seed(case["gen_seed"])} if case.get("gen_seed") is not None
                      else {})}, **kw, return_dict=False)
     assert isinstance(tup[0], tuple) and tup[0][1] is None and torch.equal(tup[0][0], out.images)   # models.py:322-323
