@@ -49,6 +49,37 @@ SD15_SCHEDULER_CONFIG = dict(
 )
 
 
+def load_stock_scheduler(model_dir=None):
+    """The scheduler ``from_pretrained`` leaves in ``pipe.scheduler`` -- what the ``default`` / ``deep_cache`` methods
+    run with (default_sd.py:15-16, deep_cache.py:17-18) and whose ``.config`` every other method feeds to
+    ``from_config`` (base_experiment.py:69-72).  A local diffusers-layout directory is read like diffusers reads it
+    (``scheduler/scheduler_config.json``: ``_class_name`` picks the class, the remaining keys are its config); without
+    one it is SD-v1.5's PNDM.  A stock class this package has no fused step for keeps its CONFIG (so the
+    ``from_config`` idiom sees the right betas / spacing / prediction type) on a PNDM stand-in, with a loud warning."""
+    path = os.path.join(model_dir, "scheduler", "scheduler_config.json") if model_dir else None
+    if not (path and os.path.isfile(path)):
+        return S.PNDMScheduler.from_config(SD15_SCHEDULER_CONFIG)
+    import json
+
+    with open(path) as f:
+        cfg = json.load(f)
+    name = cfg.pop("_class_name", "PNDMScheduler")
+    cfg = {k: v for k, v in cfg.items() if not k.startswith("_")}
+    known = {"PNDMScheduler": S.PNDMScheduler, "DDIMScheduler": S.DDIMSchedulerMy,
+             "DPMSolverMultistepScheduler": S.DPMSolverScheduler, "LCMScheduler": S.LCMScheduler}
+    if name not in known:
+        _loud(f"{path}: stock scheduler class {name!r} has no fused step here; its config is kept for the "
+              "`from_config` idiom, but the `default` / `deep_cache` methods (which run the stock scheduler itself) "
+              "would step with PNDM instead")
+        try:
+            return S.PNDMScheduler.from_config({**SD15_SCHEDULER_CONFIG, **cfg})
+        except (NotImplementedError, ValueError):         # e.g. a spacing PLMS is not fused for: config only
+            sched = S.PNDMScheduler.from_config(SD15_SCHEDULER_CONFIG)
+            sched.config.update(cfg)
+            return sched
+    return known[name].from_config(cfg)
+
+
 class PipelineOutput(SimpleNamespace):
     """``StableDiffusionPipelineOutput`` stand-in: ``.images`` and ``.nsfw_content_detected``."""
 
@@ -157,7 +188,7 @@ class _PipelineBase:
             _loud(msg)
         text = make_text_encoder(seed, text_dir, dtype=torch_dtype)
         tok = load_tokenizer(tok_dir)
-        sched = S.PNDMScheduler.from_config(SD15_SCHEDULER_CONFIG)
+        sched = load_stock_scheduler(root)
         pipe = cls(sd, VaeWeights(vae_sd), text, tok, sched, arch=arch, torch_dtype=torch_dtype, timestamps=timestamps,
                    seed=seed)
         pipe.weights_source = "random-init" if random_parts else "provided"

@@ -566,3 +566,48 @@ def test_postprocess_images_follows_diffusers():
     assert np.array_equal(np.asarray(pil[1]), (arr[1] * 255).round().astype("uint8"))
     with pytest.raises(ValueError):
         postprocess_images(x, "jpeg")
+
+
+def test_stock_scheduler_is_read_from_a_local_model_directory(tmp_path):
+    """``from_pretrained`` leaves the model directory's own scheduler in ``pipe.scheduler`` (diffusers reads
+    ``scheduler/scheduler_config.json``; the reference's ``default`` / ``deep_cache`` methods run with it and every
+    other method feeds its config to ``from_config``, base_experiment.py:69-72)."""
+    import json
+    import warnings
+
+    from sonicdiffusionbayeslab_b200 import models as M
+    from sonicdiffusionbayeslab_b200 import schedulers as S
+
+    none = M.load_stock_scheduler(None)
+    assert type(none) is S.PNDMScheduler and dict(none.config) == dict(
+        S.PNDMScheduler.from_config(M.SD15_SCHEDULER_CONFIG).config)
+    assert type(M.load_stock_scheduler(str(tmp_path))) is S.PNDMScheduler          # directory without a scheduler/
+
+    (tmp_path / "scheduler").mkdir()
+    sd15 = {"_class_name": "PNDMScheduler", "_diffusers_version": "0.6.0", "beta_end": 0.012,
+            "beta_schedule": "scaled_linear", "beta_start": 0.00085, "num_train_timesteps": 1000,
+            "set_alpha_to_one": False, "skip_prk_steps": True, "steps_offset": 1, "trained_betas": None,
+            "clip_sample": False}
+    (tmp_path / "scheduler" / "scheduler_config.json").write_text(json.dumps(sd15))
+    s = M.load_stock_scheduler(str(tmp_path))
+    assert type(s) is S.PNDMScheduler and dict(s.config) == dict(none.config)      # the shipped SD-v1.5 file
+    assert "_class_name" not in s.config and "_diffusers_version" not in s.config
+
+    ddim = dict(sd15, _class_name="DDIMScheduler", beta_schedule="linear", beta_start=0.0001, beta_end=0.02,
+                steps_offset=0)
+    (tmp_path / "scheduler" / "scheduler_config.json").write_text(json.dumps(ddim))
+    s = M.load_stock_scheduler(str(tmp_path))
+    assert type(s) is S.DDIMSchedulerMy and s.config.beta_schedule == "linear" and s.config.steps_offset == 0
+    assert torch.allclose(s.betas[[0, -1]], torch.tensor([0.0001, 0.02]))
+
+    # a stock class without a fused step (Lykon/dreamshaper-7 ships DEIS): its config survives for ``from_config``
+    deis = dict(sd15, _class_name="DEISMultistepScheduler", solver_order=2, algorithm_type="deis", solver_type="logrho",
+                lower_order_final=True, thresholding=False, prediction_type="epsilon", timestep_spacing="leading")
+    (tmp_path / "scheduler" / "scheduler_config.json").write_text(json.dumps(deis))
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        s = M.load_stock_scheduler(str(tmp_path))
+    assert any("DEISMultistepScheduler" in str(x.message) for x in w)
+    assert type(s) is S.PNDMScheduler and s.config.solver_order == 2 and s.config.algorithm_type == "deis"
+    lcm = S.LCMScheduler.from_config(s.config)                                     # consistency_model.py's idiom
+    assert lcm.config.beta_start == 0.00085 and lcm.config.steps_offset == 1
