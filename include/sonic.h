@@ -257,9 +257,11 @@ int sonic_plan_add_im2col_s2(sonic_plan_t plan, const void* x, void* y, int32_t 
                              int32_t W, int32_t C);
 int sonic_plan_add_im2col3x3(sonic_plan_t plan, const void* x, void* y, int32_t n_img, int32_t H,
                              int32_t W, int32_t C, int32_t stride);
-/* out[dim] = [cos(t f_j) | sin(t f_j)], t read from DEVICE memory at run time (graph-safe). */
 int sonic_plan_add_ln_side(sonic_plan_t plan, const float* partials, int32_t parts, int32_t M, int32_t K, float eps,
                            void* side, float* rstd);
+/* sonic_softmax_rows as a plan operator (the VAE decoder's single-head attention, src/models.py:288-302). */
+int sonic_plan_add_softmax_rows(sonic_plan_t plan, void* x, int32_t rows, int32_t cols, int64_t ld, float scale);
+/* out[dim] = [cos(t f_j) | sin(t f_j)], t read from DEVICE memory at run time (graph-safe). */
 int sonic_plan_add_timestep_embedding(sonic_plan_t plan, const float* t_dev, int32_t dim, float* out);
 /* Batched M=1 GEMV: y_j = bias_j + add_j + W_j[N_j x K] * act(x), act = SiLU if silu_in.
  * The pointer tables are HOST arrays of n_jobs device pointers (bias/add tables may be NULL). */

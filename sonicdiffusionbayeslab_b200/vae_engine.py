@@ -81,7 +81,7 @@ class VaeEngine(UNetEngine):
         for b in range(self.n):
             rows = slice(b * S, (b + 1) * S)
             self._gemm(plan, q[rows], k[rows], S, out=scores)        # S_b = Q_b K_b^T          [S, S]
-            check(lib().sonic_plan_add_softmax_rows(plan.h, K.ptr(scores), S, S, S, C.c_float(Cc ** -0.5)),
+            check(lib().sonic_plan_add_softmax_rows(plan.h, K.ptr(scores), S, S, C.c_int64(S), C.c_float(Cc ** -0.5)),
                   "sonic_plan_add_softmax_rows")
             plan.log.append(f"softmax_rows {S}x{S}")
             self._gemm(plan, wv, g[rows], S, out=vt)                 # V_b^T = W_v X_b^T         [C, S]

@@ -611,3 +611,102 @@ def test_stock_scheduler_is_read_from_a_local_model_directory(tmp_path):
     assert type(s) is S.PNDMScheduler and s.config.solver_order == 2 and s.config.algorithm_type == "deis"
     lcm = S.LCMScheduler.from_config(s.config)                                     # consistency_model.py's idiom
     assert lcm.config.beta_start == 0.00085 and lcm.config.steps_offset == 1
+
+
+def test_ctypes_structures_match_the_header_layout(tmp_path):
+    """The four argument structs of include/sonic.h as the C compiler lays them out (gcc, the platform ABI nvcc's host
+    side uses too) against the ``ctypes.Structure`` mirrors the Python host binds with (``_lib.GemmArgs``,
+    ``kernels.AttentionArgs / UpdateCoeffs / X0Post``): same size, same field names in the same order, same offsets
+    -- ctypes checks none of this at call time."""
+    import ctypes
+    import json
+    import re
+    import subprocess
+
+    from sonicdiffusionbayeslab_b200 import _lib
+    from sonicdiffusionbayeslab_b200 import kernels as K
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    header = open(os.path.join(root, "include", "sonic.h")).read()
+    mirrors = {"sonic_gemm_args": _lib.GemmArgs, "sonic_attention_args": K.AttentionArgs,
+               "sonic_update_coeffs": K.UpdateCoeffs, "sonic_x0_post": K.X0Post}
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "sonic.h"', "int main(void) {", '  printf("{");']
+    for si, (name, mirror) in enumerate(mirrors.items()):
+        body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (name, name), header, re.S).group(1)
+        body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+        fields = []
+        for decl in body.split(";"):                       # "const void* a0", "int32_t c0, ld0", "float m_x, m_e" ...
+            decl = decl.strip()
+            if decl:
+                first, *rest = decl.split(",")
+                fields += [first.split()[-1].lstrip("*")] + [r.strip().lstrip("*") for r in rest]
+        assert fields == [f[0] for f in mirror._fields_], (name, fields)          # names and order
+        lines.append('  printf("%s\\"%s\\": {\\"sizeof\\": %%zu", sizeof(%s));' % (", " if si else "", name, name))
+        for f in fields:
+            lines.append('  printf(", \\"%s\\": %%zu", offsetof(%s, %s));' % (f, name, f))
+        lines.append('  printf("}");')
+    lines += ['  printf("}\\n");', "  return 0;", "}"]
+    src = tmp_path / "layout.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "layout"
+    subprocess.run(["gcc", "-std=c11", "-I", os.path.join(root, "include"), str(src), "-o", str(exe)], check=True)
+    layout = json.loads(subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout)
+    for name, mirror in mirrors.items():
+        assert ctypes.sizeof(mirror) == layout[name]["sizeof"], name
+        for f, _ in mirror._fields_:
+            assert getattr(mirror, f).offset == layout[name][f], (name, f)
+
+
+def test_every_exported_entry_point_is_declared_in_the_header():
+    """The reverse of ``test_library_exports_every_declared_symbol``: libsonic.so exports no ``sonic_*`` entry point
+    that include/sonic.h does not declare (the clock-trace hooks ``sonic_debug_*`` of tools/ excepted)."""
+    from sonicdiffusionbayeslab_b200 import _lib
+
+    try:
+        out = subprocess.run(["nm", "-D", "--defined-only", _lib.LIB_PATH], capture_output=True, text=True,
+                             check=True).stdout
+    except (OSError, subprocess.CalledProcessError):
+        pytest.skip("nm unavailable")
+    exported = {ln.split()[-1] for ln in out.splitlines() if ln.split() and ln.split()[-1].startswith("sonic_")}
+    undeclared = sorted(n for n in exported - set(_declared_symbols()) if not n.startswith("sonic_debug_"))
+    assert not undeclared, undeclared
+
+
+def test_call_sites_pass_as_many_arguments_as_the_header_declares():
+    """ctypes checks neither the number nor the width of the arguments: every ``lib.sonic_*(...)`` call in the package,
+    bench.py and calc_clip_score.py is counted against the prototype in include/sonic.h, and every ``int64_t``
+    parameter must be passed as an explicit ``c_int64`` (a bare Python int goes out as a 32-bit C int)."""
+    import ast
+    import pathlib
+    import re
+
+    root = pathlib.Path(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    hdr = re.sub(r"/\*.*?\*/", "", (root / "include" / "sonic.h").read_text(), flags=re.S)
+    protos = {}
+    for m in re.finditer(r"\b(?:int|const char\*)\s+(sonic_\w+)\s*\(([^;{]*?)\)\s*;", hdr, re.S):
+        params = m.group(2).strip()
+        protos[m.group(1)] = [] if params in ("void", "") else [" ".join(p.split()) for p in params.split(",")]
+    assert set(protos) == set(_declared_symbols())
+    files = list((root / "sonicdiffusionbayeslab_b200").rglob("*.py")) + [root / "bench.py", root / "calc_clip_score.py",
+                                                                         root / "__graft_entry__.py"]
+    seen, problems = set(), []
+    for f in files:
+        for n in ast.walk(ast.parse(f.read_text())):
+            if not (isinstance(n, ast.Call) and isinstance(n.func, ast.Attribute) and n.func.attr.startswith("sonic_")):
+                continue
+            name, where = n.func.attr, f"{f.relative_to(root)}:{n.lineno}"
+            seen.add(name)
+            if name not in protos:
+                problems.append(f"{where}: {name} is not declared in include/sonic.h")
+                continue
+            if n.keywords or any(isinstance(a, ast.Starred) for a in n.args):
+                problems.append(f"{where}: {name} must be called with plain positional arguments")
+                continue
+            if len(n.args) != len(protos[name]):
+                problems.append(f"{where}: {name} gets {len(n.args)} arguments, the header declares {len(protos[name])}")
+                continue
+            for arg, decl in zip(n.args, protos[name]):
+                if decl.startswith("int64_t") and "c_int64" not in ast.unparse(arg):
+                    problems.append(f"{where}: {name}: `{decl}` is passed `{ast.unparse(arg)}` (not a c_int64)")
+    assert not problems, "\n".join(problems)
+    assert len(seen) >= 30                                   # the check really saw the binding's call sites
