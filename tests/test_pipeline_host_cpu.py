@@ -94,10 +94,11 @@ def harness(monkeypatch, net):
     return M, S, make, engines
 
 
-@pytest.mark.parametrize("name", list(RC.PIPELINE_CASES))
-def test_product_call_bodies_reproduce_reference_source(name, harness):
+def run_product_case(case, harness):
+    """One pipeline case (tests/refpin_cases.py format) through the PRODUCT's ``call`` body over the fake engine.
+    Returns dict(seen=[timesteps], per_step=[latents], shapes=[callback inputs], legacy=LegacyCallback or None, out,
+    secs, x0, pipe, common, kw, cb, engine)."""
     M, S, make, engines = harness
-    case = RC.PIPELINE_CASES[name]
     pe, ne, lat = RC.pipeline_inputs()
     default = S.PNDMScheduler.from_config(RC.SD15)
     seen, per_step = [], []
@@ -147,9 +148,20 @@ def test_product_call_bodies_reproduce_reference_source(name, harness):
         pipe.scheduler_inter = RC.make_scheduler(*case["inter"], module=S)
         kw = dict(num_inference_steps=case["steps"], interliving_steps=list(case["groups"]))
     out, secs, x0 = pipe(**common, **kw)
+    return dict(seen=seen, per_step=per_step, shapes=shapes, legacy=legacy, out=out, secs=secs, x0=x0, pipe=pipe,
+                common=common, kw=kw, cb=cb, edit=edit, engine=engines[-1])
+
+
+@pytest.mark.parametrize("name", list(RC.PIPELINE_CASES))
+def test_product_call_bodies_reproduce_reference_source(name, harness):
+    case = RC.PIPELINE_CASES[name]
+    r = run_product_case(case, harness)
+    seen, per_step, shapes, legacy, out, secs, x0, pipe = (r[k] for k in ("seen", "per_step", "shapes", "legacy", "out",
+                                                                          "secs", "x0", "pipe"))
+    common, kw, cb, edit = r["common"], r["kw"], r["cb"], r["edit"]
     want = torch.from_numpy(PINS[f"pipe/{name}/per_step"])
     assert seen == META["pipeline_timesteps"][name]                      # integer schedule: bit-exact
-    assert engines[-1].calls == seen                                     # one UNet evaluation per executed step
+    assert r["engine"].calls == seen                                     # one UNet evaluation per executed step
     assert len(per_step) == want.shape[0]
     scale = max(1.0, want.abs().max().item())
     worst = max((g - w).abs().max().item() for g, w in zip(per_step, want)) / scale
