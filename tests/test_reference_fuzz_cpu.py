@@ -216,3 +216,69 @@ def test_random_pipeline_case_equals_reference_source(idx, harness, net):
         assert r["shapes"] == [{k: list(v) for k, v in d.items()} for d in want["cb_shapes"]]
     if want["legacy_calls"] is not None:
         assert [c[:2] for c in r["legacy"].calls] == [c[:2] for c in want["legacy_calls"]]
+
+
+# --------------------------------------------------------------------------- DDIM / LCM / PLMS: product vs oracle
+def _drive(sched, n, B=2, seed=0, gen_seed=None, eta=None):
+    """Free-running ``step`` loop over a synthetic model-output sequence (cf. RC.run_scheduler_case)."""
+    sched.set_timesteps(n)
+    g = torch.Generator().manual_seed(100 + seed)
+    x = torch.randn(B, RC.C, RC.HW, RC.HW, generator=g)
+    gen = torch.Generator().manual_seed(gen_seed) if gen_seed is not None else None
+    outs = []
+    for t in sched.timesteps:
+        e = 0.7 * torch.randn(B, RC.C, RC.HW, RC.HW, generator=g) + 0.2 * x
+        kw = {}
+        if gen is not None:
+            kw["generator"] = gen
+        if eta is not None:
+            kw["eta"] = eta
+        out = sched.step(e, t, x, return_dict=False, **kw)
+        outs.append(out)
+        x = out[0]
+    return outs, [int(t) for t in sched.timesteps.tolist()]
+
+
+def _random_stock_config(rng):
+    kind = rng.choice(["ddim", "lcm", "pndm"])
+    over, eta, gen_seed = {}, None, None
+    if kind == "ddim":
+        over = dict(prediction_type=rng.choice(["epsilon", "sample", "v_prediction"]),
+                    set_alpha_to_one=rng.random() < 0.5, steps_offset=rng.choice([0, 1]),
+                    timestep_spacing=rng.choice(["leading", "leading", "trailing", "linspace"]),
+                    clip_sample=rng.random() < 0.3, clip_sample_range=rng.choice([1.0, 2.5]))
+        if rng.random() < 0.4:
+            eta, gen_seed = rng.choice([0.3, 1.0]), rng.randrange(1, 99)
+        n = rng.randint(1, 30)
+    elif kind == "lcm":
+        over = dict(prediction_type=rng.choice(["epsilon", "sample", "v_prediction"]),
+                    timestep_scaling=rng.choice([10.0, 5.0]), set_alpha_to_one=rng.random() < 0.5)
+        gen_seed, n = rng.randrange(1, 99), rng.randint(1, 8)
+    else:
+        over = dict(prediction_type=rng.choice(["epsilon", "v_prediction"]), steps_offset=rng.choice([0, 1]),
+                    set_alpha_to_one=rng.random() < 0.5)
+        n = rng.randint(2, 24)
+    return kind, over, n, eta, gen_seed
+
+
+STOCK = [_random_stock_config(random.Random(9000 + i)) for i in range(45)]
+
+
+@pytest.mark.parametrize("idx", range(len(STOCK)))
+def test_random_stock_scheduler_configuration_equals_oracle(idx, monkeypatch):
+    """DDIM (every prediction type, eta > 0 with the shared generator, clip_sample, spacing), LCM and PLMS: the
+    product's coefficient sets through the float64 kernel model against the oracle's restatement of the diffusers
+    formulas (SURVEY appendix A.2 -- third-party layer, no reference source of its own), free-running."""
+    from test_host_cpu import _emulated_launch
+
+    from sonicdiffusionbayeslab_b200 import schedulers as S
+
+    kind, over, n, eta, gen_seed = STOCK[idx]
+    monkeypatch.setattr(S.FusedScheduler, "_launch", _emulated_launch)
+    want, want_ts = _drive(RC.make_scheduler(kind, over, module=O), n, seed=idx, gen_seed=gen_seed, eta=eta)
+    got, got_ts = _drive(RC.make_scheduler(kind, over, module=S), n, seed=idx, gen_seed=gen_seed, eta=eta)
+    assert got_ts == want_ts, (kind, over, n)
+    for a, b in zip(got, want):
+        assert len(a) == len(b)
+        for x, y in zip(a, b):
+            assert (x - y).abs().max().item() <= 2e-5 * max(1.0, y.abs().max().item()), (kind, over, n, eta)
