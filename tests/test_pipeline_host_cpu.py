@@ -209,8 +209,16 @@ class DeepCacheFakeEngine(FakeEngine):
         return self.dc.forward(x, torch.tensor(int(t)), self.ctx, cur)
 
 
+def _random_deepcache_cases(n=14, seed=77):
+    import random
+
+    rng = random.Random(seed)
+    return [(rng.choice(["ddim", "pndm", "dpm"]), rng.randint(3, 16), rng.randint(2, 6), rng.randint(0, 11))
+            for _ in range(n)]
+
+
 @pytest.mark.parametrize("sched,steps,interval,branch", [("ddim", 12, 3, 0), ("pndm", 7, 2, 0), ("pndm", 9, 5, 4),
-                                                          ("ddim", 10, 4, 7)])
+                                                          ("ddim", 10, 4, 7)] + _random_deepcache_cases())
 def test_product_deepcache_loop_equals_oracle(sched, steps, interval, branch, harness, net, monkeypatch):
     """``DeepCacheSDHelper`` + the pipeline's full / cached decision (deep_cache.py:24-29,58; appendix A.4 -- with
     PLMS the repeated timestep maps to its FIRST index) against the oracle's wrapper semantics, through the product's
