@@ -1,0 +1,117 @@
+"""Buffer lifetimes of the recorded launch plans (tools/plan_check.py), on the CPU.
+
+Pointers are baked into a plan when it is recorded and activations come out of an exact-size free-list arena
+(unet_engine.Arena), so a tensor released one operator too early corrupts results only at the batch sizes where a later
+allocation happens to have the same rounded size -- the GPU parity tests run a handful of shapes.  Recording needs no
+device, so every plan variant is recorded here against a recorder in place of the library and checked operator by
+operator: operands live when recorded, every arena buffer read (``const`` in include/sonic.h) written since it was
+handed out (the cached DeepCache plan reads only what the full plan left resident), no double release, and the bytes
+each operator touches (rows x pitch of every GEMM / attention / norm operand, the partial-statistics tables) inside the
+arena buffer they start in.
+"""
+import ctypes as C
+import os
+import sys
+import warnings
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tools"))
+sys.path.insert(0, ROOT)
+
+import plan_check  # noqa: E402
+
+
+def test_checker_detects_injected_faults():
+    from sonicdiffusionbayeslab_b200 import kernels as K
+    from sonicdiffusionbayeslab_b200 import unet_engine as UE
+
+    with plan_check.recording() as tr:
+        lib = UE.lib()
+        arena, plan = UE.Arena(torch.device("cpu")), UE._Plan()
+        g = torch.ones(64)
+
+        def layernorm(x, y):
+            assert lib.sonic_plan_add_layernorm(plan.h, K.ptr(x), K.ptr(y), 64, 64, C.c_float(1e-5), K.ptr(g), K.ptr(g)) == 0
+
+        a, b, c = arena.alloc((64, 64)), arena.alloc((64, 64)), arena.alloc((64, 64))
+        x = torch.zeros(64, 64, dtype=torch.bfloat16)                 # not an arena buffer: an engine input
+        layernorm(x, a)
+        layernorm(a, b)
+        assert tr.problems == [] and tr.arena_reads == 1 and tr.arena_writes == 2
+        layernorm(c, b)                                               # c was never written
+        assert len(tr.problems) == 1 and "nobody has written" in tr.problems[-1]
+        arena.release(a)
+        layernorm(a, b)                                               # use after release
+        assert len(tr.problems) == 2 and "RELEASED" in tr.problems[-1]
+        d = arena.alloc((64, 64))                                     # recycles a's buffer ...
+        assert d.data_ptr() == a.data_ptr()
+        layernorm(a, b)                                               # ... so the stale pointer reads an unwritten buffer
+        assert len(tr.problems) == 3 and "nobody has written" in tr.problems[-1]
+        arena.release(b)
+        arena.release(b)
+        assert len(tr.problems) == 4 and "released twice" in tr.problems[-1]
+        e, f = arena.alloc((64, 64)), arena.alloc((128, 64))
+        layernorm(x, e)
+        n = len(tr.problems)
+        assert lib.sonic_plan_add_layernorm(plan.h, K.ptr(e), K.ptr(f), 128, 64, C.c_float(1e-5), K.ptr(g), K.ptr(g)) == 0
+        assert len(tr.problems) == n + 1 and "its arena buffer ends" in tr.problems[-1]   # 128 rows read from a 64-row buffer
+    assert UE.lib is not None and UE.Arena.alloc.__name__ == "alloc" and not torch.zeros(1).is_cuda   # hooks restored
+
+
+@pytest.fixture(scope="module")
+def packed():
+    from sonicdiffusionbayeslab_b200.unet_engine import PackedWeights
+    from sonicdiffusionbayeslab_b200.unet_spec import random_unet_state_dict
+
+    return PackedWeights(random_unet_state_dict(29), "cpu")
+
+
+@pytest.mark.parametrize("n_latents,cfg", [(1, True), (16, True), (16, False), (32, True), (64, False)])
+def test_unet_plans_have_no_lifetime_hazards(packed, n_latents, cfg):
+    """ctx + full + cached plan of every DeepCache branch 0-11 at UNet batches 2 / 16 / 32 / 64."""
+    from sonicdiffusionbayeslab_b200.unet_engine import UNetEngine
+
+    with plan_check.recording() as tr:
+        for branch in range(12):
+            tr.context = f"unet n_latents={n_latents} cfg={cfg} branch={branch}"
+            tr.raws.clear()
+            eng = UNetEngine(packed, n_latents=n_latents, cfg_dup=cfg, device="cpu", cache_branch=branch)
+            assert set(eng.plans) == {"ctx", "full", "cached"}
+        assert tr.n_ops > 12 * 380 and tr.arena_reads > 10000 and tr.arena_writes > 7000 and tr.extents_checked > 15000
+        assert tr.problems == [], "\n".join(tr.problems[:10])
+
+
+def test_vae_and_clip_plans_have_no_lifetime_hazards():
+    from sonicdiffusionbayeslab_b200.clip_engine import ClipTextEngine, ClipVisionEngine
+    from sonicdiffusionbayeslab_b200.metrics.metrics import make_clip_model
+    from sonicdiffusionbayeslab_b200.text import make_text_encoder
+    from sonicdiffusionbayeslab_b200.vae_engine import VaeEngine
+    from sonicdiffusionbayeslab_b200.vae_spec import random_vae_state_dict
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        clip, _ = make_clip_model(None)
+        text = make_text_encoder(29, None)
+    vae_sd = random_vae_state_dict(29)
+    with plan_check.recording() as tr:
+        for n_img, latent in ((1, 64), (2, 32), (16, 64)):
+            tr.context = f"vae n_img={n_img} latent={latent}"
+            tr.raws.clear()
+            VaeEngine(dict(vae_sd), n_img=n_img, latent=latent, io_dtype=torch.bfloat16, device="cpu")
+        n_vae = tr.n_ops
+        c = text.config
+        for n in (1, 32):
+            for what, make in (("clip image tower", lambda: ClipVisionEngine(clip.state_dict(), n=n, device="cpu")),
+                               ("clip text tower", lambda: ClipTextEngine(clip.state_dict(), n=n, device="cpu")),
+                               ("prompt encoder", lambda: ClipTextEngine(
+                                   text.state_dict(), n=n, seq=c.max_position_embeddings, width=c.hidden_size,
+                                   heads=c.num_attention_heads, layers=c.num_hidden_layers, mlp=c.intermediate_size,
+                                   device="cpu"))):
+                tr.context = f"{what} n={n}"
+                tr.raws.clear()                                       # one engine = one arena
+                make()
+        assert n_vae > 250 and tr.n_ops - n_vae > 300
+        assert tr.problems == [], "\n".join(tr.problems[:10])
