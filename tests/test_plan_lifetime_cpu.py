@@ -58,6 +58,27 @@ def test_checker_detects_injected_faults():
         n = len(tr.problems)
         assert lib.sonic_plan_add_layernorm(plan.h, K.ptr(e), K.ptr(f), 128, 64, C.c_float(1e-5), K.ptr(g), K.ptr(g)) == 0
         assert len(tr.problems) == n + 1 and "its arena buffer ends" in tr.problems[-1]   # 128 rows read from a 64-row buffer
+        # a GEMM writing over its own input, and an operand off the 16-byte grid
+        from sonicdiffusionbayeslab_b200._lib import GemmArgs
+
+        w = torch.zeros(64, 64, dtype=torch.bfloat16)
+
+        def gemm(a0, out, ld_out=64):
+            ga = GemmArgs()
+            ga.a0, ga.c0, ga.ld0 = a0.data_ptr(), 64, 64
+            ga.n_img, ga.H, ga.W, ga.w, ga.N, ga.taps = 1, 1, 64, w.data_ptr(), 64, 1
+            ga.out, ga.ld_out = out.data_ptr(), ld_out
+            assert lib.sonic_plan_add_conv_gemm(plan.h, C.byref(ga)) == 0
+
+        n = len(tr.problems)
+        gemm(e, f)
+        assert len(tr.problems) == n
+        gemm(e, e)
+        assert len(tr.problems) == n + 1 and "overlaps input" in tr.problems[-1]
+        gemm(e, f.view(-1)[4:].view(-1), ld_out=64)                   # starts 8 bytes into the buffer
+        assert len(tr.problems) == n + 2 and "TMA-addressable" in tr.problems[-1]
+        gemm(e, f, ld_out=68)                                         # 136-byte pitch
+        assert "TMA-addressable" in tr.problems[-1] and len(tr.problems) >= n + 3
     assert UE.lib is not None and UE.Arena.alloc.__name__ == "alloc" and not torch.zeros(1).is_cuda   # hooks restored
 
 
@@ -80,7 +101,7 @@ def test_unet_plans_have_no_lifetime_hazards(packed, n_latents, cfg):
             tr.raws.clear()
             eng = UNetEngine(packed, n_latents=n_latents, cfg_dup=cfg, device="cpu", cache_branch=branch)
             assert set(eng.plans) == {"ctx", "full", "cached"}
-        assert tr.n_ops > 12 * 380 and tr.arena_reads > 10000 and tr.arena_writes > 7000 and tr.extents_checked > 15000
+        assert tr.n_ops > 12 * 380 and tr.arena_reads > 10000 and tr.arena_writes > 7000 and tr.extents_checked > 15000 and tr.overlaps_checked > 4000
         assert tr.problems == [], "\n".join(tr.problems[:10])
 
 

@@ -13,7 +13,9 @@ operator, in execution order, for every plan variant (batch size, guidance on / 
      and the cached (DeepCache) plan reads only features the full plan left resident;
   3. the arena never hands out a live buffer and nothing is released twice;
   4. the bytes an operator touches -- from its documented semantics: rows x pitch of every GEMM / attention / norm
-     operand, the GroupNorm / LayerNorm partial-statistics tables -- stay inside the arena buffer they start in.
+     operand, the GroupNorm / LayerNorm partial-statistics tables -- stay inside the arena buffer they start in;
+  5. a GEMM / attention output never overlaps one of its own inputs (the element-wise residual may);
+  6. every TMA operand starts on a 16-byte boundary of its buffer and has a pitch that is a multiple of 16 bytes.
 
     python tools/plan_check.py            # UNet batches 2 ... 64, guidance on / off, DeepCache branches 0-11, VAE, CLIP
 """
@@ -62,7 +64,7 @@ class Tracker:
         self.funcs, self.structs = _header_constness()
         self.raws = {}                   # base pointer -> [nbytes, live, generation, generation of the last write]
         self.n_ops = 0
-        self.arena_reads = self.arena_writes = self.extents_checked = 0   # operands the checks really looked at
+        self.arena_reads = self.arena_writes = self.extents_checked = self.overlaps_checked = 0   # operands the checks really looked at
         self.problems = []
         self.context = ""
 
@@ -139,6 +141,39 @@ class Tracker:
                         self.problems.append(f"{where}: {what} needs {nbytes} bytes at {p:#x}, its arena buffer ends "
                                              f"{base + e[0] - p} bytes after that")
                     break
+
+        self._aliasing_and_alignment(name, args, where)
+
+    def _aliasing_and_alignment(self, name, args, where):
+        """5. a GEMM / attention output never overlaps one of its own inputs (other CTAs still read them; the residual,
+        added element-wise by the CTA that writes the same element, is the one in-place operand); 6. every TMA operand
+        starts on a 16-byte boundary of its buffer with a pitch that is a multiple of 16 bytes."""
+        ext = {w: (p, n) for w, p, n in self._extents(name, args) if p}
+        if name == "sonic_plan_add_conv_gemm":
+            outs, ins = ["out"], ["a0", "a1"]
+            g = args[1]._obj
+            pitches = {"a0": g.ld0, "a1": g.ld1, "out": g.ld_out, "residual": g.ld_res}
+        elif name == "sonic_plan_add_attention":
+            outs, ins = ["o"], ["q", "k", "v"]
+            a = args[1]._obj
+            pitches = {"q": a.ld_q, "k": a.ld_k, "v": a.ld_v, "o": a.ld_o}
+        else:
+            return
+        for o in outs:
+            for i in ins:
+                if o in ext and i in ext:
+                    (po, no), (pi, ni) = ext[o], ext[i]
+                    self.overlaps_checked += 1
+                    if po < pi + ni and pi < po + no:
+                        self.problems.append(f"{where}: output `{o}` [{po:#x}, +{no}) overlaps input `{i}` [{pi:#x}, +{ni})")
+        for w, ld in pitches.items():
+            if w not in ext:
+                continue
+            p = ext[w][0]
+            base = next((b for b, e in self.raws.items() if b <= p < b + e[0]), None)
+            off = p - base if base is not None else p          # non-arena tensors: torch allocations are 64-byte aligned
+            if off % 16 or (ld * 2) % 16:
+                self.problems.append(f"{where}: `{w}` is not TMA-addressable (offset {off} bytes, pitch {ld} elements)")
 
     @staticmethod
     def _extents(name, args):
