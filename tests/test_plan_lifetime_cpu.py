@@ -136,3 +136,42 @@ def test_vae_and_clip_plans_have_no_lifetime_hazards():
                 make()
         assert n_vae > 250 and tr.n_ops - n_vae > 300
         assert tr.problems == [], "\n".join(tr.problems[:10])
+
+
+def test_recorded_plans_carry_the_algorithmic_flops_of_the_roofline(packed):
+    """The roofline's numerator (bench.py ``FLOP_PER_SAMPLE_FWD``, SURVEY.md appendix B: 803.27 GFLOP per sample per UNet
+    forward; 63.25 for the DeepCache branch-0 cached step) against the work the recorded plans really contain:
+    2 M N K taps of every conv / linear launch (a folded LayerNorm's side chunk and the phase form of the upsample
+    convolutions counted as the operator they implement, as csrc/gemm.cu does) + 4 B H Sq Sk d of every attention.
+    The only excess is layout padding: conv_in reads 8 channels for 4, conv_out writes 16 for 4 (+0.05 %)."""
+    import importlib.util
+
+    from sonicdiffusionbayeslab_b200.unet_engine import UNetEngine
+
+    spec = importlib.util.spec_from_file_location("bench_for_constants", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+
+    per_plan = {}
+    with plan_check.recording() as tr:
+        record = tr.on_op
+
+        def on_op(name, args):
+            h = args[0].value
+            if name == "sonic_plan_add_conv_gemm":
+                g = args[1]._obj
+                k = g.c0 if g.row_scale else g.c0 + g.c1            # folded LayerNorm: a1 is the 64-column side tensor
+                per_plan[h] = per_plan.get(h, 0.0) + 2.0 * g.n_img * g.H * g.W * (4 if g.upsample else 1) * g.N * k * g.taps
+            elif name == "sonic_plan_add_attention":
+                a = args[1]._obj
+                per_plan[h] = per_plan.get(h, 0.0) + 4.0 * a.batch * a.heads * a.seq_q * a.seq_k * a.head_dim
+            record(name, args)
+
+        tr.on_op = on_op
+        eng = UNetEngine(packed, n_latents=4, cfg_dup=True, device="cpu", cache_branch=0)
+        flops = {name: per_plan.get(p.h.value, 0.0) for name, p in eng.plans.items()}
+    samples = 8
+    full = (flops["full"] + flops["ctx"]) / samples                  # the context K / V projections run once per call
+    cached = flops["cached"] / samples
+    assert abs(full / bench.FLOP_PER_SAMPLE_FWD - 1) < 1e-3, full
+    assert 0 <= cached / 63.25e9 - 1 < 1e-2, cached
