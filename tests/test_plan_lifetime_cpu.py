@@ -175,3 +175,46 @@ def test_recorded_plans_carry_the_algorithmic_flops_of_the_roofline(packed):
     cached = flops["cached"] / samples
     assert abs(full / bench.FLOP_PER_SAMPLE_FWD - 1) < 1e-3, full
     assert 0 <= cached / 63.25e9 - 1 < 1e-2, cached
+
+
+def test_cached_plans_read_exactly_the_resident_feature_of_the_full_plan(packed):
+    """Data flow BETWEEN the three plans of an engine, for every DeepCache branch (the GPU parity
+    tests run branches 0, 1, 2, 3 and 5): the full plan reads the 16 context K|V projections of the ctx plan; the cached
+    plan reads from the full plan exactly TWO buffers -- the feature of the up block below the cut and the GroupNorm
+    pre-reduction that travels with it -- and from the ctx plan the K|V of just the cross-attention layers it recomputes:
+    with (block i, layer j) = divmod(branch, 3) those are the down layers above the cut (2 per attention block 0-2) and
+    the up layers from the cut outwards (3 per attention block), i.e. 1, 3, 5 | 6, 8, 10 | 11, 13, 15 | 15, 15, 15."""
+    from sonicdiffusionbayeslab_b200.unet_engine import UNetEngine
+
+    expected_ctx_reads = [1, 3, 5, 6, 8, 10, 11, 13, 15, 15, 15, 15]
+    cached_ops = []
+    with plan_check.recording() as tr:
+        record = tr.on_op
+        for branch in range(12):
+            tr.raws.clear()
+            writer, cross = {}, {}
+
+            def base_of(p):
+                return next((b for b, e in tr.raws.items() if b <= p < b + e[0]), None)
+
+            def on_op(name, args):
+                h = args[0].value
+                ops = [(base_of(p), k) for p, k in tr._operands(name, args)]
+                for b, k in ops:
+                    if b is not None and k == "r" and writer.get(b, h) != h:
+                        cross.setdefault((writer[b], h), set()).add(b)
+                for b, k in ops:
+                    if b is not None and k == "w":
+                        writer[b] = h
+                record(name, args)
+
+            tr.on_op = on_op
+            eng = UNetEngine(packed, n_latents=2, cfg_dup=True, device="cpu", cache_branch=branch)
+            tr.on_op = record
+            name_of = {p.h.value: n for n, p in eng.plans.items()}
+            got = {(name_of[a], name_of[b]): len(v) for (a, b), v in cross.items()}
+            assert got == {("ctx", "full"): 16, ("full", "cached"): 2, ("ctx", "cached"): expected_ctx_reads[branch]}, (
+                branch, got)
+            cached_ops.append(len(eng.plans["cached"].log))
+        assert tr.problems == []
+    assert cached_ops == sorted(cached_ops) and cached_ops[0] < 40 and cached_ops[-1] < 342   # deeper cut, more work
