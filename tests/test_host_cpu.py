@@ -710,3 +710,75 @@ def test_call_sites_pass_as_many_arguments_as_the_header_declares():
                     problems.append(f"{where}: {name}: `{decl}` is passed `{ast.unparse(arg)}` (not a c_int64)")
     assert not problems, "\n".join(problems)
     assert len(seen) >= 30                                   # the check really saw the binding's call sites
+
+
+def test_lora_merge_peft_and_kohya_layouts(tmp_path):
+    """``load_lora_weights`` + ``fuse_lora`` (consistency_model.py:20-21): W' = W + (alpha / r) * scale * B A for the
+    diffusers / PEFT key layout and for the kohya layout the LCM-LoRA ships in (conv adapters included, text-encoder
+    adapters skipped); an adapter that matches nothing raises, a hub id (no network) warns and changes nothing."""
+    import warnings
+
+    from safetensors.torch import save_file
+
+    from sonicdiffusionbayeslab_b200 import models as M
+    from sonicdiffusionbayeslab_b200 import schedulers as S
+    from sonicdiffusionbayeslab_b200.text import HashTokenizer
+
+    g = torch.Generator().manual_seed(0)
+    lin = "down_blocks.0.attentions.0.transformer_blocks.0.attn1.to_q"
+    conv = "down_blocks.0.resnets.0.conv1"
+    base = {lin + ".weight": torch.randn(32, 24, generator=g), conv + ".weight": torch.randn(16, 8, 3, 3, generator=g),
+            conv + ".bias": torch.randn(16, generator=g)}
+
+    def pipe():
+        return M.StableDiffusionModel({k: v.clone() for k, v in base.items()}, vae=None, text_encoder=None,
+                                      tokenizer=HashTokenizer(), scheduler=S.PNDMScheduler.from_config(M.SD15_SCHEDULER_CONFIG))
+
+    r = 4
+    a_lin, b_lin = torch.randn(r, 24, generator=g), torch.randn(32, r, generator=g)
+    a_conv, b_conv = torch.randn(r, 8, 3, 3, generator=g), torch.randn(16, r, 1, 1, generator=g)
+    want_lin = lambda s: base[lin + ".weight"] + s * (b_lin @ a_lin)                                   # noqa: E731
+    want_conv = lambda s: base[conv + ".weight"] + s * (b_conv.flatten(1) @ a_conv.flatten(1)).view(16, 8, 3, 3)  # noqa: E731
+
+    peft = tmp_path / "peft.safetensors"
+    save_file({f"unet.{lin}.lora_A.weight": a_lin, f"unet.{lin}.lora_B.weight": b_lin,
+               f"unet.{conv}.lora_A.weight": a_conv, f"unet.{conv}.lora_B.weight": b_conv}, str(peft))
+    p = pipe()
+    p.load_lora_weights(str(peft))
+    p.fuse_lora()
+    assert torch.allclose(p._unet_sd[lin + ".weight"], want_lin(1.0), atol=1e-5)
+    assert torch.allclose(p._unet_sd[conv + ".weight"], want_conv(1.0), atol=1e-5)
+    assert torch.equal(p._unet_sd[conv + ".bias"], base[conv + ".bias"]) and p._engines == {} and p._weights is None
+
+    kohya = tmp_path / "kohya.safetensors"
+    alpha = 8.0                                                       # alpha / r = 2
+    save_file({f"lora_unet_{lin.replace('.', '_')}.lora_down.weight": a_lin,
+               f"lora_unet_{lin.replace('.', '_')}.lora_up.weight": b_lin,
+               f"lora_unet_{lin.replace('.', '_')}.alpha": torch.tensor(alpha),
+               f"lora_unet_{conv.replace('.', '_')}.lora_down.weight": a_conv,
+               f"lora_unet_{conv.replace('.', '_')}.lora_up.weight": b_conv,
+               f"lora_unet_{conv.replace('.', '_')}.alpha": torch.tensor(alpha),
+               "lora_te_text_model_encoder_layers_0_mlp_fc1.lora_down.weight": torch.randn(r, 8, generator=g),
+               "lora_te_text_model_encoder_layers_0_mlp_fc1.lora_up.weight": torch.randn(8, r, generator=g)}, str(kohya))
+    p = pipe()
+    p.load_lora_weights(str(kohya), adapter_scale=0.5)
+    p.fuse_lora(lora_scale=0.5)
+    s = (alpha / r) * 0.5 * 0.5
+    assert torch.allclose(p._unet_sd[lin + ".weight"], want_lin(s), atol=1e-5)
+    assert torch.allclose(p._unet_sd[conv + ".weight"], want_conv(s), atol=1e-5)
+
+    other = tmp_path / "other.safetensors"
+    save_file({"unet.mid_block.nothing_here.lora_A.weight": a_lin, "unet.mid_block.nothing_here.lora_B.weight": b_lin},
+              str(other))
+    p = pipe()
+    p.load_lora_weights(str(other))
+    with pytest.raises(ValueError, match="none of the 2 tensors"):
+        p.fuse_lora()
+
+    p = pipe()
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        p.load_lora_weights("latent-consistency/lcm-lora-sdv1-5")
+    assert any("NO adapter is applied" in str(x.message) for x in w)
+    p.fuse_lora()                                                     # nothing loaded: a no-op, weights untouched
+    assert all(torch.equal(p._unet_sd[k], v) for k, v in base.items())
