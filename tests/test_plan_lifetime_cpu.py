@@ -218,3 +218,40 @@ def test_cached_plans_read_exactly_the_resident_feature_of_the_full_plan(packed)
             cached_ops.append(len(eng.plans["cached"].log))
         assert tr.problems == []
     assert cached_ops == sorted(cached_ops) and cached_ops[0] < 40 and cached_ops[-1] < 342   # deeper cut, more work
+
+
+def test_plan_log_matches_the_operators_and_the_roofline_byte_counts_of_bench(packed):
+    """bench.py pairs the native per-operator profile with ``plan.log`` line by line and parses the GroupNorm /
+    ``ln_side`` lines for the HBM rooflines: one log line per recorded operator, in order, with the fields bench reads;
+    at the benchmarked shape (UNet batch 32) the GroupNorm traffic is SURVEY 8(d)'s 180.2 MB per sample-forward."""
+    from sonicdiffusionbayeslab_b200.unet_engine import UNetEngine
+
+    per_plan = {}
+    with plan_check.recording() as tr:
+        record = tr.on_op
+
+        def on_op(name, args):
+            per_plan.setdefault(args[0].value, []).append(name[len("sonic_plan_add_"):])
+            record(name, args)
+
+        tr.on_op = on_op
+        eng = UNetEngine(packed, n_latents=16, cfg_dup=True, device="cpu")
+        ops = {n: per_plan[p.h.value] for n, p in eng.plans.items()}
+        logs = {n: list(p.log) for n, p in eng.plans.items()}
+    gn_bytes = ln_sides = 0
+    for name in ops:
+        assert len(ops[name]) == len(logs[name]), name
+        for op, text in zip(ops[name], logs[name]):
+            head = text.split()[0]
+            assert head.startswith(op.split("_fused")[0][:6]) or (op, head) in {("conv_gemm", "gemm"), ("conv_gemm", "conv3x3"),
+                                                                               ("conv_gemm", "linear")}, (op, text)
+            if name != "full":
+                continue
+            f = dict(p.split("=") for p in text.split()[1:] if "=" in p)        # bench.py's parse
+            if op == "ln_side":
+                ln_sides += 1
+                assert int(f["rows"]) > 0 and int(f["parts"]) > 0
+            elif op.startswith("groupnorm"):
+                gn_bytes += 2 * int(f["rows"]) * int(f["C"]) * 2
+    assert ln_sides == 48 and len(logs["full"]) == 342
+    assert gn_bytes == 5767168000 and abs(gn_bytes / 32 / 180.2e6 - 1) < 1e-3
