@@ -206,3 +206,83 @@ def test_prompt_encoder_and_clip_tower_plans_compute_the_transformers_modules():
     err = (got - want).abs().max().item() / want.abs().max().item()
     print(f"\n[clip image tower] interpreted plans vs transformers CLIPVisionModel: max-abs / range {err:.2e}")
     assert err <= 3e-2, err
+
+
+@pytest.mark.parametrize("case", ["ddim_cfg", "dpmpp_deepcache_branch3", "lcm_no_cfg"])
+def test_product_pipeline_over_interpreted_plans_equals_the_oracle_loop(unet, case, monkeypatch):
+    """The whole product stack short of the kernels, on the CPU: ``StableDiffusionModel.__call__`` -> ``UNetEngine``
+    (real plan recording, ``set_context`` / ``forward`` replaying the plans through the interpreter) -> fused scheduler
+    step (float64 kernel model), against the oracle loop -- what ``__graft_entry__.smoke()`` checks on the GPU, plus a
+    DeepCache run (cached plan of branch 3 every other step) and an LCM run without guidance."""
+    from test_pipeline_host_cpu import _launch_in_place
+
+    from oracle import schedulers as O
+    from oracle.deepcache import DeepCacheOracle
+    from oracle.pipeline import denoise
+    from sonicdiffusionbayeslab_b200 import kernels as K
+    from sonicdiffusionbayeslab_b200 import models as M
+    from sonicdiffusionbayeslab_b200 import schedulers as S
+    from sonicdiffusionbayeslab_b200 import unet_engine as UE
+    from sonicdiffusionbayeslab_b200.deepcache import DeepCacheSDHelper
+    from sonicdiffusionbayeslab_b200.text import HashTokenizer
+
+    net, packed = unet
+    hw, B = 16, 1
+    g = torch.Generator().manual_seed(11)
+    pe = torch.randn(B, 77, 768, generator=g).bfloat16().float()
+    ne = torch.randn(B, 77, 768, generator=g).bfloat16().float()
+    lat = torch.randn(B, 4, hw, hw, generator=g)
+    cfg = O.SD15_SCHEDULER_CONFIG
+    if case == "ddim_cfg":
+        prod, orac, steps, guidance, dc = S.DDIMSchedulerMy.from_config(cfg), O.DDIMScheduler.from_config(cfg), 2, 7.5, None
+    elif case == "lcm_no_cfg":
+        prod, orac, steps, guidance, dc = S.LCMScheduler.from_config(cfg), O.LCMScheduler.from_config(cfg), 3, 0.0, None
+    else:
+        kw = dict(solver_order=2, algorithm_type="dpmsolver++", final_sigmas_type="zero")
+        prod, orac = S.DPMSolverScheduler.from_config(cfg, **kw), O.DPMSolverScheduler.from_config(cfg, **kw)
+        steps, guidance, dc = 4, 7.5, (2, 3)
+
+    with _Session() as s:
+        monkeypatch.setattr(UE._Plan, "run", lambda plan, stream: s.interp.run(plan.h))
+        monkeypatch.setattr(K, "stream_ptr", lambda: None)
+        monkeypatch.setattr(S.FusedScheduler, "_launch", _launch_in_place)
+        monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
+
+        def engine(self, n_latents, cfg_dup):                       # _PipelineBase.engine without the CUDA requirement
+            branch = self._deepcache["branch"] if self._deepcache else 0
+            key = (n_latents, bool(cfg_dup), branch)
+            if key not in self._engines:
+                self._engines[key] = s.build(lambda: UE.UNetEngine(
+                    packed, n_latents=n_latents, cfg_dup=cfg_dup, arch=self.arch, height=self.latent_size,
+                    width=self.latent_size, io_dtype=self.dtype, device="cpu", cache_branch=branch))
+            return self._engines[key]
+
+        monkeypatch.setattr(M._PipelineBase, "engine", engine)
+        model = M.StableDiffusionModel(packed.sd, vae=None, text_encoder=None, tokenizer=HashTokenizer(), scheduler=prod,
+                                       torch_dtype=torch.float32, latent_size=hw)
+        helper = None
+        if dc:
+            helper = DeepCacheSDHelper(pipe=model)
+            helper.set_params(cache_interval=dc[0], cache_branch_id=dc[1])
+            helper.enable()
+        kw = dict(generator=torch.Generator().manual_seed(3)) if case == "lcm_no_cfg" else {}
+        out, secs, _ = model(prompt_embeds=pe, negative_prompt_embeds=ne if guidance > 1 else None, latents=lat,
+                             num_inference_steps=steps, guidance_scale=guidance, output_type="latent", **kw)
+        kinds = list(model.last_step_kinds)
+        if helper:
+            helper.disable()
+        got = out.images.float().clone()
+        assert s.tracker.problems == []
+    oracle_dc = None
+    if dc:
+        oracle_dc = DeepCacheOracle(net)
+        oracle_dc.set_params(cache_interval=dc[0], cache_branch_id=dc[1])
+    kw = dict(generator=torch.Generator().manual_seed(3)) if case == "lcm_no_cfg" else {}
+    ref = denoise(net, orac, pe, ne, lat, steps, guidance_scale=guidance, deepcache=oracle_dc, **kw)
+    rng = max(1.0, ref["latents"].abs().max().item())
+    err = (got - ref["latents"]).abs().max().item() / rng
+    print(f"\n[{case}] product pipeline over interpreted plans vs oracle loop: max-abs / range {err:.2e} "
+          f"(range {rng:.2f}, steps {kinds})")
+    assert model.scheduler.timesteps.tolist() == ref["timesteps"]
+    assert kinds == (["full", "cached", "full", "cached"] if dc else ["full"] * len(ref["timesteps"]))
+    assert err <= 3e-2, err
