@@ -9,7 +9,8 @@ step's latents within 1.3 x stock-PyTorch-bf16's worst step + 3e-2 of the fp32 o
 tests/test_parity_abs_gpu.py makes for the unskipped loop: a bf16 UNet under CFG 7.5 is what loses ~1e-1 per step).
 A wrong solver interval or a stale history entry -- what a skipping bug would produce -- shows up at this fixture's
 magnitudes (|x| ~ 5) well above that.  (A CPU rehearsal of this very test over interpreted plans at a 16 x 16 latent --
-tools/plan_interp.py, bf16 activations -- gave engine-like worst 1.24e-1, stock-PyTorch-bf16 worst 1.13e-1.)  The host
+tools/plan_interp.py, bf16 activations -- gave engine-like worst 1.24e-1, stock-PyTorch-bf16 worst 1.13e-1; at the
+real 64 x 64 latent 1.06e-1 against 1.12e-1: profiles/r2m_cpu_rehearsal_skip_steps.txt.)  The host
 logic of the same loop is pinned to 5e-6 against the reference's own source on the CPU
 (tests/test_pipeline_host_cpu.py, case ``skip_dpmpp``).
 """
