@@ -208,7 +208,8 @@ def test_prompt_encoder_and_clip_tower_plans_compute_the_transformers_modules():
     assert err <= 3e-2, err
 
 
-@pytest.mark.parametrize("case", ["ddim_cfg", "dpmpp_deepcache_branch3", "lcm_no_cfg"])
+@pytest.mark.parametrize("case", ["ddim_cfg", "dpmpp_deepcache_branch3", "lcm_no_cfg", "two_schedulers",
+                                  "interleaved_rescale"])
 def test_product_pipeline_over_interpreted_plans_equals_the_oracle_loop(unet, case, monkeypatch):
     """The whole product stack short of the kernels, on the CPU: ``StableDiffusionModel.__call__`` -> ``UNetEngine``
     (real plan recording, ``set_context`` / ``forward`` replaying the plans through the interpreter) -> fused scheduler
@@ -218,7 +219,7 @@ def test_product_pipeline_over_interpreted_plans_equals_the_oracle_loop(unet, ca
 
     from oracle import schedulers as O
     from oracle.deepcache import DeepCacheOracle
-    from oracle.pipeline import denoise
+    from oracle.pipeline import denoise, denoise_interleaved, denoise_two
     from sonicdiffusionbayeslab_b200 import kernels as K
     from sonicdiffusionbayeslab_b200 import models as M
     from sonicdiffusionbayeslab_b200 import schedulers as S
@@ -233,7 +234,13 @@ def test_product_pipeline_over_interpreted_plans_equals_the_oracle_loop(unet, ca
     ne = torch.randn(B, 77, 768, generator=g).bfloat16().float()
     lat = torch.randn(B, 4, hw, hw, generator=g)
     cfg = O.SD15_SCHEDULER_CONFIG
-    if case == "ddim_cfg":
+    pp = dict(solver_order=2, algorithm_type="dpmsolver++")
+    cls = M.StableDiffusionModel
+    if case == "two_schedulers":                                    # DDIM for 2 steps, then DPM-Solver++ on the same grid
+        cls, prod, orac, steps, guidance, dc = M.StableDiffusionModelTwoSchedulers, None, None, 5, 7.5, None
+    elif case == "interleaved_rescale":                             # DPM-Solver++ main, DDIM on group 1, guidance_rescale
+        cls, prod, orac, steps, guidance, dc = M.StableDiffusionModelInterlivingSchedulers, None, None, 6, 7.5, None
+    elif case == "ddim_cfg":
         prod, orac, steps, guidance, dc = S.DDIMSchedulerMy.from_config(cfg), O.DDIMScheduler.from_config(cfg), 2, 7.5, None
     elif case == "lcm_no_cfg":
         prod, orac, steps, guidance, dc = S.LCMScheduler.from_config(cfg), O.LCMScheduler.from_config(cfg), 3, 0.0, None
@@ -258,16 +265,27 @@ def test_product_pipeline_over_interpreted_plans_equals_the_oracle_loop(unet, ca
             return self._engines[key]
 
         monkeypatch.setattr(M._PipelineBase, "engine", engine)
-        model = M.StableDiffusionModel(packed.sd, vae=None, text_encoder=None, tokenizer=HashTokenizer(), scheduler=prod,
-                                       torch_dtype=torch.float32, latent_size=hw)
+        model = cls(packed.sd, vae=None, text_encoder=None, tokenizer=HashTokenizer(),
+                    scheduler=prod or S.PNDMScheduler.from_config(cfg), torch_dtype=torch.float32, latent_size=hw)
         helper = None
         if dc:
             helper = DeepCacheSDHelper(pipe=model)
             helper.set_params(cache_interval=dc[0], cache_branch_id=dc[1])
             helper.enable()
         kw = dict(generator=torch.Generator().manual_seed(3)) if case == "lcm_no_cfg" else {}
-        out, secs, _ = model(prompt_embeds=pe, negative_prompt_embeds=ne if guidance > 1 else None, latents=lat,
-                             num_inference_steps=steps, guidance_scale=guidance, output_type="latent", **kw)
+        common = dict(prompt_embeds=pe, negative_prompt_embeds=ne if guidance > 1 else None, latents=lat,
+                      guidance_scale=guidance, output_type="latent")
+        if case == "two_schedulers":
+            model.scheduler_first = S.DDIMSchedulerMy.from_config(cfg)
+            model.scheduler_second = S.DPMSolverScheduler.from_config(cfg, **pp)
+            out, secs, _ = model(**common, num_inference_steps_first=steps, num_inference_steps_second=steps,
+                                 num_step_switch=2, type_switch="closest")
+        elif case == "interleaved_rescale":
+            model.scheduler_main = S.DPMSolverScheduler.from_config(cfg, **pp)
+            model.scheduler_inter = S.DDIMSchedulerMy.from_config(cfg)
+            out, secs, _ = model(**common, num_inference_steps=steps, interliving_steps=[1], guidance_rescale=0.7)
+        else:
+            out, secs, _ = model(**common, num_inference_steps=steps, **kw)
         kinds = list(model.last_step_kinds)
         if helper:
             helper.disable()
@@ -278,11 +296,24 @@ def test_product_pipeline_over_interpreted_plans_equals_the_oracle_loop(unet, ca
         oracle_dc = DeepCacheOracle(net)
         oracle_dc.set_params(cache_interval=dc[0], cache_branch_id=dc[1])
     kw = dict(generator=torch.Generator().manual_seed(3)) if case == "lcm_no_cfg" else {}
-    ref = denoise(net, orac, pe, ne, lat, steps, guidance_scale=guidance, deepcache=oracle_dc, **kw)
+    if case == "two_schedulers":
+        ref = denoise_two(net, O.DDIMScheduler.from_config(cfg), O.DPMSolverScheduler.from_config(cfg, **pp), pe, ne, lat,
+                          steps, 2, "closest", guidance_scale=guidance)
+    elif case == "interleaved_rescale":
+        ref = denoise_interleaved(net, O.DPMSolverScheduler.from_config(cfg, **pp), O.DDIMScheduler.from_config(cfg), pe,
+                                  ne, lat, steps, [1], guidance_scale=guidance, guidance_rescale=0.7)
+    else:
+        ref = denoise(net, orac, pe, ne, lat, steps, guidance_scale=guidance, deepcache=oracle_dc, **kw)
     rng = max(1.0, ref["latents"].abs().max().item())
     err = (got - ref["latents"]).abs().max().item() / rng
     print(f"\n[{case}] product pipeline over interpreted plans vs oracle loop: max-abs / range {err:.2e} "
           f"(range {rng:.2f}, steps {kinds})")
-    assert model.scheduler.timesteps.tolist() == ref["timesteps"]
-    assert kinds == (["full", "cached", "full", "cached"] if dc else ["full"] * len(ref["timesteps"]))
+    if case == "two_schedulers":
+        first, second = model.last_timesteps
+        assert ([int(t) for t in first], [int(t) for t in second]) == ref["timesteps"]
+    elif case == "interleaved_rescale":
+        assert model.last_timesteps == ref["timesteps"]
+    else:
+        assert model.scheduler.timesteps.tolist() == ref["timesteps"]
+        assert kinds == (["full", "cached", "full", "cached"] if dc else ["full"] * len(ref["timesteps"]))
     assert err <= 3e-2, err
