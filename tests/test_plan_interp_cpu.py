@@ -317,3 +317,68 @@ def test_product_pipeline_over_interpreted_plans_equals_the_oracle_loop(unet, ca
         assert model.scheduler.timesteps.tolist() == ref["timesteps"]
         assert kinds == (["full", "cached", "full", "cached"] if dc else ["full"] * len(ref["timesteps"]))
     assert err <= 3e-2, err
+
+
+@pytest.mark.parametrize("output_type", ["pil", "np"])
+def test_decode_and_postprocess_over_interpreted_plans(unet, output_type, monkeypatch):
+    """The tail of the call (models.py:287-335) with the real engines on the CPU: final latents and every step's
+    ``x0_pred[0]`` through the VAE decoder plan (``VaeEngine``, interpreted), denormalise, ``postprocess`` to PIL /
+    numpy, ``return_dict=False`` -- against the oracle loop + the oracle decoder."""
+    import numpy as np
+    from test_pipeline_host_cpu import _launch_in_place
+
+    from oracle import schedulers as O
+    from oracle.pipeline import denoise
+    from oracle.vae import make_vae
+    from sonicdiffusionbayeslab_b200 import kernels as K
+    from sonicdiffusionbayeslab_b200 import models as M
+    from sonicdiffusionbayeslab_b200 import schedulers as S
+    from sonicdiffusionbayeslab_b200 import unet_engine as UE
+    from sonicdiffusionbayeslab_b200.text import HashTokenizer
+    from sonicdiffusionbayeslab_b200.vae_spec import VaeWeights
+
+    net, packed = unet
+    vae = make_vae(29, dtype=torch.float32)
+    hw, steps = 16, 2
+    g = torch.Generator().manual_seed(21)
+    pe = torch.randn(1, 77, 768, generator=g).bfloat16().float()
+    ne = torch.randn(1, 77, 768, generator=g).bfloat16().float()
+    lat = torch.randn(1, 4, hw, hw, generator=g)
+    cfg = O.SD15_SCHEDULER_CONFIG
+    with _Session() as s:
+        monkeypatch.setattr(UE._Plan, "run", lambda plan, stream: s.interp.run(plan.h))
+        monkeypatch.setattr(K, "stream_ptr", lambda: None)
+        monkeypatch.setattr(S.FusedScheduler, "_launch", _launch_in_place)
+        monkeypatch.setattr(torch.cuda, "synchronize", lambda *a, **k: None)
+        monkeypatch.setattr(M._PipelineBase, "engine", lambda self, n, dup: self._engines.setdefault(
+            ("unet", n, dup), UE.UNetEngine(packed, n_latents=n, cfg_dup=dup, height=hw, width=hw, io_dtype=self.dtype,
+                                            device="cpu")))
+        monkeypatch.setattr(M._PipelineBase, "_decode",                      # the product's body minus the CUDA requirement
+                            lambda self, z: self.vae_engine(z.shape[0]).decode(z.to(self.dtype)).clone())
+        model = M.StableDiffusionModel(packed.sd, vae=VaeWeights(dict(vae.state_dict())), text_encoder=None,
+                                       tokenizer=HashTokenizer(), scheduler=S.DDIMSchedulerMy.from_config(cfg),
+                                       torch_dtype=torch.float32, latent_size=hw)
+        (images, nsfw), secs, x0_images = model(prompt_embeds=pe, negative_prompt_embeds=ne, latents=lat,
+                                                num_inference_steps=steps, guidance_scale=7.5, output_type=output_type,
+                                                return_dict=False)
+        assert s.tracker.problems == [] and nsfw is None
+    ref = denoise(net, O.DDIMScheduler.from_config(cfg), pe, ne, lat, steps)
+    sf = 0.18215
+
+    def decoded(z):
+        with torch.no_grad():
+            return (vae.decode(z / sf)[0] / 2 + 0.5).clamp(0, 1)
+
+    want = [decoded(ref["latents"])] + [decoded(x0) for x0 in ref["x0"]]
+    got = [images] + list(x0_images)
+    assert len(x0_images) == steps == len(ref["x0"])                          # one x0 preview per DDIM step (row 0 only)
+    for a, b in zip(got, want):
+        if output_type == "pil":
+            assert isinstance(a, list) and a[0].size == (8 * hw, 8 * hw) and a[0].mode == "RGB"
+            arr = np.stack([np.asarray(im) for im in a]).astype(np.float32) / 255.0
+        else:
+            assert isinstance(a, np.ndarray) and a.dtype == np.float32
+            arr = a
+        assert arr.shape == (1, 8 * hw, 8 * hw, 3)
+        err = np.abs(arr - b.permute(0, 2, 3, 1).numpy()).max()
+        assert err <= 4e-2, err                                              # [0, 1] images: bf16 decoder vs fp32 oracle
