@@ -42,6 +42,30 @@ def ref():
     return refexec.load_plugins(features=fake_features)
 
 
+@pytest.fixture(autouse=True)
+def _one_random_init_clip(monkeypatch):
+    """``ClipScoreMetric()`` builds a random-init CLIP ViT-B/16 (seconds each); the towers are replaced by
+    ``fake_features`` in every test here, so one instance of the weights serves them all -- the warning still fires."""
+    import warnings
+
+    from sonicdiffusionbayeslab_b200.metrics import metrics as MM
+
+    real = MM.make_clip_model
+
+    def cached(model_name_or_path=None, seed=29):
+        if "clip" not in _CACHE:
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                _CACHE["clip"] = real(model_name_or_path, seed)
+        warnings.warn("clip_score: RANDOM-INIT CLIP (cached for the tests)", RuntimeWarning, stacklevel=2)
+        return _CACHE["clip"]
+
+    monkeypatch.setattr(MM, "make_clip_model", cached)
+
+
+_CACHE = {}
+
+
 def test_time_metric_equals_reference_source(ref):
     from sonicdiffusionbayeslab_b200.metrics.metrics import TimeMetric
 
