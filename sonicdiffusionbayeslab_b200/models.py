@@ -67,17 +67,21 @@ def load_stock_scheduler(model_dir=None):
     cfg = {k: v for k, v in cfg.items() if not k.startswith("_")}
     known = {"PNDMScheduler": S.PNDMScheduler, "DDIMScheduler": S.DDIMSchedulerMy,
              "DPMSolverMultistepScheduler": S.DPMSolverScheduler, "LCMScheduler": S.LCMScheduler}
-    if name not in known:
-        _loud(f"{path}: stock scheduler class {name!r} has no fused step here; its config is kept for the "
-              "`from_config` idiom, but the `default` / `deep_cache` methods (which run the stock scheduler itself) "
-              "would step with PNDM instead")
+    why = None
+    if name in known:
         try:
-            return S.PNDMScheduler.from_config({**SD15_SCHEDULER_CONFIG, **cfg})
-        except (NotImplementedError, ValueError):         # e.g. a spacing PLMS is not fused for: config only
-            sched = S.PNDMScheduler.from_config(SD15_SCHEDULER_CONFIG)
-            sched.config.update(cfg)
-            return sched
-    return known[name].from_config(cfg)
+            return known[name].from_config(cfg)
+        except (NotImplementedError, ValueError) as e:      # an option of that class without a fused step (e.g. Karras sigmas)
+            why = f"stock scheduler {name} with this configuration is not fused here ({e})"
+    _loud(f"{path}: {why or f'stock scheduler class {name!r} has no fused step here'}; its config is kept for the "
+          "`from_config` idiom, but the `default` / `deep_cache` methods (which run the stock scheduler itself) "
+          "would step with PNDM instead")
+    try:
+        return S.PNDMScheduler.from_config({**SD15_SCHEDULER_CONFIG, **cfg})
+    except (NotImplementedError, ValueError):             # e.g. a spacing PLMS is not fused for: config only
+        sched = S.PNDMScheduler.from_config(SD15_SCHEDULER_CONFIG)
+        sched.config.update(cfg)
+        return sched
 
 
 class PipelineOutput(SimpleNamespace):

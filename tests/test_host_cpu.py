@@ -611,6 +611,14 @@ def test_stock_scheduler_is_read_from_a_local_model_directory(tmp_path):
     assert type(s) is S.PNDMScheduler and s.config.solver_order == 2 and s.config.algorithm_type == "deis"
     lcm = S.LCMScheduler.from_config(s.config)                                     # consistency_model.py's idiom
     assert lcm.config.beta_start == 0.00085 and lcm.config.steps_offset == 1
+    # a known class with an option that has no fused step: same stand-in, config kept, loud
+    karras = dict(sd15, _class_name="DPMSolverMultistepScheduler", use_karras_sigmas=True, solver_order=2)
+    (tmp_path / "scheduler" / "scheduler_config.json").write_text(json.dumps(karras))
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        s = M.load_stock_scheduler(str(tmp_path))
+    assert any("not fused here" in str(x.message) for x in w)
+    assert type(s) is S.PNDMScheduler and s.config.use_karras_sigmas is True and s.config.solver_order == 2
 
 
 def test_ctypes_structures_match_the_header_layout(tmp_path):
